@@ -1,0 +1,10 @@
+"""geomconsistentfr_b200 — B200 (sm_100a) implementation of the relight hot path of
+andrewhou1/GeomConsistentFR: ray-march shadow mask, Lambertian shading/render, RelightNet CNN.
+
+    csrc/      CUDA kernels + the C ABI (include/gfr_b200.h) -> csrc/libgfr_b200.so
+    _lib.py    ctypes binding (no fallback: raises if the library is missing)
+    ops.py     operator wrappers over the C ABI
+"""
+from . import _lib, ops  # noqa: F401
+
+__version__ = "0.1.0"

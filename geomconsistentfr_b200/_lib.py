@@ -1,0 +1,56 @@
+"""ctypes binding of libgfr_b200.so (the C ABI declared in include/gfr_b200.h).
+
+There is no fallback: if the library cannot be loaded every op raises."""
+import ctypes
+import os
+
+from . import build as _build
+
+_c_void_p, _c_int, _c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+_PROTOS = {
+    "gfr_version": [],
+    "gfr_error_string": [_c_int],
+    "gfr_mask_pack": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p],
+    "gfr_shadow_march_fwd": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_float,
+                             _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_shade_render_fwd": [_c_void_p] * 11 + [_c_int, _c_int, _c_int, _c_void_p],
+}
+_RESTYPES = {"gfr_error_string": ctypes.c_char_p}
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.isfile(path):
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this machine
+            raise RuntimeError("libgfr_b200.so is missing and could not be built (%s). "
+                               "Run `python -m geomconsistentfr_b200.build`." % e)
+    lib = ctypes.CDLL(path)
+    for name, argtypes in _PROTOS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, _c_int)
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_PROTOS)
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().gfr_error_string(code)
+        raise RuntimeError("%s failed: %s (code %d)" % (what, msg.decode() if msg else "?", code))

@@ -1,0 +1,190 @@
+// Hard-shadow ray-march (forward) for sm_100a.
+//
+// Replaces the per-sample python loop of the reference, TRAIN:374-515 / TEST1:351-496
+// (TRAIN = train_raytracing_relighting_CelebAHQ_DSSIM_8x.py, TEST1 = test_relight_single_image.py).
+//
+// Mapping: one THREAD per pixel-ray, a CTA owns a 32x8 pixel tile and all of its threads walk the
+// samples k = 0..n-1 in lock-step.  The n sample parameters travel as a kernel parameter (constant
+// bank -> uniform loads).  Sample positions and the bilinear weights are computed in fp64 with the
+// reference's exact operation order (no FMA contraction): the integer decisions (nearest pixel for the
+// face-mask test, floor/ceil for the bilinear footprint) are discontinuous, so fp32 positions flip
+// ~1e-4 of the pixels.  Everything after `.float()` in the reference (TRAIN:502) is fp32 here too.
+// The face mask is 1 bit/pixel in shared memory (8 KB for 256x256).
+#include "gfr_common.cuh"
+
+namespace {
+
+struct SampleTable { double t[GFR_MAX_SAMPLES]; };
+
+struct MarchArgs {
+  const float* depth;        // [B,H,W]
+  const uint32_t* mask_bits; // [1|B, H*W/32]
+  const float* light;        // [B,3]
+  float* dmin;               // [B,H,W]
+  uint8_t* argmin;           // [B,H,W] or null
+  float* shadow;             // [B,H,W] or null
+  int mask_stride;           // words
+  int B, H, W, n;
+  float bonus;
+};
+
+constexpr int TILE_W = 32, TILE_H = 8;
+
+// End point of the 2-D ray (pixel -> projected light) on the image rectangle, fp32, reference op order.
+// TRAIN:378-465.  Rectangle: x in [-W/2, W/2-1], y in [1-H/2, H/2].
+__device__ __forceinline__ void ray_end(float x, float y, float Lx, float Ly, float xmin, float xmax,
+                                        float ymin, float ymax, float& ex, float& ey) {
+  const float m = __fdiv_rn(__fsub_rn(Ly, y), __fadd_rn(__fsub_rn(Lx, x), 1e-4f));   // TRAIN:378
+  const float b = __fsub_rn(Ly, __fmul_rn(m, Lx));                                    // TRAIN:379
+  const int sx = Lx < xmin ? -1 : (Lx <= xmax ? 0 : 1);
+  const int sy = Ly < ymin ? -1 : (Ly <= ymax ? 0 : 1);
+  const float xe = sx < 0 ? xmin : xmax;
+  const float ye = sy < 0 ? ymin : ymax;
+  const float exy = __fadd_rn(__fmul_rn(m, xe), b);                                   // y on the x edge
+  const float eyx = __fdiv_rn(__fsub_rn(ye, b), __fadd_rn(m, 1e-4f));                 // x on the y edge
+  if (sx != 0 && sy != 0) {
+    const bool hit = (eyx >= xmin) && (eyx <= xmax);                                  // TRAIN:397-398
+    ex = hit ? eyx : xe;
+    ey = hit ? ye : exy;
+  } else if (sx != 0) {
+    ex = xe; ey = exy;
+  } else if (sy != 0) {
+    ex = eyx; ey = ye;
+  } else {
+    ex = Lx; ey = Ly;                                                                 // TRAIN:423-425
+  }
+  ex = ex < xmin ? xmin : ex;  ex = ex > xmax ? xmax : ex;                            // TRAIN:462-465
+  ey = ey < ymin ? ymin : ey;  ey = ey > ymax ? ymax : ey;
+}
+
+__device__ __forceinline__ float shadow_weight(float d) {   // TRAIN:517
+  const float e = expf(-d);
+  const float op = 1.0f + e;
+  return __fadd_rn(__fdiv_rn(__fmul_rn(-4.0f, e), __fmul_rn(op, op)), 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Variant 1: depth gathers straight from global memory through L1 (read-only path).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_W * TILE_H)
+shadow_march_fwd_l1(const MarchArgs a, const __grid_constant__ SampleTable tab) {
+  extern __shared__ uint32_t s_mask[];
+  const int b = blockIdx.z;
+  const int H = a.H, W = a.W;
+  const int words = (H * W) >> 5;
+  {
+    const uint32_t* src = a.mask_bits + (size_t)b * a.mask_stride;
+    for (int i = threadIdx.y * TILE_W + threadIdx.x; i < words; i += TILE_W * TILE_H) s_mask[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  const int col = blockIdx.x * TILE_W + threadIdx.x;
+  const int row = blockIdx.y * TILE_H + threadIdx.y;
+  const float* __restrict__ D = a.depth + (size_t)b * H * W;
+  const float halfW = 0.5f * W, halfH = 0.5f * H;
+  const float xmin = -halfW, xmax = W - halfW - 1.0f, ymin = 1.0f - halfH, ymax = halfH;
+  const float x = (float)col - halfW;            // TRAIN:52
+  const float y = halfH - (float)row;            // TRAIN:53
+  const float z = __ldg(D + row * W + col);
+  const float Lx = __ldg(a.light + 3 * b), Ly = __ldg(a.light + 3 * b + 1), Lz = __ldg(a.light + 3 * b + 2);
+
+  float ex, ey;
+  ray_end(x, y, Lx, Ly, xmin, xmax, ymin, ymax, ex, ey);
+  const double dx = (double)__fsub_rn(ex, x), dy = (double)__fsub_rn(ey, y);          // TRAIN:467
+  const double xd = (double)x, yd = (double)y;
+  const double hW = (double)halfW, hH = (double)halfH;
+  const float bcx = __fsub_rn(Lx, x), bcy = __fsub_rn(Ly, y), bcz = __fsub_rn(Lz, z); // BC, TRAIN:507
+
+  float qmin = __int_as_float(0x7f800000);   // +inf == "outside the face"
+  int kmin = 255;
+#pragma unroll 2
+  for (int k = 0; k < a.n; ++k) {
+    const double t = tab.t[k];
+    const double px = __dadd_rn(xd, __dmul_rn(t, dx));                                // TRAIN:472,480
+    const double py = __dadd_rn(yd, __dmul_rn(t, dy));
+    const int ci = __double2int_rn(px) + (W >> 1);                                    // TRAIN:472-475
+    const int ri = (H >> 1) - __double2int_rn(py);
+    const int mi = ri * W + ci;
+    const bool inside = (s_mask[mi >> 5] >> (mi & 31)) & 1u;                          // TRAIN:510
+    const double u = __dadd_rn(__dadd_rn(px, hW), -0.0001);                           // TRAIN:481,483
+    const double v = __dadd_rn(__dsub_rn(hH, py), -0.0001);                           // TRAIN:482,483
+    const int uf = __double2int_rd(u), uc = __double2int_ru(u);                       // TRAIN:486-487
+    const int vf = __double2int_rd(v), vc = __double2int_ru(v);
+    const int ufi = uf < 0 ? uf + W : uf, vfi = vf < 0 ? vf + H : vf;                 // python negative index
+    const double wu0 = __dsub_rn((double)uc, u), wu1 = __dsub_rn(u, (double)uf);
+    const double wv0 = __dsub_rn((double)vc, v), wv1 = __dsub_rn(v, (double)vf);
+    const double ul = (double)__ldg(D + vfi * W + ufi), ur = (double)__ldg(D + vfi * W + uc);
+    const double ll = (double)__ldg(D + vc * W + ufi), lr = (double)__ldg(D + vc * W + uc);
+    const double up = __dadd_rn(__dmul_rn(ul, wu0), __dmul_rn(ur, wu1));              // TRAIN:492
+    const double lo = __dadd_rn(__dmul_rn(ll, wu0), __dmul_rn(lr, wu1));              // TRAIN:493
+    const double zi = __dadd_rn(__dmul_rn(up, wv0), __dmul_rn(lo, wv1));              // TRAIN:494
+    const float ax = (float)__dsub_rn(u, hW), ay = (float)__dsub_rn(hH, v), az = (float)zi;   // TRAIN:498-502
+    const float bax = __fsub_rn(ax, x), bay = __fsub_rn(ay, y), baz = __fsub_rn(az, z);
+    const float c0 = __fsub_rn(__fmul_rn(bay, bcz), __fmul_rn(baz, bcy));             // TRAIN:508
+    const float c1 = __fsub_rn(__fmul_rn(baz, bcx), __fmul_rn(bax, bcz));
+    const float c2 = __fsub_rn(__fmul_rn(bax, bcy), __fmul_rn(bay, bcx));
+    const float q = __fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fmul_rn(c2, c2));
+    if (inside && q < qmin) { qmin = q; kmin = k; }
+  }
+  // min_k sqrt(q_k + eps)/den == sqrt(min_k q_k + eps)/den (monotone), TRAIN:509,514
+  float d;
+  if (kmin == 255) {
+    d = 1000000.0f;                                                                   // TRAIN:512
+  } else {
+    const float den = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bcx, bcx), __fmul_rn(bcy, bcy)), __fmul_rn(bcz, bcz)), 1e-4f));
+    d = __fdiv_rn(sqrtf(__fadd_rn(qmin, 1e-4f)), den);
+  }
+  if (a.bonus != 0.0f && Lx >= xmin && Lx <= xmax && Ly >= ymin && Ly <= ymax) d = __fadd_rn(d, a.bonus);   // TEST1:495-496
+  const size_t o = (size_t)b * H * W + row * W + col;
+  a.dmin[o] = d;
+  if (a.argmin) a.argmin[o] = (uint8_t)kmin;
+  if (a.shadow) a.shadow[o] = shadow_weight(d);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// mask packing
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void mask_pack_kernel(const T* __restrict__ mask, uint32_t* __restrict__ bits, size_t n_pixels) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool nz = i < n_pixels ? (mask[i] != (T)0) : false;
+  const uint32_t w = __ballot_sync(0xffffffffu, nz);
+  if ((threadIdx.x & 31) == 0 && i < n_pixels) bits[i >> 5] = w;
+}
+
+}  // namespace
+
+extern "C" int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int H, int W, uint32_t* bits, void* stream) {
+  GFR_RETURN_IF_NULL(mask); GFR_RETURN_IF_NULL(bits);
+  if (n_masks <= 0 || H <= 0 || W <= 0 || ((H * W) & 31)) return GFR_E_SHAPE;
+  const size_t n = (size_t)n_masks * H * W;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (mask_dtype) {
+    case GFR_MASK_U8: mask_pack_kernel<uint8_t><<<blocks, threads, 0, s>>>((const uint8_t*)mask, bits, n); break;
+    case GFR_MASK_F32: mask_pack_kernel<float><<<blocks, threads, 0, s>>>((const float*)mask, bits, n); break;
+    case GFR_MASK_F64: mask_pack_kernel<double><<<blocks, threads, 0, s>>>((const double*)mask, bits, n); break;
+    default: return GFR_E_ARG;
+  }
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
+                                    const float* light_pt, const double* t_host, int n, float inside_bonus,
+                                    float* d_min, uint8_t* argmin, float* shadow, int B, int H, int W, int variant,
+                                    void* stream) {
+  GFR_RETURN_IF_NULL(depth); GFR_RETURN_IF_NULL(mask_bits); GFR_RETURN_IF_NULL(light_pt);
+  GFR_RETURN_IF_NULL(t_host); GFR_RETURN_IF_NULL(d_min);
+  if (B <= 0 || H <= 0 || W <= 0 || (W % TILE_W) || (H % TILE_H) || H > 512 || W > 512 || B > 65535) return GFR_E_SHAPE;
+  if (n <= 0 || n > 255) return GFR_E_ARG;     // 255 is the "no sample inside the face" argmin code
+  if (mask_batch_stride != 0 && mask_batch_stride != (H * W) / 32) return GFR_E_ARG;
+  if (variant < 0 || variant > 1) return GFR_E_ARG;
+  SampleTable tab;
+  for (int k = 0; k < GFR_MAX_SAMPLES; ++k) tab.t[k] = k < n ? t_host[k] : 0.0;
+  MarchArgs a{depth, mask_bits, light_pt, d_min, argmin, shadow, mask_batch_stride, B, H, W, n, inside_bonus};
+  const dim3 grid(W / TILE_W, H / TILE_H, B), block(TILE_W, TILE_H);
+  const size_t smem = (size_t)(H * W / 32) * sizeof(uint32_t);
+  shadow_march_fwd_l1<<<grid, block, smem, (cudaStream_t)stream>>>(a, tab);
+  return gfr_launch_status();
+}

@@ -1,0 +1,100 @@
+"""Operator layer: thin, checked wrappers that hand torch CUDA tensors to the C ABI (include/gfr_b200.h).
+
+torch is used for device memory and the current stream only.  Every function raises if the input is not
+a contiguous CUDA tensor of the expected dtype — there is no CPU path."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+NUM_SAMPLES = 160          # TRAIN:48
+LIGHT_DISTANCE = 4013.0    # TRAIN:47
+_MASK_DTYPES = {torch.uint8: 0, torch.bool: 0, torch.float32: 1, torch.float64: 2}
+
+
+def reference_samples():
+    """The reference's sample parameters, bit-for-bit: np.arange(0.025, 0.825, 0.005) (TRAIN:468)."""
+    t = np.arange(0.025, 0.825, 0.005)
+    assert t.shape[0] == NUM_SAMPLES
+    return t
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need(t, dtype, name):
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise RuntimeError("%s must be a CUDA tensor (libgfr_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise RuntimeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def mask_pack(mask):
+    """mask [n,H,W] (u8/bool/f32/f64, CUDA) -> bits [n, H*W/32] int32 (bit set iff mask != 0; TRAIN:510)."""
+    if not (torch.is_tensor(mask) and mask.is_cuda):
+        raise RuntimeError("mask must be a CUDA tensor")
+    if mask.dtype not in _MASK_DTYPES:
+        raise RuntimeError("unsupported mask dtype %s" % mask.dtype)
+    mask = mask.contiguous()
+    n, H, W = mask.shape
+    bits = torch.empty((n, H * W // 32), dtype=torch.int32, device=mask.device)
+    rc = _lib.load().gfr_mask_pack(_ptr(mask), _MASK_DTYPES[mask.dtype], n, H, W, _ptr(bits), _stream())
+    _lib.check(rc, "gfr_mask_pack")
+    return bits
+
+
+def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0, want_argmin=False,
+                     want_shadow=False, variant=0):
+    """depth [B,1,H,W] f32; mask_bits [1|B, H*W/32] i32; light_pt [B,3] f32 -> d_min [B,H,W]
+    (+ argmin u8, + shadow).  TRAIN:374-517."""
+    depth = _need(depth, torch.float32, "depth")
+    light_pt = _need(light_pt, torch.float32, "light_pt")
+    mask_bits = _need(mask_bits, torch.int32, "mask_bits")
+    B, _, H, W = depth.shape
+    if light_pt.shape != (B, 3):
+        raise RuntimeError("light_pt must be [B,3]")
+    if mask_bits.shape[0] not in (1, B) or mask_bits.shape[1] != H * W // 32:
+        raise RuntimeError("mask_bits must be [1|B, H*W/32]")
+    t = reference_samples() if samples is None else np.ascontiguousarray(samples, dtype=np.float64)
+    dmin = torch.empty((B, H, W), dtype=torch.float32, device=depth.device)
+    arg = torch.empty((B, H, W), dtype=torch.uint8, device=depth.device) if want_argmin else None
+    shadow = torch.empty((B, H, W), dtype=torch.float32, device=depth.device) if want_shadow else None
+    stride = 0 if mask_bits.shape[0] == 1 else H * W // 32
+    rc = _lib.load().gfr_shadow_march_fwd(
+        _ptr(depth), _ptr(mask_bits), stride, _ptr(light_pt), t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]),
+        float(inside_bonus), _ptr(dmin), _ptr(arg), _ptr(shadow), B, H, W, int(variant), _stream())
+    _lib.check(rc, "gfr_shadow_march_fwd")
+    return dmin, arg, shadow
+
+
+def shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx=1570.0, fy=1570.0, cx=None, cy=None,
+                     depth_offset=1610.0, intensity=0.5, want=("shadow", "full", "final", "rendered", "normals")):
+    """TRAIN:353-369, 517-522.  Returns dict of the requested outputs."""
+    depth = _need(depth, torch.float32, "depth")
+    d_min = _need(d_min, torch.float32, "d_min")
+    light_pt = _need(light_pt, torch.float32, "light_pt")
+    ambient = _need(ambient.reshape(-1), torch.float32, "ambient")
+    B, _, H, W = depth.shape
+    if "rendered" in want:
+        albedo = _need(albedo, torch.float32, "albedo")
+    intr = np.array([fx, fy, W / 2.0 if cx is None else cx, H / 2.0 if cy is None else cy, depth_offset, intensity],
+                    dtype=np.float32)
+    dev = depth.device
+    out = {}
+    for k, shape in (("shadow", (B, H, W)), ("full", (B, H, W)), ("final", (B, H, W)), ("rendered", (B, 3, H, W)),
+                     ("normals", (B, 3, H, W))):
+        out[k] = torch.empty(shape, dtype=torch.float32, device=dev) if k in want else None
+    rc = _lib.load().gfr_shade_render_fwd(
+        _ptr(albedo) if "rendered" in want else None, _ptr(depth), _ptr(d_min), _ptr(light_pt), _ptr(ambient),
+        intr.ctypes.data_as(ctypes.c_void_p), _ptr(out["shadow"]), _ptr(out["full"]), _ptr(out["final"]),
+        _ptr(out["rendered"]), _ptr(out["normals"]), B, H, W, _stream())
+    _lib.check(rc, "gfr_shade_render_fwd")
+    return out

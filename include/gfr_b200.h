@@ -1,0 +1,85 @@
+/* gfr_b200.h — C ABI of libgfr_b200.so: the B200 (sm_100a) implementation of the relight hot path
+ * of andrewhou1/GeomConsistentFR.
+ *
+ * The reference has no FFI of its own (the path is inlined in RelightNet.forward); every entry point
+ * below therefore cites the reference LINES it replaces.  Citations are relative to the reference root:
+ *   TRAIN = train_raytracing_relighting_CelebAHQ_DSSIM_8x.py      TEST1 = test_relight_single_image.py
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and sizes; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer; the library never allocates device memory and never synchronises;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - tensors are contiguous, row-major, fp32 unless stated; images are NCHW;
+ *   - return value: 0 on success, a negative GFR_E_* argument error, or a positive cudaError_t;
+ *     gfr_error_string() describes either;
+ *   - re-entrant, no global state except the lazily resolved driver entry point for TMA descriptors.
+ */
+#ifndef GFR_B200_H_
+#define GFR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFR_OK 0
+#define GFR_E_NULL (-1)      /* a required pointer is NULL            */
+#define GFR_E_SHAPE (-2)     /* unsupported shape / size              */
+#define GFR_E_ARG (-3)       /* bad scalar argument                   */
+#define GFR_E_UNSUPPORTED (-4)
+
+#define GFR_MAX_SAMPLES 256  /* the sample table travels as a kernel parameter */
+
+int gfr_version(void);
+const char* gfr_error_string(int code);
+
+/* mask dtypes accepted by gfr_mask_pack */
+#define GFR_MASK_U8 0
+#define GFR_MASK_F32 1
+#define GFR_MASK_F64 2
+
+/* Face-mask bit packing.  The march only ever tests `mask[r, c] == 0` (TRAIN:510, TEST1:488), so the
+ * mask travels as 1 bit per pixel: bit (r*W + c) & 31 of word (r*W + c) >> 5 is set iff mask != 0.
+ * mask: [n_masks, H, W] of the given dtype; bits: [n_masks, H*W/32] uint32.  H*W must be a multiple of 32. */
+int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int H, int W, uint32_t* bits, void* stream);
+
+/* Ray-march forward: minimum point-to-ray distance over the samples, per pixel.
+ * Replaces TRAIN:374-515 / TEST1:351-496 (end points, 160 fp64 sample positions, bilinear depth,
+ * point-to-line distance, face-mask reject, min, optional "+5 when the light projects inside the image").
+ *   depth      [B,1,H,W]   raw depth (100 x the depth head), fp32
+ *   mask_bits  [1|B, H*W/32] from gfr_mask_pack; mask_batch_stride = 0 (one mask for the batch,
+ *              TEST1:488) or H*W/32 (one per image, TRAIN:510), in uint32 words
+ *   light_pt   [B,3]       light_distance * unit(L)   (TRAIN:360-363)
+ *   t_host     [n] HOST doubles: the sample parameters, exactly np.arange(0.025, 0.825, 0.005) for the
+ *              reference configuration (TRAIN:468); n <= GFR_MAX_SAMPLES
+ *   inside_bonus  0 (train) or 5 (test, TEST1:495-496)
+ *   d_min      [B,H,W] out
+ *   argmin     [B,H,W] out, uint8 index of the minimising sample (255 = every sample was outside the
+ *              face); may be NULL.  Needed by the backward.
+ *   shadow     [B,H,W] out, 1 - 4e^-d/(1+e^-d)^2 (TRAIN:517); may be NULL.
+ *   variant    0 = default; 1 = L1/global gathers (no shared-memory depth staging); used by tests/bench.
+ */
+int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
+                         const float* light_pt, const double* t_host, int n, float inside_bonus,
+                         float* d_min, uint8_t* argmin, float* shadow, int B, int H, int W, int variant,
+                         void* stream);
+
+/* Normals + Lambertian shading + shadow blend + albedo render.  Replaces TRAIN:353-369 and 517-522
+ * (kornia depth_to_normals(depth + depth_offset, K), y flip, double normalise, l = normalize(P_L - P),
+ * dir = intensity * max(n.l, 0), full = ambient + dir, s = shadow(d_min),
+ * final = s*full + (1-s)*ambient, rendered = albedo*final).
+ *   albedo [B,3,H,W]; depth [B,1,H,W]; d_min [B,H,W]; light_pt [B,3]; ambient [B]
+ *   intr_host: HOST floats {fx, fy, cx, cy, depth_offset(1610), directional_intensity(0.5)}
+ *   outputs (any may be NULL): shadow [B,H,W], full [B,H,W], final [B,H,W], rendered [B,3,H,W],
+ *   normals [B,3,H,W]
+ */
+int gfr_shade_render_fwd(const float* albedo, const float* depth, const float* d_min, const float* light_pt,
+                         const float* ambient, const float* intr_host, float* shadow, float* full,
+                         float* final_shading, float* rendered, float* normals, int B, int H, int W,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFR_B200_H_ */

@@ -138,8 +138,8 @@ def ray_endpoints(xx, yy, Lx, Ly):
     else:
         ex = torch.full((H, W), lx, dtype=torch.float32)
         ey = torch.full((H, W), ly, dtype=torch.float32)
-    ex = torch.clamp(ex, -128.0, 127.0)      # TRAIN:462-465 (hard-coded for 256x256)
-    ey = torch.clamp(ey, -127.0, 128.0)
+    ex = torch.clamp(ex, xmin, xmax)         # TRAIN:462-465 (hard-coded -128/127/-127/128 for 256x256)
+    ey = torch.clamp(ey, ymin, ymax)
     return torch.stack((ex, ey), 0)
 
 

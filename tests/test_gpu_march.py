@@ -1,0 +1,117 @@
+"""GPU parity: CUDA ray-march and shade/render (through the C ABI) vs the reference's own outputs
+(tests/golden, generated from the unmodified reference) and vs the CPU oracle on seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import relight_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+# fp32 tolerance on the shadow weight s = tanh^2(d/2) in [0,1]: positions/bilinear are fp64 exactly as the
+# reference; the fp32 tail (cross product, sqrt, exp) differs from torch by a few ulp.
+SHADOW_TOL = 5e-6
+TAGS = ["right_mid", "right_above", "right_below", "left_mid", "left_above", "left_below",
+        "mid_above", "mid_below", "inside", "grazing"]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from geomconsistentfr_b200 import ops
+    return ops
+
+
+@pytest.fixture(scope="module")
+def march():
+    return np.load(os.path.join(G, "march.npz"))
+
+
+def _light_pt(L):
+    return O.light_point(torch.as_tensor(L, dtype=torch.float32).view(-1, 3))[1]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("tag", TAGS)
+def test_march_vs_reference_golden(ops, march, tag, variant):
+    depth = torch.from_numpy(march["depth"]).view(1, 1, 256, 256).cuda()
+    bits = ops.mask_pack(torch.from_numpy(march["mask_u8"]).view(1, 256, 256).cuda())
+    P_L = _light_pt(march["light_" + tag]).cuda()
+    _, _, s = ops.shadow_march_fwd(depth, bits, P_L, inside_bonus=5.0, want_shadow=True, variant=variant)
+    diff = np.abs(s[0].cpu().numpy() - march["shadow_" + tag])
+    assert diff.max() <= SHADOW_TOL, (tag, diff.max(), int((diff > SHADOW_TOL).sum()))
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("H,W,B", [(64, 64, 3), (96, 128, 2), (256, 256, 2)])
+def test_march_vs_oracle_seeded(ops, H, W, B, variant):
+    """Per-image masks (TRAIN:510), argmin, d_min, odd sizes; lights from all quadrants incl. inside."""
+    g = torch.Generator().manual_seed(1234 + H + W)
+    lights = [(0.7, 0.3, 0.6), (-0.4, -0.6, 0.7), (0.02, 0.01, 0.999)][:B]
+    depth = torch.zeros(B, 1, H, W)
+    masks = torch.zeros(B, H, W, dtype=torch.uint8)
+    for b in range(B):
+        d, m = O.synthetic_face(seed=b + H, H=H, W=W, noise=2.0)
+        depth[b, 0] = d + 3.0 * torch.rand(H, W, generator=g)
+        masks[b] = m
+    P_L = _light_pt(lights)
+    d_ref, a_ref = O.shadow_march(depth, masks, P_L, inside_bonus=5.0, return_argmin=True)
+    bits = ops.mask_pack(masks.cuda())
+    d, a, s = ops.shadow_march_fwd(depth.cuda(), bits, P_L.cuda(), inside_bonus=5.0, want_argmin=True,
+                                   want_shadow=True, variant=variant)
+    d, a, s = d.cpu(), a.cpu(), s.cpu()
+    finite = d_ref < 1e5
+    assert torch.equal(finite, d < 1e5)
+    assert (d - d_ref)[finite].abs().max() <= 2e-5 * max(1.0, float(d_ref[finite].max()))
+    assert (s - O.shadow_weight(d_ref)).abs().max() <= SHADOW_TOL
+    # argmin: identical except at exact fp32 ties between neighbouring samples
+    a_ref = torch.where(finite, a_ref, torch.full_like(a_ref, 255))
+    assert (a.long() != a_ref).float().mean() < 1e-3
+
+
+def test_march_shared_mask_equals_per_image_mask(ops, march):
+    depth = torch.from_numpy(march["depth"]).view(1, 1, 256, 256).repeat(3, 1, 1, 1).cuda()
+    m = torch.from_numpy(march["mask_u8"]).view(1, 256, 256).cuda()
+    P_L = _light_pt([march["light_" + t] for t in TAGS[:3]]).cuda()
+    d1, _, _ = ops.shadow_march_fwd(depth, ops.mask_pack(m), P_L)
+    d3, _, _ = ops.shadow_march_fwd(depth, ops.mask_pack(m.repeat(3, 1, 1)), P_L)
+    assert torch.equal(d1, d3)
+
+
+def test_mask_pack_dtypes(ops, march):
+    m = torch.from_numpy(march["mask_u8"]).view(1, 256, 256)
+    ref = ops.mask_pack(m.cuda())
+    for t in (m.float() / 255.0, m.double() / 255.0, m > 0):
+        assert torch.equal(ops.mask_pack(t.cuda()), ref)
+    flat = (m.view(-1) != 0).numpy()
+    words = ref.cpu().numpy().view(np.uint32).reshape(-1)
+    bits = ((words[:, None] >> np.arange(32, dtype=np.uint32)[None]) & 1).astype(bool).reshape(-1)
+    assert np.array_equal(bits, flat)
+
+
+def test_shade_render_vs_oracle(ops, march):
+    """TRAIN:353-369, 517-522 on the golden depth: normals, full/final shading, rendered.
+    Tolerance 2e-5 absolute (all outputs are O(1); fp32 with a different summation order)."""
+    B = 3
+    depth = torch.from_numpy(march["depth"]).view(1, 1, 256, 256).repeat(B, 1, 1, 1)
+    depth = depth + torch.arange(B).view(B, 1, 1, 1) * 7.0
+    g = torch.Generator().manual_seed(7)
+    albedo = torch.rand(B, 3, 256, 256, generator=g)
+    d_min = 6.0 * torch.rand(B, 256, 256, generator=g)
+    amb = torch.tensor([0.31, 0.45, 0.12])
+    P_L = _light_pt([march["light_" + t] for t in ("right_above", "left_below", "inside")])
+    n, _, amb_l, full = O.shade(depth, O.intrinsic_matrix(), P_L, amb)
+    s = O.shadow_weight(d_min)
+    fin, rend = O.render(albedo, s, full, amb_l)
+    out = ops.shade_render_fwd(albedo.cuda(), depth.cuda(), d_min.cuda(), P_L.cuda(), amb.cuda())
+    for k, ref in (("normals", n), ("full", full), ("final", fin), ("rendered", rend), ("shadow", s)):
+        assert (out[k].cpu() - ref).abs().max() <= 2e-5, k
+
+
+def test_ops_reject_cpu_tensors(ops):
+    with pytest.raises(RuntimeError):
+        ops.mask_pack(torch.zeros(1, 256, 256, dtype=torch.uint8))
+    with pytest.raises(RuntimeError):
+        ops.shadow_march_fwd(torch.zeros(1, 1, 256, 256), torch.zeros(1, 2048, dtype=torch.int32), torch.zeros(1, 3))
