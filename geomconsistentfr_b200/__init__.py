@@ -4,7 +4,9 @@ andrewhou1/GeomConsistentFR: ray-march shadow mask, Lambertian shading/render, R
     csrc/      CUDA kernels + the C ABI (include/gfr_b200.h) -> csrc/libgfr_b200.so
     _lib.py    ctypes binding (no fallback: raises if the library is missing)
     ops.py     operator wrappers over the C ABI
+    relightnet.py  drop-in RelightNet (reference constructor attrs, state_dict keys, forward signatures)
 """
 from . import _lib, ops  # noqa: F401
+from .relightnet import RelightNet, intrinsic_matrix  # noqa: F401
 
 __version__ = "0.1.0"

@@ -98,3 +98,67 @@ def shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx=1570.0, fy=1570
         _ptr(out["rendered"]), _ptr(out["normals"]), B, H, W, _stream())
     _lib.check(rc, "gfr_shade_render_fwd")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# CNN building blocks (fp32 direct path)
+# ---------------------------------------------------------------------------------------------------
+_ACT = {None: 0, "none": 0, "lrelu": 1, "sigmoid": 2}
+
+
+def conv2d_fwd(x, w, bias, res=None, post=None, post_shift=0, act="lrelu", ups_in=False, out_scale=1.0):
+    """out = out_scale * (act(conv(x') + bias + res) + up(post)).  x: logical NCHW view (any strides);
+    w [Cout,Cin,K,K] (BN folded); see include/gfr_b200.h gfr_conv2d_fwd."""
+    if not (x.is_cuda and x.dtype == torch.float32):
+        raise RuntimeError("conv2d_fwd: x must be a CUDA fp32 tensor")
+    w = _need(w, torch.float32, "w")
+    bias = _need(bias, torch.float32, "bias")
+    N, Cin, Hin, Win = x.shape
+    H, W = (Hin * 2, Win * 2) if ups_in else (Hin, Win)
+    Cout, Cin_w, K, _ = w.shape
+    if Cin_w != Cin:
+        raise RuntimeError("conv2d_fwd: Cin mismatch")
+    if res is not None:
+        res = _need(res, torch.float32, "res")
+        assert res.shape == (N, Cout, H, W)
+    if post is not None:
+        post = _need(post, torch.float32, "post")
+        assert post.shape == (N, Cout, H >> post_shift, W >> post_shift)
+    out = torch.empty((N, Cout, H, W), dtype=torch.float32, device=x.device)
+    strides = (ctypes.c_longlong * 4)(*x.stride())
+    rc = _lib.load().gfr_conv2d_fwd(_ptr(x), ctypes.cast(strides, ctypes.c_void_p), _ptr(w), _ptr(bias), _ptr(res),
+                                    _ptr(post), _ptr(out), N, Cin, Cout, H, W, K, int(bool(ups_in)), int(post_shift),
+                                    _ACT[act], float(out_scale), _stream())
+    _lib.check(rc, "gfr_conv2d_fwd")
+    return out
+
+
+def maxpool2_fwd(x):
+    x = _need(x, torch.float32, "x")
+    N, C, H, W = x.shape
+    out = torch.empty((N, C, H // 2, W // 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().gfr_maxpool2_fwd(_ptr(x), _ptr(out), N * C, H // 2, W // 2, _stream()), "gfr_maxpool2_fwd")
+    return out
+
+
+def upsample2_fwd(x, add=None):
+    x = _need(x, torch.float32, "x")
+    N, C, H, W = x.shape
+    if add is not None:
+        add = _need(add, torch.float32, "add")
+    out = torch.empty((N, C, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().gfr_upsample2_fwd(_ptr(x), _ptr(add), _ptr(out), N * C, 2 * H, 2 * W, _stream()),
+               "gfr_upsample2_fwd")
+    return out
+
+
+def light_head_fwd(feat, c_first, w1, b1, w2, b2):
+    """feat [N,C,h,w] contiguous; channels [c_first, c_first+27) -> [N,4] (TRAIN:225-232)."""
+    feat = _need(feat, torch.float32, "feat")
+    N, C, h, w = feat.shape
+    out = torch.empty((N, 4), dtype=torch.float32, device=feat.device)
+    rc = _lib.load().gfr_light_head_fwd(_ptr(feat), C * h * w, int(c_first), h * w, _ptr(_need(w1, torch.float32, "w1")),
+                                        _ptr(_need(b1, torch.float32, "b1")), _ptr(_need(w2, torch.float32, "w2")),
+                                        _ptr(_need(b2, torch.float32, "b2")), _ptr(out), N, _stream())
+    _lib.check(rc, "gfr_light_head_fwd")
+    return out

@@ -1,0 +1,236 @@
+"""Drop-in `RelightNet` for the reference's call sites.
+
+Mirrors `class RelightNet(nn.Module)` of train_raytracing_relighting_CelebAHQ_DSSIM_8x.py:38-524 (TRAIN) and
+test_relight_single_image.py:12-505 (TEST1): same constructor attributes, same parameter / buffer names (so
+`load_state_dict(torch.load('model/model_epoch99.pth'))` is strict-clean, 400 keys), and both forward
+signatures:
+
+    TRAIN:196   forward(img[B,H,W,3], epoch, intrinsic_matrix[1,3,3], masks[B,H,W,1])            -> 8-tuple (TRAIN:524)
+    TEST1:169   forward(img, epoch, intrinsic_matrix, mask[H,W,1], target_lighting[B,3,1,1],
+                        target_ambient_values[B,1,1], batch_mask)                                 -> 10-tuple (TEST1:505)
+
+All compute runs in libgfr_b200.so (CUDA, sm_100a) through geomconsistentfr_b200.ops; torch holds the
+parameters and the device memory.  There is no CPU path: CPU inputs are copied to the module's device.
+The nn.Conv2d / nn.BatchNorm2d members are parameter containers only — their forward is never called.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+ENCODER_LAYERS = [  # (name, cin, cout, k)   TRAIN:58-70
+    ("conv_c1_og", 3, 16, 5), ("conv_h1_1", 16, 16, 3), ("conv_h1_2", 16, 16, 3),
+    ("conv_h2_1", 16, 32, 3), ("conv_h2_2", 32, 32, 3), ("conv_shortcut_h1_out", 16, 32, 3),
+    ("conv_h3_1", 32, 64, 3), ("conv_h3_2", 64, 64, 3), ("conv_shortcut_h2_out", 32, 64, 3),
+    ("conv_h4_1", 64, 155, 3), ("conv_h4_2", 155, 155, 3), ("conv_shortcut_h3_out", 64, 155, 3),
+]
+# decoder stages: (block, cin, cout) for the h5..h7 up-blocks and the matching encoder-skip blocks  TRAIN:91-114
+_UP_BLOCKS = [("h5", "shortcut_all_features", 128, 64, "s1"), ("h6", "shortcut_h5_out", 64, 32, "s2"),
+              ("h7", "shortcut_h6_out", 32, 16, "s3")]
+_EPOCH_GATES = {"s1": 8, "s2": 10, "s3": 12, "s4": 14}     # TRAIN:245,258,271,283
+
+
+def _bn_name(layer):
+    return "bn_" + layer.split("_", 1)[1]
+
+
+class RelightNet(nn.Module):
+    def __init__(self, batch_size=1):
+        super().__init__()
+        self.batch_size = batch_size          # TRAIN:41 (3) / TEST1:15 (1); here only a default — B comes from the input
+        self.img_height = 256
+        self.img_width = 256
+        self.lr = 0.0001
+        self.df_dim = 64
+        self.directional_intensity = 0.5
+        self.light_distance = 4013.0
+        self.num_sample_points = 160
+        self.GD_ratio = 5
+        self.focal_length = 1570.0            # TRAIN:572-573 (read back from intrinsic_matrix at call time)
+        self.depth_offset = 1610.0            # TRAIN:353
+        self.march_variant = 0
+
+        for name, cin, cout, k in ENCODER_LAYERS:
+            setattr(self, name, nn.Conv2d(cin, cout, k, padding=(k // 2, k // 2)))
+            setattr(self, _bn_name(name), nn.BatchNorm2d(cout))
+        self.linear_SL1 = nn.Linear(27, 128)
+        self.linear_SL2 = nn.Linear(128, 4)
+        for p in ("albedo", "depth"):
+            for blk, sc, cin, cout, skip in _UP_BLOCKS:
+                self._add("deconv_%s_%s_1" % (p, blk), nn.ConvTranspose2d, cin, cout, 3)
+                self._add("deconv_%s_%s_2" % (p, blk), nn.ConvTranspose2d, cout, cout, 3)
+                self._add("deconv_%s_%s" % (p, sc), nn.ConvTranspose2d, cin, cout, 3)
+                self._add("conv_%s_skip_%s_1" % (p, skip), nn.Conv2d, cout, cout, 3)
+                self._add("conv_%s_skip_%s_2" % (p, skip), nn.Conv2d, cout, cout, 3)
+            self._add("deconv_%s_h8_1" % p, nn.ConvTranspose2d, 16, 16, 3)
+            self._add("deconv_%s_h8_2" % p, nn.ConvTranspose2d, 16, 16, 3)
+            self._add("conv_%s_skip_s4_1" % p, nn.Conv2d, 16, 16, 3)
+            self._add("conv_%s_skip_s4_2" % p, nn.Conv2d, 16, 16, 3)
+            self._add("conv_%s_c2_1" % p, nn.Conv2d, 16, 16, 3)
+            self._add("conv_%s_c2_2" % p, nn.Conv2d, 16, 16, 1)
+            self._add("conv_%s_c2_3" % p, nn.Conv2d, 16, 16, 1)
+            setattr(self, "conv_%s_c2_o" % p, nn.Conv2d(16, 3 if p == "albedo" else 1, 1))
+        self._folded = None
+        self._folded_key = None
+
+    def _add(self, name, mod, cin, cout, k):
+        setattr(self, name, mod(cin, cout, k, padding=(k // 2, k // 2)))
+        setattr(self, _bn_name(name), nn.BatchNorm2d(cout))
+
+    # ------------------------------------------------------------------ reference-compatible attributes
+    @property
+    def xx(self):      # TRAIN:52,54 — not a Parameter in the reference either (absent from the state_dict)
+        dev = self.conv_c1_og.weight.device
+        c = torch.arange(self.img_width, dtype=torch.float32, device=dev) - self.img_width / 2.0
+        return c.view(1, 1, -1).repeat(self.batch_size, self.img_height, 1)
+
+    @property
+    def yy(self):      # TRAIN:53,55
+        dev = self.conv_c1_og.weight.device
+        r = self.img_height / 2.0 - torch.arange(self.img_height, dtype=torch.float32, device=dev)
+        return r.view(1, -1, 1).repeat(self.batch_size, 1, self.img_width)
+
+    @property
+    def device(self):
+        return self.conv_c1_og.weight.device
+
+    # ------------------------------------------------------------------ eval-mode weights: BN folded into the conv
+    def _fold_key(self):
+        return tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers()) + (str(self.device),)
+
+    @torch.no_grad()
+    def _folded_weights(self):
+        key = self._fold_key()
+        if self._folded is not None and self._folded_key == key:
+            return self._folded
+        f = {}
+        for name, mod in self.named_children():
+            if not isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
+                continue
+            w = mod.weight.detach().float()
+            if isinstance(mod, nn.ConvTranspose2d):          # stride-1 deconv == conv with swapped, flipped kernel
+                w = w.transpose(0, 1).flip(2, 3)
+            b = mod.bias.detach().float()
+            bn = getattr(self, _bn_name(name), None)
+            if bn is not None:
+                scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+                w = w * scale.view(-1, 1, 1, 1)
+                b = (b - bn.running_mean) * scale + bn.bias.detach()
+            f[name] = (w.contiguous(), b.contiguous())
+        self._folded, self._folded_key = f, key
+        return f
+
+    # ------------------------------------------------------------------ CNN (eval mode), TRAIN:197-350
+    def _cnn_eval(self, img, epoch):
+        f = self._folded_weights()
+
+        def conv(name, x, **kw):
+            w, b = f[name]
+            return ops.conv2d_fwd(x, w, b, **kw)
+
+        x = img.permute(0, 3, 1, 2)                                         # TRAIN:197 (a view; strides go to the kernel)
+        c1_og = conv("conv_c1_og", x)
+        c1 = ops.maxpool2_fwd(c1_og)
+        h1_og = conv("conv_h1_2", conv("conv_h1_1", c1), res=c1)
+        h1 = ops.maxpool2_fwd(h1_og)
+        h2_og = conv("conv_h2_2", conv("conv_h2_1", h1), res=conv("conv_shortcut_h1_out", h1, act=None))
+        h2 = ops.maxpool2_fwd(h2_og)
+        h3_og = conv("conv_h3_2", conv("conv_h3_1", h2), res=conv("conv_shortcut_h2_out", h2, act=None))
+        h3 = ops.maxpool2_fwd(h3_og)
+        h4 = conv("conv_h4_2", conv("conv_h4_1", h3), res=conv("conv_shortcut_h3_out", h3, act=None))
+        sl = ops.light_head_fwd(h4, 128, self.linear_SL1.weight, self.linear_SL1.bias,
+                                self.linear_SL2.weight, self.linear_SL2.bias)          # [B,4]  TRAIN:225-232
+        idf = h4[:, 0:128]                                                  # channel slice, read in place
+        skips = {"s1": h3_og, "s2": h2_og, "s3": h1_og, "s4": c1_og}
+        outs = []
+        for p in ("albedo", "depth"):
+            h = idf
+            for blk, sc, cin, cout, skip in _UP_BLOCKS:
+                a = conv("deconv_%s_%s_1" % (p, blk), h)
+                s = conv("deconv_%s_%s" % (p, sc), h, act=None)
+                t = conv("deconv_%s_%s_2" % (p, blk), a, res=s)             # lrelu(shortcut + h_2) at low res
+                h = self._up_and_skip(conv, p, skip, t, skips[skip], epoch)
+            a = conv("deconv_%s_h8_1" % p, h)
+            t = conv("deconv_%s_h8_2" % p, a, res=h)                        # TRAIN:276-277 (identity shortcut)
+            h = self._up_and_skip(conv, p, "s4", t, skips["s4"], epoch)
+            h = conv("conv_%s_c2_1" % p, h)
+            h = conv("conv_%s_c2_2" % p, h)
+            h = conv("conv_%s_c2_3" % p, h)
+            if p == "albedo":
+                outs.append(conv("conv_albedo_c2_o", h, act="sigmoid"))    # TRAIN:290
+            else:
+                outs.append(conv("conv_depth_c2_o", h, act=None, out_scale=100.0))   # TRAIN:350
+        return outs[0], outs[1], sl
+
+    @staticmethod
+    def _up_and_skip(conv, p, skip, t, enc, epoch):
+        """up2(t) [+ lrelu(enc + bn(conv(lrelu(bn(conv(enc))))))] — TRAIN:240-246 and the three like it.
+        With the gate on, the upsample+add is the epilogue of the second skip conv."""
+        if epoch > _EPOCH_GATES[skip]:
+            s1 = conv("conv_%s_skip_%s_1" % (p, skip), enc)
+            return conv("conv_%s_skip_%s_2" % (p, skip), s1, res=enc, post=t, post_shift=1)
+        return ops.upsample2_fwd(t)
+
+    # ------------------------------------------------------------------ geometry after the CNN
+    def _intrinsics(self, intrinsic_matrix):
+        """fx, fy, cx, cy as host floats.  The reference hands a CUDA tensor (TRAIN:618); reading it back is a
+        device sync, so the values are cached per (storage, version)."""
+        key = (intrinsic_matrix.data_ptr(), intrinsic_matrix._version, str(intrinsic_matrix.device))
+        if getattr(self, "_intr_cache", (None,))[0] != key:
+            K = intrinsic_matrix.detach().to("cpu", torch.float64).reshape(-1, 3, 3)[0]
+            self._intr_cache = (key, (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])))
+        return self._intr_cache[1]
+
+    def _render(self, albedo, depth, mask_bits, light_dir, ambient_values, intrinsic_matrix, inside_bonus, clamp_z):
+        B, _, H, W = depth.shape
+        L = light_dir.reshape(B, 3)
+        if clamp_z:                                                         # TRAIN:357-359
+            L = torch.cat((L[:, 0:2], torch.clamp(L[:, 2:3], min=0.0)), 1)
+        unit = torch.nn.functional.normalize(L, p=2, dim=1)                 # TRAIN:360
+        light_pt = (self.light_distance * unit).contiguous()                # TRAIN:362
+        d_min, _, _ = ops.shadow_march_fwd(depth, mask_bits, light_pt, inside_bonus=inside_bonus,
+                                           variant=self.march_variant)
+        fx, fy, cx, cy = self._intrinsics(intrinsic_matrix)
+        o = ops.shade_render_fwd(albedo, depth, d_min, light_pt, ambient_values, fx, fy, cx, cy,
+                                 self.depth_offset, self.directional_intensity)
+        ambient_light = ambient_values.view(B, 1, 1).expand(B, H, W)        # TRAIN:368 (`.repeat` there; a view here)
+        return o, ambient_light, unit.view(B, 3, 1, 1)
+
+    # ------------------------------------------------------------------ forward: both reference signatures
+    def forward(self, img, epoch, intrinsic_matrix, mask, target_lighting=None, target_ambient_values=None,
+                batch_mask=None):
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("RelightNet (geomconsistentfr_b200) runs on CUDA only; call .cuda() first")
+        if self.training:
+            raise NotImplementedError("train-mode (batch-statistics BN + backward) is not built yet; call .eval()")
+        img = img.to(dev, torch.float32, non_blocking=True)
+        B, H, W, _ = img.shape
+        test_mode = target_lighting is not None
+        with torch.no_grad():
+            albedo, depth, sl = self._cnn_eval(img, epoch)
+            if test_mode:                                                   # TEST1:169-505
+                m = mask.to(dev, non_blocking=True).reshape(1, H, W)
+                bits = ops.mask_pack(m)
+                ambient_values = (sl[:, 0] - 0.1).contiguous()              # TEST1:342
+                light = target_lighting.to(dev, torch.float32, non_blocking=True)
+                o, amb_l, unit = self._render(albedo, depth, bits, light, ambient_values, intrinsic_matrix, 5.0, False)
+                return (albedo, depth, o["shadow"], amb_l, o["full"], o["rendered"], unit,
+                        ambient_values.view(B, 1, 1), o["final"], o["normals"])
+            m = mask.to(dev, non_blocking=True).reshape(B, H, W)            # TRAIN:196-524
+            bits = ops.mask_pack(m)
+            ambient_values = sl[:, 0].contiguous()                          # TRAIN:367
+            o, amb_l, unit = self._render(albedo, depth, bits, sl[:, 1:4], ambient_values, intrinsic_matrix, 0.0, True)
+            return (albedo, depth, o["shadow"], amb_l, o["full"], o["rendered"], unit, ambient_values.view(B, 1, 1))
+
+
+def intrinsic_matrix(H=256, W=256, focal=1570.0):
+    """The camera matrix the reference builds at TRAIN:571-577 (float64, [1,3,3])."""
+    K = np.zeros((1, 3, 3))
+    K[:, 0, 0] = focal
+    K[:, 1, 1] = focal
+    K[:, 2, 2] = 1.0
+    K[:, 0, 2] = W / 2.0
+    K[:, 1, 2] = H / 2.0
+    return torch.from_numpy(K)

@@ -79,6 +79,35 @@ int gfr_shade_render_fwd(const float* albedo, const float* depth, const float* d
                          float* final_shading, float* rendered, float* normals, int B, int H, int W,
                          void* stream);
 
+/* fp32 convolution with fused epilogue (exact-fp32 CNN path).  Replaces one
+ * Conv2d / ConvTranspose2d(stride 1) + BatchNorm2d(eval, folded into w/bias by the caller) + residual add +
+ * LeakyReLU(0.2) / sigmoid + skip add + nearest x2 upsample step of RelightNet (TRAIN:197-350, TEST1:170-323):
+ *     out = out_scale * ( act( conv(in') + bias + res ) + up(post) )
+ *   in      activations; element strides {sN, sC, sH, sW} in in_strides_host (HOST, 4 x int64) so that an NHWC
+ *           image (TRAIN:197 permute) or a channel slice (TRAIN:225) is read in place; in' = in, or its nearest
+ *           x2 upsampling when ups_in = 1 (TRAIN:240 etc.; `in` is then [N,Cin,H/2,W/2])
+ *   w       [Cout,Cin,K,K], K in {1,3,5}, stride 1, padding K/2 (a ConvTranspose2d(k=3,s=1,p=1) weight must be
+ *           passed as w.transpose(0,1).flip(2,3))
+ *   res     [N,Cout,H,W] or NULL; post [N,Cout,H>>post_shift,W>>post_shift] or NULL
+ *   act     0 none, 1 LeakyReLU(0.2), 2 sigmoid
+ */
+int gfr_conv2d_fwd(const float* in, const long long* in_strides_host, const float* w, const float* bias,
+                   const float* res, const float* post, float* out, int N, int Cin, int Cout, int H, int W, int K,
+                   int ups_in, int post_shift, int act, float out_scale, void* stream);
+
+/* 2x2/2 max pool, NCHW: in [NC, 2*Ho, 2*Wo] -> out [NC, Ho, Wo]  (TRAIN:201,206,212,218). */
+int gfr_maxpool2_fwd(const float* in, float* out, int NC, int Ho, int Wo, void* stream);
+
+/* nearest x2 upsample with optional add: out[NC,Ho,Wo] = up2(in[NC,Ho/2,Wo/2]) (+ add[NC,Ho,Wo])
+ * (nn.Upsample(scale_factor=2, mode='nearest'), TRAIN:240,253,266,278 when the epoch gate is off). */
+int gfr_upsample2_fwd(const float* in, const float* add, float* out, int NC, int Ho, int Wo, void* stream);
+
+/* Light head (TRAIN:225-232): global average pool of channels [c_first, c_first+27) of feat [N,C,HW]
+ * (feat_batch_stride = C*HW elements), Linear 27->128 (w1 [128,27], b1), LeakyReLU(0.2), Linear 128->4
+ * (w2 [4,128], b2) -> out [N,4] = {ambient, lx, ly, lz}. */
+int gfr_light_head_fwd(const float* feat, long long feat_batch_stride, int c_first, int HW, const float* w1,
+                       const float* b1, const float* w2, const float* b2, float* out, int N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
