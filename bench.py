@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py — relit faces/s at 256x256 (ray-march shadow + shading + RelightNet CNN), BASELINE.json configs[1]:
+batch 8 per GPU, full relight forward, fp32, eval mode, epoch-99 weights, synthetic inputs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  A "step" is one forward over one batch of 8 faces per GPU.
+  value      faces/s, whole job, inputs resident in HBM, device-timed (CUDA events per step on the launching
+             stream, L2 flushed between steps, max over ranks)
+  e2e        faces/s through RelightRunner.relight_host: pinned host image/mask/light -> H2D -> forward -> D2H of
+             rendered_images, all inside the timed region
+  roofline   the ray-march kernel (the metric BASELINE.json names): algorithmic bytes / CUDA-event duration
+  cpu_baseline / --impl reference: the CPU oracle port of the reference forward (oracle/relight_oracle.py, torch
+             CPU, all host threads) on a bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+B_PER_GPU = 8
+H = W = 256
+MARCH_BYTES_PER_FACE = 786432          # depth f32 + mask f32 + d_min f32
+MARCH_SAMPLES_PER_FACE = 160 * H * W
+CNN_FLOP_PER_FACE = 4.54e9
+METRIC = "relit faces/sec @256x256 (shadow+CNN)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synthetic_batch(B, seed):
+    """Synthetic 256x256 faces: image U(0,1) (seeded), elliptical face mask, one of the 18 light directions."""
+    from oracle.relight_oracle import LIGHTS_18, synthetic_face
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand(B, H, W, 3, generator=g)
+    _, m = synthetic_face(seed=seed)
+    mask = (m * 255).to(torch.uint8).view(1, H, W)
+    light = torch.tensor([LIGHTS_18[(seed + i) % 18] for i in range(B)], dtype=torch.float32).view(B, 3, 1, 1)
+    return img, mask, light
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self._stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j] == "Active" for r in self.rows)]
+        busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_forward_faces_per_s(n_faces, threads):
+    """The CPU oracle port of the reference forward (TEST1:169-505), B=1 per call like the reference."""
+    from oracle import relight_oracle as O
+    torch.set_num_threads(threads)
+    net = O.RelightNetOracle()
+    net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"))
+    net.eval()
+    K = O.intrinsic_matrix()
+    times = []
+    with torch.no_grad():
+        for i in range(n_faces):
+            img, mask, light = synthetic_batch(1, 100 + i)
+            m = mask.view(H, W, 1).double() / 255.0
+            t0 = time.perf_counter()
+            net.forward_test(img, 200, K, m, light[:1])
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port, kind 'port'), rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = os.cpu_count() or 1
+    total = args.warmup + args.steps
+    times = cpu_forward_faces_per_s(total, threads)[args.warmup:]
+    ms = 1e3 * sum(times) / len(times)
+    v = 1e3 / ms
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "faces/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: full relight forward 256x256 fp32 (CNN + normals + 160-sample ray-march + render)",
+                   "step": "bounded sample: 1 face per step (the reference's own batch size, TEST1:15)"},
+        "cpu_baseline": {"value": v, "unit": "faces/s", "cores": threads, "kind": "port",
+                         "sample": "%d faces, B=1 each, torch CPU oracle port of TEST1:169-505" % len(times)},
+        "e2e": {"value": v, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-faces", type=int, default=6, help="faces in the bounded CPU-baseline sample")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from geomconsistentfr_b200 import RelightNet, RelightRunner, ops
+    net = RelightNet()
+    net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"), strict=True)
+    net = net.float().cuda().eval()
+    B = B_PER_GPU
+    runner = RelightRunner(net, B, use_graph=not args.no_graph)
+    stream = runner.stream
+
+    # distinct synthetic batches, host-pinned (for e2e) and device-resident (for value)
+    n_pool = 4
+    host = [tuple(t.pin_memory() for t in synthetic_batch(B, 1000 * rank + i)) for i in range(n_pool)]
+    dev = [tuple(t.cuda() for t in h) for h in host]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """CUDA events around each step on the launching stream; L2 flushed (untimed) between steps."""
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        pairs = []
+        with torch.cuda.stream(stream):
+            for i in range(steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn(i)
+                e1.record(stream)
+                pairs.append((e0, e1))
+        barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in pairs)
+        if dist is not None:
+            t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms
+
+    # ---- value: inputs resident in HBM
+    def step_device(i):
+        runner.set_inputs(*dev[i % n_pool])
+        runner.run()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    n0 = ops.launch_count()
+    total_ms = timed(step_device, args.steps, args.warmup)
+    launches = runner.launches_per_run * args.steps if runner.graph is not None else \
+        (ops.launch_count() - n0) * args.steps // (args.steps + args.warmup)
+    ms_per_step = total_ms / args.steps
+    value = world * B * 1e3 / ms_per_step
+
+    # ---- e2e: host buffers through the public runner API, copies inside the timed region
+    def step_host(i):
+        runner.relight_host(*host[i % n_pool])
+
+    e2e_ms = timed(step_host, args.steps, args.warmup) / args.steps
+    clocks = sampler.stop()
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = B * 3 * H * W * 4
+
+    # ---- roofline: the ray-march kernel on the depth maps of the last forward, CUDA events on the same stream
+    depth = runner.out[1]
+    bits = ops.mask_pack(dev[0][1].view(1, H, W))
+    light_pt = (net.light_distance * torch.nn.functional.normalize(dev[0][2].view(B, 3), dim=1)).contiguous()
+
+    def step_march(i):
+        ops.shadow_march_fwd(depth, bits, light_pt, inside_bonus=5.0, variant=net.march_variant)
+
+    march_ms = timed(step_march, max(args.steps, 20), 3) / max(args.steps, 20)
+    hbm_peak, peak_src = peaks()
+    achieved = MARCH_BYTES_PER_FACE * B / (march_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "march_traffic.json")
+    if os.path.isfile(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: batch 8 per GPU, full relight forward 256x256 fp32 "
+                               "(RelightNet CNN + normals + 160-sample ray-march + Lambert render), eval, epoch-99 weights",
+                   "global_batch": world * B, "parallelism": "dp%d (faces sharded, no collective)" % world,
+                   "l2": "256 MiB flush written between timed steps (untimed)",
+                   "cuda_graph": runner.graph is not None},
+        "e2e": {"value": world * B * 1e3 / e2e_ms, "unit": "faces/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "shadow_march_fwd", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                     "ms_per_launch": march_ms, "share_of_step": march_ms / ms_per_step,
+                     "note": "algorithmic bytes 786432 B/face; the kernel is ALU-bound (~700 flop/B), see DESIGN.md",
+                     "gsamples_per_s": MARCH_SAMPLES_PER_FACE * B / (march_ms * 1e-3) / 1e9},
+    }
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        t = cpu_forward_faces_per_s(args.cpu_faces, threads)[1:]
+        line["cpu_baseline"] = {"value": len(t) / sum(t), "unit": "faces/s", "cores": threads, "kind": "port",
+                                "sample": "%d faces (1 warm-up dropped), B=1 each, torch CPU oracle port of TEST1:169-505"
+                                          % len(t)}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

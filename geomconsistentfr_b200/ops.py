@@ -21,6 +21,18 @@ def reference_samples():
     return t
 
 
+_launches = 0     # kernels launched through the C ABI (each entry point launches exactly one kernel)
+
+
+def launch_count():
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -47,7 +59,7 @@ def mask_pack(mask):
     n, H, W = mask.shape
     bits = torch.empty((n, H * W // 32), dtype=torch.int32, device=mask.device)
     rc = _lib.load().gfr_mask_pack(_ptr(mask), _MASK_DTYPES[mask.dtype], n, H, W, _ptr(bits), _stream())
-    _lib.check(rc, "gfr_mask_pack")
+    _lib.check(rc, "gfr_mask_pack"); _count()
     return bits
 
 
@@ -71,7 +83,7 @@ def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0,
     rc = _lib.load().gfr_shadow_march_fwd(
         _ptr(depth), _ptr(mask_bits), stride, _ptr(light_pt), t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]),
         float(inside_bonus), _ptr(dmin), _ptr(arg), _ptr(shadow), B, H, W, int(variant), _stream())
-    _lib.check(rc, "gfr_shadow_march_fwd")
+    _lib.check(rc, "gfr_shadow_march_fwd"); _count()
     return dmin, arg, shadow
 
 
@@ -96,7 +108,7 @@ def shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx=1570.0, fy=1570
         _ptr(albedo) if "rendered" in want else None, _ptr(depth), _ptr(d_min), _ptr(light_pt), _ptr(ambient),
         intr.ctypes.data_as(ctypes.c_void_p), _ptr(out["shadow"]), _ptr(out["full"]), _ptr(out["final"]),
         _ptr(out["rendered"]), _ptr(out["normals"]), B, H, W, _stream())
-    _lib.check(rc, "gfr_shade_render_fwd")
+    _lib.check(rc, "gfr_shade_render_fwd"); _count()
     return out
 
 
@@ -129,7 +141,7 @@ def conv2d_fwd(x, w, bias, res=None, post=None, post_shift=0, act="lrelu", ups_i
     rc = _lib.load().gfr_conv2d_fwd(_ptr(x), ctypes.cast(strides, ctypes.c_void_p), _ptr(w), _ptr(bias), _ptr(res),
                                     _ptr(post), _ptr(out), N, Cin, Cout, H, W, K, int(bool(ups_in)), int(post_shift),
                                     _ACT[act], float(out_scale), _stream())
-    _lib.check(rc, "gfr_conv2d_fwd")
+    _lib.check(rc, "gfr_conv2d_fwd"); _count()
     return out
 
 
@@ -138,6 +150,7 @@ def maxpool2_fwd(x):
     N, C, H, W = x.shape
     out = torch.empty((N, C, H // 2, W // 2), dtype=torch.float32, device=x.device)
     _lib.check(_lib.load().gfr_maxpool2_fwd(_ptr(x), _ptr(out), N * C, H // 2, W // 2, _stream()), "gfr_maxpool2_fwd")
+    _count()
     return out
 
 
@@ -149,6 +162,7 @@ def upsample2_fwd(x, add=None):
     out = torch.empty((N, C, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
     _lib.check(_lib.load().gfr_upsample2_fwd(_ptr(x), _ptr(add), _ptr(out), N * C, 2 * H, 2 * W, _stream()),
                "gfr_upsample2_fwd")
+    _count()
     return out
 
 
@@ -160,5 +174,5 @@ def light_head_fwd(feat, c_first, w1, b1, w2, b2):
     rc = _lib.load().gfr_light_head_fwd(_ptr(feat), C * h * w, int(c_first), h * w, _ptr(_need(w1, torch.float32, "w1")),
                                         _ptr(_need(b1, torch.float32, "b1")), _ptr(_need(w2, torch.float32, "w2")),
                                         _ptr(_need(b2, torch.float32, "b2")), _ptr(out), N, _stream())
-    _lib.check(rc, "gfr_light_head_fwd")
+    _lib.check(rc, "gfr_light_head_fwd"); _count()
     return out
