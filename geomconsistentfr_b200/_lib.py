@@ -20,8 +20,16 @@ _PROTOS = {
     "gfr_maxpool2_fwd": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_upsample2_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_light_head_fwd": [_c_void_p, ctypes.c_longlong, _c_int, _c_int] + [_c_void_p] * 5 + [_c_int, _c_void_p],
+    # tensor-core path (C4 layout)
+    "gfr_nchw_to_c4": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_c4_to_nchw": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_conv_tc_pack_size": [_c_int, _c_int, _c_int],
+    "gfr_conv_tc_pack_weights": [_c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_conv3x3_tc_fwd": [_c_void_p] * 6 + [_c_int] * 8 + [_c_float, _c_int, _c_void_p],
+    "gfr_maxpool2_c4_fwd": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_upsample2_c4_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
 }
-_RESTYPES = {"gfr_error_string": ctypes.c_char_p}
+_RESTYPES = {"gfr_error_string": ctypes.c_char_p, "gfr_conv_tc_pack_size": ctypes.c_longlong}
 
 _lib = None
 

@@ -176,3 +176,88 @@ def light_head_fwd(feat, c_first, w1, b1, w2, b2):
                                         _ptr(_need(b2, torch.float32, "b2")), _ptr(out), N, _stream())
     _lib.check(rc, "gfr_light_head_fwd"); _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core CNN path: C4 activation layout [N][ceil(C/4)][H][W][4]
+# ---------------------------------------------------------------------------------------------------
+class C4:
+    """An activation tensor in the C4 layout: data [N, ceil(C/4), H, W, 4] fp32 CUDA + the logical channel count."""
+    __slots__ = ("data", "C")
+
+    def __init__(self, data, C):
+        self.data, self.C = data, C
+
+    @property
+    def shape(self):
+        N, _, H, W, _ = self.data.shape
+        return (N, self.C, H, W)
+
+
+def _c4_empty(N, C, H, W, device):
+    return torch.empty((N, (C + 3) // 4, H, W, 4), dtype=torch.float32, device=device)
+
+
+def nchw_to_c4(x):
+    x = _need(x, torch.float32, "x")
+    N, C, H, W = x.shape
+    out = _c4_empty(N, C, H, W, x.device)
+    _lib.check(_lib.load().gfr_nchw_to_c4(_ptr(x), _ptr(out), N, C, H, W, _stream()), "gfr_nchw_to_c4"); _count()
+    return C4(out, C)
+
+
+def c4_to_nchw(x):
+    N, C, H, W = x.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.data.device)
+    _lib.check(_lib.load().gfr_c4_to_nchw(_ptr(x.data), _ptr(out), N, C, H, W, _stream()), "gfr_c4_to_nchw"); _count()
+    return out
+
+
+def conv_tc_pack_weights(w, NT):
+    """w [Cout,Cin,3,3] fp32 (any device) -> packed CUDA/CPU tensor on w's device (host-side packing, model-load time)."""
+    wc = w.detach().to("cpu", torch.float32).contiguous()
+    Cout, Cin, K, _ = wc.shape
+    assert K == 3
+    n = _lib.load().gfr_conv_tc_pack_size(Cin, Cout, NT)
+    if n < 0:
+        raise RuntimeError("gfr_conv_tc_pack_size: bad arguments")
+    packed = torch.empty(n, dtype=torch.float32)
+    rc = _lib.load().gfr_conv_tc_pack_weights(ctypes.c_void_p(wc.data_ptr()), Cin, Cout, NT, ctypes.c_void_p(packed.data_ptr()))
+    _lib.check(rc, "gfr_conv_tc_pack_weights")
+    return packed.to(w.device)
+
+
+def conv3x3_tc_fwd(x, w_packed, bias, Cout, NT, res=None, post=None, post_shift=0, act="lrelu", out_scale=1.0,
+                   precision=3):
+    """x: C4; w_packed from conv_tc_pack_weights(w, NT); out = out_scale*(act(conv(x)+bias+res) + up(post)) as C4."""
+    N, Cin, H, W = x.shape
+    w_packed = _need(w_packed, torch.float32, "w_packed")
+    bias = _need(bias, torch.float32, "bias")
+    if not x.data.is_cuda:
+        raise RuntimeError("conv3x3_tc_fwd: x must be on CUDA")
+    out = _c4_empty(N, Cout, H, W, x.data.device)
+    if res is not None:
+        assert res.shape == (N, Cout, H, W)
+    if post is not None:
+        assert post.shape == (N, Cout, H >> post_shift, W >> post_shift)
+    rc = _lib.load().gfr_conv3x3_tc_fwd(_ptr(x.data), _ptr(w_packed), _ptr(bias), _ptr(res.data if res is not None else None),
+                                        _ptr(post.data if post is not None else None), _ptr(out), N, Cin, Cout, H, W, NT,
+                                        int(post_shift), _ACT[act], float(out_scale), int(precision), _stream())
+    _lib.check(rc, "gfr_conv3x3_tc_fwd"); _count()
+    return C4(out, Cout)
+
+
+def maxpool2_c4_fwd(x):
+    N, C, H, W = x.shape
+    out = _c4_empty(N, C, H // 2, W // 2, x.data.device)
+    _lib.check(_lib.load().gfr_maxpool2_c4_fwd(_ptr(x.data), _ptr(out), N * ((C + 3) // 4), H // 2, W // 2, _stream()),
+               "gfr_maxpool2_c4_fwd"); _count()
+    return C4(out, C)
+
+
+def upsample2_c4_fwd(x, add=None):
+    N, C, H, W = x.shape
+    out = _c4_empty(N, C, 2 * H, 2 * W, x.data.device)
+    _lib.check(_lib.load().gfr_upsample2_c4_fwd(_ptr(x.data), _ptr(add.data if add is not None else None), _ptr(out),
+                                                N * ((C + 3) // 4), 2 * H, 2 * W, _stream()), "gfr_upsample2_c4_fwd"); _count()
+    return C4(out, C)

@@ -95,6 +95,39 @@ int gfr_conv2d_fwd(const float* in, const long long* in_strides_host, const floa
                    const float* res, const float* post, float* out, int N, int Cin, int Cout, int H, int W, int K,
                    int ups_in, int post_shift, int act, float out_scale, void* stream);
 
+/* ---- tensor-core (tcgen05) CNN path ------------------------------------------------------------------------
+ * Activations of this path use the "C4" layout [N][ceil(C/4)][H][W][4] fp32 (channel c of pixel (y,x) lives in
+ * group c/4, slot c%4; the slots past C in the last group hold zeros).  All C4 pointers must be 16-byte aligned. */
+
+/* NCHW <-> C4 layout conversion. */
+int gfr_nchw_to_c4(const float* in, float* out, int N, int C, int H, int W, void* stream);
+int gfr_c4_to_nchw(const float* in, float* out, int N, int C, int H, int W, void* stream);
+
+/* Weight packing for gfr_conv3x3_tc_fwd (HOST function, host pointers).  w_host is [Cout,Cin,3,3] (BN folded; a
+ * ConvTranspose2d(k=3,s=1,p=1) weight as w.transpose(0,1).flip(2,3)).  The packed buffer holds, for every
+ * (NT-channel output tile, 16-channel input step), the tf32 "hi" and "lo" halves of the weights as K-major UMMA
+ * core matrices: [n_tile][cin_step][hi|lo][tap 0..8][4-channel group 0..3][n 0..NT-1][4].  NT in {16,32,64}.
+ * gfr_conv_tc_pack_size returns the number of floats (negative on a bad argument). */
+long long gfr_conv_tc_pack_size(int Cin, int Cout, int NT);
+int gfr_conv_tc_pack_weights(const float* w_host, int Cin, int Cout, int NT, float* packed_host);
+
+/* 3x3 convolution (stride 1, padding 1) on the tcgen05 tensor cores, 3xTF32 (fp32-grade accuracy), fused epilogue
+ *     out = out_scale * ( act( conv(in) + bias + res ) + up(post) )
+ * Replaces one Conv2d / ConvTranspose2d(s=1) + BatchNorm2d(eval) + residual add + LeakyReLU + skip add + nearest x2
+ * upsample step of RelightNet (TRAIN:197-350, TEST1:170-323) for layers with Cin >= 16.
+ *   in [N,Cin,H,W] C4; w_packed (device) from gfr_conv_tc_pack_weights with the same NT; bias [Cout] (device);
+ *   res C4 [N,Cout,H,W] or NULL; post C4 [N,Cout,H>>post_shift,W>>post_shift] or NULL; out C4 [N,Cout,H,W];
+ *   act 0 none, 1 LeakyReLU(0.2), 2 sigmoid;
+ *   precision 3 = 3xTF32 (hi*hi + lo*hi + hi*lo, the parity default), 1 = single-pass TF32 (what cuDNN does under
+ *   torch.backends.cudnn.allow_tf32, the reference's default on Ampere+; not parity-grade for the depth head). */
+int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const float* bias, const float* res, const float* post,
+                       float* out, int N, int Cin, int Cout, int H, int W, int NT, int post_shift, int act,
+                       float out_scale, int precision, void* stream);
+
+/* 2x2/2 max pool and nearest x2 upsample (+ optional add) in the C4 layout; NC4 = N * ceil(C/4). */
+int gfr_maxpool2_c4_fwd(const float* in, float* out, int NC4, int Ho, int Wo, void* stream);
+int gfr_upsample2_c4_fwd(const float* in, const float* add, float* out, int NC4, int Ho, int Wo, void* stream);
+
 /* 2x2/2 max pool, NCHW: in [NC, 2*Ho, 2*Wo] -> out [NC, Ho, Wo]  (TRAIN:201,206,212,218). */
 int gfr_maxpool2_fwd(const float* in, float* out, int NC, int Ho, int Wo, void* stream);
 
