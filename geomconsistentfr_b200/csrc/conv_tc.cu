@@ -6,20 +6,28 @@
 //
 // Activation layout ("C4"): [N][C/4][H][W][4] fp32 — 4-channel groups innermost, so one pixel x one channel group is
 // a 16-byte unit.  That is exactly the 16-byte row of a K-major, un-swizzled UMMA core matrix (8 rows x 16 B), so a
-// TMA box {4ch, 10 px, 18 rows, 4 groups} lands in shared memory as [group][row][px][4] and the A operand of every
+// TMA box {10 px x 4ch, 18 rows, 4 groups} lands in shared memory as [group][row][px][4] and the A operand of every
 // one of the nine filter taps is the SAME tile addressed through a descriptor whose start address is shifted by
 // (ky*10 + kx)*16 bytes: M = 128 output pixels = 16 rows x 8 px (row pitch 160 B = SBO), K = 8 channels = two core
 // matrices 2880 B apart (LBO).  Image borders and channel padding come from TMA out-of-bounds zero fill.
 //
-// 3xTF32: every fp32 operand is split x = hi + lo with hi = tf32(x); D += lo*Whi + hi*Wlo + hi*Whi (the dropped
-// lo*lo term is ~2^-22 relative).  Activations are split in shared memory by the CTA after the TMA lands, weights are
-// split and packed once on the host (gfr_conv_tc_pack_weights).
+// 3xTF32: every fp32 operand is split x = hi + lo with hi = tf32(x); conv = hi*Whi + (hi*Wlo + lo*Whi) (the dropped
+// lo*lo term is ~2^-22 relative).  Activations are split in shared memory after the TMA lands, weights are split and
+// packed once on the host (gfr_conv_tc_pack_weights) as [Whi | Wlo] side by side in N, so one MMA of width 2*NT
+// computes hi*Whi into the "main" accumulator columns and hi*Wlo into the "correction" columns, and a second MMA of
+// width NT adds lo*Whi to the correction columns: 2 instead of 3 A-operand reads per K step.
 //
-// One CTA (128 threads) owns a 128-pixel x NT-channel output tile at a time and loops over its tiles; per 16 input
-// channels: TMA -> split -> 54 MMAs (9 taps x 2 K-steps x 3 products, issued by one thread) -> commit.  Epilogue:
-// tcgen05.ld (one thread per pixel, NT accumulators), bias + residual + activation + up2(post) + scale, 128-byte
-// coalesced float4 stores.  Several CTAs are resident per SM so load / split / MMA / epilogue phases of different
-// tiles overlap.
+// Accumulator rounding.  The tensor core accumulates into TMEM with truncation, so a long chain of MMAs into one
+// accumulator drifts towards zero (measured: mean error grows linearly with Cin, anti-correlated with the sign of the
+// result).  The chain is therefore cut every 16 input channels: each pipeline step starts a fresh accumulator, and the
+// epilogue warps add (main + correction) into fp32 registers with round-to-nearest.
+//
+// Warp-specialised CTA (320 threads), S-slot shared-memory ring, double-buffered accumulators:
+//   warp 0      TMA producer   : per step, box load of the fp32 tile (+ bulk copy of the step's weights when Cin > 16)
+//   warps 2-5   splitters      : fp32 tile -> tf32 hi (in place) + lo, fence.proxy.async, arrive
+//   warp 1      MMA issuer     : 36 tcgen05.mma per step (9 taps x 2 K-steps x 2), commit -> frees the slot + signals
+//   warps 6-9   epilogue       : tcgen05.ld (thread = pixel), register accumulation; after the last step bias +
+//                                residual + activation + up2(post) + scale, 128-byte coalesced float4 stores
 #include "gfr_common.cuh"
 #include "tc_common.cuh"
 
@@ -36,6 +44,7 @@ constexpr int CB = 16;                                  // input channels per pi
 constexpr uint32_t A_BYTES = (CB / 4) * HALO_H * HALO_W * 16;     // 11520
 constexpr uint32_t A_LBO = HALO_H * HALO_W * 16;        // 2880: next 4-channel group
 constexpr uint32_t A_SBO = HALO_W * 16;                 // 160: next tile row (8 pixels further in M)
+constexpr int NUM_THREADS = 320;
 
 struct ConvTcArgs {
   const float* wpk;    // packed weights, see gfr_conv_tc_pack_weights
@@ -46,129 +55,176 @@ struct ConvTcArgs {
   int N, Cin, Cout, H, W;
   int ncb, tiles_x, tiles_y, m_tiles;
   int post_shift, act;
-  int products;        // bit 0: hi*Whi, bit 1: lo*Whi, bit 2: hi*Wlo  (7 = 3xTF32, 1 = single-pass TF32)
+  int single_pass;     // 1: hi*Whi only (plain TF32)
   float out_scale;
 };
 
 template <int NT>
 struct Smem {
-  static constexpr uint32_t W_HALF = 9 * (CB / 4) * NT * 16;       // hi (or lo) weights of one 16-channel step
-  static constexpr uint32_t OFF_A_HI = 0, OFF_A_LO = A_BYTES, OFF_W = 2 * A_BYTES;
-  static constexpr uint32_t OFF_BAR = OFF_W + 2 * W_HALF;
-  static constexpr uint32_t BYTES = OFF_BAR + 32;
-  static constexpr uint32_t TMEM_COLS = NT <= 32 ? 32 : (NT <= 64 ? 64 : 128);
+  static constexpr int STAGES = NT <= 32 ? 3 : 2;
+  static constexpr uint32_t W_STEP = 9 * (CB / 4) * 2 * NT * 16;   // [tap][group][hi|lo][n][4] of one 16-channel step
+  // resident-weights mode (Cin <= 16): [W][slot: A_hi, A_lo] ; streaming mode: [slot: A_hi, A_lo, W]
+  static constexpr uint32_t SLOT_RES = 2 * A_BYTES, SLOT_STR = 2 * A_BYTES + W_STEP;
+  static constexpr uint32_t BYTES_RES = W_STEP + STAGES * SLOT_RES + 128;
+  static constexpr uint32_t BYTES_STR = STAGES * SLOT_STR + 128;
+  static constexpr uint32_t TMEM_COLS = 4 * NT <= 32 ? 32 : (4 * NT <= 64 ? 64 : (4 * NT <= 128 ? 128 : 256));
 };
 
 template <int NT>
-__global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a) {
+__global__ void __launch_bounds__(NUM_THREADS, NT <= 32 ? 2 : 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a) {
   using S = Smem<NT>;
+  constexpr int STAGES = S::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t sA_hi = smem_u32(smem + S::OFF_A_HI), sA_lo = smem_u32(smem + S::OFF_A_LO);
-  const uint32_t sW = smem_u32(smem + S::OFF_W);
-  const uint32_t bar_full = smem_u32(smem + S::OFF_BAR), bar_done = bar_full + 8;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S::OFF_BAR + 16);
+  const bool resident = a.ncb == 1;
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t slot_bytes = resident ? S::SLOT_RES : S::SLOT_STR;
+  const uint32_t slots0 = smem0 + (resident ? S::W_STEP : 0u);
+  const uint32_t bars = slots0 + STAGES * slot_bytes;               // 8-byte aligned (all sizes are multiples of 128)
+  // barrier map: full[s] = bars + 8 s, ready[s] = +24, empty[s] = +48, accfull[p] = +72, accempty[p] = +88, tmem slot +104
+  const uint32_t bar_full = bars, bar_ready = bars + 24, bar_empty = bars + 48, bar_accfull = bars + 72, bar_accempty = bars + 88;
+  uint8_t* gen_bars = smem + (bars - smem0);
 
   if (tid == 0) {
-    mbar_init(bar_full, 1);
-    mbar_init(bar_done, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_ready + 8 * s, 128);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int p = 0; p < 2; ++p) {
+      mbar_init(bar_accfull + 8 * p, 1);
+      mbar_init(bar_accempty + 8 * p, 128);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tm_in);
   }
-  if (warp == 0) tmem_alloc(smem_u32(smem + S::OFF_BAR + 16), S::TMEM_COLS);
+  if (warp == 1) tmem_alloc(bars + 104, S::TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_bars + 104);
 
-  const int n0 = blockIdx.y * NT;                       // first output channel of this CTA
-  const int C4out = (a.Cout + 3) >> 2;
-  const float* wsrc = a.wpk + (size_t)blockIdx.y * a.ncb * (2 * S::W_HALF / 4);
-  constexpr uint32_t IDESC = umma_idesc_tf32(128, NT);
-  uint32_t ph_full = 0, ph_done = 0;
-  bool w_loaded = false;
+  const int n_my_tiles = (a.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_steps = n_my_tiles * a.ncb;
 
-  for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
-    const int tx = mt % a.tiles_x;
-    const int t2 = mt / a.tiles_x;
-    const int ty = t2 % a.tiles_y;
-    const int n = t2 / a.tiles_y;
-    const int x0 = tx * TILE_PX_W, y0 = ty * TILE_PX_H;
-
-    for (int cb = 0; cb < a.ncb; ++cb) {
-      if (tid == 0) {
-        const bool need_w = (a.ncb > 1) || !w_loaded;
-        mbar_expect_tx(bar_full, A_BYTES + (need_w ? 2 * S::W_HALF : 0));
-        tma_load_5d(sA_hi, &tm_in, bar_full, 0, x0 - 1, y0 - 1, cb * (CB / 4), n);
-        if (need_w) bulk_load(sW, wsrc + (size_t)cb * (2 * S::W_HALF / 4), 2 * S::W_HALF, bar_full);
-      }
-      w_loaded = true;
-      mbar_wait(bar_full, ph_full);
-      ph_full ^= 1;
-
-      // ---- split the fp32 tile into tf32 hi (in place) and lo
-      {
-        float4* hi4 = reinterpret_cast<float4*>(smem + S::OFF_A_HI);
-        float4* lo4 = reinterpret_cast<float4*>(smem + S::OFF_A_LO);
-#pragma unroll
-        for (int i = tid; i < (int)(A_BYTES / 16); i += 128) {
-          const float4 v = hi4[i];
-          float4 h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          hi4[i] = h;
-          lo4[i] = l;
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const float* wsrc = a.wpk + (size_t)blockIdx.y * a.ncb * (S::W_STEP / 4);
+      int g = 0;
+      for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
+        const int tx = mt % a.tiles_x, t2 = mt / a.tiles_x;
+        const int ty = t2 % a.tiles_y, n = t2 / a.tiles_y;
+        for (int cb = 0; cb < a.ncb; ++cb, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(bar_empty + 8 * s, ((g / STAGES) & 1) ^ 1);
+          const uint32_t slot = slots0 + s * slot_bytes;
+          const bool load_w = !resident || g == 0;
+          mbar_expect_tx(bar_full + 8 * s, A_BYTES + (load_w ? S::W_STEP : 0u));
+          tma_load_4d(slot, &tm_in, bar_full + 8 * s, (tx * TILE_PX_W - 1) * 4, ty * TILE_PX_H - 1, cb * (CB / 4), n);
+          if (load_w) bulk_load(resident ? smem0 : slot + 2 * A_BYTES, wsrc + (size_t)cb * (S::W_STEP / 4), S::W_STEP, bar_full + 8 * s);
         }
       }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      __syncthreads();
-
-      if (tid == 0) {
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_2N = umma_idesc_tf32(128, 2 * NT), IDESC_N = umma_idesc_tf32(128, NT);
+      constexpr uint32_t B_LBO = 2 * NT * 16, B_TAP = (CB / 4) * B_LBO;
+      for (int g = 0; g < n_steps; ++g) {
+        const int s = g % STAGES, p = g & 1;
+        mbar_wait(bar_ready + 8 * s, (g / STAGES) & 1);
+        mbar_wait(bar_accempty + 8 * p, ((g >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        uint32_t acc = cb > 0 ? 1u : 0u;
+        const uint32_t slot = slots0 + s * slot_bytes;
+        const uint32_t wbase = resident ? smem0 : slot + 2 * A_BYTES;
+        const uint64_t dA_hi0 = umma_desc_kmajor_noswz(slot, A_LBO, A_SBO);
+        const uint64_t dA_lo0 = umma_desc_kmajor_noswz(slot + A_BYTES, A_LBO, A_SBO);
+        const uint64_t dB0 = umma_desc_kmajor_noswz(wbase, B_LBO, 128u);
+        const uint32_t d_main = tmem + (uint32_t)(p * 2 * NT), d_corr = d_main + NT;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t aoff = (uint32_t)((tap / 3) * HALO_W + (tap % 3)) * 16u;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const uint32_t ao = aoff + (uint32_t)j * 2u * A_LBO;
-            const uint32_t bo = (uint32_t)tap * ((CB / 4) * NT * 16u) + (uint32_t)j * 2u * (NT * 16u);
-            const uint64_t dA_hi = umma_desc_kmajor_noswz(sA_hi + ao, A_LBO, A_SBO);
-            const uint64_t dA_lo = umma_desc_kmajor_noswz(sA_lo + ao, A_LBO, A_SBO);
-            const uint64_t dB_hi = umma_desc_kmajor_noswz(sW + bo, NT * 16u, 128u);
-            const uint64_t dB_lo = umma_desc_kmajor_noswz(sW + S::W_HALF + bo, NT * 16u, 128u);
-            if (a.products & 2) { umma_tf32(tmem, dA_lo, dB_hi, IDESC, acc); acc = 1u; }
-            if (a.products & 4) { umma_tf32(tmem, dA_hi, dB_lo, IDESC, acc); acc = 1u; }
-            if (a.products & 1) { umma_tf32(tmem, dA_hi, dB_hi, IDESC, acc); acc = 1u; }
+            const uint32_t ao = ((uint32_t)((tap / 3) * HALO_W + (tap % 3)) * 16u + (uint32_t)j * 2u * A_LBO) >> 4;
+            const uint32_t bo = ((uint32_t)tap * B_TAP + (uint32_t)j * 2u * B_LBO) >> 4;
+            const uint32_t first = (tap == 0 && j == 0) ? 0u : 1u;
+            if (a.single_pass) {
+              umma_tf32(d_main, dA_hi0 + ao, dB0 + bo, IDESC_N, first);
+            } else {
+              umma_tf32(d_main, dA_hi0 + ao, dB0 + bo, IDESC_2N, first);      // main += hi*Whi ; corr += hi*Wlo
+              umma_tf32(d_corr, dA_lo0 + ao, dB0 + bo, IDESC_N, 1u);          // corr += lo*Whi
+            }
           }
         }
-        umma_commit(bar_done);
+        umma_commit(bar_empty + 8 * s);       // the slot may be refilled once these MMAs have read it
+        umma_commit(bar_accfull + 8 * p);     // and the accumulators of this step are complete
       }
-      mbar_wait(bar_done, ph_done);
-      ph_done ^= 1;
     }
-
-    // ---- epilogue: thread = pixel (TMEM lane), NT accumulators
-    tc_fence_after_sync();
-    {
-      const int m = warp * 32 + lane;
-      const int y = y0 + (m >> 3), x = x0 + (m & 7);
-      const bool ok = y < a.H && x < a.W;
-      const int pH = a.H >> a.post_shift, pW = a.W >> a.post_shift;
+  } else if (warp < 6) {
+    // =============================== splitters (128 threads) ===============================
+    const int st = tid - 64;
+    for (int g = 0; g < n_steps; ++g) {
+      const int s = g % STAGES;
+      mbar_wait(bar_full + 8 * s, (g / STAGES) & 1);
+      float4* hi4 = reinterpret_cast<float4*>(smem + (slots0 - smem0) + s * slot_bytes);
+      float4* lo4 = reinterpret_cast<float4*>(smem + (slots0 - smem0) + s * slot_bytes + A_BYTES);
 #pragma unroll
-      for (int g = 0; g < NT / 16; ++g) {
-        uint32_t r[16];
-        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 16), r);
-        tmem_ld_wait();
+      for (int i = st; i < (int)(A_BYTES / 16); i += 128) {
+        const float4 v = hi4[i];
+        float4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+        hi4[i] = h;
+        lo4[i] = l;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_ready + 8 * s);
+    }
+  } else {
+    // =============================== epilogue (128 threads, thread = pixel = TMEM lane) ===============================
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const int n0 = blockIdx.y * NT;
+    const int C4out = (a.Cout + 3) >> 2;
+    const int pH = a.H >> a.post_shift, pW = a.W >> a.post_shift;
+    int g = 0;
+    for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
+      const int tx = mt % a.tiles_x, t2 = mt / a.tiles_x;
+      const int ty = t2 % a.tiles_y, n = t2 / a.tiles_y;
+      float sum[NT];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int co = n0 + g * 16 + q * 4;
-          const int cq = co >> 2;
-          if (!ok || cq >= C4out) continue;
+      for (int c = 0; c < NT; ++c) sum[c] = 0.f;
+      for (int cb = 0; cb < a.ncb; ++cb, ++g) {
+        const int p = g & 1;
+        mbar_wait(bar_accfull + 8 * p, (g >> 1) & 1);
+        tc_fence_after_sync();
+        const uint32_t t_main = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 2 * NT);
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t rm[16], rc[16];
+          tmem_ld16(t_main + c0, rm);
+          if (!a.single_pass) tmem_ld16(t_main + NT + c0, rc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float part = a.single_pass ? __uint_as_float(rm[e]) : __uint_as_float(rm[e]) + __uint_as_float(rc[e]);
+            sum[c0 + e] += part;
+          }
+        }
+        tc_fence_before_sync();
+        mbar_arrive(bar_accempty + 8 * p);
+      }
+      const int y = ty * TILE_PX_H + (m >> 3), x = tx * TILE_PX_W + (m & 7);
+      if (y < a.H && x < a.W) {
+#pragma unroll
+        for (int c0 = 0; c0 < NT; c0 += 4) {
+          const int co = n0 + c0, cq = co >> 2;
+          if (cq >= C4out) break;
           float v[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r[q * 4 + e]) + (co + e < a.Cout ? __ldg(a.bias + co + e) : 0.f);
+          for (int e = 0; e < 4; ++e) v[e] = sum[c0 + e] + (co + e < a.Cout ? __ldg(a.bias + co + e) : 0.f);
           const size_t o = ((((size_t)n * C4out + cq) * a.H + y) * a.W + x) * 4;
           if (a.res) {
             const float4 rr = __ldg(reinterpret_cast<const float4*>(a.res + o));
@@ -186,16 +242,15 @@ __global__ void __launch_bounds__(128) conv3x3_tc_kernel(const __grid_constant__
             const float4 pp = __ldg(reinterpret_cast<const float4*>(a.post + po));
             v[0] += pp.x; v[1] += pp.y; v[2] += pp.z; v[3] += pp.w;
           }
-          float4 ov;
-          ov.x = v[0] * a.out_scale; ov.y = v[1] * a.out_scale; ov.z = v[2] * a.out_scale; ov.w = v[3] * a.out_scale;
-          *reinterpret_cast<float4*>(a.out + o) = ov;
+          *reinterpret_cast<float4*>(a.out + o) =
+              make_float4(v[0] * a.out_scale, v[1] * a.out_scale, v[2] * a.out_scale, v[3] * a.out_scale);
         }
       }
     }
-    tc_fence_before_sync();
-    __syncthreads();          // every TMEM read of this tile is done before the next tile's first MMA overwrites it
   }
-  if (warp == 0) tmem_dealloc(tmem, S::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, S::TMEM_COLS);
 }
 
 // ---- TMA descriptor for a C4 activation tensor ---------------------------------------------------------
@@ -226,15 +281,16 @@ int sm_count() {
   return n;
 }
 
-// tensor [N][C4][H][W][4] fp32; box {4, bw, bh, 4 groups, 1}
+// tensor [N][C4][H][W][4] fp32 described as 4-D {W*4, H, C4, N} (pixel and 4-channel slot merged: one contiguous
+// 16*bw-byte run per box row — a 16-byte innermost TMA dimension costs one request per pixel); box {4*bw, bh, 4 groups, 1}
 int make_c4_map(CUtensorMap* tm, const float* base, int N, int C4, int H, int W, int bw, int bh) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return GFR_E_UNSUPPORTED;
-  const cuuint64_t dims[5] = {4, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C4, (cuuint64_t)N};
-  const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)C4 * H * W * 16};
-  const cuuint32_t box[5] = {4, (cuuint32_t)bw, (cuuint32_t)bh, CB / 4, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+  const cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)C4, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)C4 * H * W * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)bw * 4, (cuuint32_t)bh, CB / 4, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? GFR_OK : GFR_E_ARG;
@@ -245,18 +301,21 @@ int launch_tc(const CUtensorMap& tm, const ConvTcArgs& a, cudaStream_t s) {
   using S = Smem<NT>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES);
+    const uint32_t mx = S::BYTES_RES > S::BYTES_STR ? S::BYTES_RES : S::BYTES_STR;
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
+  const uint32_t bytes = a.ncb == 1 ? S::BYTES_RES : S::BYTES_STR;
   const int n_tiles = gfr_ceil_div(a.Cout, NT);
-  int occ = (int)(220u * 1024u / S::BYTES);
-  if (occ > 4) occ = 4;
+  int occ = (int)(225u * 1024u / (bytes + 1024u));
+  const int occ_max = NT <= 32 ? 2 : 1;
+  if (occ > occ_max) occ = occ_max;
   if (occ < 1) occ = 1;
   int gx = (sm_count() * occ) / n_tiles;
   if (gx < 1) gx = 1;
   if (gx > a.m_tiles) gx = a.m_tiles;
-  conv3x3_tc_kernel<NT><<<dim3(gx, n_tiles), 128, S::BYTES, s>>>(tm, a);
+  conv3x3_tc_kernel<NT><<<dim3(gx, n_tiles), NUM_THREADS, bytes, s>>>(tm, a);
   return gfr_launch_status();
 }
 
@@ -343,9 +402,9 @@ extern "C" int gfr_conv_tc_pack_weights(const float* w_host, int Cin, int Cout, 
   size_t o = 0;
   for (int nt = 0; nt < n_tiles; ++nt)
     for (int cb = 0; cb < ncb; ++cb)
-      for (int part = 0; part < 2; ++part)
-        for (int tap = 0; tap < 9; ++tap)
-          for (int kc = 0; kc < CB / 4; ++kc)
+      for (int tap = 0; tap < 9; ++tap)
+        for (int kc = 0; kc < CB / 4; ++kc)
+          for (int part = 0; part < 2; ++part)
             for (int n = 0; n < NT; ++n)
               for (int e = 0; e < 4; ++e, ++o) {
                 const int co = nt * NT + n, ci = cb * CB + kc * 4 + e;
@@ -365,7 +424,7 @@ extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const 
                                   int post_shift, int act, float out_scale, int precision, void* stream) {
   GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w_packed); GFR_RETURN_IF_NULL(bias); GFR_RETURN_IF_NULL(out);
   if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
-  if (post_shift < 0 || post_shift > 1 || act < 0 || act > 2 || precision < 1 || precision > 7) return GFR_E_ARG;
+  if (post_shift < 0 || post_shift > 1 || act < 0 || act > 2 || (precision != 1 && precision != 3)) return GFR_E_ARG;
   if (post && post_shift && ((H | W) & 1)) return GFR_E_SHAPE;
   if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(out) |
        reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(post)) & 15)
@@ -377,7 +436,7 @@ extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const 
   a.tiles_x = gfr_ceil_div(W, TILE_PX_W); a.tiles_y = gfr_ceil_div(H, TILE_PX_H);
   a.m_tiles = N * a.tiles_x * a.tiles_y;
   a.post_shift = post_shift; a.act = act; a.out_scale = out_scale;
-  a.products = precision == 3 ? 7 : precision;      // 3 is the documented alias of 'all three products'
+  a.single_pass = precision == 1;
   CUtensorMap tm;
   const int rc = make_c4_map(&tm, in, N, (Cin + 3) / 4, H, W, HALO_W, HALO_H);
   if (rc != GFR_OK) return rc;

@@ -106,7 +106,7 @@ int gfr_c4_to_nchw(const float* in, float* out, int N, int C, int H, int W, void
 /* Weight packing for gfr_conv3x3_tc_fwd (HOST function, host pointers).  w_host is [Cout,Cin,3,3] (BN folded; a
  * ConvTranspose2d(k=3,s=1,p=1) weight as w.transpose(0,1).flip(2,3)).  The packed buffer holds, for every
  * (NT-channel output tile, 16-channel input step), the tf32 "hi" and "lo" halves of the weights as K-major UMMA
- * core matrices: [n_tile][cin_step][hi|lo][tap 0..8][4-channel group 0..3][n 0..NT-1][4].  NT in {16,32,64}.
+ * core matrices: [n_tile][cin_step][tap 0..8][4-channel group 0..3][hi|lo][n 0..NT-1][4].  NT in {16,32,64}.
  * gfr_conv_tc_pack_size returns the number of floats (negative on a bad argument). */
 long long gfr_conv_tc_pack_size(int Cin, int Cout, int NT);
 int gfr_conv_tc_pack_weights(const float* w_host, int Cin, int Cout, int NT, float* packed_host);

@@ -61,7 +61,12 @@ def test_conv3x3_tc_epilogue():
     b = torch.randn(C, device="cuda", generator=g)
     res = torch.randn(N, C, H, W, device="cuda", generator=g)
     post = torch.randn(N, C, H // 2, W // 2, device="cuda", generator=g)
-    ref = 3.0 * (F.leaky_relu(F.conv2d(x, w, b, padding=1) + res, 0.2) + F.interpolate(post, scale_factor=2, mode="nearest"))
+    def f(t):
+        return 3.0 * (F.leaky_relu(F.conv2d(x.to(t), w.to(t), b.to(t), padding=1) + res.to(t), 0.2)
+                      + F.interpolate(post.to(t), scale_factor=2, mode="nearest"))
+    ref = f(torch.float64)
+    ref32 = (f(torch.float32).double() - ref).abs().max().item()
     out = ops.conv3x3_tc_fwd(ops.nchw_to_c4(x), ops.conv_tc_pack_weights(w, 32), b, C, 32, res=ops.nchw_to_c4(res),
                              post=ops.nchw_to_c4(post), post_shift=1, act="lrelu", out_scale=3.0)
-    assert (ops.c4_to_nchw(out) - ref).abs().max().item() <= 2e-5
+    err = (ops.c4_to_nchw(out).double() - ref).abs().max().item()
+    assert err <= max(4.0 * ref32, 1e-5), (err, ref32)

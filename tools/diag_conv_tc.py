@@ -12,7 +12,7 @@ for (N, Cin, Cout, S) in [(2, 16, 16, 32), (2, 64, 64, 16), (2, 128, 64, 16), (2
     e32 = (F.conv2d(x, w, b, padding=1).double() - ref)
     print("Cin %d Cout %d: torch fp32 max %.2e mean %.2e" % (Cin, Cout, e32.abs().max(), e32.abs().mean()))
     for NT in (16, 32, 64):
-        for prec in (1, 3, 5, 6, 7):
+        for prec in (1, 3):
             out = ops.c4_to_nchw(ops.conv3x3_tc_fwd(ops.nchw_to_c4(x), ops.conv_tc_pack_weights(w, NT), b, Cout, NT, act=None, precision=prec))
             if prec == 7 or prec == 3:
                 e = out.double() - ref
