@@ -283,11 +283,11 @@ int sm_count() {
 
 // tensor [N][C4][H][W][4] fp32 described as 4-D {W*4, H, C4, N} (pixel and 4-channel slot merged: one contiguous
 // 16*bw-byte run per box row — a 16-byte innermost TMA dimension costs one request per pixel); box {4*bw, bh, 4 groups, 1}
-int make_c4_map(CUtensorMap* tm, const float* base, int N, int C4, int H, int W, int bw, int bh) {
+int make_c4_map(CUtensorMap* tm, const float* base, int N, int C4, int C4_alloc, int H, int W, int bw, int bh) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return GFR_E_UNSUPPORTED;
   const cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)C4, (cuuint64_t)N};
-  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)C4 * H * W * 16};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)C4_alloc * H * W * 16};
   const cuuint32_t box[4] = {(cuuint32_t)bw * 4, (cuuint32_t)bh, CB / 4, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
@@ -420,12 +420,14 @@ extern "C" int gfr_conv_tc_pack_weights(const float* w_host, int Cin, int Cout, 
 }
 
 extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const float* bias, const float* res,
-                                  const float* post, float* out, int N, int Cin, int Cout, int H, int W, int NT,
-                                  int post_shift, int act, float out_scale, int precision, void* stream) {
+                                  const float* post, float* out, int N, int Cin, int in_groups, int Cout, int H, int W,
+                                  int NT, int post_shift, int act, float out_scale, int precision, void* stream) {
   GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w_packed); GFR_RETURN_IF_NULL(bias); GFR_RETURN_IF_NULL(out);
   if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
   if (post_shift < 0 || post_shift > 1 || act < 0 || act > 2 || (precision != 1 && precision != 3)) return GFR_E_ARG;
   if (post && post_shift && ((H | W) & 1)) return GFR_E_SHAPE;
+  if (in_groups == 0) in_groups = (Cin + 3) / 4;
+  if (in_groups < (Cin + 3) / 4) return GFR_E_ARG;
   if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(out) |
        reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(post)) & 15)
     return GFR_E_ARG;
@@ -438,7 +440,7 @@ extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const 
   a.post_shift = post_shift; a.act = act; a.out_scale = out_scale;
   a.single_pass = precision == 1;
   CUtensorMap tm;
-  const int rc = make_c4_map(&tm, in, N, (Cin + 3) / 4, H, W, HALO_W, HALO_H);
+  const int rc = make_c4_map(&tm, in, N, (Cin + 3) / 4, in_groups, H, W, HALO_W, HALO_H);
   if (rc != GFR_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   switch (NT) {

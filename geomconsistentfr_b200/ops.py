@@ -228,9 +228,14 @@ def conv_tc_pack_weights(w, NT):
 
 
 def conv3x3_tc_fwd(x, w_packed, bias, Cout, NT, res=None, post=None, post_shift=0, act="lrelu", out_scale=1.0,
-                   precision=3):
-    """x: C4; w_packed from conv_tc_pack_weights(w, NT); out = out_scale*(act(conv(x)+bias+res) + up(post)) as C4."""
+                   precision=3, cin=None):
+    """x: C4; w_packed from conv_tc_pack_weights(w, NT); out = out_scale*(act(conv(x)+bias+res) + up(post)) as C4.
+    cin < x.C reads only the leading cin channels of x (TRAIN:225 feature split), in place."""
     N, Cin, H, W = x.shape
+    groups = x.data.shape[1]
+    if cin is not None:
+        assert cin <= Cin and cin % 4 == 0
+        Cin = cin
     w_packed = _need(w_packed, torch.float32, "w_packed")
     bias = _need(bias, torch.float32, "bias")
     if not x.data.is_cuda:
@@ -241,7 +246,7 @@ def conv3x3_tc_fwd(x, w_packed, bias, Cout, NT, res=None, post=None, post_shift=
     if post is not None:
         assert post.shape == (N, Cout, H >> post_shift, W >> post_shift)
     rc = _lib.load().gfr_conv3x3_tc_fwd(_ptr(x.data), _ptr(w_packed), _ptr(bias), _ptr(res.data if res is not None else None),
-                                        _ptr(post.data if post is not None else None), _ptr(out), N, Cin, Cout, H, W, NT,
+                                        _ptr(post.data if post is not None else None), _ptr(out), N, Cin, groups, Cout, H, W, NT,
                                         int(post_shift), _ACT[act], float(out_scale), int(precision), _stream())
     _lib.check(rc, "gfr_conv3x3_tc_fwd"); _count()
     return C4(out, Cout)
@@ -261,3 +266,39 @@ def upsample2_c4_fwd(x, add=None):
     _lib.check(_lib.load().gfr_upsample2_c4_fwd(_ptr(x.data), _ptr(add.data if add is not None else None), _ptr(out),
                                                 N * ((C + 3) // 4), 2 * H, 2 * W, _stream()), "gfr_upsample2_c4_fwd"); _count()
     return C4(out, C)
+
+
+def stem_conv_fwd(img, w_host, b_host, pool=True):
+    """img [N,H,W,3] fp32 CUDA; w_host [16,3,5,5], b_host [16] CPU tensors (BN folded) -> (C4 [N,16,H,W], pooled C4)."""
+    img = _need(img, torch.float32, "img")
+    N, H, W, _ = img.shape
+    out = _c4_empty(N, 16, H, W, img.device)
+    pooled = _c4_empty(N, 16, H // 2, W // 2, img.device) if pool else None
+    rc = _lib.load().gfr_stem_conv_fwd(_ptr(img), ctypes.c_void_p(w_host.data_ptr()), ctypes.c_void_p(b_host.data_ptr()),
+                                       _ptr(out), _ptr(pooled), N, H, W, _stream())
+    _lib.check(rc, "gfr_stem_conv_fwd"); _count()
+    return C4(out, 16), (C4(pooled, 16) if pool else None)
+
+
+def head_1x1_fwd(x, w2, b2, w3, b3, wo, bo, act=None, out_scale=1.0):
+    """x C4 [N,16,H,W]; weights are CPU tensors (BN folded) -> NCHW [N,n_out,H,W]."""
+    N, C, H, W = x.shape
+    assert C == 16
+    n_out = wo.shape[0]
+    out = torch.empty((N, n_out, H, W), dtype=torch.float32, device=x.data.device)
+    hp = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = _lib.load().gfr_head_1x1_fwd(_ptr(x.data), hp(w2), hp(b2), hp(w3), hp(b3), hp(wo), hp(bo), _ptr(out), N, H, W, n_out,
+                                      _ACT[act], float(out_scale), _stream())
+    _lib.check(rc, "gfr_head_1x1_fwd"); _count()
+    return out
+
+
+def light_head_c4_fwd(feat, c_first, w1, b1, w2, b2):
+    """feat C4 [N,C,h,w]; channels [c_first, c_first+27) -> [N,4] (TRAIN:225-232)."""
+    N, C, h, w = feat.shape
+    out = torch.empty((N, 4), dtype=torch.float32, device=feat.data.device)
+    rc = _lib.load().gfr_light_head_c4_fwd(_ptr(feat.data), C, int(c_first), h * w, _ptr(_need(w1, torch.float32, "w1")),
+                                           _ptr(_need(b1, torch.float32, "b1")), _ptr(_need(w2, torch.float32, "w2")),
+                                           _ptr(_need(b2, torch.float32, "b2")), _ptr(out), N, _stream())
+    _lib.check(rc, "gfr_light_head_c4_fwd"); _count()
+    return out

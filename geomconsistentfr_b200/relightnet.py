@@ -50,6 +50,8 @@ class RelightNet(nn.Module):
         self.focal_length = 1570.0            # TRAIN:572-573 (read back from intrinsic_matrix at call time)
         self.depth_offset = 1610.0            # TRAIN:353
         self.march_variant = 0
+        self.cnn_impl = "tc"                  # "tc": tcgen05 3xTF32 convs on C4 activations; "direct": exact-fp32 CUDA-core convs
+        self.tc_precision = 3                 # 3 = 3xTF32 (parity grade), 1 = single-pass TF32
 
         for name, cin, cout, k in ENCODER_LAYERS:
             setattr(self, name, nn.Conv2d(cin, cout, k, padding=(k // 2, k // 2)))
@@ -73,6 +75,8 @@ class RelightNet(nn.Module):
             setattr(self, "conv_%s_c2_o" % p, nn.Conv2d(16, 3 if p == "albedo" else 1, 1))
         self._folded = None
         self._folded_key = None
+        self._tc = None
+        self._tc_key = None
 
     def _add(self, name, mod, cin, cout, k):
         setattr(self, name, mod(cin, cout, k, padding=(k // 2, k // 2)))
@@ -121,8 +125,77 @@ class RelightNet(nn.Module):
         self._folded, self._folded_key = f, key
         return f
 
-    # ------------------------------------------------------------------ CNN (eval mode), TRAIN:197-350
+    @torch.no_grad()
+    def _tc_weights(self):
+        """Per-layer operands of the tensor-core path: 3x3 layers packed for gfr_conv3x3_tc_fwd (device), stem and
+        1x1 tail weights on the host (they travel as kernel parameters)."""
+        key = self._fold_key()
+        if self._tc is not None and self._tc_key == key:
+            return self._tc
+        f = self._folded_weights()
+        t = {}
+        for name, (w, b) in f.items():
+            Cout, Cin, K, _ = w.shape
+            if K == 3 and Cin >= 16:
+                NT = 16 if Cout <= 16 else 32
+                t[name] = (ops.conv_tc_pack_weights(w, NT), b, Cout, NT)
+            else:
+                t[name] = (w.cpu().contiguous(), b.cpu().contiguous())
+        self._tc, self._tc_key = t, key
+        return t
+
+    # ------------------------------------------------------------------ CNN (eval mode) on the tensor cores, TRAIN:197-350
+    def _cnn_eval_tc(self, img, epoch):
+        t = self._tc_weights()
+        prec = self.tc_precision
+
+        def conv(name, x, **kw):
+            wp, b, Cout, NT = t[name]
+            return ops.conv3x3_tc_fwd(x, wp, b, Cout, NT, precision=prec, **kw)
+
+        c1_og, c1 = ops.stem_conv_fwd(img, *t["conv_c1_og"])                # TRAIN:197-201 (conv + BN + LReLU + pool)
+        h1_og = conv("conv_h1_2", conv("conv_h1_1", c1), res=c1)
+        h1 = ops.maxpool2_c4_fwd(h1_og)
+        h2_og = conv("conv_h2_2", conv("conv_h2_1", h1), res=conv("conv_shortcut_h1_out", h1, act=None))
+        h2 = ops.maxpool2_c4_fwd(h2_og)
+        h3_og = conv("conv_h3_2", conv("conv_h3_1", h2), res=conv("conv_shortcut_h2_out", h2, act=None))
+        h3 = ops.maxpool2_c4_fwd(h3_og)
+        h4 = conv("conv_h4_2", conv("conv_h4_1", h3), res=conv("conv_shortcut_h3_out", h3, act=None))
+        sl = ops.light_head_c4_fwd(h4, 128, self.linear_SL1.weight, self.linear_SL1.bias,
+                                   self.linear_SL2.weight, self.linear_SL2.bias)        # [B,4]  TRAIN:225-232
+        skips = {"s1": h3_og, "s2": h2_og, "s3": h1_og, "s4": c1_og}
+        outs = []
+        for p in ("albedo", "depth"):
+            h, cin = h4, 128                                                # TRAIN:225: the first 128 channels, in place
+            for blk, sc, _, cout, skip in _UP_BLOCKS:
+                a = conv("deconv_%s_%s_1" % (p, blk), h, cin=cin)
+                s = conv("deconv_%s_%s" % (p, sc), h, cin=cin, act=None)
+                tt = conv("deconv_%s_%s_2" % (p, blk), a, res=s)
+                h, cin = self._up_and_skip_tc(conv, p, skip, tt, skips[skip], epoch), None
+            a = conv("deconv_%s_h8_1" % p, h)
+            tt = conv("deconv_%s_h8_2" % p, a, res=h)
+            h = self._up_and_skip_tc(conv, p, "s4", tt, skips["s4"], epoch)
+            h = conv("conv_%s_c2_1" % p, h)
+            w2, b2 = t["conv_%s_c2_2" % p]
+            w3, b3 = t["conv_%s_c2_3" % p]
+            wo, bo = t["conv_%s_c2_o" % p]
+            if p == "albedo":
+                outs.append(ops.head_1x1_fwd(h, w2, b2, w3, b3, wo, bo, act="sigmoid"))              # TRAIN:285-290
+            else:
+                outs.append(ops.head_1x1_fwd(h, w2, b2, w3, b3, wo, bo, act=None, out_scale=100.0))  # TRAIN:345-350
+        return outs[0], outs[1], sl
+
+    @staticmethod
+    def _up_and_skip_tc(conv, p, skip, t, enc, epoch):
+        if epoch > _EPOCH_GATES[skip]:
+            s1 = conv("conv_%s_skip_%s_1" % (p, skip), enc)
+            return conv("conv_%s_skip_%s_2" % (p, skip), s1, res=enc, post=t, post_shift=1)
+        return ops.upsample2_c4_fwd(t)
+
+    # ------------------------------------------------------------------ CNN (eval mode), exact fp32 on CUDA cores
     def _cnn_eval(self, img, epoch):
+        if self.cnn_impl == "tc":
+            return self._cnn_eval_tc(img.contiguous(), epoch)
         f = self._folded_weights()
 
         def conv(name, x, **kw):

@@ -115,14 +115,33 @@ int gfr_conv_tc_pack_weights(const float* w_host, int Cin, int Cout, int NT, flo
  *     out = out_scale * ( act( conv(in) + bias + res ) + up(post) )
  * Replaces one Conv2d / ConvTranspose2d(s=1) + BatchNorm2d(eval) + residual add + LeakyReLU + skip add + nearest x2
  * upsample step of RelightNet (TRAIN:197-350, TEST1:170-323) for layers with Cin >= 16.
- *   in [N,Cin,H,W] C4; w_packed (device) from gfr_conv_tc_pack_weights with the same NT; bias [Cout] (device);
+ *   in [N,Cin,H,W] C4, read in place from a buffer that holds in_groups >= ceil(Cin/4) channel groups per image
+ *   (0 = dense; > ceil(Cin/4) reads the leading channels of a wider tensor, TRAIN:225); w_packed (device) from gfr_conv_tc_pack_weights with the same NT; bias [Cout] (device);
  *   res C4 [N,Cout,H,W] or NULL; post C4 [N,Cout,H>>post_shift,W>>post_shift] or NULL; out C4 [N,Cout,H,W];
  *   act 0 none, 1 LeakyReLU(0.2), 2 sigmoid;
  *   precision 3 = 3xTF32 (hi*hi + lo*hi + hi*lo, the parity default), 1 = single-pass TF32 (what cuDNN does under
  *   torch.backends.cudnn.allow_tf32, the reference's default on Ampere+; not parity-grade for the depth head). */
 int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const float* bias, const float* res, const float* post,
-                       float* out, int N, int Cin, int Cout, int H, int W, int NT, int post_shift, int act,
-                       float out_scale, int precision, void* stream);
+                       float* out, int N, int Cin, int in_groups, int Cout, int H, int W, int NT, int post_shift,
+                       int act, float out_scale, int precision, void* stream);
+
+/* Stem: conv_c1_og (5x5, 3 -> 16, padding 2) + BatchNorm(eval, folded) + LeakyReLU(0.2) on the NHWC image, with the
+ * first 2x2 max pool fused (TRAIN:197-201).  img [N,H,W,3]; w_host [16,3,5,5] and bias_host [16] are HOST pointers
+ * (they travel as kernel parameters); out C4 [N,16,H,W]; pooled C4 [N,16,H/2,W/2] or NULL. */
+int gfr_stem_conv_fwd(const float* img, const float* w_host, const float* bias_host, float* out, float* pooled, int N,
+                      int H, int W, void* stream);
+
+/* Decoder tail: c2_2 and c2_3 (1x1, 16 -> 16, BN folded, LeakyReLU) and c2_o (1x1, 16 -> n_out) fused per pixel
+ * (TRAIN:285-290 albedo: n_out 3, act 2 = sigmoid; TRAIN:345-350 depth: n_out 1, act 0, out_scale 100).
+ * in C4 [N,16,H,W]; all weights/biases are HOST pointers ([16,16],[16],[16,16],[16],[n_out,16],[n_out]);
+ * out NCHW [N,n_out,H,W]. */
+int gfr_head_1x1_fwd(const float* in, const float* w2_host, const float* b2_host, const float* w3_host,
+                     const float* b3_host, const float* wo_host, const float* bo_host, float* out, int N, int H, int W,
+                     int n_out, int act, float out_scale, void* stream);
+
+/* gfr_light_head_fwd on a C4 feature map feat [N,C,HW]: channels [c_first, c_first+27). */
+int gfr_light_head_c4_fwd(const float* feat, int C, int c_first, int HW, const float* w1, const float* b1,
+                          const float* w2, const float* b2, float* out, int N, void* stream);
 
 /* 2x2/2 max pool and nearest x2 upsample (+ optional add) in the C4 layout; NC4 = N * ceil(C/4). */
 int gfr_maxpool2_c4_fwd(const float* in, float* out, int NC4, int Ho, int Wo, void* stream);

@@ -70,3 +70,47 @@ def test_conv3x3_tc_epilogue():
                              post=ops.nchw_to_c4(post), post_shift=1, act="lrelu", out_scale=3.0)
     err = (ops.c4_to_nchw(out).double() - ref).abs().max().item()
     assert err <= max(4.0 * ref32, 1e-5), (err, ref32)
+
+
+def test_stem_conv_vs_torch():
+    """conv_c1_og 5x5 3->16 + folded BN + LeakyReLU + fused 2x2 max pool on the NHWC image (TRAIN:197-201); exact fp32."""
+    from geomconsistentfr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.rand(2, 64, 96, 3, device="cuda", generator=g)
+    w = torch.randn(16, 3, 5, 5, device="cuda", generator=g) * 0.1
+    b = torch.randn(16, device="cuda", generator=g)
+    ref = F.leaky_relu(F.conv2d(img.permute(0, 3, 1, 2), w, b, padding=2), 0.2)
+    out, pooled = ops.stem_conv_fwd(img, w.cpu().contiguous(), b.cpu().contiguous())
+    assert (ops.c4_to_nchw(out) - ref).abs().max().item() <= 5e-6
+    assert (ops.c4_to_nchw(pooled) - F.max_pool2d(ref, 2)).abs().max().item() <= 5e-6
+
+
+@pytest.mark.parametrize("n_out,act,scale", [(3, "sigmoid", 1.0), (1, None, 100.0)])
+def test_head_1x1_vs_torch(n_out, act, scale):
+    """c2_2 -> c2_3 -> c2_o 1x1 chain fused per pixel (TRAIN:285-290, 345-350); exact fp32."""
+    from geomconsistentfr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(2, 16, 32, 64, device="cuda", generator=g)
+    w2, w3 = (torch.randn(16, 16, device="cuda", generator=g) * 0.3 for _ in range(2))
+    b2, b3 = (torch.randn(16, device="cuda", generator=g) * 0.1 for _ in range(2))
+    wo = torch.randn(n_out, 16, device="cuda", generator=g) * 0.3
+    bo = torch.randn(n_out, device="cuda", generator=g) * 0.1
+    h = F.leaky_relu(F.conv2d(x, w2.view(16, 16, 1, 1), b2), 0.2)
+    h = F.leaky_relu(F.conv2d(h, w3.view(16, 16, 1, 1), b3), 0.2)
+    ref = F.conv2d(h, wo.view(n_out, 16, 1, 1), bo)
+    ref = (torch.sigmoid(ref) if act == "sigmoid" else ref) * scale
+    c = lambda t: t.cpu().contiguous()
+    out = ops.head_1x1_fwd(ops.nchw_to_c4(x), c(w2), c(b2), c(w3), c(b3), c(wo), c(bo), act=act, out_scale=scale)
+    assert (out - ref).abs().max().item() <= 2e-6 * scale + 1e-6
+
+
+def test_conv3x3_tc_channel_slice():
+    """cin < C reads the leading channels of a wider C4 tensor in place (TRAIN:225 feature split)."""
+    from geomconsistentfr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(2, 155, 16, 16, device="cuda", generator=g)
+    w = torch.randn(64, 128, 3, 3, device="cuda", generator=g) / 34.0
+    b = torch.zeros(64, device="cuda")
+    ref = F.conv2d(x[:, :128], w, b, padding=1)
+    out = ops.conv3x3_tc_fwd(ops.nchw_to_c4(x), ops.conv_tc_pack_weights(w, 32), b, 64, 32, act=None, cin=128)
+    assert (ops.c4_to_nchw(out) - ref).abs().max().item() <= 1e-5

@@ -39,14 +39,20 @@ def _inputs(ffhq, idx):
     return x
 
 
+@pytest.mark.parametrize("impl", ["tc", "direct"])
 @pytest.mark.parametrize("epoch", [200, 11, 0])
-def test_cnn_vs_oracle(net, oracle_net, ffhq, epoch):
-    """fp32 direct-conv CNN (BN folded) vs torch fp32 on CPU, all epoch gates (TRAIN:245,258,271,283).
+def test_cnn_vs_oracle(net, oracle_net, ffhq, epoch, impl):
+    """CNN (BN folded; "tc" = tcgen05 3xTF32 convs, "direct" = exact-fp32 CUDA-core convs) vs torch fp32 on CPU, all
+    epoch gates (TRAIN:245,258,271,283).
     Tolerances: albedo (sigmoid, [0,1]) 2e-5; light head 2e-5; depth = 100 x head, |depth| ~ 150: 5e-3."""
     x = _inputs(ffhq, [0, 5])
     with torch.no_grad():
         a_ref, d_ref, sl_ref = oracle_net.cnn(x, epoch)
-        a, d, sl = net._cnn_eval(x.cuda(), epoch)
+        net.cnn_impl = impl
+        try:
+            a, d, sl = net._cnn_eval(x.cuda(), epoch)
+        finally:
+            net.cnn_impl = "tc"
     assert (a.cpu() - a_ref).abs().max() <= 2e-5
     assert (sl.cpu() - sl_ref).abs().max() <= 2e-5
     assert (d.cpu() - d_ref).abs().max() <= 5e-3
