@@ -196,6 +196,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
       float sum[NT];
 #pragma unroll
       for (int c = 0; c < NT; ++c) sum[c] = 0.f;
+      // residual / skip operands are fetched before the accumulators are waited for: their L2 latency overlaps the MMAs
+      const int y = ty * TILE_PX_H + (m >> 3), x = tx * TILE_PX_W + (m & 7);
+      const bool ok = y < a.H && x < a.W;
+      const size_t o_base = (((size_t)n * C4out * a.H + y) * a.W + x) * 4;            // + cq * H*W*4
+      const size_t o_plane = (size_t)a.H * a.W * 4;
+      // NT <= 16: into registers; wider tiles: an L2 prefetch (no registers), the loads themselves come after the MMAs
+      constexpr bool PREF_REGS = NT <= 16;
+      float4 rres[PREF_REGS ? NT / 4 : 1], rpost[PREF_REGS ? NT / 4 : 1];
+#pragma unroll
+      for (int c0 = 0; c0 < NT; c0 += 4) {
+        const int cq = (n0 + c0) >> 2;
+        if (PREF_REGS) {
+          rres[c0 / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          rpost[c0 / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (ok && cq < C4out) {
+          const size_t po = ((((size_t)n * C4out + cq) * pH + (y >> a.post_shift)) * pW + (x >> a.post_shift)) * 4;
+          if (PREF_REGS) {
+            if (a.res) rres[c0 / 4] = __ldg(reinterpret_cast<const float4*>(a.res + o_base + (size_t)cq * o_plane));
+            if (a.post) rpost[c0 / 4] = __ldg(reinterpret_cast<const float4*>(a.post + po));
+          } else {
+            if (a.res) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + o_base + (size_t)cq * o_plane));
+            if (a.post) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.post + po));
+          }
+        }
+      }
       for (int cb = 0; cb < a.ncb; ++cb, ++g) {
         const int p = g & 1;
         mbar_wait(bar_accfull + 8 * p, (g >> 1) & 1);
@@ -216,20 +242,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
         tc_fence_before_sync();
         mbar_arrive(bar_accempty + 8 * p);
       }
-      const int y = ty * TILE_PX_H + (m >> 3), x = tx * TILE_PX_W + (m & 7);
-      if (y < a.H && x < a.W) {
+      if (ok) {
 #pragma unroll
         for (int c0 = 0; c0 < NT; c0 += 4) {
           const int co = n0 + c0, cq = co >> 2;
-          if (cq >= C4out) break;
+          if (cq >= C4out) continue;
           float v[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[e] = sum[c0 + e] + (co + e < a.Cout ? __ldg(a.bias + co + e) : 0.f);
-          const size_t o = ((((size_t)n * C4out + cq) * a.H + y) * a.W + x) * 4;
-          if (a.res) {
-            const float4 rr = __ldg(reinterpret_cast<const float4*>(a.res + o));
-            v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+          float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), pp = rr;
+          if (PREF_REGS) {
+            rr = rres[c0 / 4]; pp = rpost[c0 / 4];
+          } else {
+            if (a.res) rr = __ldg(reinterpret_cast<const float4*>(a.res + o_base + (size_t)cq * o_plane));
+            if (a.post) pp = __ldg(reinterpret_cast<const float4*>(a.post + ((((size_t)n * C4out + cq) * pH + (y >> a.post_shift)) * pW + (x >> a.post_shift)) * 4));
           }
+          v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
           if (a.act == 1) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : 0.2f * v[e];
@@ -237,12 +265,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = 1.0f / (1.0f + expf(-v[e]));
           }
-          if (a.post) {
-            const size_t po = ((((size_t)n * C4out + cq) * pH + (y >> a.post_shift)) * pW + (x >> a.post_shift)) * 4;
-            const float4 pp = __ldg(reinterpret_cast<const float4*>(a.post + po));
-            v[0] += pp.x; v[1] += pp.y; v[2] += pp.z; v[3] += pp.w;
-          }
-          *reinterpret_cast<float4*>(a.out + o) =
+          v[0] += pp.x; v[1] += pp.y; v[2] += pp.z; v[3] += pp.w;
+          *reinterpret_cast<float4*>(a.out + o_base + (size_t)cq * o_plane) =
               make_float4(v[0] * a.out_scale, v[1] * a.out_scale, v[2] * a.out_scale, v[3] * a.out_scale);
         }
       }

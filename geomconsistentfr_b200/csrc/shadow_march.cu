@@ -106,6 +106,7 @@ shadow_march_fwd_l1(const MarchArgs a, const __grid_constant__ SampleTable tab) 
     const int ri = (H >> 1) - __double2int_rn(py);
     const int mi = ri * W + ci;
     const bool inside = (s_mask[mi >> 5] >> (mi & 31)) & 1u;                          // TRAIN:510
+    if (!inside) continue;        // the reference computes the sample and then overwrites it with 1e6 (TRAIN:510-512)
     const double u = __dadd_rn(__dadd_rn(px, hW), -0.0001);                           // TRAIN:481,483
     const double v = __dadd_rn(__dsub_rn(hH, py), -0.0001);                           // TRAIN:482,483
     const int uf = __double2int_rd(u), uc = __double2int_ru(u);                       // TRAIN:486-487
@@ -124,7 +125,7 @@ shadow_march_fwd_l1(const MarchArgs a, const __grid_constant__ SampleTable tab) 
     const float c1 = __fsub_rn(__fmul_rn(baz, bcx), __fmul_rn(bax, bcz));
     const float c2 = __fsub_rn(__fmul_rn(bax, bcy), __fmul_rn(bay, bcx));
     const float q = __fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fmul_rn(c2, c2));
-    if (inside && q < qmin) { qmin = q; kmin = k; }
+    if (q < qmin) { qmin = q; kmin = k; }
   }
   // min_k sqrt(q_k + eps)/den == sqrt(min_k q_k + eps)/den (monotone), TRAIN:509,514
   float d;

@@ -164,8 +164,8 @@ class RelightNet(nn.Module):
         sl = ops.light_head_c4_fwd(h4, 128, self.linear_SL1.weight, self.linear_SL1.bias,
                                    self.linear_SL2.weight, self.linear_SL2.bias)        # [B,4]  TRAIN:225-232
         skips = {"s1": h3_og, "s2": h2_og, "s3": h1_og, "s4": c1_og}
-        outs = []
-        for p in ("albedo", "depth"):
+
+        def decoder(p):
             h, cin = h4, 128                                                # TRAIN:225: the first 128 channels, in place
             for blk, sc, _, cout, skip in _UP_BLOCKS:
                 a = conv("deconv_%s_%s_1" % (p, blk), h, cin=cin)
@@ -180,10 +180,26 @@ class RelightNet(nn.Module):
             w3, b3 = t["conv_%s_c2_3" % p]
             wo, bo = t["conv_%s_c2_o" % p]
             if p == "albedo":
-                outs.append(ops.head_1x1_fwd(h, w2, b2, w3, b3, wo, bo, act="sigmoid"))              # TRAIN:285-290
-            else:
-                outs.append(ops.head_1x1_fwd(h, w2, b2, w3, b3, wo, bo, act=None, out_scale=100.0))  # TRAIN:345-350
-        return outs[0], outs[1], sl
+                return ops.head_1x1_fwd(h, w2, b2, w3, b3, wo, bo, act="sigmoid")              # TRAIN:285-290
+            return ops.head_1x1_fwd(h, w2, b2, w3, b3, wo, bo, act=None, out_scale=100.0)      # TRAIN:345-350
+
+        # the two decoders are independent (TRAIN:235-290 / 293-350): the depth decoder runs on a side stream so the
+        # small low-resolution layers of one overlap those of the other (under graph capture: two parallel branches)
+        cur = torch.cuda.current_stream()
+        side = self._side_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            depth = decoder("depth")
+        albedo = decoder("albedo")
+        cur.wait_stream(side)
+        depth.record_stream(cur)
+        return albedo, depth, sl
+
+    def _side_stream(self):
+        dev = self.device
+        if getattr(self, "_side", None) is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+        return self._side
 
     @staticmethod
     def _up_and_skip_tc(conv, p, skip, t, enc, epoch):
