@@ -143,6 +143,113 @@ shadow_march_fwd_l1(const MarchArgs a, const __grid_constant__ SampleTable tab) 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Variant 0 (default): the same arithmetic with the int <-> fp64 and fp32 -> fp64 conversions taken off the XU pipe.
+// ncu on variant 1: XU (conversion) pipe 81 % busy, fp64 pipe 22 % — the 17 F2I/I2F/F2F per sample were the bound.
+//   * round-half-even, floor and ceil come from one fp64 add of 1.5 * 2^52: the sum's low word IS the integer and
+//     (sum - magic) is its fp64 value, so no F2I and no I2F is issued (exact for |v| < 2^51; same ties as np.round);
+//   * the depth map is widened to fp64 once per launch by a pre-pass (depth64), so the four gathers per sample need
+//     no F2F; the only conversions left are the three fp64 -> fp32 casts of TRAIN:502.
+// ---------------------------------------------------------------------------------------------------
+constexpr double kMagic = 6755399441055744.0;   // 2^52 + 2^51
+
+__device__ __forceinline__ void round_parts(double v, int& r, double& rd) {
+  const double s = __dadd_rn(v, kMagic);
+  r = __double2loint(s);
+  rd = __dsub_rn(s, kMagic);
+}
+
+__global__ void __launch_bounds__(TILE_W * TILE_H, 4)
+shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, const __grid_constant__ SampleTable tab) {
+  extern __shared__ uint32_t s_mask[];
+  const int b = blockIdx.z;
+  const int H = a.H, W = a.W;
+  const int words = (H * W) >> 5;
+  {
+    const uint32_t* src = a.mask_bits + (size_t)b * a.mask_stride;
+    for (int i = threadIdx.y * TILE_W + threadIdx.x; i < words; i += TILE_W * TILE_H) s_mask[i] = __ldg(src + i);
+  }
+  __syncthreads();
+
+  const int col = blockIdx.x * TILE_W + threadIdx.x;
+  const int row = blockIdx.y * TILE_H + threadIdx.y;
+  const double* __restrict__ D = depth64 + (size_t)b * H * W;
+  const float halfW = 0.5f * W, halfH = 0.5f * H;
+  const float xmin = -halfW, xmax = W - halfW - 1.0f, ymin = 1.0f - halfH, ymax = halfH;
+  const float x = (float)col - halfW;            // TRAIN:52
+  const float y = halfH - (float)row;            // TRAIN:53
+  const float z = __ldg(a.depth + (size_t)b * H * W + row * W + col);
+  const float Lx = __ldg(a.light + 3 * b), Ly = __ldg(a.light + 3 * b + 1), Lz = __ldg(a.light + 3 * b + 2);
+
+  float ex, ey;
+  ray_end(x, y, Lx, Ly, xmin, xmax, ymin, ymax, ex, ey);
+  const double dx = (double)__fsub_rn(ex, x), dy = (double)__fsub_rn(ey, y);          // TRAIN:467
+  double xd = (double)x, yd = (double)y;
+  asm volatile("" : "+d"(xd), "+d"(yd));     // keep them in registers: ptxas otherwise re-converts x, y every sample (2 XU ops)
+  const double hW = (double)halfW, hH = (double)halfH;
+  const float bcx = __fsub_rn(Lx, x), bcy = __fsub_rn(Ly, y), bcz = __fsub_rn(Lz, z); // BC, TRAIN:507
+  const int cW = W >> 1, cH = H >> 1;
+
+  float qmin = __int_as_float(0x7f800000);   // +inf == "outside the face"
+  int kmin = 255;
+#pragma unroll 2
+  for (int k = 0; k < a.n; ++k) {
+    const double t = tab.t[k];
+    const double px = __dadd_rn(xd, __dmul_rn(t, dx));                                // TRAIN:472,480
+    const double py = __dadd_rn(yd, __dmul_rn(t, dy));
+    const int ci = __double2loint(__dadd_rn(px, kMagic)) + cW;                        // TRAIN:472-475 (np.round: half to even)
+    const int ri = cH - __double2loint(__dadd_rn(py, kMagic));
+    const int mi = ri * W + ci;
+    if (!((s_mask[mi >> 5] >> (mi & 31)) & 1u)) continue;                             // TRAIN:510-512
+    const double u = __dadd_rn(__dadd_rn(px, hW), -0.0001);                           // TRAIN:481,483
+    const double v = __dadd_rn(__dsub_rn(hH, py), -0.0001);                           // TRAIN:482,483
+    // floor / ceil: the same magic add in round-down / round-up mode (TRAIN:486-487)
+    const double sfu = __dadd_rd(u, kMagic), scu = __dadd_ru(u, kMagic);
+    const double sfv = __dadd_rd(v, kMagic), scv = __dadd_ru(v, kMagic);
+    const int uf = __double2loint(sfu), uc = __double2loint(scu);
+    const int vf = __double2loint(sfv), vc = __double2loint(scv);
+    const double ufd = __dsub_rn(sfu, kMagic), ucd = __dsub_rn(scu, kMagic);
+    const double vfd = __dsub_rn(sfv, kMagic), vcd = __dsub_rn(scv, kMagic);
+    const unsigned ufi = uf < 0 ? uf + W : uf, vfi = vf < 0 ? vf + H : vf;            // python negative index
+    const double wu0 = __dsub_rn(ucd, u), wu1 = __dsub_rn(u, ufd);
+    const double wv0 = __dsub_rn(vcd, v), wv1 = __dsub_rn(v, vfd);
+    const unsigned r0 = vfi * (unsigned)W, r1 = (unsigned)vc * (unsigned)W;
+    const double ul = __ldg(D + (r0 + ufi)), ur = __ldg(D + (r0 + (unsigned)uc));
+    const double ll = __ldg(D + (r1 + ufi)), lr = __ldg(D + (r1 + (unsigned)uc));
+    const double up = __dadd_rn(__dmul_rn(ul, wu0), __dmul_rn(ur, wu1));              // TRAIN:492
+    const double lo = __dadd_rn(__dmul_rn(ll, wu0), __dmul_rn(lr, wu1));              // TRAIN:493
+    const double zi = __dadd_rn(__dmul_rn(up, wv0), __dmul_rn(lo, wv1));              // TRAIN:494
+    const float ax = (float)__dsub_rn(u, hW), ay = (float)__dsub_rn(hH, v), az = (float)zi;   // TRAIN:498-502
+    const float bax = __fsub_rn(ax, x), bay = __fsub_rn(ay, y), baz = __fsub_rn(az, z);
+    const float c0 = __fsub_rn(__fmul_rn(bay, bcz), __fmul_rn(baz, bcy));             // TRAIN:508
+    const float c1 = __fsub_rn(__fmul_rn(baz, bcx), __fmul_rn(bax, bcz));
+    const float c2 = __fsub_rn(__fmul_rn(bax, bcy), __fmul_rn(bay, bcx));
+    const float q = __fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fmul_rn(c2, c2));
+    if (q < qmin) { qmin = q; kmin = k; }
+  }
+  float d;
+  if (kmin == 255) {
+    d = 1000000.0f;                                                                   // TRAIN:512
+  } else {
+    const float den = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bcx, bcx), __fmul_rn(bcy, bcy)), __fmul_rn(bcz, bcz)), 1e-4f));
+    d = __fdiv_rn(sqrtf(__fadd_rn(qmin, 1e-4f)), den);
+  }
+  if (a.bonus != 0.0f && Lx >= xmin && Lx <= xmax && Ly >= ymin && Ly <= ymax) d = __fadd_rn(d, a.bonus);   // TEST1:495-496
+  const size_t o = (size_t)b * H * W + row * W + col;
+  a.dmin[o] = d;
+  if (a.argmin) a.argmin[o] = (uint8_t)kmin;
+  if (a.shadow) a.shadow[o] = shadow_weight(d);
+}
+
+__global__ void widen_depth_kernel(const float4* __restrict__ in, double* __restrict__ out, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(in + i);
+  double2* o = reinterpret_cast<double2*>(out + 4 * i);
+  o[0] = make_double2((double)v.x, (double)v.y);
+  o[1] = make_double2((double)v.z, (double)v.w);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // mask packing
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
@@ -173,8 +280,8 @@ extern "C" int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int 
 
 extern "C" int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
                                     const float* light_pt, const double* t_host, int n, float inside_bonus,
-                                    float* d_min, uint8_t* argmin, float* shadow, int B, int H, int W, int variant,
-                                    void* stream) {
+                                    float* d_min, uint8_t* argmin, float* shadow, double* depth64_scratch, int B, int H,
+                                    int W, int variant, void* stream) {
   GFR_RETURN_IF_NULL(depth); GFR_RETURN_IF_NULL(mask_bits); GFR_RETURN_IF_NULL(light_pt);
   GFR_RETURN_IF_NULL(t_host); GFR_RETURN_IF_NULL(d_min);
   if (B <= 0 || H <= 0 || W <= 0 || (W % TILE_W) || (H % TILE_H) || H > 512 || W > 512 || B > 65535) return GFR_E_SHAPE;
@@ -186,6 +293,12 @@ extern "C" int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bit
   MarchArgs a{depth, mask_bits, light_pt, d_min, argmin, shadow, mask_batch_stride, B, H, W, n, inside_bonus};
   const dim3 grid(W / TILE_W, H / TILE_H, B), block(TILE_W, TILE_H);
   const size_t smem = (size_t)(H * W / 32) * sizeof(uint32_t);
-  shadow_march_fwd_l1<<<grid, block, smem, (cudaStream_t)stream>>>(a, tab);
+  if (variant == 0 && depth64_scratch != nullptr && ((size_t)B * H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0) {
+    const size_t n4 = (size_t)B * H * W / 4;
+    widen_depth_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch, n4);
+    shadow_march_fwd_fast<<<grid, block, smem, (cudaStream_t)stream>>>(a, depth64_scratch, tab);
+  } else {
+    shadow_march_fwd_l1<<<grid, block, smem, (cudaStream_t)stream>>>(a, tab);
+  }
   return gfr_launch_status();
 }

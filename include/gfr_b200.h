@@ -58,12 +58,15 @@ int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int H, int W, u
  *   argmin     [B,H,W] out, uint8 index of the minimising sample (255 = every sample was outside the
  *              face); may be NULL.  Needed by the backward.
  *   shadow     [B,H,W] out, 1 - 4e^-d/(1+e^-d)^2 (TRAIN:517); may be NULL.
- *   variant    0 = default; 1 = L1/global gathers (no shared-memory depth staging); used by tests/bench.
+ *   depth64_scratch  [B,H,W] doubles of caller-owned scratch (the kernel widens the depth map into it once so
+ *              the per-sample gathers need no fp32->fp64 conversion); NULL selects variant 1.
+ *   variant    0 = default (conversion-free rounding + fp64 depth scratch, 2 launches); 1 = reference-literal
+ *              conversions (cvt.rni/floor/ceil per sample, 1 launch); both are bit-identical, used by tests/bench.
  */
 int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
                          const float* light_pt, const double* t_host, int n, float inside_bonus,
-                         float* d_min, uint8_t* argmin, float* shadow, int B, int H, int W, int variant,
-                         void* stream);
+                         float* d_min, uint8_t* argmin, float* shadow, double* depth64_scratch, int B, int H, int W,
+                         int variant, void* stream);
 
 /* Normals + Lambertian shading + shadow blend + albedo render.  Replaces TRAIN:353-369 and 517-522
  * (kornia depth_to_normals(depth + depth_offset, K), y flip, double normalise, l = normalize(P_L - P),
