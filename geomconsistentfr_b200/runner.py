@@ -1,20 +1,22 @@
 """Static-shape inference runner for the relight forward (TEST1:582-588 call site): device-resident input /
 output buffers, the ~65 kernel launches of one forward captured once in a CUDA graph and replayed, and a
-host-buffer entry (`relight_host`) that stages through pinned memory on the same stream.
+host-buffer entry (`relight_host`) that stages through pinned memory.
 
-torch supplies the memory, the stream and the graph object; every captured node is a libgfr_b200 kernel."""
+`lanes` > 1 builds that many independent copies (buffers + stream + graph).  Successive `relight_host` calls rotate
+over the lanes, so the host->device copy of batch i+1 and the device->host copy of batch i-1 overlap the kernels of
+batch i (separate copy engines), and the small low-resolution layers of two forwards share the SMs.
+
+torch supplies the memory, the streams and the graph objects; every captured node is a libgfr_b200 kernel."""
 import torch
 
 from . import ops
 from .relightnet import intrinsic_matrix
 
 
-class RelightRunner:
-    def __init__(self, net, batch, epoch=200, H=256, W=256, shared_mask=True, use_graph=True):
-        if not next(net.parameters()).is_cuda:
-            raise RuntimeError("RelightRunner needs the module on a CUDA device")
-        self.net, self.B, self.epoch, self.H, self.W = net.eval(), batch, epoch, H, W
+class _Lane:
+    def __init__(self, net, batch, epoch, H, W, shared_mask, use_graph):
         dev = net.device
+        self.net, self.B, self.epoch, self.H, self.W = net, batch, epoch, H, W
         self.stream = torch.cuda.Stream(device=dev)
         self.K = intrinsic_matrix(H, W)                    # host; values are read once and cached
         self.img = torch.zeros(batch, H, W, 3, device=dev)
@@ -25,8 +27,9 @@ class RelightRunner:
         self.out = None
         self.graph = None
         self.launches_per_run = 0
+        self.pin_out = None
         with torch.cuda.stream(self.stream):
-            for _ in range(2):                             # warm up (folds BN, caches intrinsics, fills the allocator)
+            for _ in range(2):                             # warm up (folds BN, packs weights, fills the allocator)
                 n0 = ops.launch_count()
                 self.out = self._forward()
                 self.launches_per_run = ops.launch_count() - n0
@@ -36,21 +39,18 @@ class RelightRunner:
                 with torch.cuda.graph(self.graph, stream=self.stream):
                     self.out = self._forward()
         self.stream.synchronize()
-        self._pin_in = self._pin_out = None
 
     def _forward(self):
         m = self.mask.view(self.H, self.W, 1) if self.mask.shape[0] == 1 else self.mask.view(self.B, self.H, self.W, 1)
         return self.net(self.img, self.epoch, self.K, m, self.light, self.ambient, None)
 
     def set_inputs(self, img, mask, light):
-        """Device-side copy of new inputs into the static buffers (on the runner's stream)."""
         with torch.cuda.stream(self.stream):
             self.img.copy_(img, non_blocking=True)
             self.mask.copy_(mask.reshape(self.mask.shape), non_blocking=True)
             self.light.copy_(light.reshape(self.light.shape), non_blocking=True)
 
     def run(self):
-        """Enqueue one forward on the runner's stream; outputs are in self.out (the reference's 10-tuple)."""
         with torch.cuda.stream(self.stream):
             if self.graph is not None:
                 self.graph.replay()
@@ -58,19 +58,61 @@ class RelightRunner:
                 self.out = self._forward()
         return self.out
 
+
+class RelightRunner:
+    def __init__(self, net, batch, epoch=200, H=256, W=256, shared_mask=True, use_graph=True, lanes=1):
+        if not next(net.parameters()).is_cuda:
+            raise RuntimeError("RelightRunner needs the module on a CUDA device")
+        self.net, self.B, self.epoch, self.H, self.W = net.eval(), batch, epoch, H, W
+        self.lanes = [_Lane(self.net, batch, epoch, H, W, shared_mask, use_graph) for _ in range(max(1, lanes))]
+        self._next = 0
+        self._last = self.lanes[0]
+
+    # ---- single-lane view (lane 0): the device-resident API
+    @property
+    def stream(self):
+        return self.lanes[0].stream
+
+    @property
+    def graph(self):
+        return self.lanes[0].graph
+
+    @property
+    def out(self):
+        return self._last.out
+
+    @property
+    def launches_per_run(self):
+        return self.lanes[0].launches_per_run
+
+    def set_inputs(self, img, mask, light):
+        """Device-side copy of new inputs into lane 0's static buffers (on its stream)."""
+        self.lanes[0].set_inputs(img, mask, light)
+
+    def run(self):
+        """Enqueue one forward on lane 0's stream; outputs are in self.out (the reference's 10-tuple)."""
+        self._last = self.lanes[0]
+        return self.lanes[0].run()
+
+    # ---- host-buffer entry, rotating over the lanes
     def relight_host(self, img_host, mask_host, light_host, rendered_host=None):
-        """Host buffers in, host buffer out: H2D of image/mask/light, forward, D2H of rendered_images.
-        Host tensors should be pinned for the copies to be asynchronous.  Returns the host tensor; the caller
-        synchronises the runner's stream (or calls .synchronize())."""
+        """Host buffers in, host buffer out: H2D of image/mask/light, forward, D2H of rendered_images, all on the
+        stream of the next lane.  Host tensors should be pinned for the copies to be asynchronous.  Returns
+        (host tensor, lane stream); the caller synchronises that stream (or calls .synchronize()) before reading —
+        and before reusing the same lane's default output buffer `lanes` calls later."""
+        lane = self.lanes[self._next]
+        self._next = (self._next + 1) % len(self.lanes)
+        self._last = lane
         if rendered_host is None:
-            if self._pin_out is None:
-                self._pin_out = torch.empty((self.B, 3, self.H, self.W), dtype=torch.float32).pin_memory()
-            rendered_host = self._pin_out
-        self.set_inputs(img_host, mask_host, light_host)
-        self.run()
-        with torch.cuda.stream(self.stream):
-            rendered_host.copy_(self.out[5], non_blocking=True)
-        return rendered_host
+            if lane.pin_out is None:
+                lane.pin_out = torch.empty((self.B, 3, self.H, self.W), dtype=torch.float32).pin_memory()
+            rendered_host = lane.pin_out
+        lane.set_inputs(img_host, mask_host, light_host)
+        lane.run()
+        with torch.cuda.stream(lane.stream):
+            rendered_host.copy_(lane.out[5], non_blocking=True)
+        return rendered_host, lane.stream
 
     def synchronize(self):
-        self.stream.synchronize()
+        for lane in self.lanes:
+            lane.stream.synchronize()
