@@ -82,6 +82,26 @@ int gfr_shade_render_fwd(const float* albedo, const float* depth, const float* d
                          float* final_shading, float* rendered, float* normals, int B, int H, int W,
                          void* stream);
 
+/* Ray-march backward (what autograd does for TRAIN:374-517): the min over samples routes the gradient to the arg-min
+ * sample, which is re-evaluated with the forward's arithmetic; gradients flow to the pixel's depth, the four bilinear
+ * corners of the sample, and the light point — directly (BC = P_L - P) and through the sample position (end point <-
+ * slope/intercept <- projected light, TRAIN:378-458; none where the end point is clamped or the light projects inside
+ * the image).  g_dmin [B,H,W] = dL/d(d_min); argmin from gfr_shadow_march_fwd; t_host / n as in the forward.
+ * g_depth [B,H,W] and g_light [B,3] are ACCUMULATED into (atomicAdd): zero-fill them first. */
+int gfr_shadow_march_bwd(const float* depth, const float* light_pt, const uint8_t* argmin, const float* g_dmin,
+                         const double* t_host, int n, float* g_depth, float* g_light, int B, int H, int W,
+                         void* stream);
+
+/* Backward of gfr_shade_render_fwd (autograd through TRAIN:353-369, 517-522).  Upstream gradients g_shadow, g_full,
+ * g_final [B,H,W], g_rendered, g_normals [B,3,H,W] may each be NULL (= zero).  Outputs: g_albedo [B,3,H,W] (written;
+ * may be NULL), g_dmin [B,H,W] (written; may be NULL), and ACCUMULATED (zero-fill first): g_depth [B,H,W],
+ * g_light [B,3], g_ambient [B]. */
+int gfr_shade_render_bwd(const float* albedo, const float* depth, const float* d_min, const float* light_pt,
+                         const float* ambient, const float* intr_host, const float* g_shadow, const float* g_full,
+                         const float* g_final, const float* g_rendered, const float* g_normals, float* g_albedo,
+                         float* g_depth, float* g_dmin, float* g_light, float* g_ambient, int B, int H, int W,
+                         void* stream);
+
 /* fp32 convolution with fused epilogue (exact-fp32 CNN path).  Replaces one
  * Conv2d / ConvTranspose2d(stride 1) + BatchNorm2d(eval, folded into w/bias by the caller) + residual add +
  * LeakyReLU(0.2) / sigmoid + skip add + nearest x2 upsample step of RelightNet (TRAIN:197-350, TEST1:170-323):
