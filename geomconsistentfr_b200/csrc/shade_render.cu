@@ -15,6 +15,7 @@ struct ShadeArgs {
   const float* ambient; // [B]
   float* shadow; float* full; float* final_shading; float* rendered; float* normals;
   int B, H, W;
+  int lpf;              // lights per face: pair b reads albedo / depth / ambient of face b / lpf
   float fx, fy, cx, cy, depth_offset, intensity;
 };
 
@@ -27,10 +28,10 @@ __device__ __forceinline__ void normalize3(float& a, float& b, float& c) {   // 
 __global__ void __launch_bounds__(256) shade_render_fwd_kernel(const ShadeArgs a) {
   const int col = blockIdx.x * 32 + threadIdx.x;
   const int row = blockIdx.y * 8 + threadIdx.y;
-  const int b = blockIdx.z;
+  const int b = blockIdx.z, f = b / a.lpf;
   const int H = a.H, W = a.W;
   if (col >= W || row >= H) return;
-  const float* __restrict__ D = a.depth + (size_t)b * H * W;
+  const float* __restrict__ D = a.depth + (size_t)f * H * W;
   const size_t pix = (size_t)row * W + col;
   const size_t o = (size_t)b * H * W + pix;
 
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(256) shade_render_fwd_kernel(const ShadeArgs a
   normalize3(lx, ly, lz);
   const float ndotl = (nx * lx + ny * ly) + nz * lz;
   const float directional = a.intensity * fmaxf(ndotl, 0.0f);
-  const float amb = __ldg(a.ambient + b);
+  const float amb = __ldg(a.ambient + f);
   const float full = amb + directional;
 
   // --- shadow weight + blend + render, TRAIN:517-522
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) shade_render_fwd_kernel(const ShadeArgs a
   if (a.final_shading) a.final_shading[o] = fin;
   const size_t plane = (size_t)H * W;
   if (a.rendered) {
-    const float* A = a.albedo + (size_t)b * 3 * plane + pix;
+    const float* A = a.albedo + (size_t)f * 3 * plane + pix;
     float* R = a.rendered + (size_t)b * 3 * plane + pix;
     R[0] = __ldg(A) * fin; R[plane] = __ldg(A + plane) * fin; R[2 * plane] = __ldg(A + 2 * plane) * fin;
   }
@@ -95,12 +96,13 @@ __global__ void __launch_bounds__(256) shade_render_fwd_kernel(const ShadeArgs a
 extern "C" int gfr_shade_render_fwd(const float* albedo, const float* depth, const float* d_min, const float* light_pt,
                                     const float* ambient, const float* intr_host, float* shadow, float* full,
                                     float* final_shading, float* rendered, float* normals, int B, int H, int W,
-                                    void* stream) {
+                                    int lights_per_face, void* stream) {
   GFR_RETURN_IF_NULL(depth); GFR_RETURN_IF_NULL(d_min); GFR_RETURN_IF_NULL(light_pt);
   GFR_RETURN_IF_NULL(ambient); GFR_RETURN_IF_NULL(intr_host);
   if (rendered != nullptr && albedo == nullptr) return GFR_E_NULL;
   if (B <= 0 || H <= 0 || W <= 0 || B > 65535) return GFR_E_SHAPE;
-  ShadeArgs a{albedo, depth, d_min, light_pt, ambient, shadow, full, final_shading, rendered, normals, B, H, W,
+  if (lights_per_face < 1 || B % lights_per_face) return GFR_E_ARG;
+  ShadeArgs a{albedo, depth, d_min, light_pt, ambient, shadow, full, final_shading, rendered, normals, B, H, W, lights_per_face,
               intr_host[0], intr_host[1], intr_host[2], intr_host[3], intr_host[4], intr_host[5]};
   const dim3 grid(gfr_ceil_div(W, 32), gfr_ceil_div(H, 8), B), block(32, 8);
   shade_render_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a);

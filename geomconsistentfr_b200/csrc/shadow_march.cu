@@ -25,6 +25,7 @@ struct MarchArgs {
   float* shadow;             // [B,H,W] or null
   int mask_stride;           // words
   int B, H, W, n;
+  int lpf;                   // lights per face: (face, light) pair b reads depth / mask of face b / lpf
   float bonus;
 };
 
@@ -69,18 +70,18 @@ __device__ __forceinline__ float shadow_weight(float d) {   // TRAIN:517
 __global__ void __launch_bounds__(TILE_W * TILE_H)
 shadow_march_fwd_l1(const MarchArgs a, const __grid_constant__ SampleTable tab) {
   extern __shared__ uint32_t s_mask[];
-  const int b = blockIdx.z;
+  const int b = blockIdx.z, f = b / a.lpf;
   const int H = a.H, W = a.W;
   const int words = (H * W) >> 5;
   {
-    const uint32_t* src = a.mask_bits + (size_t)b * a.mask_stride;
+    const uint32_t* src = a.mask_bits + (size_t)f * a.mask_stride;
     for (int i = threadIdx.y * TILE_W + threadIdx.x; i < words; i += TILE_W * TILE_H) s_mask[i] = __ldg(src + i);
   }
   __syncthreads();
 
   const int col = blockIdx.x * TILE_W + threadIdx.x;
   const int row = blockIdx.y * TILE_H + threadIdx.y;
-  const float* __restrict__ D = a.depth + (size_t)b * H * W;
+  const float* __restrict__ D = a.depth + (size_t)f * H * W;
   const float halfW = 0.5f * W, halfH = 0.5f * H;
   const float xmin = -halfW, xmax = W - halfW - 1.0f, ymin = 1.0f - halfH, ymax = halfH;
   const float x = (float)col - halfW;            // TRAIN:52
@@ -161,23 +162,23 @@ __device__ __forceinline__ void round_parts(double v, int& r, double& rd) {
 __global__ void __launch_bounds__(TILE_W * TILE_H, 4)
 shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, const __grid_constant__ SampleTable tab) {
   extern __shared__ uint32_t s_mask[];
-  const int b = blockIdx.z;
+  const int b = blockIdx.z, f = b / a.lpf;
   const int H = a.H, W = a.W;
   const int words = (H * W) >> 5;
   {
-    const uint32_t* src = a.mask_bits + (size_t)b * a.mask_stride;
+    const uint32_t* src = a.mask_bits + (size_t)f * a.mask_stride;
     for (int i = threadIdx.y * TILE_W + threadIdx.x; i < words; i += TILE_W * TILE_H) s_mask[i] = __ldg(src + i);
   }
   __syncthreads();
 
   const int col = blockIdx.x * TILE_W + threadIdx.x;
   const int row = blockIdx.y * TILE_H + threadIdx.y;
-  const double* __restrict__ D = depth64 + (size_t)b * H * W;
+  const double* __restrict__ D = depth64 + (size_t)f * H * W;
   const float halfW = 0.5f * W, halfH = 0.5f * H;
   const float xmin = -halfW, xmax = W - halfW - 1.0f, ymin = 1.0f - halfH, ymax = halfH;
   const float x = (float)col - halfW;            // TRAIN:52
   const float y = halfH - (float)row;            // TRAIN:53
-  const float z = __ldg(a.depth + (size_t)b * H * W + row * W + col);
+  const float z = __ldg(a.depth + (size_t)f * H * W + row * W + col);
   const float Lx = __ldg(a.light + 3 * b), Ly = __ldg(a.light + 3 * b + 1), Lz = __ldg(a.light + 3 * b + 2);
 
   float ex, ey;
@@ -281,20 +282,22 @@ extern "C" int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int 
 extern "C" int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
                                     const float* light_pt, const double* t_host, int n, float inside_bonus,
                                     float* d_min, uint8_t* argmin, float* shadow, double* depth64_scratch, int B, int H,
-                                    int W, int variant, void* stream) {
+                                    int W, int lights_per_face, int variant, void* stream) {
   GFR_RETURN_IF_NULL(depth); GFR_RETURN_IF_NULL(mask_bits); GFR_RETURN_IF_NULL(light_pt);
   GFR_RETURN_IF_NULL(t_host); GFR_RETURN_IF_NULL(d_min);
   if (B <= 0 || H <= 0 || W <= 0 || (W % TILE_W) || (H % TILE_H) || H > 512 || W > 512 || B > 65535) return GFR_E_SHAPE;
   if (n <= 0 || n > 255) return GFR_E_ARG;     // 255 is the "no sample inside the face" argmin code
   if (mask_batch_stride != 0 && mask_batch_stride != (H * W) / 32) return GFR_E_ARG;
   if (variant < 0 || variant > 1) return GFR_E_ARG;
+  if (lights_per_face < 1 || B % lights_per_face) return GFR_E_ARG;
+  const int faces = B / lights_per_face;
   SampleTable tab;
   for (int k = 0; k < GFR_MAX_SAMPLES; ++k) tab.t[k] = k < n ? t_host[k] : 0.0;
-  MarchArgs a{depth, mask_bits, light_pt, d_min, argmin, shadow, mask_batch_stride, B, H, W, n, inside_bonus};
+  MarchArgs a{depth, mask_bits, light_pt, d_min, argmin, shadow, mask_batch_stride, B, H, W, n, lights_per_face, inside_bonus};
   const dim3 grid(W / TILE_W, H / TILE_H, B), block(TILE_W, TILE_H);
   const size_t smem = (size_t)(H * W / 32) * sizeof(uint32_t);
-  if (variant == 0 && depth64_scratch != nullptr && ((size_t)B * H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0) {
-    const size_t n4 = (size_t)B * H * W / 4;
+  if (variant == 0 && depth64_scratch != nullptr && ((size_t)faces * H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0) {
+    const size_t n4 = (size_t)faces * H * W / 4;
     widen_depth_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch, n4);
     shadow_march_fwd_fast<<<grid, block, smem, (cudaStream_t)stream>>>(a, depth64_scratch, tab);
   } else {

@@ -65,37 +65,42 @@ def mask_pack(mask):
 
 def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0, want_argmin=False,
                      want_shadow=False, variant=0):
-    """depth [B,1,H,W] f32; mask_bits [1|B, H*W/32] i32; light_pt [B,3] f32 -> d_min [B,H,W]
-    (+ argmin u8, + shadow).  TRAIN:374-517."""
+    """depth [F,1,H,W] f32; mask_bits [1|F, H*W/32] i32; light_pt [B,3] f32 with B = F * L (L lights per face, pair b
+    uses face b // L) -> d_min [B,H,W] (+ argmin u8, + shadow).  TRAIN:374-517."""
     depth = _need(depth, torch.float32, "depth")
     light_pt = _need(light_pt, torch.float32, "light_pt")
     mask_bits = _need(mask_bits, torch.int32, "mask_bits")
-    B, _, H, W = depth.shape
-    if light_pt.shape != (B, 3):
-        raise RuntimeError("light_pt must be [B,3]")
-    if mask_bits.shape[0] not in (1, B) or mask_bits.shape[1] != H * W // 32:
-        raise RuntimeError("mask_bits must be [1|B, H*W/32]")
+    F, _, H, W = depth.shape
+    B = light_pt.shape[0]
+    if light_pt.dim() != 2 or light_pt.shape[1] != 3 or B % F:
+        raise RuntimeError("light_pt must be [F*L,3]")
+    if mask_bits.shape[0] not in (1, F) or mask_bits.shape[1] != H * W // 32:
+        raise RuntimeError("mask_bits must be [1|F, H*W/32]")
     t = reference_samples() if samples is None else np.ascontiguousarray(samples, dtype=np.float64)
     dmin = torch.empty((B, H, W), dtype=torch.float32, device=depth.device)
     arg = torch.empty((B, H, W), dtype=torch.uint8, device=depth.device) if want_argmin else None
     shadow = torch.empty((B, H, W), dtype=torch.float32, device=depth.device) if want_shadow else None
     stride = 0 if mask_bits.shape[0] == 1 else H * W // 32
-    scratch = torch.empty((B, H, W), dtype=torch.float64, device=depth.device) if variant == 0 else None
+    scratch = torch.empty((F, H, W), dtype=torch.float64, device=depth.device) if variant == 0 else None
     rc = _lib.load().gfr_shadow_march_fwd(
         _ptr(depth), _ptr(mask_bits), stride, _ptr(light_pt), t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]),
-        float(inside_bonus), _ptr(dmin), _ptr(arg), _ptr(shadow), _ptr(scratch), B, H, W, int(variant), _stream())
+        float(inside_bonus), _ptr(dmin), _ptr(arg), _ptr(shadow), _ptr(scratch), B, H, W, B // F, int(variant), _stream())
     _lib.check(rc, "gfr_shadow_march_fwd"); _count(2 if variant == 0 else 1)
     return dmin, arg, shadow
 
 
 def shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx=1570.0, fy=1570.0, cx=None, cy=None,
                      depth_offset=1610.0, intensity=0.5, want=("shadow", "full", "final", "rendered", "normals")):
-    """TRAIN:353-369, 517-522.  Returns dict of the requested outputs."""
+    """TRAIN:353-369, 517-522.  albedo/depth/ambient hold F faces, d_min/light_pt B = F * L (face, light) pairs.
+    Returns dict of the requested outputs ([B,...])."""
     depth = _need(depth, torch.float32, "depth")
     d_min = _need(d_min, torch.float32, "d_min")
     light_pt = _need(light_pt, torch.float32, "light_pt")
     ambient = _need(ambient.reshape(-1), torch.float32, "ambient")
-    B, _, H, W = depth.shape
+    F, _, H, W = depth.shape
+    B = d_min.shape[0]
+    if B % F or light_pt.shape != (B, 3) or ambient.shape[0] != F:
+        raise RuntimeError("shade_render_fwd: d_min/light_pt must hold F*L pairs, ambient F faces")
     if "rendered" in want:
         albedo = _need(albedo, torch.float32, "albedo")
     intr = np.array([fx, fy, W / 2.0 if cx is None else cx, H / 2.0 if cy is None else cy, depth_offset, intensity],
@@ -108,7 +113,7 @@ def shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx=1570.0, fy=1570
     rc = _lib.load().gfr_shade_render_fwd(
         _ptr(albedo) if "rendered" in want else None, _ptr(depth), _ptr(d_min), _ptr(light_pt), _ptr(ambient),
         intr.ctypes.data_as(ctypes.c_void_p), _ptr(out["shadow"]), _ptr(out["full"]), _ptr(out["final"]),
-        _ptr(out["rendered"]), _ptr(out["normals"]), B, H, W, _stream())
+        _ptr(out["rendered"]), _ptr(out["normals"]), B, H, W, B // F, _stream())
     _lib.check(rc, "gfr_shade_render_fwd"); _count()
     return out
 

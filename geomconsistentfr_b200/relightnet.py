@@ -314,6 +314,38 @@ class RelightNet(nn.Module):
             return (albedo, depth, o["shadow"], amb_l, o["full"], o["rendered"], unit, ambient_values.view(B, 1, 1))
 
 
+    # ------------------------------------------------------------------ one CNN pass, many lights (TESTB:565-583 sweep)
+    @torch.no_grad()
+    def relight_sweep(self, img, epoch, intrinsic_matrix, mask, lights):
+        """Relight F faces under L lights with ONE CNN pass per face (the reference re-runs the whole network for every
+        light of its 18-direction Multi-PIE sweep, TESTB:565-583).  img [F,H,W,3]; mask [H,W,1] (shared) or [F,H,W,1];
+        lights [L,3] (shared by all faces) or [F,L,3].  Semantics per (face, light) are those of the TEST1 forward
+        (ambient = predicted - 0.1, +5 inside-image bonus).  Returns a dict with rendered [F,L,3,H,W], shadow / final
+        [F,L,H,W], and the per-face albedo, depth, normals-independent ambient."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("RelightNet (geomconsistentfr_b200) runs on CUDA only; call .cuda() first")
+        img = img.to(dev, torch.float32, non_blocking=True)
+        F_, H, W, _ = img.shape
+        lights = lights.to(dev, torch.float32)
+        if lights.dim() == 2:
+            lights = lights.unsqueeze(0).expand(F_, -1, -1)
+        L = lights.shape[1]
+        albedo, depth, sl = self._cnn_eval(img, epoch)
+        m = mask.to(dev, non_blocking=True)
+        bits = ops.mask_pack(m.reshape(-1, H, W))
+        ambient = (sl[:, 0] - 0.1).contiguous()                                          # TEST1:342
+        unit = torch.nn.functional.normalize(lights.reshape(F_ * L, 3), p=2, dim=1)
+        light_pt = (self.light_distance * unit).contiguous()
+        d_min, _, _ = ops.shadow_march_fwd(depth, bits, light_pt, inside_bonus=5.0, variant=self.march_variant)
+        fx, fy, cx, cy = self._intrinsics(intrinsic_matrix)
+        o = ops.shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx, fy, cx, cy, self.depth_offset,
+                                 self.directional_intensity, want=("shadow", "final", "rendered"))
+        return dict(rendered=o["rendered"].view(F_, L, 3, H, W), shadow=o["shadow"].view(F_, L, H, W),
+                    final=o["final"].view(F_, L, H, W), albedo=albedo, depth=depth, ambient=ambient,
+                    unit_light=unit.view(F_, L, 3))
+
+
 def intrinsic_matrix(H=256, W=256, focal=1570.0):
     """The camera matrix the reference builds at TRAIN:571-577 (float64, [1,3,3])."""
     K = np.zeros((1, 3, 3))

@@ -60,13 +60,16 @@ int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int H, int W, u
  *   shadow     [B,H,W] out, 1 - 4e^-d/(1+e^-d)^2 (TRAIN:517); may be NULL.
  *   depth64_scratch  [B,H,W] doubles of caller-owned scratch (the kernel widens the depth map into it once so
  *              the per-sample gathers need no fp32->fp64 conversion); NULL selects variant 1.
+ *   lights_per_face  L >= 1: B counts (face, light) pairs, pair b uses the depth map and mask of face b / L (depth,
+ *              depth64_scratch and per-image masks then hold B / L entries) — one CNN pass relit under L lights
+ *              (the reference's 18-light Multi-PIE sweep, TESTB:565-583).  1 = one light per face.
  *   variant    0 = default (conversion-free rounding + fp64 depth scratch, 2 launches); 1 = reference-literal
  *              conversions (cvt.rni/floor/ceil per sample, 1 launch); both are bit-identical, used by tests/bench.
  */
 int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
                          const float* light_pt, const double* t_host, int n, float inside_bonus,
                          float* d_min, uint8_t* argmin, float* shadow, double* depth64_scratch, int B, int H, int W,
-                         int variant, void* stream);
+                         int lights_per_face, int variant, void* stream);
 
 /* Normals + Lambertian shading + shadow blend + albedo render.  Replaces TRAIN:353-369 and 517-522
  * (kornia depth_to_normals(depth + depth_offset, K), y flip, double normalise, l = normalize(P_L - P),
@@ -76,11 +79,13 @@ int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask
  *   intr_host: HOST floats {fx, fy, cx, cy, depth_offset(1610), directional_intensity(0.5)}
  *   outputs (any may be NULL): shadow [B,H,W], full [B,H,W], final [B,H,W], rendered [B,3,H,W],
  *   normals [B,3,H,W]
+ *   lights_per_face L: as in gfr_shadow_march_fwd — albedo, depth and ambient hold B / L faces, d_min / light_pt /
+ *   the outputs B (face, light) pairs.
  */
 int gfr_shade_render_fwd(const float* albedo, const float* depth, const float* d_min, const float* light_pt,
                          const float* ambient, const float* intr_host, float* shadow, float* full,
                          float* final_shading, float* rendered, float* normals, int B, int H, int W,
-                         void* stream);
+                         int lights_per_face, void* stream);
 
 /* Ray-march backward (what autograd does for TRAIN:374-517): the min over samples routes the gradient to the arg-min
  * sample, which is re-evaluated with the forward's arithmetic; gradients flow to the pixel's depth, the four bilinear

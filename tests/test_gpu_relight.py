@@ -117,3 +117,19 @@ def test_train_signature_in_eval_mode_vs_oracle(net, oracle_net, ffhq):
         tol = 5e-3 if k == 1 else 2e-3
         assert a.shape == b.shape, k
         assert (a.cpu() - b).abs().max() <= tol, (k, float((a.cpu() - b).abs().max()))
+
+
+def test_relight_sweep_equals_per_light_forward(net, ffhq):
+    """One CNN pass + L lights (relight_sweep) == L full forwards (TESTB:565-583 semantics), bit for bit."""
+    from geomconsistentfr_b200 import intrinsic_matrix
+    K = intrinsic_matrix().cuda()
+    x = _inputs(ffhq, [2, 7]).cuda()
+    m = torch.from_numpy(ffhq["masks"][2].astype(np.float64).reshape(256, 256, 1)).cuda() / 255.0
+    lights = torch.tensor(O.LIGHTS_18[3:6], dtype=torch.float32)
+    sw = net.relight_sweep(x, 200, K, m, lights)
+    assert sw["rendered"].shape == (2, 3, 3, 256, 256)
+    for j in range(3):
+        tl = lights[j].view(1, 3, 1, 1).expand(2, 3, 1, 1).contiguous().cuda()
+        o = net(x, 200, K, m, tl, torch.full((2, 1, 1), 0.5).cuda(), None)
+        assert torch.equal(sw["rendered"][:, j], o[5])
+        assert torch.equal(sw["shadow"][:, j], o[2])
