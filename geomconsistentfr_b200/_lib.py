@@ -22,6 +22,10 @@ _PROTOS = {
     "gfr_maxpool2_fwd": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_upsample2_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_light_head_fwd": [_c_void_p, ctypes.c_longlong, _c_int, _c_int] + [_c_void_p] * 5 + [_c_int, _c_void_p],
+    "gfr_ssim_fwd": [_c_void_p] * 4 + [_c_int, _c_int, _c_int, _c_float, _c_void_p],
+    "gfr_ssim_bwd": [_c_void_p] * 5 + [_c_int, _c_int, _c_int, _c_void_p],
+    "gfr_masked_losses": [_c_void_p] * 12 + [_c_int, _c_int, _c_int, _c_void_p],
+    "gfr_adam_step": [_c_void_p] * 4 + [ctypes.c_longlong, _c_int, _c_float, _c_float, _c_float, _c_float, _c_float, _c_void_p],
     # tensor-core path (C4 layout)
     "gfr_nchw_to_c4": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_c4_to_nchw": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],

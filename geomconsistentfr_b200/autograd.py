@@ -70,3 +70,105 @@ class ShadeRender(torch.autograd.Function):
             _ptr(g_dmin), _ptr(g_light), _ptr(g_amb), B, H, W, _stream())
         _lib.check(rc, "gfr_shade_render_bwd"); ops._count()
         return g_albedo, g_depth, g_dmin, g_light, g_amb, None
+
+
+class SSIMPlanes(torch.autograd.Function):
+    """per = SSIMPlanes.apply(X[N,C,H,W], Y[N,C,H,W], data_range) -> [N,C] mean SSIM of every plane (the `.mean(-1)` of
+    pytorch_msssim._ssim, TRAIN:643).  Gradient w.r.t. X only (Y is the target image)."""
+
+    @staticmethod
+    def forward(ctx, X, Y, data_range=1.0):
+        X, Y = _need(X, torch.float32, "X"), _need(Y, torch.float32, "Y")
+        N, C, H, W = X.shape
+        P = N * C
+        sums = torch.zeros(P, dtype=torch.float64, device=X.device)
+        gm = torch.empty((3, P, H - 10, W - 10), dtype=torch.float32, device=X.device) if X.requires_grad else None
+        rc = _lib.load().gfr_ssim_fwd(_ptr(X), _ptr(Y), _ptr(sums), _ptr(gm), P, H, W, float(data_range), _stream())
+        _lib.check(rc, "gfr_ssim_fwd"); ops._count()
+        ctx.save_for_backward(X, Y, gm)
+        return (sums / float((H - 10) * (W - 10))).to(torch.float32).view(N, C)
+
+    @staticmethod
+    def backward(ctx, g_per):
+        X, Y, gm = ctx.saved_tensors
+        N, C, H, W = X.shape
+        scale = (g_per.reshape(-1).to(torch.float32) / float((H - 10) * (W - 10))).contiguous()
+        gX = torch.empty_like(X)
+        rc = _lib.load().gfr_ssim_bwd(_ptr(X), _ptr(Y), _ptr(gm), _ptr(scale), _ptr(gX), N * C, H, W, _stream())
+        _lib.check(rc, "gfr_ssim_bwd"); ops._count()
+        return gX, None, None
+
+
+def dssim_loss(composite, target, weight=8.0):
+    """TRAIN:643: weight * (1 - ssim(composite, target, data_range=1, size_average=True, nonnegative_ssim=True)) / 2."""
+    per = SSIMPlanes.apply(composite, target, 1.0)
+    return weight * (1.0 - torch.relu(per).mean()) / 2.0
+
+
+class MaskedLosses(torch.autograd.Function):
+    """recon, depth_l, albedo_l = MaskedLosses.apply(rendered, depth, albedo, img_nchw, depth_gt, albedo_gt, mask_fill, mask)
+    — the three masked terms of TRAIN:633-639 (fp64 sums like the reference) with their gradients from one kernel pass."""
+
+    @staticmethod
+    def forward(ctx, rendered, depth, albedo, img_nchw, depth_gt, albedo_gt, mask_fill, mask):
+        f = lambda t, n: _need(t, torch.float32, n)
+        rendered, depth, albedo = f(rendered, "rendered"), f(depth, "depth"), f(albedo, "albedo")
+        img_nchw, depth_gt, albedo_gt = f(img_nchw, "img"), f(depth_gt, "depth_gt"), f(albedo_gt, "albedo_gt")
+        mask_fill, mask = f(mask_fill, "mask_fill"), f(mask, "mask")
+        N, _, H, W = rendered.shape
+        sums = torch.empty(5, dtype=torch.float64, device=rendered.device)
+        g_r, g_d, g_a = torch.empty_like(rendered), torch.empty_like(depth), torch.empty_like(albedo)
+        rc = _lib.load().gfr_masked_losses(_ptr(rendered), _ptr(img_nchw), _ptr(depth), _ptr(depth_gt), _ptr(albedo),
+                                           _ptr(albedo_gt), _ptr(mask_fill), _ptr(mask), _ptr(sums), _ptr(g_r), _ptr(g_d),
+                                           _ptr(g_a), N, H, W, _stream())
+        _lib.check(rc, "gfr_masked_losses"); ops._count(2)
+        ctx.save_for_backward(g_r, g_d, g_a)
+        return 20.0 * sums[2] / (3.0 * sums[0]), sums[3] / sums[1], 5.0 * sums[4] / sums[0]
+
+    @staticmethod
+    def backward(ctx, g_recon, g_depth_l, g_albedo_l):
+        g_r, g_d, g_a = ctx.saved_tensors
+        return (g_r * g_recon.to(torch.float32), g_d * g_depth_l.to(torch.float32), g_a * g_albedo_l.to(torch.float32),
+                None, None, None, None, None)
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8) over ONE flat fp32 buffer that the parameters are views of
+    (TRAIN:589-590, 656) — a single fused kernel per step; `grad_scale` folds the 1/world_size of the data-parallel
+    gradient all-reduce."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        o = 0
+        with torch.no_grad():
+            for p in self.params:                      # re-seat every parameter (and its .grad) as a view of the flat buffers
+                k = p.numel()
+                self.flat[o:o + k].copy_(p.reshape(-1))
+                p.data = self.flat[o:o + k].view_as(p)
+                p.grad = self.grad[o:o + k].view_as(p)
+                o += k
+        self.lr, self.betas, self.eps, self.step_count = lr, betas, eps, 0
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def all_reduce_grads(self, group=None):
+        """ONE collective per optimiser step over the flat gradient buffer (sum); returns the 1/world factor."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return 1.0
+        dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / dist.get_world_size(group)
+
+    def step(self, grad_scale=1.0):
+        self.step_count += 1
+        rc = _lib.load().gfr_adam_step(_ptr(self.flat), _ptr(self.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
+                                       self.flat.numel(), self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
+                                       float(grad_scale), _stream())
+        _lib.check(rc, "gfr_adam_step"); ops._count()

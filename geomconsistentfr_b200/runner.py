@@ -13,6 +13,14 @@ from . import ops
 from .relightnet import intrinsic_matrix
 
 
+def shard_faces(n_faces, rank, world):
+    """Data-parallel inference: faces are independent, rank r relights the contiguous slice [lo, hi) and
+    no data-path collective is needed."""
+    base, rem = divmod(n_faces, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 class _Lane:
     def __init__(self, net, batch, epoch, H, W, shared_mask, use_graph):
         dev = net.device

@@ -107,6 +107,33 @@ int gfr_shade_render_bwd(const float* albedo, const float* depth, const float* d
                          float* g_depth, float* g_dmin, float* g_light, float* g_ambient, int B, int H, int W,
                          void* stream);
 
+/* ---- training losses and optimiser (TRAIN:589-590, 633-656) ---------------------------------------------------
+ * SSIM (pytorch_msssim.ssim at TRAIN:643: 11-tap Gaussian sigma 1.5, VALID, per (n,c) plane).  X, Y [P,H,W] with
+ * P = N*C planes.  Forward: plane_sums [P] doubles are ACCUMULATED (zero-fill first) with the sum of the
+ * (H-10)x(W-10) SSIM map of each plane (mean = sum / ((H-10)(W-10))); grad_maps [3,P,H-10,W-10] (may be NULL) receives
+ * dS/dmu_x, dS/dE[xx], dS/dE[xy] for the backward.  Backward: g_X [P,H,W] = plane_scale[p] * (transposed filter of the
+ * three maps), plane_scale[p] = dL/d(mean SSIM of plane p) / ((H-10)(W-10)). */
+int gfr_ssim_fwd(const float* X, const float* Y, double* plane_sums, float* grad_maps, int P, int H, int W,
+                 float data_range, void* stream);
+int gfr_ssim_bwd(const float* X, const float* Y, const float* grad_maps, const float* plane_scale, float* g_X, int P,
+                 int H, int W, void* stream);
+
+/* Masked reconstruction / depth / albedo losses with their gradients (TRAIN:633-639).  rendered, img_nchw, albedo
+ * [N,3,H,W]; depth, depth_gt, albedo_gt, mask_fill, mask [N,H,W].  sums5 (5 doubles, overwritten):
+ *   {sum(mask_fill), sum(mask), sum((mask_fill*(rendered-img))^2), sum|mask*(depth-depth_gt)|,
+ *    sum|mask_fill*(mean_c albedo - albedo_gt)|}
+ * so recon = 20*s[2]/(3*s[0]), depth = s[3]/s[1], albedo = 5*s[4]/s[0].  g_rendered / g_depth / g_albedo (each may be
+ * NULL) receive the gradients of those three loss terms. */
+int gfr_masked_losses(const float* rendered, const float* img_nchw, const float* depth, const float* depth_gt,
+                      const float* albedo, const float* albedo_gt, const float* mask_fill, const float* mask,
+                      double* sums5, float* g_rendered, float* g_depth, float* g_albedo, int N, int H, int W,
+                      void* stream);
+
+/* One torch.optim.Adam step (no weight decay, no amsgrad; TRAIN:589-590, 656) over a flat fp32 parameter buffer:
+ * step >= 1 is the 1-based step count; grads are multiplied by grad_scale first (1/world_size after an all-reduce). */
+int gfr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step, float lr,
+                  float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 /* fp32 convolution with fused epilogue (exact-fp32 CNN path).  Replaces one
  * Conv2d / ConvTranspose2d(stride 1) + BatchNorm2d(eval, folded into w/bias by the caller) + residual add +
  * LeakyReLU(0.2) / sigmoid + skip add + nearest x2 upsample step of RelightNet (TRAIN:197-350, TEST1:170-323):
