@@ -26,6 +26,20 @@ _PROTOS = {
     "gfr_ssim_bwd": [_c_void_p] * 5 + [_c_int, _c_int, _c_int, _c_void_p],
     "gfr_masked_losses": [_c_void_p] * 12 + [_c_int, _c_int, _c_int, _c_void_p],
     "gfr_adam_step": [_c_void_p] * 4 + [ctypes.c_longlong, _c_int, _c_float, _c_float, _c_float, _c_float, _c_float, _c_void_p],
+    # train-mode CNN
+    "gfr_conv_tc_pack_weights_dev": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p],
+    "gfr_bn_train_stats": [_c_void_p] * 10 + [_c_int] * 4 + [_c_float, _c_float, _c_void_p],
+    "gfr_bn_apply_fwd": [_c_void_p] * 6 + [_c_int] * 6 + [_c_void_p],
+    "gfr_bn_apply_bwd": [_c_void_p] * 11 + [_c_int] * 5 + [_c_void_p],
+    "gfr_conv3x3_wgrad": [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p],
+    "gfr_maxpool2_c4_bwd": [_c_void_p] * 3 + [_c_int] * 3 + [_c_void_p],
+    "gfr_sumpool2_c4": [_c_void_p] * 2 + [_c_int] * 3 + [_c_void_p],
+    "gfr_avgpool_c4_fwd": [_c_void_p] * 2 + [_c_int] * 5 + [_c_void_p],
+    "gfr_avgpool_c4_bwd": [_c_void_p] * 2 + [_c_int] * 5 + [_c_void_p],
+    "gfr_pw_conv16_fwd": [_c_void_p] * 4 + [_c_int] * 6 + [_c_float, _c_void_p],
+    "gfr_pw_conv16_bwd": [_c_void_p] * 7 + [_c_int] * 6 + [_c_float, _c_void_p],
+    "gfr_stem_conv_train_fwd": [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p],
+    "gfr_stem_conv_wgrad": [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p],
     # tensor-core path (C4 layout)
     "gfr_nchw_to_c4": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_c4_to_nchw": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],

@@ -1,0 +1,812 @@
+// Train-mode building blocks of the RelightNet CNN (the reference never calls .eval() while training, TRAIN:561-563,
+// so every BatchNorm uses BATCH statistics and cannot be folded into the convolution).  C4 activation layout
+// [N][C/4][H][W][4] throughout (see conv_tc.cu).  TRAIN = train_raytracing_relighting_CelebAHQ_DSSIM_8x.py.
+//
+//   pack      — device-side weight packing for gfr_conv3x3_tc_fwd (weights change every optimiser step): tf32 hi/lo
+//               split + UMMA core-matrix layout, for Conv2d and ConvTranspose2d parameters, forward or data-gradient
+//               (dgrad of a stride-1 3x3 conv is the same convolution with the transposed, flipped kernel)
+//   bn_stats  — per-channel sum / sum of squares over (N,H,W), fp64 accumulation
+//   bn_final  — mean, 1/sqrt(var+eps) -> per-channel scale/shift; running-statistics update (momentum 0.1, unbiased var)
+//   bn_apply  — y = act(scale*x + shift + res) + up2(post)   (BatchNorm + residual + LeakyReLU + skip/upsample add)
+//   bn_bwd    — reduction (sum g, sum g*xhat) and elementwise input gradient of the same block
+//   wgrad     — weight gradient of the 3x3 convolution (CUDA cores, fp32)
+//   pw        — 1x1 convolutions of the decoder tails (16 -> 16 raw, 16 -> 1|3 with sigmoid / scale), fwd + bwd
+//   pools     — 2x2 max-pool backward, 2x2 sum (backward of the nearest x2 upsample), 27-channel global average pool
+#include "gfr_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float tf32_rna_dev(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// ------------------------------------------------------------------------------------------------- pack
+// packed[n_tile][cin_step][tap][group][hi|lo][n][4]; value(o, i, tap) = w[o*so + i*si + (flip ? 8 - tap : tap)]
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ packed, long long total, int O, int I,
+                                    int NT, long long so, long long si, int flip) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int e = (int)(idx & 3);
+  long long t = idx >> 2;
+  const int n = (int)(t % NT); t /= NT;
+  const int part = (int)(t & 1); t >>= 1;
+  const int kc = (int)(t & 3); t >>= 2;
+  const int tap = (int)(t % 9); t /= 9;
+  const int ncb = (I + 15) / 16;
+  const int cb = (int)(t % ncb);
+  const int nt = (int)(t / ncb);
+  const int o = nt * NT + n, i = cb * 16 + kc * 4 + e;
+  float v = 0.f;
+  if (o < O && i < I) {
+    const float x = __ldg(w + o * so + i * si + (flip ? 8 - tap : tap));
+    const float hi = tf32_rna_dev(x);
+    v = part == 0 ? hi : tf32_rna_dev(x - hi);
+  }
+  packed[idx] = v;
+}
+
+// ------------------------------------------------------------------------------------------------- BN statistics
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float4* __restrict__ x, double* __restrict__ sums, int N, int C4,
+                                                        int HW, int chunks) {
+  // grid (chunks, C4, N): a CTA reduces a contiguous chunk of one (n, group) plane; sums = [2][C4*4]
+  __shared__ double s_red[8][8];
+  const int g = blockIdx.y, n = blockIdx.z;
+  const int per = (HW + chunks - 1) / chunks;
+  const int lo = blockIdx.x * per, hi = min(lo + per, HW);
+  const float4* p = x + ((size_t)n * C4 + g) * HW;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  double ds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int cnt = 0;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    const float4 v = __ldg(p + i);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+    if (++cnt == 32) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { ds[e] += s[e]; ds[4 + e] += q[e]; s[e] = 0.f; q[e] = 0.f; }
+      cnt = 0;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { ds[e] += s[e]; ds[4 + e] += q[e]; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    double v = ds[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[e][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+    const int e = threadIdx.x & 3, which = threadIdx.x >> 2;
+    atomicAdd(sums + (size_t)which * C4 * 4 + g * 4 + e, t);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out, float* __restrict__ scale, float* __restrict__ shift, int C, int Cpad,
+                                   double count, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cpad) return;
+  if (c >= C) { scale[c] = 0.f; shift[c] = 0.f; mean_out[c] = 0.f; rstd_out[c] = 0.f; return; }   // padded channel slots stay 0
+  const double m = sums[c] / count;
+  double var = sums[Cpad + c] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma[c];
+  mean_out[c] = (float)m; rstd_out[c] = rstd;
+  scale[c] = g * rstd;
+  shift[c] = beta[c] - (float)m * g * rstd;
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * count / (count - 1.0));
+  }
+}
+
+struct BnApplyArgs {
+  const float4* x; const float4* res; const float4* post; float4* y;
+  const float* scale; const float* shift;      // [C4*4]
+  int C4, H, W, post_shift, act;
+  long long total;                              // N*C4*H*W
+};
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  const int HW = a.H * a.W;
+  const int g = (int)((i / HW) % a.C4);
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale) + g), sh = __ldg(reinterpret_cast<const float4*>(a.shift) + g);
+  const float4 v = __ldg(a.x + i);
+  float r[4] = {fmaf(sc.x, v.x, sh.x), fmaf(sc.y, v.y, sh.y), fmaf(sc.z, v.z, sh.z), fmaf(sc.w, v.w, sh.w)};
+  if (a.res) { const float4 t = __ldg(a.res + i); r[0] += t.x; r[1] += t.y; r[2] += t.z; r[3] += t.w; }
+  if (a.act == 1) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) r[e] = r[e] > 0.f ? r[e] : 0.2f * r[e];
+  }
+  if (a.post) {
+    const int p = (int)(i % HW), y = p / a.W, x = p % a.W;
+    const long long nc = i / HW;
+    const int pW = a.W >> a.post_shift, pH = a.H >> a.post_shift;
+    const float4 t = __ldg(a.post + (nc * pH + (y >> a.post_shift)) * pW + (x >> a.post_shift));
+    r[0] += t.x; r[1] += t.y; r[2] += t.z; r[3] += t.w;
+  }
+  a.y[i] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
+// ------------------------------------------------------------------------------------------------- BN backward
+// pre = scale*x + shift + res ; y = act(pre) (+ post).  g_pre = g_y * act'(pre).
+// reduce: sums[0][c] = sum g_pre, sums[1][c] = sum g_pre * xhat,  xhat = (x - mean) * rstd
+struct BnBwdArgs {
+  const float4* x; const float4* res; const float4* gy;
+  const float* scale; const float* shift; const float* mean; const float* rstd; const float* gamma_pad;   // [C4*4]
+  double* sums;                // [2][C4*4]
+  float4* gx; float4* gres;    // apply phase outputs (gres may be null)
+  int N, C4, HW, act, chunks;
+  double count;
+};
+
+__device__ __forceinline__ void bn_gpre(const BnBwdArgs& a, size_t i, int g, float (&gp)[4], float (&xh)[4]) {
+  const float4 v = __ldg(a.x + i), gy = __ldg(a.gy + i);
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale) + g), sh = __ldg(reinterpret_cast<const float4*>(a.shift) + g);
+  const float4 mu = __ldg(reinterpret_cast<const float4*>(a.mean) + g), rs = __ldg(reinterpret_cast<const float4*>(a.rstd) + g);
+  float pre[4] = {fmaf(sc.x, v.x, sh.x), fmaf(sc.y, v.y, sh.y), fmaf(sc.z, v.z, sh.z), fmaf(sc.w, v.w, sh.w)};
+  if (a.res) { const float4 t = __ldg(a.res + i); pre[0] += t.x; pre[1] += t.y; pre[2] += t.z; pre[3] += t.w; }
+  const float gyv[4] = {gy.x, gy.y, gy.z, gy.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) gp[e] = (a.act == 1 && pre[e] <= 0.f) ? 0.2f * gyv[e] : gyv[e];
+  xh[0] = (v.x - mu.x) * rs.x; xh[1] = (v.y - mu.y) * rs.y; xh[2] = (v.z - mu.z) * rs.z; xh[3] = (v.w - mu.w) * rs.w;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
+  __shared__ double s_red[8][8];
+  const int g = blockIdx.y, n = blockIdx.z;
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int lo = blockIdx.x * per, hi = min(lo + per, a.HW);
+  const size_t base = ((size_t)n * a.C4 + g) * a.HW;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double ds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int cnt = 0;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    float gp[4], xh[4];
+    bn_gpre(a, base + i, g, gp, xh);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { s[e] += gp[e]; s[4 + e] += gp[e] * xh[e]; }
+    if (++cnt == 32) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { ds[e] += s[e]; s[e] = 0.f; }
+      cnt = 0;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ds[e] += s[e];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    double v = ds[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[e][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+    const int e = threadIdx.x & 3, which = threadIdx.x >> 2;
+    atomicAdd(a.sums + (size_t)which * a.C4 * 4 + g * 4 + e, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
+  const long long total = (long long)a.N * a.C4 * a.HW;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = (int)((i / a.HW) % a.C4);
+  float gp[4], xh[4];
+  bn_gpre(a, (size_t)i, g, gp, xh);
+  if (a.gres) a.gres[i] = make_float4(gp[0], gp[1], gp[2], gp[3]);
+  float out[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = g * 4 + e;
+    const float sg = (float)(a.sums[c] / a.count), sgx = (float)(a.sums[a.C4 * 4 + c] / a.count);
+    out[e] = __ldg(a.gamma_pad + c) * __ldg(a.rstd + c) * (gp[e] - sg - xh[e] * sgx);
+  }
+  a.gx[i] = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+// ------------------------------------------------------------------------------------------------- wgrad 3x3
+// dW_eff[co][ci][tap] += sum_{n,y,x} g[n,co,y,x] * in[n,ci,y+ky-1,x+kx-1].  A CTA owns a 16(co) x 16(ci) block and a
+// strided subset of the 64x8-pixel tiles; thread (co, ci) keeps the 9 taps in registers; one atomicAdd round at the end.
+constexpr int WG_TW = 32, WG_TH = 8;
+constexpr int WG_IP = WG_TW + 4;                          // input row pitch (floats), keeps float4 alignment
+constexpr int WG_IPLANE = (WG_TH + 2) * WG_IP + 4;        // 364: channel-plane pitch, 364 % 32 = 12 spreads the 16 channels over the banks
+constexpr int WG_GPLANE = WG_TH * WG_TW;
+
+struct WgradArgs {
+  const float* in; const float* g;     // C4 [N][Cin4_alloc][H][W][4], C4 [N][Cout4][H][W][4]
+  float* dw;                           // element (co, ci, tap) at dw[co*so + ci*si + (flip ? 8 - tap : tap)]  +=
+  int N, Cin, Cout, in_groups, H, W;
+  long long so, si; int flip;
+  int tiles_x, tiles_y, n_tiles;
+};
+
+__global__ void __launch_bounds__(256) wgrad3x3_kernel(const WgradArgs a) {
+  __shared__ __align__(16) float s_in[16 * WG_IPLANE];
+  __shared__ __align__(16) float s_g[16 * WG_GPLANE];
+  const int tid = threadIdx.x;
+  const int co_l = tid >> 4, ci_l = tid & 15;
+  const int cob = blockIdx.y * 16, cib = blockIdx.z * 16;
+  const int C4out = (a.Cout + 3) >> 2;
+  const size_t plane4 = (size_t)a.H * a.W * 4;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int tx = tile % a.tiles_x, t2 = tile / a.tiles_x;
+    const int ty = t2 % a.tiles_y, n = t2 / a.tiles_y;
+    const int x0 = tx * WG_TW, y0 = ty * WG_TH;
+    __syncthreads();
+    for (int i = tid; i < 4 * (WG_TH + 2) * (WG_TW + 2); i += 256) {          // input halo tile: 4 groups = 16 channels
+      const int c = i % (WG_TW + 2), r = (i / (WG_TW + 2)) % (WG_TH + 2), q = i / ((WG_TW + 2) * (WG_TH + 2));
+      const int gy = y0 + r - 1, gx = x0 + c - 1, grp = (cib >> 2) + q;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && grp * 4 < a.Cin)
+        v = __ldg(reinterpret_cast<const float4*>(a.in + ((size_t)n * a.in_groups + grp) * plane4 + ((size_t)gy * a.W + gx) * 4));
+      float* d = s_in + (q * 4) * WG_IPLANE + r * WG_IP + c;
+      d[0] = v.x; d[WG_IPLANE] = v.y; d[2 * WG_IPLANE] = v.z; d[3 * WG_IPLANE] = v.w;
+    }
+    for (int i = tid; i < 4 * WG_TH * WG_TW; i += 256) {
+      const int c = i % WG_TW, r = (i / WG_TW) % WG_TH, q = i / (WG_TW * WG_TH);
+      const int gy = y0 + r, gx = x0 + c, grp = (cob >> 2) + q;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy < a.H && gx < a.W && grp < C4out)
+        v = __ldg(reinterpret_cast<const float4*>(a.g + ((size_t)n * C4out + grp) * plane4 + ((size_t)gy * a.W + gx) * 4));
+      float* d = s_g + (q * 4) * WG_GPLANE + r * WG_TW + c;
+      d[0] = v.x; d[WG_GPLANE] = v.y; d[2 * WG_GPLANE] = v.z; d[3 * WG_GPLANE] = v.w;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int r = 0; r < WG_TH; ++r) {
+#pragma unroll 4
+      for (int c = 0; c < WG_TW; c += 4) {
+        const float4 gv = *reinterpret_cast<const float4*>(s_g + co_l * WG_GPLANE + r * WG_TW + c);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float* row = s_in + ci_l * WG_IPLANE + (r + ky) * WG_IP + c;
+          const float4 i4 = *reinterpret_cast<const float4*>(row);
+          const float i5 = row[4], i6 = row[5];
+          acc[ky * 3 + 0] += gv.x * i4.x + gv.y * i4.y + gv.z * i4.z + gv.w * i4.w;
+          acc[ky * 3 + 1] += gv.x * i4.y + gv.y * i4.z + gv.z * i4.w + gv.w * i5;
+          acc[ky * 3 + 2] += gv.x * i4.z + gv.y * i4.w + gv.z * i5 + gv.w * i6;
+        }
+      }
+    }
+  }
+  const int co = cob + co_l, ci = cib + ci_l;
+  if (co < a.Cout && ci < a.Cin) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(a.dw + co * a.so + ci * a.si + (a.flip ? 8 - t : t), acc[t]);
+  }
+}
+
+// per-channel sum of a C4 tensor (bias gradient): sums[C4*4] += sum over (N,H,W)
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float4* __restrict__ x, float* __restrict__ out, int C4, int HW, int chunks) {
+  __shared__ float s_red[4][8];
+  const int g = blockIdx.y, n = blockIdx.z;
+  const int per = (HW + chunks - 1) / chunks;
+  const int lo = blockIdx.x * per, hi = min(lo + per, HW);
+  const float4* p = x + ((size_t)n * C4 + g) * HW;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = lo + threadIdx.x; i < hi; i += 256) { const float4 v = __ldg(p + i); s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v = s[e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[e][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
+    atomicAdd(out + g * 4 + threadIdx.x, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- pools
+__global__ void maxpool2_c4_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gy, float4* __restrict__ gx,
+                                       long long n_out, int Ho, int Wo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over pooled positions [NC4][Ho][Wo]
+  if (i >= n_out) return;
+  const int xo = (int)(i % Wo);
+  const long long t = i / Wo;
+  const int yo = (int)(t % Ho);
+  const long long nc = t / Ho;
+  const long long b = (nc * (2 * Ho) + 2 * yo) * (2LL * Wo) + 2 * xo;
+  const long long off[4] = {b, b + 1, b + 2 * Wo, b + 2 * Wo + 1};
+  float v[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const float4 q = __ldg(x + off[k]); v[k][0] = q.x; v[k][1] = q.y; v[k][2] = q.z; v[k][3] = q.w; }
+  const float4 g4 = __ldg(gy + i);
+  const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+  float o[4][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    int best = 0;                                   // first maximum in scan order, like torch's max_pool2d backward
+#pragma unroll
+    for (int k = 1; k < 4; ++k) if (v[k][e] > v[best][e]) best = k;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k][e] = k == best ? g[e] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) gx[off[k]] = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+}
+
+__global__ void sumpool2_c4_kernel(const float4* __restrict__ x, float4* __restrict__ out, long long n_out, int Ho, int Wo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const int xo = (int)(i % Wo);
+  const long long t = i / Wo;
+  const int yo = (int)(t % Ho);
+  const long long nc = t / Ho;
+  const float4* p = x + (nc * (2 * Ho) + 2 * yo) * (2LL * Wo) + 2 * xo;
+  const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2 * Wo), d = __ldg(p + 2 * Wo + 1);
+  out[i] = make_float4(a.x + b.x + c.x + d.x, a.y + b.y + c.y + d.y, a.z + b.z + c.z + d.z, a.w + b.w + c.w + d.w);
+}
+
+// channels [c_first, c_first + n_ch) of a C4 map: out[n][c] = mean over HW (forward) / gx[n, c, :] = g[n][c] / HW (backward, +=0 elsewhere untouched)
+__global__ void __launch_bounds__(128) avgpool_c4_kernel(const float* __restrict__ feat, float* __restrict__ out, int C4, int c_first,
+                                                          int n_ch, int HW) {
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < n_ch; c += 4) {
+    const int ch = c_first + c;
+    const float* f = feat + (((size_t)n * C4 + (ch >> 2)) * HW) * 4 + (ch & 3);
+    float s = 0.f;
+    for (int i = lane; i < HW; i += 32) s += __ldg(f + (size_t)i * 4);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[n * n_ch + c] = s / (float)HW;
+  }
+}
+
+__global__ void avgpool_c4_bwd_kernel(const float* __restrict__ g, float* __restrict__ gfeat, int C4, int c_first, int n_ch, int HW,
+                                      long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [N][n_ch][HW]
+  if (i >= total) return;
+  const int p = (int)(i % HW);
+  const long long t = i / HW;
+  const int c = (int)(t % n_ch);
+  const long long n = t / n_ch;
+  const int ch = c_first + c;
+  gfeat[(((size_t)n * C4 + (ch >> 2)) * HW + p) * 4 + (ch & 3)] += __ldg(g + n * n_ch + c) / (float)HW;
+}
+
+// ------------------------------------------------------------------------------------------------- 1x1 convolutions (Cin = 16)
+struct PwArgs {
+  const float* in;    // C4 [N,16,H,W]
+  const float* w;     // [Cout,16] device
+  const float* bias;  // [Cout] device
+  float* out;         // C4 [N,16,H,W] (planar = 0) or NCHW [N,Cout,H,W] (planar = 1)
+  long long hw, total;
+  int Cout, planar, act; float scale;
+};
+
+__global__ void __launch_bounds__(256) pw_conv16_fwd_kernel(const PwArgs a) {
+  __shared__ float s_w[16][16];
+  __shared__ float s_b[16];
+  for (int i = threadIdx.x; i < 16 * 16; i += 256) s_w[i >> 4][i & 15] = (i >> 4) < a.Cout ? __ldg(a.w + i) : 0.f;
+  if (threadIdx.x < 16) s_b[threadIdx.x] = threadIdx.x < a.Cout ? __ldg(a.bias + threadIdx.x) : 0.f;
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total) return;
+  const long long n = i / a.hw, p = i % a.hw;
+  const float4* src = reinterpret_cast<const float4*>(a.in) + n * 4 * a.hw + p;
+  float x[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const float4 v = __ldg(src + q * a.hw); x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w; }
+  float y[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    float s = s_b[o];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s = fmaf(s_w[o][c], x[c], s);
+    if (a.act == 2) s = 1.0f / (1.0f + expf(-s));
+    y[o] = s * a.scale;
+  }
+  if (a.planar) {
+    for (int o = 0; o < a.Cout; ++o) a.out[(n * a.Cout + o) * a.hw + p] = y[o];
+  } else {
+    float4* dst = reinterpret_cast<float4*>(a.out) + n * 4 * a.hw + p;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q * a.hw] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+  }
+}
+
+struct PwBwdArgs {
+  const float* in;    // C4 [N,16,H,W]   forward input
+  const float* w;     // [Cout,16]
+  const float* gout;  // C4 [N,16,H,W] (planar 0) or NCHW [N,Cout,H,W] (planar 1): gradient w.r.t. the forward OUTPUT
+  const float* out;   // forward output (needed for act = 2 sigmoid), same layout as gout; may be null for act 0
+  float* gin;         // C4 [N,16,H,W]
+  float* gw;          // [Cout,16] +=
+  float* gb;          // [Cout]    +=
+  long long hw, total;
+  int Cout, planar, act; float scale;
+};
+
+__global__ void __launch_bounds__(256) pw_conv16_bwd_kernel(const PwBwdArgs a) {
+  __shared__ float s_w[16][16];
+  __shared__ float s_acc[17][16];      // [ci or 16 = bias][co]
+  for (int i = threadIdx.x; i < 16 * 16; i += 256) s_w[i >> 4][i & 15] = (i >> 4) < a.Cout ? __ldg(a.w + i) : 0.f;
+  for (int i = threadIdx.x; i < 17 * 16; i += 256) s_acc[i >> 4][i & 15] = 0.f;
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float x[16], g[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { x[c] = 0.f; g[c] = 0.f; }
+  if (i < a.total) {
+    const long long n = i / a.hw, p = i % a.hw;
+    const float4* src = reinterpret_cast<const float4*>(a.in) + n * 4 * a.hw + p;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float4 v = __ldg(src + q * a.hw); x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w; }
+    if (a.planar) {
+      for (int o = 0; o < a.Cout; ++o) {
+        float go = __ldg(a.gout + (n * a.Cout + o) * a.hw + p) * a.scale;
+        if (a.act == 2) { const float yv = __ldg(a.out + (n * a.Cout + o) * a.hw + p) / a.scale; go *= yv * (1.f - yv); }
+        g[o] = go;
+      }
+    } else {
+      const float4* gs = reinterpret_cast<const float4*>(a.gout) + n * 4 * a.hw + p;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const float4 v = __ldg(gs + q * a.hw); g[4 * q] = v.x * a.scale; g[4 * q + 1] = v.y * a.scale; g[4 * q + 2] = v.z * a.scale; g[4 * q + 3] = v.w * a.scale; }
+    }
+    float gi[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float s = 0.f;
+#pragma unroll
+      for (int o = 0; o < 16; ++o) s = fmaf(s_w[o][c], g[o], s);
+      gi[c] = s;
+    }
+    float4* dst = reinterpret_cast<float4*>(a.gin) + n * 4 * a.hw + p;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q * a.hw] = make_float4(gi[4 * q], gi[4 * q + 1], gi[4 * q + 2], gi[4 * q + 3]);
+  }
+  // weight / bias gradients: warp-reduce each (co, ci) product, then shared and global atomics
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    if (o >= a.Cout) break;
+#pragma unroll
+    for (int c = 0; c < 17; ++c) {
+      float v = c < 16 ? g[o] * x[c < 16 ? c : 0] : g[o];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane == 0) atomicAdd(&s_acc[c][o], v);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 17 * 16; k += 256) {
+    const int c = k >> 4, o = k & 15;
+    if (o >= a.Cout) continue;
+    const float v = s_acc[c][o];
+    if (v != 0.f) atomicAdd(c < 16 ? a.gw + o * 16 + c : a.gb + o, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- stem, train mode
+// conv_c1_og with DEVICE weights (they change every step): raw output (bias added, no BN / activation / pool).
+constexpr int SD_TW = 32, SD_TH = 16, SD_IW = SD_TW + 4, SD_IH = SD_TH + 4;
+
+__global__ void __launch_bounds__(128) stem_conv_dev_kernel(const float* __restrict__ img_all, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out, int H, int W) {
+  __shared__ __align__(16) float s_in[3][SD_IH][SD_IW];
+  __shared__ __align__(16) float s_w[25 * 3][16];       // [tap*3 + ci][co]
+  __shared__ float s_b[16];
+  const int tid = threadIdx.x;
+  const int tiles_x = gfr_ceil_div(W, SD_TW);
+  const int x0 = (blockIdx.x % tiles_x) * SD_TW, y0 = (blockIdx.x / tiles_x) * SD_TH;
+  const int n = blockIdx.y;
+  const float* __restrict__ img = img_all + (size_t)n * H * W * 3;
+  for (int i = tid; i < 16 * 75; i += 128) {             // w [16][3][25]
+    const int co = i / 75, rem = i % 75, ci = rem / 25, tap = rem % 25;
+    s_w[tap * 3 + ci][co] = __ldg(w + i);
+  }
+  if (tid < 16) s_b[tid] = __ldg(bias + tid);
+  for (int i = tid; i < SD_IH * SD_IW * 3; i += 128) {
+    const int r = i / (SD_IW * 3), rem = i % (SD_IW * 3);
+    const int c = rem / 3, ch = rem % 3;
+    const int gy = y0 + r - 2, gx = x0 + c - 2;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(img + ((size_t)gy * W + gx) * 3 + ch);
+    s_in[ch][r][c] = v;
+  }
+  __syncthreads();
+  const int tx = tid % (SD_TW / 2), ty = tid / (SD_TW / 2);
+  float acc[4][16];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[p][c] = s_b[c];
+#pragma unroll 1
+  for (int ci = 0; ci < 3; ++ci) {
+    float win[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; c += 2) {
+        const float2 v = *reinterpret_cast<const float2*>(&s_in[ci][2 * ty + r][2 * tx + c]);
+        win[r][c] = v.x; win[r][c + 1] = v.y;
+      }
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const float4* wp = reinterpret_cast<const float4*>(&s_w[(ky * 5 + kx) * 3 + ci][0]);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 w4 = wp[c4];
+          const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            acc[0][c] = fmaf(wv[e], win[ky][kx], acc[0][c]);
+            acc[1][c] = fmaf(wv[e], win[ky][kx + 1], acc[1][c]);
+            acc[2][c] = fmaf(wv[e], win[ky + 1][kx], acc[2][c]);
+            acc[3][c] = fmaf(wv[e], win[ky + 1][kx + 1], acc[3][c]);
+          }
+        }
+      }
+  }
+  const int oy = y0 + 2 * ty, ox = x0 + 2 * tx;
+  if (oy >= H || ox >= W) return;
+  const size_t plane = (size_t)H * W;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float* o = out + (((size_t)n * 4 + q) * plane + (size_t)oy * W + ox) * 4;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0][q * 4], acc[0][q * 4 + 1], acc[0][q * 4 + 2], acc[0][q * 4 + 3]);
+    if (ox + 1 < W) *reinterpret_cast<float4*>(o + 4) = make_float4(acc[1][q * 4], acc[1][q * 4 + 1], acc[1][q * 4 + 2], acc[1][q * 4 + 3]);
+    if (oy + 1 < H) {
+      *reinterpret_cast<float4*>(o + (size_t)W * 4) = make_float4(acc[2][q * 4], acc[2][q * 4 + 1], acc[2][q * 4 + 2], acc[2][q * 4 + 3]);
+      if (ox + 1 < W) *reinterpret_cast<float4*>(o + (size_t)W * 4 + 4) = make_float4(acc[3][q * 4], acc[3][q * 4 + 1], acc[3][q * 4 + 2], acc[3][q * 4 + 3]);
+    }
+  }
+}
+
+// dW[co][ci][tap] += sum g[n,co,y,x] * img[n,y+ky-2,x+kx-2,ci]; bias gradient alongside.  Persistent CTAs over 32x16 tiles;
+// thread t owns outputs t, t+256, ... of the 1200 (+16 bias) and scans the tile.
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ img_all, const float* __restrict__ g, float* __restrict__ dw,
+                                                          float* __restrict__ db, int N, int H, int W) {
+  __shared__ float s_in[3][SD_IH][SD_IW];
+  __shared__ float s_g[16][SD_TH][SD_TW + 1];
+  const int tid = threadIdx.x;
+  const int tiles_x = gfr_ceil_div(W, SD_TW), tiles_y = gfr_ceil_div(H, SD_TH), n_tiles = N * tiles_x * tiles_y;
+  constexpr int NOUT = 1216, PER = (NOUT + 255) / 256;     // 1200 weights + 16 biases
+  float acc[PER];
+  int o_co[PER], o_ci[PER], o_ky[PER], o_kx[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    acc[k] = 0.f;
+    const int o = tid + k * 256;
+    if (o < 1200) { o_co[k] = o / 75; const int rem = o % 75; o_ci[k] = rem / 25; o_ky[k] = (rem % 25) / 5; o_kx[k] = rem % 5; }
+    else { o_co[k] = o - 1200; o_ci[k] = -1; o_ky[k] = 0; o_kx[k] = 0; }
+  }
+  const size_t plane = (size_t)H * W;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, t2 = tile / tiles_x, ty = t2 % tiles_y, n = t2 / tiles_y;
+    const int x0 = tx * SD_TW, y0 = ty * SD_TH;
+    const float* img = img_all + (size_t)n * H * W * 3;
+    __syncthreads();
+    for (int i = tid; i < SD_IH * SD_IW * 3; i += 256) {
+      const int r = i / (SD_IW * 3), rem = i % (SD_IW * 3), c = rem / 3, ch = rem % 3;
+      const int gy = y0 + r - 2, gx = x0 + c - 2;
+      s_in[ch][r][c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(img + ((size_t)gy * W + gx) * 3 + ch) : 0.f;
+    }
+    for (int i = tid; i < 4 * SD_TH * SD_TW; i += 256) {
+      const int c = i % SD_TW, r = (i / SD_TW) % SD_TH, q = i / (SD_TW * SD_TH);
+      const int gy = y0 + r, gx = x0 + c;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy < H && gx < W) v = __ldg(reinterpret_cast<const float4*>(g + (((size_t)n * 4 + q) * plane + (size_t)gy * W + gx) * 4));
+      s_g[q * 4][r][c] = v.x; s_g[q * 4 + 1][r][c] = v.y; s_g[q * 4 + 2][r][c] = v.z; s_g[q * 4 + 3][r][c] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      if (tid + k * 256 >= NOUT) continue;
+      float a = 0.f;
+      if (o_ci[k] >= 0) {
+        for (int r = 0; r < SD_TH; ++r)
+#pragma unroll 8
+          for (int c = 0; c < SD_TW; ++c) a = fmaf(s_g[o_co[k]][r][c], s_in[o_ci[k]][r + o_ky[k]][c + o_kx[k]], a);
+      } else {
+        for (int r = 0; r < SD_TH; ++r)
+#pragma unroll 8
+          for (int c = 0; c < SD_TW; ++c) a += s_g[o_co[k]][r][c];
+      }
+      acc[k] += a;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int o = tid + k * 256;
+    if (o < 1200) atomicAdd(dw + o, acc[k]);
+    else if (o < NOUT) atomicAdd(db + (o - 1200), acc[k]);
+  }
+}
+
+int chunks_for(int N, int C4, int HW) {
+  int chunks = (148 * 4) / (N * C4 > 0 ? N * C4 : 1);
+  if (chunks < 1) chunks = 1;
+  const int maxc = (HW + 255) / 256;
+  return chunks > maxc ? maxc : chunks;
+}
+
+}  // namespace
+
+extern "C" int gfr_conv_tc_pack_weights_dev(const float* w, int is_transposed_conv, int for_dgrad, int Cin, int Cout, int NT,
+                                            float* packed, void* stream) {
+  GFR_RETURN_IF_NULL(w); GFR_RETURN_IF_NULL(packed);
+  if (Cin <= 0 || Cout <= 0 || (NT != 16 && NT != 32 && NT != 64)) return GFR_E_ARG;
+  // Cin / Cout are those of the LAYER (forward direction).  The packed operand computes O outputs from I inputs:
+  const int O = for_dgrad ? Cin : Cout, I = for_dgrad ? Cout : Cin;
+  long long so, si; int flip;
+  if (!is_transposed_conv) {        // Conv2d parameter [Cout][Cin][3][3]
+    if (!for_dgrad) { so = (long long)Cin * 9; si = 9; flip = 0; } else { so = 9; si = (long long)Cin * 9; flip = 1; }
+  } else {                          // ConvTranspose2d parameter [Cin][Cout][3][3]; forward = conv with w.transpose(0,1).flip(2,3)
+    if (!for_dgrad) { so = 9; si = (long long)Cout * 9; flip = 1; } else { so = (long long)Cout * 9; si = 9; flip = 0; }
+  }
+  const long long total = (long long)gfr_ceil_div(O, NT) * gfr_ceil_div(I, 16) * 9 * 4 * 2 * NT * 4;
+  pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, packed, total, O, I, NT, so, si, flip);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_bn_train_stats(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                  double* sums_scratch, float* mean, float* rstd, float* scale, float* shift, int N, int C, int H,
+                                  int W, float eps, float momentum, void* stream) {
+  GFR_RETURN_IF_NULL(x); GFR_RETURN_IF_NULL(gamma); GFR_RETURN_IF_NULL(beta); GFR_RETURN_IF_NULL(sums_scratch);
+  GFR_RETURN_IF_NULL(mean); GFR_RETURN_IF_NULL(rstd); GFR_RETURN_IF_NULL(scale); GFR_RETURN_IF_NULL(shift);
+  if (N <= 0 || N > 65535 || C <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
+  const int C4 = (C + 3) / 4, HW = H * W;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums_scratch, 0, (size_t)2 * C4 * 4 * sizeof(double), s);
+  if (e != cudaSuccess) return (int)e;
+  const int chunks = chunks_for(N, C4, HW);
+  bn_stats_kernel<<<dim3(chunks, C4, N), 256, 0, s>>>(reinterpret_cast<const float4*>(x), sums_scratch, N, C4, HW, chunks);
+  bn_finalize_kernel<<<gfr_ceil_div(C4 * 4, 128), 128, 0, s>>>(sums_scratch, gamma, beta, running_mean, running_var, mean, rstd, scale,
+                                                              shift, C, C4 * 4, (double)N * HW, eps, momentum);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_bn_apply_fwd(const float* x, const float* scale, const float* shift, const float* res, const float* post,
+                                float* y, int N, int C, int H, int W, int post_shift, int act, void* stream) {
+  GFR_RETURN_IF_NULL(x); GFR_RETURN_IF_NULL(scale); GFR_RETURN_IF_NULL(shift); GFR_RETURN_IF_NULL(y);
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
+  if (post_shift < 0 || post_shift > 1 || act < 0 || act > 1) return GFR_E_ARG;
+  const int C4 = (C + 3) / 4;
+  BnApplyArgs a{reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(res), reinterpret_cast<const float4*>(post),
+                reinterpret_cast<float4*>(y), scale, shift, C4, H, W, post_shift, act, (long long)N * C4 * H * W};
+  bn_apply_kernel<<<(unsigned)((a.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_bn_apply_bwd(const float* x, const float* res, const float* g_y, const float* scale, const float* shift,
+                                const float* mean, const float* rstd, const float* gamma_pad, double* sums_scratch, float* g_x,
+                                float* g_res, int N, int C, int H, int W, int act, void* stream) {
+  GFR_RETURN_IF_NULL(x); GFR_RETURN_IF_NULL(g_y); GFR_RETURN_IF_NULL(scale); GFR_RETURN_IF_NULL(shift); GFR_RETURN_IF_NULL(mean);
+  GFR_RETURN_IF_NULL(rstd); GFR_RETURN_IF_NULL(gamma_pad); GFR_RETURN_IF_NULL(sums_scratch); GFR_RETURN_IF_NULL(g_x);
+  if (N <= 0 || N > 65535 || C <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
+  const int C4 = (C + 3) / 4, HW = H * W;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums_scratch, 0, (size_t)2 * C4 * 4 * sizeof(double), s);
+  if (e != cudaSuccess) return (int)e;
+  BnBwdArgs a{reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(res), reinterpret_cast<const float4*>(g_y), scale,
+              shift, mean, rstd, gamma_pad, sums_scratch, reinterpret_cast<float4*>(g_x), reinterpret_cast<float4*>(g_res), N, C4, HW, act,
+              chunks_for(N, C4, HW), (double)N * HW};
+  bn_bwd_reduce_kernel<<<dim3(a.chunks, C4, N), 256, 0, s>>>(a);
+  const long long total = (long long)N * C4 * HW;
+  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_conv3x3_wgrad(const float* in, const float* g_out, float* g_w, float* g_bias, int is_transposed_conv, int N,
+                                 int Cin, int in_groups, int Cout, int H, int W, void* stream) {
+  GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(g_out); GFR_RETURN_IF_NULL(g_w);
+  if (N <= 0 || N > 65535 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
+  if (in_groups == 0) in_groups = (Cin + 3) / 4;
+  if (in_groups < (Cin + 3) / 4) return GFR_E_ARG;
+  WgradArgs a;
+  a.in = in; a.g = g_out; a.dw = g_w; a.N = N; a.Cin = Cin; a.Cout = Cout; a.in_groups = in_groups; a.H = H; a.W = W;
+  if (!is_transposed_conv) { a.so = (long long)Cin * 9; a.si = 9; a.flip = 0; }     // dW_param[co][ci][tap]
+  else { a.so = 9; a.si = (long long)Cout * 9; a.flip = 1; }                         // dW_param[ci][co][8 - tap]
+  a.tiles_x = gfr_ceil_div(W, WG_TW); a.tiles_y = gfr_ceil_div(H, WG_TH); a.n_tiles = N * a.tiles_x * a.tiles_y;
+  const int gy = gfr_ceil_div(Cout, 16), gz = gfr_ceil_div(Cin, 16);
+  int gx = (148 * 2) / (gy * gz);
+  if (gx < 1) gx = 1;
+  if (gx > a.n_tiles) gx = a.n_tiles;
+  cudaStream_t s = (cudaStream_t)stream;
+  wgrad3x3_kernel<<<dim3(gx, gy, gz), 256, 0, s>>>(a);
+  if (g_bias) {
+    const int C4 = (Cout + 3) / 4, chunks = chunks_for(N, C4, H * W);
+    channel_sum_kernel<<<dim3(chunks, C4, N), 256, 0, s>>>(reinterpret_cast<const float4*>(g_out), g_bias, C4, H * W, chunks);
+  }
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_maxpool2_c4_bwd(const float* x, const float* g_y, float* g_x, int NC4, int Ho, int Wo, void* stream) {
+  GFR_RETURN_IF_NULL(x); GFR_RETURN_IF_NULL(g_y); GFR_RETURN_IF_NULL(g_x);
+  if (NC4 <= 0 || Ho <= 0 || Wo <= 0) return GFR_E_SHAPE;
+  const long long n = (long long)NC4 * Ho * Wo;
+  maxpool2_c4_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(g_y), reinterpret_cast<float4*>(g_x), n, Ho, Wo);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_sumpool2_c4(const float* x, float* out, int NC4, int Ho, int Wo, void* stream) {
+  GFR_RETURN_IF_NULL(x); GFR_RETURN_IF_NULL(out);
+  if (NC4 <= 0 || Ho <= 0 || Wo <= 0) return GFR_E_SHAPE;
+  const long long n = (long long)NC4 * Ho * Wo;
+  sumpool2_c4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out), n, Ho, Wo);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_avgpool_c4_fwd(const float* feat, float* out, int N, int C, int c_first, int n_ch, int HW, void* stream) {
+  GFR_RETURN_IF_NULL(feat); GFR_RETURN_IF_NULL(out);
+  if (N <= 0 || C <= 0 || HW <= 0 || c_first < 0 || n_ch <= 0 || c_first + n_ch > C) return GFR_E_SHAPE;
+  avgpool_c4_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(feat, out, (C + 3) / 4, c_first, n_ch, HW);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_avgpool_c4_bwd(const float* g, float* g_feat, int N, int C, int c_first, int n_ch, int HW, void* stream) {
+  GFR_RETURN_IF_NULL(g); GFR_RETURN_IF_NULL(g_feat);
+  if (N <= 0 || C <= 0 || HW <= 0 || c_first < 0 || n_ch <= 0 || c_first + n_ch > C) return GFR_E_SHAPE;
+  const long long total = (long long)N * n_ch * HW;
+  avgpool_c4_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, g_feat, (C + 3) / 4, c_first, n_ch, HW, total);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_pw_conv16_fwd(const float* in, const float* w, const float* bias, float* out, int N, int Cout, int H, int W,
+                                 int planar_out, int act, float out_scale, void* stream) {
+  GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w); GFR_RETURN_IF_NULL(bias); GFR_RETURN_IF_NULL(out);
+  if (N <= 0 || H <= 0 || W <= 0 || Cout < 1 || Cout > 16) return GFR_E_SHAPE;
+  if ((act != 0 && act != 2) || (!planar_out && Cout != 16)) return GFR_E_ARG;
+  PwArgs a{in, w, bias, out, (long long)H * W, (long long)N * H * W, Cout, planar_out, act, out_scale};
+  pw_conv16_fwd_kernel<<<(unsigned)((a.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_pw_conv16_bwd(const float* in, const float* w, const float* g_out, const float* out, float* g_in, float* g_w,
+                                 float* g_bias, int N, int Cout, int H, int W, int planar_out, int act, float out_scale, void* stream) {
+  GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w); GFR_RETURN_IF_NULL(g_out); GFR_RETURN_IF_NULL(g_in); GFR_RETURN_IF_NULL(g_w);
+  GFR_RETURN_IF_NULL(g_bias);
+  if (N <= 0 || H <= 0 || W <= 0 || Cout < 1 || Cout > 16) return GFR_E_SHAPE;
+  if ((act != 0 && act != 2) || (!planar_out && Cout != 16) || (act == 2 && (out == nullptr || !planar_out))) return GFR_E_ARG;
+  PwBwdArgs a{in, w, g_out, out, g_in, g_w, g_bias, (long long)H * W, (long long)N * H * W, Cout, planar_out, act, out_scale};
+  pw_conv16_bwd_kernel<<<(unsigned)((a.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_stem_conv_train_fwd(const float* img, const float* w, const float* bias, float* out_raw, int N, int H, int W,
+                                       void* stream) {
+  GFR_RETURN_IF_NULL(img); GFR_RETURN_IF_NULL(w); GFR_RETURN_IF_NULL(bias); GFR_RETURN_IF_NULL(out_raw);
+  if (N <= 0 || N > 65535 || H <= 0 || W <= 0) return GFR_E_SHAPE;
+  const dim3 grid(gfr_ceil_div(W, SD_TW) * gfr_ceil_div(H, SD_TH), N);
+  stem_conv_dev_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(img, w, bias, out_raw, H, W);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_stem_conv_wgrad(const float* img, const float* g_out, float* g_w, float* g_bias, int N, int H, int W, void* stream) {
+  GFR_RETURN_IF_NULL(img); GFR_RETURN_IF_NULL(g_out); GFR_RETURN_IF_NULL(g_w); GFR_RETURN_IF_NULL(g_bias);
+  if (N <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
+  const int n_tiles = N * gfr_ceil_div(W, SD_TW) * gfr_ceil_div(H, SD_TH);
+  const int grid = n_tiles < 148 * 2 ? n_tiles : 148 * 2;
+  stem_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, g_out, g_w, g_bias, N, H, W);
+  return gfr_launch_status();
+}

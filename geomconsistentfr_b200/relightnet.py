@@ -17,7 +17,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, train_ops
+from .autograd import ShadeRender, ShadowMarch
 
 ENCODER_LAYERS = [  # (name, cin, cout, k)   TRAIN:58-70
     ("conv_c1_og", 3, 16, 5), ("conv_h1_1", 16, 16, 3), ("conv_h1_2", 16, 16, 3),
@@ -208,6 +209,79 @@ class RelightNet(nn.Module):
             return conv("conv_%s_skip_%s_2" % (p, skip), s1, res=enc, post=t, post_shift=1)
         return ops.upsample2_c4_fwd(t)
 
+    # ------------------------------------------------------------------ CNN, TRAIN mode (batch-statistics BN, autograd)
+    def _cnn_train(self, img, epoch):
+        """TRAIN:197-350 with the module in train() mode, as the reference trains (TRAIN:561-563): every BatchNorm uses
+        batch statistics and updates its running buffers; every unit is an autograd Function over library kernels
+        (train_ops).  Returns albedo [B,3,H,W], depth [B,1,H,W], SL_lin2 [B,4], all autograd-tracked."""
+        T = train_ops
+
+        def unit(name, x, res=None, post=None, post_shift=0, act=1):
+            mod, bn = getattr(self, name), getattr(self, _bn_name(name))
+            meta = dict(cin=mod.in_channels, cout=mod.out_channels, deconv=isinstance(mod, nn.ConvTranspose2d), act=act,
+                        post_shift=post_shift, bn=bn)
+            return T.ConvBNAct.apply(x, mod.weight, mod.bias, bn.weight, bn.bias, res, post, meta)
+
+        def up_and_skip(p, skip, t, enc):
+            if epoch > _EPOCH_GATES[skip]:
+                s1 = unit("conv_%s_skip_%s_1" % (p, skip), enc)
+                return unit("conv_%s_skip_%s_2" % (p, skip), s1, res=enc, post=t, post_shift=1)
+            return T.Upsample2.apply(t)
+
+        bn0 = self.bn_c1_og
+        c1_og = T.StemBNAct.apply(img, self.conv_c1_og.weight, self.conv_c1_og.bias, bn0.weight, bn0.bias, bn0)
+        c1 = T.MaxPool2.apply(c1_og)
+        h1_og = unit("conv_h1_2", unit("conv_h1_1", c1), res=c1)
+        h1 = T.MaxPool2.apply(h1_og)
+        h2_og = unit("conv_h2_2", unit("conv_h2_1", h1), res=unit("conv_shortcut_h1_out", h1, act=0))
+        h2 = T.MaxPool2.apply(h2_og)
+        h3_og = unit("conv_h3_2", unit("conv_h3_1", h2), res=unit("conv_shortcut_h2_out", h2, act=0))
+        h3 = T.MaxPool2.apply(h3_og)
+        h4 = unit("conv_h4_2", unit("conv_h4_1", h3), res=unit("conv_shortcut_h3_out", h3, act=0))
+        pooled = T.AvgPoolChannels.apply(h4, 155, 128, 27)                                        # TRAIN:226-230
+        sl = self.linear_SL2(torch.nn.functional.leaky_relu(self.linear_SL1(pooled), 0.2))         # [B,4], 3.5 kMAC of glue
+        skips = {"s1": h3_og, "s2": h2_og, "s3": h1_og, "s4": c1_og}
+        outs = []
+        for p in ("albedo", "depth"):
+            h = h4                                                       # the first two convs read channels 0..127 in place
+            for blk, sc, _, cout, skip in _UP_BLOCKS:
+                a = unit("deconv_%s_%s_1" % (p, blk), h)
+                s = unit("deconv_%s_%s" % (p, sc), h, act=0)
+                tt = unit("deconv_%s_%s_2" % (p, blk), a, res=s)
+                h = up_and_skip(p, skip, tt, skips[skip])
+            a = unit("deconv_%s_h8_1" % p, h)
+            tt = unit("deconv_%s_h8_2" % p, a, res=h)
+            h = up_and_skip(p, "s4", tt, skips["s4"])
+            h = unit("conv_%s_c2_1" % p, h)
+            for name in ("conv_%s_c2_2" % p, "conv_%s_c2_3" % p):
+                mod, bn = getattr(self, name), getattr(self, _bn_name(name))
+                h = T.PwConvBNAct.apply(h, mod.weight.view(16, 16), mod.bias, bn.weight, bn.bias, bn)
+            mod = getattr(self, "conv_%s_c2_o" % p)
+            if p == "albedo":
+                outs.append(T.PwHead.apply(h, mod.weight.view(3, 16), mod.bias, 2, 1.0))           # TRAIN:289-290
+            else:
+                outs.append(T.PwHead.apply(h, mod.weight.view(1, 16), mod.bias, 0, 100.0))         # TRAIN:349-350
+        return outs[0], outs[1], sl
+
+    def _forward_train(self, img, epoch, intrinsic_matrix, masks):
+        """TRAIN:196-524, differentiable: CNN (train mode) -> ShadowMarch / ShadeRender autograd Functions."""
+        dev = self.device
+        img = img.to(dev, torch.float32, non_blocking=True).contiguous()
+        B, H, W, _ = img.shape
+        albedo, depth, sl = self._cnn_train(img, epoch)
+        with torch.no_grad():
+            bits = ops.mask_pack(masks.to(dev, non_blocking=True).reshape(B, H, W))
+        ambient_values = sl[:, 0]                                                                  # TRAIN:367
+        L = torch.cat((sl[:, 1:3], torch.clamp(sl[:, 3:4], min=0.0)), 1)                           # TRAIN:357-359
+        unit = torch.nn.functional.normalize(L, p=2, dim=1)                                        # TRAIN:360
+        light_pt = self.light_distance * unit                                                      # TRAIN:362
+        d_min = ShadowMarch.apply(depth, bits, light_pt, 0.0)
+        fx, fy, cx, cy = self._intrinsics(intrinsic_matrix)
+        intr = (fx, fy, cx, cy, self.depth_offset, self.directional_intensity)
+        shadow, full, _, rendered, _ = ShadeRender.apply(albedo, depth, d_min, light_pt, ambient_values, intr)
+        ambient_light = ambient_values.view(B, 1, 1).expand(B, H, W)
+        return (albedo, depth, shadow, ambient_light, full, rendered, unit.view(B, 3, 1, 1), ambient_values.view(B, 1, 1))
+
     # ------------------------------------------------------------------ CNN (eval mode), exact fp32 on CUDA cores
     def _cnn_eval(self, img, epoch):
         if self.cnn_impl == "tc":
@@ -293,7 +367,9 @@ class RelightNet(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("RelightNet (geomconsistentfr_b200) runs on CUDA only; call .cuda() first")
         if self.training:
-            raise NotImplementedError("train-mode (batch-statistics BN + backward) is not built yet; call .eval()")
+            if target_lighting is not None:
+                raise NotImplementedError("the TEST1 signature (given target lighting) is an inference call: use .eval()")
+            return self._forward_train(img, epoch, intrinsic_matrix, mask)
         img = img.to(dev, torch.float32, non_blocking=True)
         B, H, W, _ = img.shape
         test_mode = target_lighting is not None

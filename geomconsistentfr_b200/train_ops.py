@@ -1,0 +1,268 @@
+"""Train-mode units of the RelightNet CNN as torch.autograd.Functions over libgfr_b200 kernels (C4 activations).
+
+The reference trains with batch-statistics BatchNorm (it never calls .eval(), TRAIN:561-563), so conv and BN cannot be
+folded: a unit is  conv (tcgen05, raw output) -> batch statistics -> y = act(BN(raw) + res) + up(post)  and its
+backward is  BN/activation backward (two passes) -> dgrad (the same tcgen05 kernel with the transposed + flipped
+operand) + wgrad (CUDA cores).  TRAIN = train_raytracing_relighting_CelebAHQ_DSSIM_8x.py, lines 197-350."""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+from .ops import C4, _ptr, _stream
+
+_EPS, _MOMENTUM = 1e-5, 0.1          # nn.BatchNorm2d defaults (TRAIN:59 ff.)
+
+
+def _chk(rc, what, n=1):
+    _lib.check(rc, what)
+    ops._count(n)
+
+
+def _pack_dev(w, deconv, dgrad, Cin, Cout, NT):
+    O, I = (Cin, Cout) if dgrad else (Cout, Cin)
+    n = _lib.load().gfr_conv_tc_pack_size(I, O, NT)
+    packed = torch.empty(n, dtype=torch.float32, device=w.device)
+    _chk(_lib.load().gfr_conv_tc_pack_weights_dev(_ptr(w), int(deconv), int(dgrad), Cin, Cout, NT, _ptr(packed), _stream()),
+         "gfr_conv_tc_pack_weights_dev")
+    return packed
+
+
+def _nt_for(cout):
+    return 16 if cout <= 16 else 32
+
+
+def _conv_raw(x_data, cin, packed, bias, Cout, NT):
+    """raw = conv3x3(x[:, :cin]) + bias on the tensor cores (3xTF32), C4 in / C4 out."""
+    N, G, H, W, _ = x_data.shape
+    out = torch.empty((N, (Cout + 3) // 4, H, W, 4), dtype=torch.float32, device=x_data.device)
+    _chk(_lib.load().gfr_conv3x3_tc_fwd(_ptr(x_data), _ptr(packed), _ptr(bias), None, None, _ptr(out), N, cin, G, Cout, H, W, NT,
+                                        0, 0, 1.0, 3, _stream()), "gfr_conv3x3_tc_fwd")
+    return out
+
+
+class _BN:
+    """Batch statistics + apply + backward of one BatchNorm2d over a C4 tensor (shared by the unit Functions)."""
+
+    @staticmethod
+    def stats(raw, C, bn):
+        N, G, H, W, _ = raw.shape
+        dev = raw.device
+        sums = torch.empty(2 * G * 4, dtype=torch.float64, device=dev)
+        mean, rstd, scale, shift = (torch.empty(G * 4, dtype=torch.float32, device=dev) for _ in range(4))
+        track = bn.training and bn.track_running_stats
+        _chk(_lib.load().gfr_bn_train_stats(_ptr(raw), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean) if track else None,
+                                            _ptr(bn.running_var) if track else None, _ptr(sums), _ptr(mean), _ptr(rstd),
+                                            _ptr(scale), _ptr(shift), N, C, H, W, float(bn.eps), float(bn.momentum), _stream()),
+             "gfr_bn_train_stats", 2)
+        if track:
+            bn.num_batches_tracked += 1
+        return mean, rstd, scale, shift
+
+    @staticmethod
+    def apply(raw, C, scale, shift, res, post, post_shift, act):
+        N, G, H, W, _ = raw.shape
+        y = torch.empty_like(raw)
+        _chk(_lib.load().gfr_bn_apply_fwd(_ptr(raw), _ptr(scale), _ptr(shift), _ptr(res), _ptr(post), _ptr(y), N, C, H, W,
+                                          int(post_shift), int(act), _stream()), "gfr_bn_apply_fwd")
+        return y
+
+    @staticmethod
+    def backward(raw, C, res, g_y, mean, rstd, scale, shift, gamma, act, want_res):
+        """-> g_raw, g_res, g_gamma, g_beta"""
+        N, G, H, W, _ = raw.shape
+        dev = raw.device
+        gamma_pad = torch.zeros(G * 4, dtype=torch.float32, device=dev)
+        gamma_pad[:C] = gamma
+        sums = torch.empty(2 * G * 4, dtype=torch.float64, device=dev)
+        g_raw = torch.empty_like(raw)
+        g_res = torch.empty_like(raw) if want_res else None
+        _chk(_lib.load().gfr_bn_apply_bwd(_ptr(raw), _ptr(res), _ptr(g_y), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
+                                          _ptr(gamma_pad), _ptr(sums), _ptr(g_raw), _ptr(g_res), N, C, H, W, int(act), _stream()),
+             "gfr_bn_apply_bwd", 2)
+        s = sums.view(2, G * 4)[:, :C].to(torch.float32)
+        return g_raw, g_res, s[1].contiguous(), s[0].contiguous()
+
+
+def _sumpool2(g):
+    N, G, H, W, _ = g.shape
+    out = torch.empty((N, G, H // 2, W // 2, 4), dtype=torch.float32, device=g.device)
+    _chk(_lib.load().gfr_sumpool2_c4(_ptr(g), _ptr(out), N * G, H // 2, W // 2, _stream()), "gfr_sumpool2_c4")
+    return out
+
+
+class ConvBNAct(torch.autograd.Function):
+    """y = act(BN_train(conv3x3(x[:, :cin]) + b) + res) + up(post).  Tensors are C4 `data` arrays."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, res, post, meta):
+        cin, Cout, deconv, act, post_shift, bn = meta["cin"], meta["cout"], meta["deconv"], meta["act"], meta["post_shift"], meta["bn"]
+        NT = _nt_for(Cout)
+        raw = _conv_raw(x, cin, _pack_dev(w, deconv, False, cin, Cout, NT), b, Cout, NT)
+        mean, rstd, scale, shift = _BN.stats(raw, Cout, bn)
+        y = _BN.apply(raw, Cout, scale, shift, res, post, post_shift, act)
+        ctx.save_for_backward(x, w, raw, res, mean, rstd, scale, shift, gamma)
+        ctx.meta = meta
+        ctx.has = (res is not None, post is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, w, raw, res, mean, rstd, scale, shift, gamma = ctx.saved_tensors
+        m = ctx.meta
+        cin, Cout, deconv, act, post_shift = m["cin"], m["cout"], m["deconv"], m["act"], m["post_shift"]
+        has_res, has_post = ctx.has
+        g_y = g_y.contiguous()
+        N, G, H, W, _ = x.shape
+        g_post = None
+        if has_post:
+            g_post = _sumpool2(g_y) if post_shift else g_y
+        g_raw, g_res, g_gamma, g_beta = _BN.backward(raw, Cout, res, g_y, mean, rstd, scale, shift, gamma, act, has_res)
+        # data gradient: the same tensor-core convolution, Cout -> cin, transposed + flipped kernel
+        g_x = None
+        if ctx.needs_input_grad[0]:
+            NTd = _nt_for(cin)
+            zero_b = torch.zeros(cin, dtype=torch.float32, device=x.device)
+            g_in = _conv_raw(g_raw, Cout, _pack_dev(w, deconv, True, cin, Cout, NTd), zero_b, cin, NTd)
+            if g_in.shape[1] == G:
+                g_x = g_in
+            else:                                   # the layer read only the leading channels of a wider tensor (TRAIN:225)
+                g_x = torch.zeros_like(x)
+                g_x[:, :g_in.shape[1]] = g_in
+        g_w = torch.zeros_like(w)
+        g_b4 = torch.zeros(((Cout + 3) // 4) * 4, dtype=torch.float32, device=x.device)
+        _chk(_lib.load().gfr_conv3x3_wgrad(_ptr(x), _ptr(g_raw), _ptr(g_w), _ptr(g_b4), int(deconv), N, cin, G, Cout, H, W, _stream()),
+             "gfr_conv3x3_wgrad", 2)
+        return g_x, g_w, g_b4[:Cout].contiguous(), g_gamma, g_beta, g_res, g_post, None
+
+
+class StemBNAct(torch.autograd.Function):
+    """c1_og = LeakyReLU(BN_train(conv5x5(img) + b)) on the NHWC image (TRAIN:197-200).  No gradient w.r.t. the image."""
+
+    @staticmethod
+    def forward(ctx, img, w, b, gamma, beta, bn):
+        N, H, W, _ = img.shape
+        raw = torch.empty((N, 4, H, W, 4), dtype=torch.float32, device=img.device)
+        _chk(_lib.load().gfr_stem_conv_train_fwd(_ptr(img), _ptr(w), _ptr(b), _ptr(raw), N, H, W, _stream()), "gfr_stem_conv_train_fwd")
+        mean, rstd, scale, shift = _BN.stats(raw, 16, bn)
+        y = _BN.apply(raw, 16, scale, shift, None, None, 0, 1)
+        ctx.save_for_backward(img, raw, mean, rstd, scale, shift, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        img, raw, mean, rstd, scale, shift, gamma = ctx.saved_tensors
+        N, H, W, _ = img.shape
+        g_raw, _, g_gamma, g_beta = _BN.backward(raw, 16, None, g_y.contiguous(), mean, rstd, scale, shift, gamma, 1, False)
+        g_w = torch.zeros((16, 3, 5, 5), dtype=torch.float32, device=img.device)
+        g_b = torch.zeros(16, dtype=torch.float32, device=img.device)
+        _chk(_lib.load().gfr_stem_conv_wgrad(_ptr(img), _ptr(g_raw), _ptr(g_w), _ptr(g_b), N, H, W, _stream()), "gfr_stem_conv_wgrad")
+        return None, g_w, g_b, g_gamma, g_beta, None
+
+
+class MaxPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        N, G, H, W, _ = x.shape
+        y = torch.empty((N, G, H // 2, W // 2, 4), dtype=torch.float32, device=x.device)
+        _chk(_lib.load().gfr_maxpool2_c4_fwd(_ptr(x), _ptr(y), N * G, H // 2, W // 2, _stream()), "gfr_maxpool2_c4_fwd")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        (x,) = ctx.saved_tensors
+        N, G, H, W, _ = x.shape
+        g_x = torch.empty_like(x)
+        _chk(_lib.load().gfr_maxpool2_c4_bwd(_ptr(x), _ptr(g_y.contiguous()), _ptr(g_x), N * G, H // 2, W // 2, _stream()),
+             "gfr_maxpool2_c4_bwd")
+        return g_x
+
+
+class Upsample2(torch.autograd.Function):
+    """nearest x2 (TRAIN:240 ...) when the epoch gate keeps the skip branch off."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, G, H, W, _ = x.shape
+        y = torch.empty((N, G, 2 * H, 2 * W, 4), dtype=torch.float32, device=x.device)
+        _chk(_lib.load().gfr_upsample2_c4_fwd(_ptr(x), None, _ptr(y), N * G, 2 * H, 2 * W, _stream()), "gfr_upsample2_c4_fwd")
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        return _sumpool2(g_y.contiguous())
+
+
+class PwConvBNAct(torch.autograd.Function):
+    """y = LeakyReLU(BN_train(conv1x1(x) + b)), 16 -> 16 (c2_2, c2_3; TRAIN:286-287)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, bn):
+        N, G, H, W, _ = x.shape
+        raw = torch.empty_like(x)
+        _chk(_lib.load().gfr_pw_conv16_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(raw), N, 16, H, W, 0, 0, 1.0, _stream()), "gfr_pw_conv16_fwd")
+        mean, rstd, scale, shift = _BN.stats(raw, 16, bn)
+        y = _BN.apply(raw, 16, scale, shift, None, None, 0, 1)
+        ctx.save_for_backward(x, w, raw, mean, rstd, scale, shift, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        x, w, raw, mean, rstd, scale, shift, gamma = ctx.saved_tensors
+        N, G, H, W, _ = x.shape
+        g_raw, _, g_gamma, g_beta = _BN.backward(raw, 16, None, g_y.contiguous(), mean, rstd, scale, shift, gamma, 1, False)
+        g_x = torch.empty_like(x)
+        g_w = torch.zeros_like(w)
+        g_b = torch.zeros(16, dtype=torch.float32, device=x.device)
+        _chk(_lib.load().gfr_pw_conv16_bwd(_ptr(x), _ptr(w), _ptr(g_raw), None, _ptr(g_x), _ptr(g_w), _ptr(g_b), N, 16, H, W, 0, 0,
+                                           1.0, _stream()), "gfr_pw_conv16_bwd")
+        return g_x, g_w, g_b, g_gamma, g_beta, None
+
+
+class PwHead(torch.autograd.Function):
+    """out = scale * act(conv1x1(x) + b), 16 -> n_out, NCHW planes (c2_o + sigmoid / x100; TRAIN:289-290, 349-350)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, scale):
+        N, G, H, W, _ = x.shape
+        n_out = w.shape[0]
+        out = torch.empty((N, n_out, H, W), dtype=torch.float32, device=x.device)
+        _chk(_lib.load().gfr_pw_conv16_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(out), N, n_out, H, W, 1, act, float(scale), _stream()),
+             "gfr_pw_conv16_fwd")
+        ctx.save_for_backward(x, w, out)
+        ctx.cfg = (act, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, w, out = ctx.saved_tensors
+        act, scale = ctx.cfg
+        N, G, H, W, _ = x.shape
+        n_out = w.shape[0]
+        g_x = torch.empty_like(x)
+        g_w = torch.zeros_like(w)
+        g_b = torch.zeros(n_out, dtype=torch.float32, device=x.device)
+        _chk(_lib.load().gfr_pw_conv16_bwd(_ptr(x), _ptr(w), _ptr(g_out.contiguous()), _ptr(out), _ptr(g_x), _ptr(g_w), _ptr(g_b), N,
+                                           n_out, H, W, 1, act, float(scale), _stream()), "gfr_pw_conv16_bwd")
+        return g_x, g_w, g_b, None, None
+
+
+class AvgPoolChannels(torch.autograd.Function):
+    """[N, n_ch] = mean over (H,W) of channels [c_first, c_first + n_ch) of a C4 map (TRAIN:226-230)."""
+
+    @staticmethod
+    def forward(ctx, x, C, c_first, n_ch):
+        N, G, H, W, _ = x.shape
+        out = torch.empty((N, n_ch), dtype=torch.float32, device=x.device)
+        _chk(_lib.load().gfr_avgpool_c4_fwd(_ptr(x), _ptr(out), N, C, c_first, n_ch, H * W, _stream()), "gfr_avgpool_c4_fwd")
+        ctx.cfg = (x.shape, C, c_first, n_ch)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, C, c_first, n_ch = ctx.cfg
+        N, G, H, W, _ = shape
+        g_x = torch.zeros(shape, dtype=torch.float32, device=g.device)
+        _chk(_lib.load().gfr_avgpool_c4_bwd(_ptr(g.contiguous()), _ptr(g_x), N, C, c_first, n_ch, H * W, _stream()), "gfr_avgpool_c4_bwd")
+        return g_x, None, None, None

@@ -134,6 +134,65 @@ int gfr_masked_losses(const float* rendered, const float* img_nchw, const float*
 int gfr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step, float lr,
                   float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- train-mode CNN building blocks (the reference trains with BATCH-statistics BatchNorm: it never calls .eval(),
+ * TRAIN:561-563) — all activations C4 -------------------------------------------------------------------------- */
+
+/* Device-side packing for gfr_conv3x3_tc_fwd (weights change every optimiser step).  w is the layer PARAMETER on the
+ * device: Conv2d [Cout,Cin,3,3] (is_transposed_conv 0) or ConvTranspose2d [Cin,Cout,3,3] (1; its forward is a conv
+ * with w.transpose(0,1).flip(2,3)).  for_dgrad 0: operand of the forward (Cin -> Cout); 1: operand of the
+ * data-gradient, itself a 3x3 conv Cout -> Cin with the transposed + flipped kernel.  Same layout / size as
+ * gfr_conv_tc_pack_weights (gfr_conv_tc_pack_size(I, O, NT) floats, O/I = outputs/inputs of the packed operand). */
+int gfr_conv_tc_pack_weights_dev(const float* w, int is_transposed_conv, int for_dgrad, int Cin, int Cout, int NT,
+                                 float* packed, void* stream);
+
+/* BatchNorm2d, training mode, part 1: batch statistics of x [N,C,H,W] (C4) -> mean, rstd = 1/sqrt(var_biased + eps),
+ * scale = gamma*rstd, shift = beta - mean*scale (all [4*ceil(C/4)] floats, padded slots 0); running_mean/var (may be
+ * NULL) are updated like torch (momentum, unbiased variance).  sums_scratch: 2*4*ceil(C/4) doubles. */
+int gfr_bn_train_stats(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                       double* sums_scratch, float* mean, float* rstd, float* scale, float* shift, int N, int C, int H,
+                       int W, float eps, float momentum, void* stream);
+
+/* part 2: y = act(scale*x + shift + res) + up(post)  — BatchNorm + residual add + LeakyReLU(0.2) (act 1) + skip /
+ * nearest-x2-upsample add, the epilogue of gfr_conv3x3_tc_fwd as its own pass.  res/post may be NULL. */
+int gfr_bn_apply_fwd(const float* x, const float* scale, const float* shift, const float* res, const float* post,
+                     float* y, int N, int C, int H, int W, int post_shift, int act, void* stream);
+
+/* Backward of part 1+2 w.r.t. x and res given g_y = dL/dy (the `post` branch's gradient is g_y itself, or its 2x2 sum
+ * — gfr_sumpool2_c4 — when it was upsampled): g_res (may be NULL) = g_y*act'(pre); g_x = gamma*rstd*(g_pre - mean(g_pre)
+ * - xhat*mean(g_pre*xhat)).  After the call sums_scratch holds [sum g_pre | sum g_pre*xhat] = [d beta | d gamma]
+ * (2 x 4*ceil(C/4) doubles).  gamma_pad: gamma padded with zeros to 4*ceil(C/4). */
+int gfr_bn_apply_bwd(const float* x, const float* res, const float* g_y, const float* scale, const float* shift,
+                     const float* mean, const float* rstd, const float* gamma_pad, double* sums_scratch, float* g_x,
+                     float* g_res, int N, int C, int H, int W, int act, void* stream);
+
+/* Weight (and bias) gradient of a 3x3 stride-1 convolution: g_w (+=, parameter layout: Conv2d [Cout,Cin,3,3] or
+ * ConvTranspose2d [Cin,Cout,3,3]) and g_bias [4*ceil(Cout/4)] (+=, may be NULL) from the layer input `in`
+ * (in_groups as in gfr_conv3x3_tc_fwd) and g_out = dL/d(conv output).  fp32 on CUDA cores. */
+int gfr_conv3x3_wgrad(const float* in, const float* g_out, float* g_w, float* g_bias, int is_transposed_conv, int N,
+                      int Cin, int in_groups, int Cout, int H, int W, void* stream);
+
+/* 2x2 max-pool backward (gradient to the first maximum, like torch), 2x2 sum (backward of the nearest x2 upsample),
+ * global average pool of channels [c_first, c_first+n_ch) of a C4 map -> [N,n_ch] and its backward (+= into g_feat). */
+int gfr_maxpool2_c4_bwd(const float* x, const float* g_y, float* g_x, int NC4, int Ho, int Wo, void* stream);
+int gfr_sumpool2_c4(const float* x, float* out, int NC4, int Ho, int Wo, void* stream);
+int gfr_avgpool_c4_fwd(const float* feat, float* out, int N, int C, int c_first, int n_ch, int HW, void* stream);
+int gfr_avgpool_c4_bwd(const float* g, float* g_feat, int N, int C, int c_first, int n_ch, int HW, void* stream);
+
+/* 1x1 convolution with 16 input channels and DEVICE weights w [Cout,16], bias [Cout] (the decoder tails in train mode,
+ * TRAIN:285-290, 345-350): out = out_scale * act(w x + b); planar_out 0: C4 [N,16,H,W] (Cout = 16), 1: NCHW
+ * [N,Cout,H,W]; act 0 | 2 (sigmoid).  Backward: g_in (written), g_w / g_bias (+=) from g_out = dL/d(out). */
+int gfr_pw_conv16_fwd(const float* in, const float* w, const float* bias, float* out, int N, int Cout, int H, int W,
+                      int planar_out, int act, float out_scale, void* stream);
+int gfr_pw_conv16_bwd(const float* in, const float* w, const float* g_out, const float* out, float* g_in, float* g_w,
+                      float* g_bias, int N, int Cout, int H, int W, int planar_out, int act, float out_scale, void* stream);
+
+/* Stem in train mode: conv_c1_og (5x5, 3 -> 16) with DEVICE weights w [16,3,5,5], bias [16] on the NHWC image -> raw
+ * conv output C4 [N,16,H,W] (BatchNorm / LeakyReLU / pool follow as separate passes); and its weight/bias gradient
+ * (+=) from g_out = dL/d(raw). */
+int gfr_stem_conv_train_fwd(const float* img, const float* w, const float* bias, float* out_raw, int N, int H, int W,
+                            void* stream);
+int gfr_stem_conv_wgrad(const float* img, const float* g_out, float* g_w, float* g_bias, int N, int H, int W, void* stream);
+
 /* fp32 convolution with fused epilogue (exact-fp32 CNN path).  Replaces one
  * Conv2d / ConvTranspose2d(stride 1) + BatchNorm2d(eval, folded into w/bias by the caller) + residual add +
  * LeakyReLU(0.2) / sigmoid + skip add + nearest x2 upsample step of RelightNet (TRAIN:197-350, TEST1:170-323):

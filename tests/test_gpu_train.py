@@ -1,0 +1,120 @@
+"""GPU parity of the TRAIN-mode path (batch-statistics BatchNorm, autograd through every unit) against what the
+UNMODIFIED reference produced in train() mode for B = 3 (tests/golden/train.npz, made by oracle/make_golden.py:
+TRAIN forward + loss.backward() with loss = masked L2 recon + DSSIM, TRAIN:633,643), plus unit-level gradient checks
+against torch autograd (cuDNN fp32)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-20))
+
+
+@pytest.mark.parametrize("deconv,cin,cout,S,res,post", [
+    (False, 16, 16, 32, True, True), (True, 32, 16, 32, False, False), (False, 64, 155, 16, True, False),
+    (True, 128, 64, 16, False, False),
+])
+def test_conv_bn_act_unit_vs_torch_autograd(deconv, cin, cout, S, res, post):
+    from geomconsistentfr_b200 import ops, train_ops as T
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    N = 3
+    mod = (torch.nn.ConvTranspose2d if deconv else torch.nn.Conv2d)(cin, cout, 3, padding=1).cuda()
+    bn = torch.nn.BatchNorm2d(cout).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.normal_(generator=g)
+    ctot = cin + (27 if cin == 128 else 0)                      # exercise "leading channels of a wider tensor"
+    x = torch.randn(N, ctot, S, S, device="cuda", generator=g)
+    r = torch.randn(N, cout, S, S, device="cuda", generator=g) if res else None
+    p = torch.randn(N, cout, S // 2, S // 2, device="cuda", generator=g) if post else None
+    Gy = torch.randn(N, cout, S, S, device="cuda", generator=g)
+    # torch reference
+    xr = x.clone().requires_grad_()
+    rr = r.clone().requires_grad_() if res else None
+    pr = p.clone().requires_grad_() if post else None
+    pre = bn(mod(xr[:, :cin]))
+    y_ref = F.leaky_relu(pre + rr if res else pre, 0.2)
+    if post:
+        y_ref = y_ref + F.interpolate(pr, scale_factor=2, mode="nearest")
+    (y_ref * Gy).sum().backward()
+    ref = dict(w=mod.weight.grad.clone(), b=mod.bias.grad.clone(), gamma=bn.weight.grad.clone(), beta=bn.bias.grad.clone(),
+               x=xr.grad.clone())
+    for q in (mod.weight, mod.bias, bn.weight, bn.bias):
+        q.grad = None
+    bn2 = torch.nn.BatchNorm2d(cout).cuda()
+    # ours
+    xc = ops.nchw_to_c4(x).data.requires_grad_()
+    rc = ops.nchw_to_c4(r).data.requires_grad_() if res else None
+    pc = ops.nchw_to_c4(p).data.requires_grad_() if post else None
+    meta = dict(cin=cin, cout=cout, deconv=deconv, act=1, post_shift=1 if post else 0, bn=bn2)
+    bn2.weight.data.copy_(bn.weight.data); bn2.bias.data.copy_(bn.bias.data)
+    y = T.ConvBNAct.apply(xc, mod.weight, mod.bias, bn2.weight, bn2.bias, rc, pc, meta)
+    got_y = ops.c4_to_nchw(ops.C4(y.detach(), cout))
+    assert (got_y - y_ref.detach()).abs().max() <= 2e-4
+    assert (bn2.running_mean - bn.running_mean).abs().max() <= 1e-5 and (bn2.running_var - bn.running_var).abs().max() <= 1e-4
+    (y * ops.nchw_to_c4(Gy).data).sum().backward()
+    assert _rel(mod.weight.grad, ref["w"]) <= 2e-3
+    assert _rel(bn2.weight.grad, ref["gamma"]) <= 2e-3 and _rel(bn2.bias.grad, ref["beta"]) <= 2e-3
+    assert mod.bias.grad.abs().max() <= 1e-3 * max(1.0, float(ref["w"].abs().max()))      # exactly 0 in exact arithmetic (BN removes the mean)
+    assert _rel(ops.c4_to_nchw(ops.C4(xc.grad, ctot)), ref["x"]) <= 2e-3
+    if res:
+        assert _rel(ops.c4_to_nchw(ops.C4(rc.grad, cout)), rr.grad) <= 1e-4
+    if post:
+        assert _rel(ops.c4_to_nchw(ops.C4(pc.grad, cout)), pr.grad) <= 1e-4
+
+
+@pytest.fixture(scope="module")
+def train_net():
+    from geomconsistentfr_b200 import RelightNet
+    n = RelightNet(batch_size=3)
+    n.load_state_dict(torch.load(os.path.join(G, "model_epoch99.pth"), map_location="cpu"), strict=True)
+    return n.float().cuda().train()
+
+
+def test_train_mode_forward_and_gradients_vs_reference(train_net):
+    """Forward (train-mode BN) and the gradients the reference's autograd produced, for the reference's own B = 3."""
+    from geomconsistentfr_b200 import dssim_loss, intrinsic_matrix
+    t = np.load(os.path.join(G, "train.npz"))
+    f = np.load(os.path.join(G, "ffhq.npz"))
+    x = torch.from_numpy(f["q"][t["sel"]] / 1020.0).float().cuda()
+    mt = torch.from_numpy(t["masks01"].astype(np.float64)).view(3, 256, 256, 1).cuda()
+    train_net.zero_grad()
+    out = train_net(x, 200, intrinsic_matrix().cuda(), mt)
+    assert len(out) == 8
+    albedo, depth, shadow, amb_l, full, rendered, unit_l, amb_v = out
+    depth.retain_grad()
+    tol = dict(albedo=5e-5, depth=2e-2, shadow=5e-3, rendered=5e-3)
+    for k, v in (("albedo", albedo), ("depth", depth), ("shadow", shadow), ("rendered", rendered)):
+        d = np.abs(v.detach().cpu().numpy() - t[k]).max()
+        assert d <= tol[k], (k, d)
+    assert np.abs(unit_l.detach().cpu().numpy().reshape(3, 3) - t["unit_light"]).max() <= 2e-5
+    assert np.abs(amb_v.detach().cpu().numpy().reshape(3) - t["ambient"]).max() <= 2e-5
+    m3 = mt.permute(0, 3, 1, 2).repeat(1, 3, 1, 1).float()
+    target = x.permute(0, 3, 1, 2).contiguous()
+    comp = rendered * m3 + (1.0 - m3) * target
+    loss = 20.0 * torch.sum((rendered * m3 - target * m3) ** 2) / torch.sum(m3) + dssim_loss(comp, target)   # TRAIN:633,643
+    assert abs(float(loss) - float(t["loss"])) <= 2e-4 * float(t["loss"])
+    loss.backward()
+    gd, gd_ref = depth.grad.cpu().numpy(), t["grad_depth"]
+    assert np.abs(gd - gd_ref).sum() / np.abs(gd_ref).sum() <= 2e-2
+    for name, got in (("grad_sl2_w", train_net.linear_SL2.weight.grad), ("grad_sl2_b", train_net.linear_SL2.bias.grad),
+                      ("grad_depth_head_w", train_net.conv_depth_c2_o.weight.grad),
+                      ("grad_albedo_head_w", train_net.conv_albedo_c2_o.weight.grad)):
+        ref = t[name]
+        err = np.abs(got.cpu().numpy() - ref).max() / np.abs(ref).max()
+        assert err <= 2e-2, (name, err)
+    # every parameter received a finite gradient
+    for n_, p_ in train_net.named_parameters():
+        assert p_.grad is not None and torch.isfinite(p_.grad).all(), n_
