@@ -131,6 +131,71 @@ def run_reference(args):
         "gpu_launches": 0}))
 
 
+def run_train(args, rank, world, local, dist):
+    """configs[2]/[3]: generator training step (TRAIN:618, 633-645 minus the PatchGAN terms, 655-656), B = 16 per GPU,
+    synthetic batch resident on the device, one NCCL all-reduce of the flat gradient buffer per step."""
+    from geomconsistentfr_b200 import RelightNet, intrinsic_matrix, ops
+    from geomconsistentfr_b200.trainer import GeneratorStep
+    from oracle.relight_oracle import LIGHTS_18, synthetic_face
+    B = 16
+    net = RelightNet(batch_size=B)
+    net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"), strict=True)
+    net = net.float().cuda().train()
+    step = GeneratorStep(net, intrinsic_matrix().cuda(), group=None)
+    g = torch.Generator().manual_seed(rank)
+    img = torch.rand(B, H, W, 3, generator=g).cuda()
+    faces = [synthetic_face(seed=rank * B + i) for i in range(B)]
+    mf = torch.stack([f[1] for f in faces]).float().cuda()
+    depth_gt = (torch.stack([f[0] for f in faces]) * 0.5).cuda()
+    albedo_gt = torch.rand(B, H, W, generator=g).cuda()
+    light_gt = torch.tensor([[0.5, *LIGHTS_18[(rank + i) % 18]] for i in range(B)], dtype=torch.float32).cuda()
+
+    batch = (mf, mf, depth_gt, albedo_gt, light_gt)
+    n_pre = ops.launch_count()
+    step.step(img, 200, *batch)
+    launches_per_step = ops.launch_count() - n_pre
+    if args.no_graph:
+        stream = torch.cuda.current_stream()
+        one = lambda: step.step(img, 200, *batch)
+    else:
+        step.capture(img, 200, *batch)
+        stream = step._stream
+        one = lambda: step.step_graphed(img, *batch)
+    for _ in range(max(args.warmup, 3)):
+        one()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    n0 = ops.launch_count() - launches_per_step * args.steps if not args.no_graph else ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        total, _ = one()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "training faces/sec @256x256 (generator step)", "value": world * B * args.steps * 1e3 / ms, "unit": "faces/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 convs)", "data": "synthetic",
+            "config": {"workload": "configs[2]/[3]: generator training step, batch 16 per GPU, 256x256: train-mode RelightNet fwd + "
+                                   "masked recon/depth/albedo + ambient + light + DSSIM losses + backward + flat-gradient "
+                                   "all-reduce + fused Adam; PatchGAN terms not built", "global_batch": world * B,
+                       "parallelism": "dp%d, one all_reduce of %.1f MB per step" % (world, step.opt.grad.numel() * 4 / 1e6),
+                       "working_set": "activations of one step (> L2) are rewritten every step", "cuda_graph": not args.no_graph},
+            "gpu_launches": int(ops.launch_count() - n0), "final_loss": float(total)}))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -140,6 +205,9 @@ def main():
     ap.add_argument("--cpu-faces", type=int, default=6, help="faces in the bounded CPU-baseline sample")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--lanes", type=int, default=2, help="runner lanes the e2e (host-buffer) path rotates over")
+    ap.add_argument("--workload", default="forward", choices=["forward", "train"],
+                    help="forward = configs[1] (the default bench line); train = configs[2]/[3]: generator training step, "
+                         "B=16 per GPU, one flat-gradient all-reduce per step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -155,6 +223,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    if args.workload == "train":
+        return run_train(args, rank, world, local, dist)
 
     from geomconsistentfr_b200 import RelightNet, RelightRunner, ops
     net = RelightNet()

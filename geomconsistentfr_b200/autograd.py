@@ -153,7 +153,8 @@ class FlatAdam:
                 p.data = self.flat[o:o + k].view_as(p)
                 p.grad = self.grad[o:o + k].view_as(p)
                 o += k
-        self.lr, self.betas, self.eps, self.step_count = lr, betas, eps, 0
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.state = torch.zeros(3, dtype=torch.float32, device=dev)       # {step, 1-b1^t, sqrt(1-b2^t)} advanced on the device
 
     def zero_grad(self):
         self.grad.zero_()
@@ -167,8 +168,7 @@ class FlatAdam:
         return 1.0 / dist.get_world_size(group)
 
     def step(self, grad_scale=1.0):
-        self.step_count += 1
         rc = _lib.load().gfr_adam_step(_ptr(self.flat), _ptr(self.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
-                                       self.flat.numel(), self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
+                                       self.flat.numel(), _ptr(self.state), self.lr, self.betas[0], self.betas[1], self.eps,
                                        float(grad_scale), _stream())
-        _lib.check(rc, "gfr_adam_step"); ops._count()
+        _lib.check(rc, "gfr_adam_step"); ops._count(2)

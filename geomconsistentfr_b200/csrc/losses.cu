@@ -211,10 +211,20 @@ __global__ void __launch_bounds__(256) masked_losses_kernel(const MaskedLossArgs
 }
 
 // ------------------------------------------------------------------------------------------------- Adam
+// step counter on the device (so the whole training step can live in a CUDA graph): state = {step, 1-beta1^step, sqrt(1-beta2^step)}
+__global__ void adam_tick_kernel(float* __restrict__ state, float beta1, float beta2) {
+  const float t = state[0] + 1.0f;
+  state[0] = t;
+  state[1] = 1.0f - powf(beta1, t);
+  state[2] = sqrtf(1.0f - powf(beta2, t));
+}
+
 __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                 long long n, float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+                                 long long n, float lr, float beta1, float beta2, float eps, const float* __restrict__ state,
+                                 float grad_scale) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const float bc1 = __ldg(state + 1), bc2_sqrt = __ldg(state + 2);
   const float gi = g[i] * grad_scale;
   const float mi = beta1 * m[i] + (1.f - beta1) * gi;          // torch.optim.Adam (no amsgrad, no weight decay)
   const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
@@ -279,14 +289,14 @@ extern "C" int gfr_masked_losses(const float* rendered, const float* img_nchw, c
   return gfr_launch_status();
 }
 
-extern "C" int gfr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step,
+extern "C" int gfr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state3,
                              float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
   GFR_RETURN_IF_NULL(params); GFR_RETURN_IF_NULL(grads); GFR_RETURN_IF_NULL(exp_avg); GFR_RETURN_IF_NULL(exp_avg_sq);
+  GFR_RETURN_IF_NULL(state3);
   if (n <= 0) return GFR_E_SHAPE;
-  if (step < 1) return GFR_E_ARG;
-  const float bc1 = 1.0f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
-  adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
-                                                                                 beta2, eps, bc1, bc2_sqrt, grad_scale);
+  cudaStream_t s = (cudaStream_t)stream;
+  adam_tick_kernel<<<1, 1, 0, s>>>(state3, beta1, beta2);
+  adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, state3,
+                                                              grad_scale);
   return gfr_launch_status();
 }

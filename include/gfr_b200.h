@@ -129,9 +129,11 @@ int gfr_masked_losses(const float* rendered, const float* img_nchw, const float*
                       double* sums5, float* g_rendered, float* g_depth, float* g_albedo, int N, int H, int W,
                       void* stream);
 
-/* One torch.optim.Adam step (no weight decay, no amsgrad; TRAIN:589-590, 656) over a flat fp32 parameter buffer:
- * step >= 1 is the 1-based step count; grads are multiplied by grad_scale first (1/world_size after an all-reduce). */
-int gfr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step, float lr,
+/* One torch.optim.Adam step (no weight decay, no amsgrad; TRAIN:589-590, 656) over a flat fp32 parameter buffer.
+ * state3: 3 device floats {step count, 1-beta1^step, sqrt(1-beta2^step)}, zero-initialised by the caller and advanced
+ * on the device by every call (no host-side counter, so the whole training step can be replayed from a CUDA graph);
+ * grads are multiplied by grad_scale first (1/world_size after an all-reduce). */
+int gfr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state3, float lr,
                   float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* ---- train-mode CNN building blocks (the reference trains with BATCH-statistics BatchNorm: it never calls .eval(),

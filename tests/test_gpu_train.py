@@ -118,3 +118,59 @@ def test_train_mode_forward_and_gradients_vs_reference(train_net):
     # every parameter received a finite gradient
     for n_, p_ in train_net.named_parameters():
         assert p_.grad is not None and torch.isfinite(p_.grad).all(), n_
+
+
+def test_generator_step_losses_and_all_gradients_vs_oracle():
+    """One full generator step body (TRAIN:618, 633-645 without the two PatchGAN terms, 655) on the library kernels vs the
+    CPU oracle in train() mode differentiated by torch autograd: every loss term and EVERY parameter gradient."""
+    from geomconsistentfr_b200 import RelightNet, intrinsic_matrix
+    from geomconsistentfr_b200.trainer import GeneratorStep
+    from oracle import relight_oracle as O
+    f = np.load(os.path.join(G, "ffhq.npz"))
+    sel = [0, 4]
+    B = len(sel)
+    sd = torch.load(os.path.join(G, "model_epoch99.pth"), map_location="cpu")
+    img = torch.from_numpy(f["q"][sel] / 1020.0).float()
+    mf = torch.from_numpy((f["masks"][sel] > 128).astype(np.float32))
+    m = mf.clone(); m[:, 100:140, 90:170] = 0                                # the depth mask excludes nose/mouth (TRAIN:610 vs 612)
+    gen = torch.Generator().manual_seed(1)
+    depth_gt = torch.stack([O.synthetic_face(seed=s)[0] for s in (1, 2)]) * 0.5
+    albedo_gt = torch.rand(B, 256, 256, generator=gen)
+    light_gt = torch.tensor([[0.45, 0.5145, 0.0, 0.8575], [0.55, -0.5843, 0.0, 0.8115]])
+
+    # ---- oracle (CPU, train mode)
+    ref = O.RelightNetOracle(); ref.load_state_dict(sd); ref.train()
+    out = ref.forward_train(img, 200, O.intrinsic_matrix(), mf.double().view(B, 256, 256, 1))
+    albedo, depth, _, _, _, rendered, unit_l, amb_v = out
+    m3 = mf[:, None].repeat(1, 3, 1, 1).double(); target = img.permute(0, 3, 1, 2)
+    terms_ref = dict(
+        recon=20.0 * ((rendered * m3 - target * m3) ** 2).sum() / m3.sum(),
+        depth=(depth[:, 0] * m.double() - depth_gt * m.double()).abs().sum() / m.double().sum(),
+        ambient=2.5 * (amb_v.reshape(B) - light_gt[:, 0]).abs().mean(),
+        lighting=torch.sum(1 - torch.sum(unit_l.reshape(B, 3) * light_gt[:, 1:4], dim=1)) / B,
+        albedo=5.0 * (albedo.mean(1) * mf.double() - albedo_gt * mf.double()).abs().sum() / mf.double().sum(),
+        DSSIM=8.0 * (1 - O.ssim((rendered * m3 + (1 - m3) * target).float(), target, data_range=1.0, size_average=True,
+                                nonnegative_ssim=True)) / 2.0)
+    sum(terms_ref.values()).backward()
+
+    # ---- library
+    net = RelightNet(batch_size=B); net.load_state_dict(sd, strict=True); net = net.float().cuda().train()
+    step = GeneratorStep(net, intrinsic_matrix().cuda())
+    c = lambda t: t.cuda()
+    step.opt.zero_grad()
+    o = net(c(img), 200, step.K, c(mf).view(B, 256, 256, 1))
+    total, terms = step.losses(o, c(img), c(mf), c(m), c(depth_gt), c(albedo_gt), c(light_gt))
+    for k in terms_ref:
+        a, b = float(terms[k]), float(terms_ref[k])
+        assert abs(a - b) <= 2e-3 * max(abs(b), 1e-3), (k, a, b)
+    total.backward()
+    worst = {}
+    for (n1, p1), (n2, p2) in zip(net.named_parameters(), ref.named_parameters()):
+        assert n1 == n2
+        if n1.endswith(".bias") and ("conv" in n1 or "deconv" in n1) and not n1.endswith("c2_o.bias"):
+            continue                                  # conv bias before a train-mode BN: gradient is 0 up to rounding on both sides
+        g1, g2 = p1.grad.cpu(), p2.grad
+        worst[n1] = float((g1 - g2).abs().max() / (g2.abs().max() + 1e-12))
+    bad = {k: v for k, v in worst.items() if v > 3e-2}
+    assert not bad, bad
+    assert np.median(list(worst.values())) <= 5e-3
