@@ -443,9 +443,8 @@ struct PwBwdArgs {
 
 __global__ void __launch_bounds__(256) pw_conv16_bwd_kernel(const PwBwdArgs a) {
   __shared__ float s_w[16][16];
-  __shared__ float s_acc[17][16];      // [ci or 16 = bias][co]
+  __shared__ float s_x[256][17], s_g[256][17];     // this CTA's 256 pixels: forward input and output gradient
   for (int i = threadIdx.x; i < 16 * 16; i += 256) s_w[i >> 4][i & 15] = (i >> 4) < a.Cout ? __ldg(a.w + i) : 0.f;
-  for (int i = threadIdx.x; i < 17 * 16; i += 256) s_acc[i >> 4][i & 15] = 0.f;
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float x[16], g[16];
@@ -479,25 +478,22 @@ __global__ void __launch_bounds__(256) pw_conv16_bwd_kernel(const PwBwdArgs a) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) dst[q * a.hw] = make_float4(gi[4 * q], gi[4 * q + 1], gi[4 * q + 2], gi[4 * q + 3]);
   }
-  // weight / bias gradients: warp-reduce each (co, ci) product, then shared and global atomics
-  const int lane = threadIdx.x & 31;
+  // weight / bias gradients: the CTA's [256 px x 16] tiles of x and g go through shared memory, thread (o, c) reduces
+  // its product over the 256 pixels, one global atomicAdd per (o, c) and CTA
 #pragma unroll
-  for (int o = 0; o < 16; ++o) {
-    if (o >= a.Cout) break;
-#pragma unroll
-    for (int c = 0; c < 17; ++c) {
-      float v = c < 16 ? g[o] * x[c < 16 ? c : 0] : g[o];
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-      if (lane == 0) atomicAdd(&s_acc[c][o], v);
-    }
-  }
+  for (int c = 0; c < 16; ++c) { s_x[threadIdx.x][c] = x[c]; s_g[threadIdx.x][c] = g[c]; }
   __syncthreads();
-  for (int k = threadIdx.x; k < 17 * 16; k += 256) {
-    const int c = k >> 4, o = k & 15;
-    if (o >= a.Cout) continue;
-    const float v = s_acc[c][o];
-    if (v != 0.f) atomicAdd(c < 16 ? a.gw + o * 16 + c : a.gb + o, v);
+  const int o = threadIdx.x >> 4, c = threadIdx.x & 15;
+  if (o < a.Cout) {
+    float acc = 0.f, accb = 0.f;
+#pragma unroll 8
+    for (int px = 0; px < 256; ++px) {
+      const float gv = s_g[px][o];
+      acc = fmaf(gv, s_x[px][c], acc);
+      accb += gv;
+    }
+    if (acc != 0.f) atomicAdd(a.gw + o * 16 + c, acc);
+    if (c == 0 && accb != 0.f) atomicAdd(a.gb + o, accb);
   }
 }
 
