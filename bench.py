@@ -110,6 +110,29 @@ def cpu_forward_faces_per_s(n_faces, threads):
     return times
 
 
+def gpu_port_faces_per_s(n_faces):
+    """The same oracle port on cuda:0 (torch eager: cuDNN convs + the per-sample tensor program of TEST1:351-498, with its
+    per-image host syncs), B = 1 per call like the reference: the closest stand-in for "the reference's 1-GPU PyTorch
+    throughput" that can run on this box (the reference itself cannot travel here)."""
+    from oracle import relight_oracle as O
+    net = O.RelightNetOracle()
+    net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"))
+    net = net.cuda().eval()
+    K = O.intrinsic_matrix().cuda()
+    times = []
+    with torch.no_grad():
+        for i in range(n_faces + 2):
+            img, mask, light = synthetic_batch(1, 100 + i)
+            img, light = img.cuda(), light.cuda()
+            m = (mask.view(H, W, 1).double() / 255.0).cuda()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            net.forward_test(img, 200, K, m, light[:1])
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+    return times[2:]
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port, kind 'port'), rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -204,7 +227,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-faces", type=int, default=6, help="faces in the bounded CPU-baseline sample")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--lanes", type=int, default=2, help="runner lanes the e2e (host-buffer) path rotates over")
+    ap.add_argument("--lanes", type=int, default=3, help="runner lanes the e2e (host-buffer) path rotates over")
     ap.add_argument("--workload", default="forward", choices=["forward", "train"],
                     help="forward = configs[1] (the default bench line); train = configs[2]/[3]: generator training step, "
                          "B=16 per GPU, one flat-gradient all-reduce per step")
@@ -362,6 +385,12 @@ def main():
         line["cpu_baseline"] = {"value": len(t) / sum(t), "unit": "faces/s", "cores": threads, "kind": "port",
                                 "sample": "%d faces (1 warm-up dropped), B=1 each, torch CPU oracle port of TEST1:169-505"
                                           % len(t)}
+        try:
+            tg = gpu_port_faces_per_s(8)
+            line["reference_gpu_port"] = {"value": len(tg) / sum(tg), "unit": "faces/s", "kind": "port",
+                                          "sample": "%d faces, B=1 each, the torch oracle port (TEST1:169-505) run eagerly on cuda:0" % len(tg)}
+        except Exception as e:                      # informational only
+            line["reference_gpu_port"] = {"unavailable": str(e)[:200]}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

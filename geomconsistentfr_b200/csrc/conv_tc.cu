@@ -32,6 +32,7 @@
 #include "tc_common.cuh"
 
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 using namespace gfr_tc;
@@ -56,6 +57,7 @@ struct ConvTcArgs {
   int ncb, tiles_x, tiles_y, m_tiles;
   int post_shift, act;
   int single_pass;     // 1: hi*Whi only (plain TF32)
+  int static_w;        // 1: the packed weights were not written by the preceding kernel: fetch them before griddepcontrol.wait
   float out_scale;
 };
 
@@ -107,23 +109,37 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
 
   const int n_my_tiles = (a.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_steps = n_my_tiles * a.ncb;
+  griddep_launch_dependents();        // PDL: the next layer may start its prologue (barriers, TMEM, weight fetch) now
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       const float* wsrc = a.wpk + (size_t)blockIdx.y * a.ncb * (S::W_STEP / 4);
+      // PDL prologue: the first ring slots are armed and (static weights) their weight copies are in flight before the
+      // previous layer has finished; the activation loads follow griddepcontrol.wait.
+      const int n_pre = n_steps < STAGES ? n_steps : STAGES;
+      for (int g = 0; g < n_pre; ++g) {
+        const bool load_w = !resident || g == 0;
+        mbar_expect_tx(bar_full + 8 * g, A_BYTES + (load_w ? S::W_STEP : 0u));
+        if (load_w && a.static_w)
+          bulk_load(resident ? smem0 : slots0 + g * slot_bytes + 2 * A_BYTES, wsrc + (size_t)(g % a.ncb) * (S::W_STEP / 4), S::W_STEP, bar_full + 8 * g);
+      }
+      griddep_wait();
       int g = 0;
       for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
         const int tx = mt % a.tiles_x, t2 = mt / a.tiles_x;
         const int ty = t2 % a.tiles_y, n = t2 / a.tiles_y;
         for (int cb = 0; cb < a.ncb; ++cb, ++g) {
           const int s = g % STAGES;
-          mbar_wait(bar_empty + 8 * s, ((g / STAGES) & 1) ^ 1);
           const uint32_t slot = slots0 + s * slot_bytes;
           const bool load_w = !resident || g == 0;
-          mbar_expect_tx(bar_full + 8 * s, A_BYTES + (load_w ? S::W_STEP : 0u));
+          if (g >= n_pre) {
+            mbar_wait(bar_empty + 8 * s, ((g / STAGES) & 1) ^ 1);
+            mbar_expect_tx(bar_full + 8 * s, A_BYTES + (load_w ? S::W_STEP : 0u));
+          }
           tma_load_4d(slot, &tm_in, bar_full + 8 * s, (tx * TILE_PX_W - 1) * 4, ty * TILE_PX_H - 1, cb * (CB / 4), n);
-          if (load_w) bulk_load(resident ? smem0 : slot + 2 * A_BYTES, wsrc + (size_t)cb * (S::W_STEP / 4), S::W_STEP, bar_full + 8 * s);
+          if (load_w && (g >= n_pre || !a.static_w))
+            bulk_load(resident ? smem0 : slot + 2 * A_BYTES, wsrc + (size_t)cb * (S::W_STEP / 4), S::W_STEP, bar_full + 8 * s);
         }
       }
     }
@@ -189,6 +205,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
     const int n0 = blockIdx.y * NT;
     const int C4out = (a.Cout + 3) >> 2;
     const int pH = a.H >> a.post_shift, pW = a.W >> a.post_shift;
+    griddep_wait();                                       // residual / skip operands and the output buffer belong to earlier kernels
     int g = 0;
     for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
       const int tx = mt % a.tiles_x, t2 = mt / a.tiles_x;
@@ -339,8 +356,19 @@ int launch_tc(const CUtensorMap& tm, const ConvTcArgs& a, cudaStream_t s) {
   int gx = (sm_count() * occ) / n_tiles;
   if (gx < 1) gx = 1;
   if (gx > a.m_tiles) gx = a.m_tiles;
-  conv3x3_tc_kernel<NT><<<dim3(gx, n_tiles), NUM_THREADS, bytes, s>>>(tm, a);
-  return gfr_launch_status();
+  static const bool no_pdl = getenv("GFR_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, n_tiles);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NT>, tm, a);
+  return e == cudaSuccess ? gfr_launch_status() : (int)e;
 }
 
 inline float tf32_rn_host(float x) {
@@ -445,7 +473,7 @@ extern "C" int gfr_conv_tc_pack_weights(const float* w_host, int Cin, int Cout, 
 
 extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const float* bias, const float* res,
                                   const float* post, float* out, int N, int Cin, int in_groups, int Cout, int H, int W,
-                                  int NT, int post_shift, int act, float out_scale, int precision, void* stream) {
+                                  int NT, int post_shift, int act, float out_scale, int precision, int weights_static, void* stream) {
   GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w_packed); GFR_RETURN_IF_NULL(bias); GFR_RETURN_IF_NULL(out);
   if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
   if (post_shift < 0 || post_shift > 1 || act < 0 || act > 2 || (precision != 1 && precision != 3)) return GFR_E_ARG;
@@ -463,6 +491,7 @@ extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const 
   a.m_tiles = N * a.tiles_x * a.tiles_y;
   a.post_shift = post_shift; a.act = act; a.out_scale = out_scale;
   a.single_pass = precision == 1;
+  a.static_w = weights_static ? 1 : 0;
   CUtensorMap tm;
   const int rc = make_c4_map(&tm, in, N, (Cin + 3) / 4, in_groups, H, W, HALO_W, HALO_H);
   if (rc != GFR_OK) return rc;

@@ -253,7 +253,7 @@ def conv3x3_tc_fwd(x, w_packed, bias, Cout, NT, res=None, post=None, post_shift=
         assert post.shape == (N, Cout, H >> post_shift, W >> post_shift)
     rc = _lib.load().gfr_conv3x3_tc_fwd(_ptr(x.data), _ptr(w_packed), _ptr(bias), _ptr(res.data if res is not None else None),
                                         _ptr(post.data if post is not None else None), _ptr(out), N, Cin, groups, Cout, H, W, NT,
-                                        int(post_shift), _ACT[act], float(out_scale), int(precision), _stream())
+                                        int(post_shift), _ACT[act], float(out_scale), int(precision), 1, _stream())
     _lib.check(rc, "gfr_conv3x3_tc_fwd"); _count()
     return C4(out, Cout)
 

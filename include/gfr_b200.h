@@ -236,10 +236,13 @@ int gfr_conv_tc_pack_weights(const float* w_host, int Cin, int Cout, int NT, flo
  *   res C4 [N,Cout,H,W] or NULL; post C4 [N,Cout,H>>post_shift,W>>post_shift] or NULL; out C4 [N,Cout,H,W];
  *   act 0 none, 1 LeakyReLU(0.2), 2 sigmoid;
  *   precision 3 = 3xTF32 (hi*hi + lo*hi + hi*lo, the parity default), 1 = single-pass TF32 (what cuDNN does under
- *   torch.backends.cudnn.allow_tf32, the reference's default on Ampere+; not parity-grade for the depth head). */
+ *   torch.backends.cudnn.allow_tf32, the reference's default on Ampere+; not parity-grade for the depth head);
+ *   weights_static 1: w_packed was NOT written by the kernel that precedes this call in the stream (inference) — the
+ *   kernel is launched with programmatic dependent launch and fetches its weights while the previous layer is still
+ *   running; 0 (training: the pack kernel precedes the conv) fetches them after the dependency has resolved. */
 int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const float* bias, const float* res, const float* post,
                        float* out, int N, int Cin, int in_groups, int Cout, int H, int W, int NT, int post_shift,
-                       int act, float out_scale, int precision, void* stream);
+                       int act, float out_scale, int precision, int weights_static, void* stream);
 
 /* Stem: conv_c1_og (5x5, 3 -> 16, padding 2) + BatchNorm(eval, folded) + LeakyReLU(0.2) on the NHWC image, with the
  * first 2x2 max pool fused (TRAIN:197-201).  img [N,H,W,3]; w_host [16,3,5,5] and bias_host [16] are HOST pointers

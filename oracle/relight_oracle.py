@@ -46,7 +46,9 @@ def depth_to_normals(depth, camera_matrix, normalize_points=False):
     cross-correlation; normals = normalize(cross(d/du, d/dv))."""
     B, _, H, W = depth.shape
     K = camera_matrix.to(depth.dtype)
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=depth.dtype), torch.arange(W, dtype=depth.dtype), indexing="ij")
+    dev = depth.device
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=depth.dtype, device=dev), torch.arange(W, dtype=depth.dtype, device=dev),
+                            indexing="ij")
     fx, fy = K[:, 0, 0].view(-1, 1, 1), K[:, 1, 1].view(-1, 1, 1)
     cx, cy = K[:, 0, 2].view(-1, 1, 1), K[:, 1, 2].view(-1, 1, 1)
     x = (xs[None] - cx) / fx
@@ -56,7 +58,7 @@ def depth_to_normals(depth, camera_matrix, normalize_points=False):
     if normalize_points:
         pts = F.normalize(pts, dim=1, p=2)
     xyz = pts * depth
-    kx = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]], dtype=depth.dtype) / 8.0
+    kx = torch.tensor([[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]], dtype=depth.dtype, device=dev) / 8.0
     k = torch.stack([kx, kx.t()])[:, None]
     g = F.conv2d(F.pad(xyz.reshape(B * 3, 1, H, W), (1, 1, 1, 1), mode="replicate"), k).view(B, 3, 2, H, W)
     a, b = g[:, :, 0], g[:, :, 1]
@@ -69,7 +71,7 @@ def ssim(X, Y, data_range=255, size_average=True, win_size=11, win_sigma=1.5, wi
     nonnegative_ssim=True).  Separable VALID 11-tap Gaussian per channel."""
     c = torch.arange(win_size, dtype=torch.float32) - win_size // 2
     w = torch.exp(-(c ** 2) / (2 * win_sigma ** 2))
-    w = (w / w.sum()).to(X.dtype)
+    w = (w / w.sum()).to(X.dtype).to(X.device)
 
     def gf(x):
         C = x.shape[1]
@@ -89,10 +91,10 @@ def ssim(X, Y, data_range=255, size_average=True, win_size=11, win_sigma=1.5, wi
 # --------------------------------------------------------------------------------------
 # geometry: pixel grid, light point, ray end points
 # --------------------------------------------------------------------------------------
-def pixel_grid(H=IMG, W=IMG):
+def pixel_grid(H=IMG, W=IMG, device="cpu"):
     """TRAIN:51-55: xx = col - W/2, yy = H/2 - row (fp32)."""
-    cols = torch.arange(W, dtype=torch.float32)[None, :].expand(H, W)
-    rows = torch.arange(H, dtype=torch.float32)[:, None].expand(H, W)
+    cols = torch.arange(W, dtype=torch.float32, device=device)[None, :].expand(H, W)
+    rows = torch.arange(H, dtype=torch.float32, device=device)[:, None].expand(H, W)
     return (cols - W / 2.0).contiguous(), (H / 2.0 - rows).contiguous()
 
 
@@ -116,11 +118,11 @@ def ray_endpoints(xx, yy, Lx, Ly):
     lx, ly = float(Lx.detach()) if torch.is_tensor(Lx) else float(Lx), float(Ly.detach()) if torch.is_tensor(Ly) else float(Ly)
 
     def x_edge(xe):
-        x = torch.full((H, W), xe, dtype=torch.float32)
+        x = torch.full((H, W), xe, dtype=torch.float32, device=xx.device)
         return x, slopes * x + intercepts
 
     def y_edge(ye):
-        y = torch.full((H, W), ye, dtype=torch.float32)
+        y = torch.full((H, W), ye, dtype=torch.float32, device=xx.device)
         return (y - intercepts) / (slopes + 0.0001), y
 
     xe = xmin if lx < xmin else (xmax if lx > xmax else None)
@@ -136,8 +138,8 @@ def ray_endpoints(xx, yy, Lx, Ly):
     elif ye is not None:
         ex, ey = y_edge(ye)
     else:
-        ex = torch.full((H, W), lx, dtype=torch.float32)
-        ey = torch.full((H, W), ly, dtype=torch.float32)
+        ex = torch.full((H, W), lx, dtype=torch.float32, device=xx.device)
+        ey = torch.full((H, W), ly, dtype=torch.float32, device=xx.device)
     ex = torch.clamp(ex, xmin, xmax)         # TRAIN:462-465 (hard-coded -128/127/-127/128 for 256x256)
     ey = torch.clamp(ey, ymin, ymax)
     return torch.stack((ex, ey), 0)
@@ -211,8 +213,8 @@ def shadow_march(depth, mask, light_pt, t0=T0, dt=DT, n=NUM_SAMPLES, inside_bonu
     """depth (B,1,H,W) f32; mask (B|1,H,W) (any dtype; ==0 means outside the face);
     light_pt (B,3) f32 = 4013*unit(L).  Returns d_min (B,H,W) f32 (TRAIN:374-515)."""
     B, _, H, W = depth.shape
-    xx, yy = pixel_grid(H, W)
-    t = sample_increments(t0, dt, n)
+    xx, yy = pixel_grid(H, W, depth.device)
+    t = sample_increments(t0, dt, n).to(depth.device)
     outs, args = [], []
     for i in range(B):
         m = mask[i if mask.shape[0] > 1 else 0]
@@ -247,8 +249,8 @@ def shade(depth, K, light_pt, ambient_values):
     Returns normals (B,3,H,W) [after the y flip and 2nd normalise], directional (B,H,W),
     ambient_light (B,H,W), full_shading (B,H,W)."""
     B, _, H, W = depth.shape
-    xx, yy = pixel_grid(H, W)
-    n = depth_to_normals(depth + DEPTH_OFFSET, K)
+    xx, yy = pixel_grid(H, W, depth.device)
+    n = depth_to_normals(depth + DEPTH_OFFSET, K.to(depth.device))
     n = torch.cat((n[:, 0:1], -n[:, 1:2], n[:, 2:3]), 1)                  # TRAIN:354
     P = torch.cat((xx.expand(B, 1, H, W), yy.expand(B, 1, H, W), depth), 1)
     l = F.normalize(light_pt.view(B, 3, 1, 1) - P, p=2, dim=1)            # TRAIN:364
