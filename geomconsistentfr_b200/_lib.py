@@ -45,14 +45,17 @@ _PROTOS = {
     "gfr_c4_to_nchw": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_conv_tc_pack_size": [_c_int, _c_int, _c_int],
     "gfr_conv_tc_pack_weights": [_c_void_p, _c_int, _c_int, _c_int, _c_void_p],
-    "gfr_conv3x3_tc_fwd": [_c_void_p] * 6 + [_c_int] * 9 + [_c_float, _c_int, _c_int, _c_void_p],
+    "gfr_conv3x3_tc_fwd": [_c_void_p] * 6 + [_c_int] * 9 + [_c_float, _c_int, _c_int, _c_float, _c_float, _c_void_p],
+    "gfr_conv_tc_pack_size_f16": [_c_int, _c_int, _c_int],
+    "gfr_conv_tc_pack_weights_f16": [_c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
     "gfr_stem_conv_fwd": [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p],
     "gfr_head_1x1_fwd": [_c_void_p] * 8 + [_c_int] * 5 + [_c_float, _c_void_p],
     "gfr_light_head_c4_fwd": [_c_void_p, _c_int, _c_int, _c_int] + [_c_void_p] * 5 + [_c_int, _c_void_p],
     "gfr_maxpool2_c4_fwd": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_upsample2_c4_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
 }
-_RESTYPES = {"gfr_error_string": ctypes.c_char_p, "gfr_conv_tc_pack_size": ctypes.c_longlong}
+_RESTYPES = {"gfr_error_string": ctypes.c_char_p, "gfr_conv_tc_pack_size": ctypes.c_longlong,
+             "gfr_conv_tc_pack_size_f16": ctypes.c_longlong}
 
 _lib = None
 

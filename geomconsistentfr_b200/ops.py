@@ -233,8 +233,28 @@ def conv_tc_pack_weights(w, NT):
     return packed.to(w.device)
 
 
+X_SCALE_F16 = 64.0     # activations are multiplied by 2^6 before the fp16 pair split (|x| < 1000 stays finite)
+
+
+def conv_tc_pack_weights_f16(w):
+    """w [Cout,Cin,3,3] -> (packed, w_scale, NT) for precision=2 (fp16 pair split); w_scale = the largest power of two
+    with max|w| * w_scale <= 2^14."""
+    wc = w.detach().to("cpu", torch.float32).contiguous()
+    Cout, Cin, K, _ = wc.shape
+    assert K == 3
+    NT = 16 if Cout <= 16 else 32
+    mx = float(wc.abs().max())
+    w_scale = 2.0 ** min(12, int(np.floor(np.log2(16384.0 / max(mx, 1e-30)))))
+    n = _lib.load().gfr_conv_tc_pack_size_f16(Cin, Cout, NT)
+    packed = torch.empty(n, dtype=torch.float32)
+    rc = _lib.load().gfr_conv_tc_pack_weights_f16(ctypes.c_void_p(wc.data_ptr()), Cin, Cout, NT, ctypes.c_float(w_scale),
+                                                  ctypes.c_void_p(packed.data_ptr()))
+    _lib.check(rc, "gfr_conv_tc_pack_weights_f16")
+    return packed.to(w.device), w_scale, NT
+
+
 def conv3x3_tc_fwd(x, w_packed, bias, Cout, NT, res=None, post=None, post_shift=0, act="lrelu", out_scale=1.0,
-                   precision=3, cin=None):
+                   precision=3, cin=None, w_scale=1.0):
     """x: C4; w_packed from conv_tc_pack_weights(w, NT); out = out_scale*(act(conv(x)+bias+res) + up(post)) as C4.
     cin < x.C reads only the leading cin channels of x (TRAIN:225 feature split), in place."""
     N, Cin, H, W = x.shape
@@ -253,7 +273,8 @@ def conv3x3_tc_fwd(x, w_packed, bias, Cout, NT, res=None, post=None, post_shift=
         assert post.shape == (N, Cout, H >> post_shift, W >> post_shift)
     rc = _lib.load().gfr_conv3x3_tc_fwd(_ptr(x.data), _ptr(w_packed), _ptr(bias), _ptr(res.data if res is not None else None),
                                         _ptr(post.data if post is not None else None), _ptr(out), N, Cin, groups, Cout, H, W, NT,
-                                        int(post_shift), _ACT[act], float(out_scale), int(precision), 1, _stream())
+                                        int(post_shift), _ACT[act], float(out_scale), int(precision), 1, X_SCALE_F16, float(w_scale),
+                                        _stream())
     _lib.check(rc, "gfr_conv3x3_tc_fwd"); _count()
     return C4(out, Cout)
 

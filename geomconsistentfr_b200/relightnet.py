@@ -52,7 +52,7 @@ class RelightNet(nn.Module):
         self.depth_offset = 1610.0            # TRAIN:353
         self.march_variant = 0
         self.cnn_impl = "tc"                  # "tc": tcgen05 3xTF32 convs on C4 activations; "direct": exact-fp32 CUDA-core convs
-        self.tc_precision = 3                 # 3 = 3xTF32 (parity grade), 1 = single-pass TF32
+        self.tc_precision = 3                 # 3 = 3xTF32, 2 = fp16 pair split (same ~22-bit products, half the operand bytes), 1 = TF32
 
         for name, cin, cout, k in ENCODER_LAYERS:
             setattr(self, name, nn.Conv2d(cin, cout, k, padding=(k // 2, k // 2)))
@@ -130,7 +130,7 @@ class RelightNet(nn.Module):
     def _tc_weights(self):
         """Per-layer operands of the tensor-core path: 3x3 layers packed for gfr_conv3x3_tc_fwd (device), stem and
         1x1 tail weights on the host (they travel as kernel parameters)."""
-        key = self._fold_key()
+        key = self._fold_key() + (self.tc_precision,)
         if self._tc is not None and self._tc_key == key:
             return self._tc
         f = self._folded_weights()
@@ -138,8 +138,12 @@ class RelightNet(nn.Module):
         for name, (w, b) in f.items():
             Cout, Cin, K, _ = w.shape
             if K == 3 and Cin >= 16:
-                NT = 16 if Cout <= 16 else 32
-                t[name] = (ops.conv_tc_pack_weights(w, NT), b, Cout, NT)
+                if self.tc_precision == 2:                   # fp16 pair split: per-layer power-of-two weight scale
+                    packed, w_scale, NT = ops.conv_tc_pack_weights_f16(w)
+                    t[name] = (packed, b, Cout, NT, w_scale)
+                else:
+                    NT = 16 if Cout <= 16 else 32
+                    t[name] = (ops.conv_tc_pack_weights(w, NT), b, Cout, NT, 1.0)
             else:
                 t[name] = (w.cpu().contiguous(), b.cpu().contiguous())
         self._tc, self._tc_key = t, key
@@ -151,8 +155,8 @@ class RelightNet(nn.Module):
         prec = self.tc_precision
 
         def conv(name, x, **kw):
-            wp, b, Cout, NT = t[name]
-            return ops.conv3x3_tc_fwd(x, wp, b, Cout, NT, precision=prec, **kw)
+            wp, b, Cout, NT, w_scale = t[name]
+            return ops.conv3x3_tc_fwd(x, wp, b, Cout, NT, precision=prec, w_scale=w_scale, **kw)
 
         c1_og, c1 = ops.stem_conv_fwd(img, *t["conv_c1_og"])                # TRAIN:197-201 (conv + BN + LReLU + pool)
         h1_og = conv("conv_h1_2", conv("conv_h1_1", c1), res=c1)

@@ -37,7 +37,7 @@ def _conv_raw(x_data, cin, packed, bias, Cout, NT):
     N, G, H, W, _ = x_data.shape
     out = torch.empty((N, (Cout + 3) // 4, H, W, 4), dtype=torch.float32, device=x_data.device)
     _chk(_lib.load().gfr_conv3x3_tc_fwd(_ptr(x_data), _ptr(packed), _ptr(bias), None, None, _ptr(out), N, cin, G, Cout, H, W, NT,
-                                        0, 0, 1.0, 3, 0, _stream()), "gfr_conv3x3_tc_fwd")
+                                        0, 0, 1.0, 3, 0, 1.0, 1.0, _stream()), "gfr_conv3x3_tc_fwd")
     return out
 
 

@@ -227,6 +227,12 @@ int gfr_c4_to_nchw(const float* in, float* out, int N, int C, int H, int W, void
 long long gfr_conv_tc_pack_size(int Cin, int Cout, int NT);
 int gfr_conv_tc_pack_weights(const float* w_host, int Cin, int Cout, int NT, float* packed_host);
 
+/* The same for precision = 2 (fp16 pair split): weights are multiplied by w_scale (a power of two that keeps
+ * |w|*w_scale < 65000, chosen by the caller from max|w|) and stored as fp16 pairs w1 = fp16(w s), w2 = fp16(w s - w1):
+ * [n_tile][cin_step][tap][8-channel chunk 0..1][w1|w2][n 0..NT-1][8 halfs].  Size in floats. */
+long long gfr_conv_tc_pack_size_f16(int Cin, int Cout, int NT);
+int gfr_conv_tc_pack_weights_f16(const float* w_host, int Cin, int Cout, int NT, float w_scale, float* packed_host);
+
 /* 3x3 convolution (stride 1, padding 1) on the tcgen05 tensor cores, 3xTF32 (fp32-grade accuracy), fused epilogue
  *     out = out_scale * ( act( conv(in) + bias + res ) + up(post) )
  * Replaces one Conv2d / ConvTranspose2d(s=1) + BatchNorm2d(eval) + residual add + LeakyReLU + skip add + nearest x2
@@ -235,14 +241,18 @@ int gfr_conv_tc_pack_weights(const float* w_host, int Cin, int Cout, int NT, flo
  *   (0 = dense; > ceil(Cin/4) reads the leading channels of a wider tensor, TRAIN:225); w_packed (device) from gfr_conv_tc_pack_weights with the same NT; bias [Cout] (device);
  *   res C4 [N,Cout,H,W] or NULL; post C4 [N,Cout,H>>post_shift,W>>post_shift] or NULL; out C4 [N,Cout,H,W];
  *   act 0 none, 1 LeakyReLU(0.2), 2 sigmoid;
- *   precision 3 = 3xTF32 (hi*hi + lo*hi + hi*lo, the parity default), 1 = single-pass TF32 (what cuDNN does under
- *   torch.backends.cudnn.allow_tf32, the reference's default on Ampere+; not parity-grade for the depth head);
+ *   precision 3 = 3xTF32 (hi*hi + lo*hi + hi*lo; full fp32 exponent range: training, gradients), 1 = single-pass TF32
+ *   (what cuDNN does under torch.backends.cudnn.allow_tf32, the reference's default on Ampere+; not parity-grade for
+ *   the depth head), 2 = fp16 pair split (kind::f16, K = 16 per MMA: half the shared-memory operand bytes and MMA count
+ *   of 3xTF32 at the same ~22-bit products; operands are x*x_scale and w*w_scale as fp16 pairs, so |x|*x_scale and
+ *   |w|*w_scale must stay below 65504 — inference on bounded activations; w_packed from gfr_conv_tc_pack_weights_f16);
  *   weights_static 1: w_packed was NOT written by the kernel that precedes this call in the stream (inference) — the
  *   kernel is launched with programmatic dependent launch and fetches its weights while the previous layer is still
  *   running; 0 (training: the pack kernel precedes the conv) fetches them after the dependency has resolved. */
 int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const float* bias, const float* res, const float* post,
                        float* out, int N, int Cin, int in_groups, int Cout, int H, int W, int NT, int post_shift,
-                       int act, float out_scale, int precision, int weights_static, void* stream);
+                       int act, float out_scale, int precision, int weights_static, float x_scale, float w_scale,
+                       void* stream);
 
 /* Stem: conv_c1_og (5x5, 3 -> 16, padding 2) + BatchNorm(eval, folded) + LeakyReLU(0.2) on the NHWC image, with the
  * first 2x2 max pool fused (TRAIN:197-201).  img [N,H,W,3]; w_host [16,3,5,5] and bias_host [16] are HOST pointers

@@ -114,3 +114,20 @@ def test_conv3x3_tc_channel_slice():
     ref = F.conv2d(x[:, :128], w, b, padding=1)
     out = ops.conv3x3_tc_fwd(ops.nchw_to_c4(x), ops.conv_tc_pack_weights(w, 32), b, 64, 32, act=None, cin=128)
     assert (ops.c4_to_nchw(out) - ref).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("N,Cin,Cout,S", [(2, 16, 16, 64), (2, 32, 64, 32), (1, 155, 155, 16), (2, 128, 64, 16)])
+def test_conv3x3_tc_fp16_pair_split_vs_torch(N, Cin, Cout, S):
+    """precision=2 (kind::f16, x = h1 + h2 and w = w1 + w2 as scaled fp16 pairs): same error class as 3xTF32, on
+    activations of RelightNet-like magnitude (|x| up to ~25) including small values (fp16-subnormal corrections)."""
+    from geomconsistentfr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(Cin * 7 + Cout)
+    x = torch.randn(N, Cin, S, S, device="cuda", generator=g) * torch.rand(N, Cin, S, S, device="cuda", generator=g) ** 4 * 20.0
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3.0 * Cin ** 0.5)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    wp, w_scale, NT = ops.conv_tc_pack_weights_f16(w)
+    out = ops.conv3x3_tc_fwd(ops.nchw_to_c4(x), wp, b, Cout, NT, act=None, precision=2, w_scale=w_scale)
+    err = (ops.c4_to_nchw(out).double() - ref).abs().max().item()
+    ref32 = (F.conv2d(x, w, b, padding=1).double() - ref).abs().max().item()
+    assert err <= max(4.0 * ref32, 2e-6 * float(ref.abs().max())), (err, ref32)

@@ -83,12 +83,14 @@ def _interior(mask_u8):
     return box == 49
 
 
-def test_ten_shipped_pngs_batched(net, ffhq):
+@pytest.mark.parametrize("precision", [3, 2])
+def test_ten_shipped_pngs_batched(net, ffhq, precision):
     """The reference's known-answer vectors, FFHQ_relighting_results/*.png (TEST1:614-620 composite), mask
     interior, <= 1 grey level.  All 10 faces go through ONE batched forward per distinct light (the
     reference runs B=1)."""
     from geomconsistentfr_b200 import intrinsic_matrix
     K = intrinsic_matrix().cuda()
+    net.tc_precision = precision
     for i in range(10):
         x = _inputs(ffhq, i)
         m = torch.from_numpy(ffhq["masks"][i].astype(np.float64).reshape(256, 256, 1)) / 255.0
@@ -101,6 +103,7 @@ def test_ten_shipped_pngs_batched(net, ffhq):
         diff = np.abs(bgr - ffhq["pngs_bgr"][i].astype(np.float64))[inside]
         assert diff.max() <= 1.0, (str(ffhq["names"][i]), diff.max())
         assert diff.mean() < 0.02
+    net.tc_precision = 3
 
 
 def test_train_signature_in_eval_mode_vs_oracle(net, oracle_net, ffhq):
