@@ -52,7 +52,8 @@ class RelightNet(nn.Module):
         self.depth_offset = 1610.0            # TRAIN:353
         self.march_variant = 0
         self.cnn_impl = "tc"                  # "tc": tcgen05 3xTF32 convs on C4 activations; "direct": exact-fp32 CUDA-core convs
-        self.tc_precision = 3                 # 3 = 3xTF32, 2 = fp16 pair split (same ~22-bit products, half the operand bytes), 1 = TF32
+        self.tc_precision = 2                 # eval-mode convs: 2 = fp16 pair split (~22-bit products, half the operand bytes; needs
+                                              # |activation| < 4095 — an overflow shows up as inf/NaN, not silently), 3 = 3xTF32, 1 = TF32
 
         for name, cin, cout, k in ENCODER_LAYERS:
             setattr(self, name, nn.Conv2d(cin, cout, k, padding=(k // 2, k // 2)))

@@ -39,7 +39,7 @@ def _inputs(ffhq, idx):
     return x
 
 
-@pytest.mark.parametrize("impl", ["tc", "direct"])
+@pytest.mark.parametrize("impl", ["tc", "tc-f16", "direct"])
 @pytest.mark.parametrize("epoch", [200, 11, 0])
 def test_cnn_vs_oracle(net, oracle_net, ffhq, epoch, impl):
     """CNN (BN folded; "tc" = tcgen05 3xTF32 convs, "direct" = exact-fp32 CUDA-core convs) vs torch fp32 on CPU, all
@@ -48,11 +48,11 @@ def test_cnn_vs_oracle(net, oracle_net, ffhq, epoch, impl):
     x = _inputs(ffhq, [0, 5])
     with torch.no_grad():
         a_ref, d_ref, sl_ref = oracle_net.cnn(x, epoch)
-        net.cnn_impl = impl
+        net.cnn_impl, net.tc_precision = ("tc", 2) if impl == "tc-f16" else (impl, 3)      # "tc" = 3xTF32
         try:
             a, d, sl = net._cnn_eval(x.cuda(), epoch)
         finally:
-            net.cnn_impl = "tc"
+            net.cnn_impl, net.tc_precision = "tc", 2
     assert (a.cpu() - a_ref).abs().max() <= 2e-5
     assert (sl.cpu() - sl_ref).abs().max() <= 2e-5
     assert (d.cpu() - d_ref).abs().max() <= 5e-3
@@ -103,7 +103,7 @@ def test_ten_shipped_pngs_batched(net, ffhq, precision):
         diff = np.abs(bgr - ffhq["pngs_bgr"][i].astype(np.float64))[inside]
         assert diff.max() <= 1.0, (str(ffhq["names"][i]), diff.max())
         assert diff.mean() < 0.02
-    net.tc_precision = 3
+    net.tc_precision = 2
 
 
 def test_train_signature_in_eval_mode_vs_oracle(net, oracle_net, ffhq):

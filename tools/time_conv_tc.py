@@ -32,6 +32,8 @@ for (Cin, Cout, S, NT) in [(16, 16, 16, 16), (16, 16, 256, 16), (16, 16, 128, 16
     xc = ops.nchw_to_c4(x); wp = ops.conv_tc_pack_weights(w, NT)
     us_tc = t(lambda: ops.conv3x3_tc_fwd(xc, wp, b, Cout, NT))
     us_1 = t(lambda: ops.conv3x3_tc_fwd(xc, wp, b, Cout, NT, precision=1))
+    wp16, ws16, nt16 = ops.conv_tc_pack_weights_f16(w)
+    us_16 = t(lambda: ops.conv3x3_tc_fwd(xc, wp16, b, Cout, nt16, precision=2, w_scale=ws16))
     us_d = t(lambda: ops.conv2d_fwd(x, w, b))
     mac = B * S * S * Cin * Cout * 9
-    print("%3d->%3d @%3d NT=%2d: tc %8.1f us (%6.2f TMAC/s)   1xTF32 %8.1f us   direct %8.1f us" % (Cin, Cout, S, NT, us_tc, mac / us_tc / 1e6, us_1, us_d))
+    print("%3d->%3d @%3d NT=%2d: tc %8.1f us (%6.2f TMAC/s)   1xTF32 %8.1f us   fp16x2(NT%d) %8.1f us   direct %8.1f us" % (Cin, Cout, S, NT, us_tc, mac / us_tc / 1e6, us_1, nt16, us_16, us_d))
