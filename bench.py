@@ -158,13 +158,16 @@ def run_train(args, rank, world, local, dist):
     """configs[2]/[3]: generator training step (TRAIN:618, 633-645 minus the PatchGAN terms, 655-656), B = 16 per GPU,
     synthetic batch resident on the device, one NCCL all-reduce of the flat gradient buffer per step."""
     from geomconsistentfr_b200 import RelightNet, intrinsic_matrix, ops
-    from geomconsistentfr_b200.trainer import GeneratorStep
+    from geomconsistentfr_b200 import PatchGAN
+    from geomconsistentfr_b200.trainer import GeneratorStep, TrainStep
     from oracle.relight_oracle import LIGHTS_18, synthetic_face
     B = 16
     net = RelightNet(batch_size=B)
     net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"), strict=True)
     net = net.float().cuda().train()
-    step = GeneratorStep(net, intrinsic_matrix().cuda(), group=None)
+    torch.manual_seed(0)
+    full = not args.no_gan
+    step = TrainStep(net, PatchGAN().cuda(), intrinsic_matrix().cuda()) if full else GeneratorStep(net, intrinsic_matrix().cuda())
     g = torch.Generator().manual_seed(rank)
     img = torch.rand(B, H, W, 3, generator=g).cuda()
     faces = [synthetic_face(seed=rank * B + i) for i in range(B)]
@@ -177,15 +180,22 @@ def run_train(args, rank, world, local, dist):
     n_pre = ops.launch_count()
     step.step(img, 200, *batch)
     launches_per_step = ops.launch_count() - n_pre
+    it = [0]                                             # iteration counter: the discriminator updates every GD_ratio-th (TRAIN:624)
+
+    def kw():
+        it[0] += 1
+        return dict(j=it[0] - 1) if full else {}
+
     if args.no_graph:
         stream = torch.cuda.current_stream()
-        one = lambda: step.step(img, 200, *batch)
+        one = lambda: step.step(img, 200, *batch, **kw())
     else:
         step.capture(img, 200, *batch)
         stream = step._stream
-        one = lambda: step.step_graphed(img, *batch)
+        one = lambda: step.step_graphed(img, *batch, **kw())
     for _ in range(max(args.warmup, 3)):
         one()
+    it[0] = 0
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -205,12 +215,13 @@ def run_train(args, rank, world, local, dist):
         ms = float(t.item())
     if rank == 0:
         print(json.dumps({
-            "metric": "training faces/sec @256x256 (generator step)", "value": world * B * args.steps * 1e3 / ms, "unit": "faces/s",
+            "metric": "training faces/sec @256x256 (%s)" % ("full iteration: generator + PatchGAN" if full else "generator step"), "value": world * B * args.steps * 1e3 / ms, "unit": "faces/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 convs)", "data": "synthetic",
             "config": {"workload": "configs[2]/[3]: generator training step, batch 16 per GPU, 256x256: train-mode RelightNet fwd + "
                                    "masked recon/depth/albedo + ambient + light + DSSIM losses + backward + flat-gradient "
-                                   "all-reduce + fused Adam; PatchGAN terms not built", "global_batch": world * B,
+                                   "all-reduce + fused Adam" + ("; PatchGAN x3 passes, discriminator Adam step every 5th iteration (TRAIN:617-656)" if full else
+                                                               "; PatchGAN terms skipped (--no-gan)"), "global_batch": world * B,
                        "parallelism": "dp%d, one all_reduce of %.1f MB per step" % (world, step.opt.grad.numel() * 4 / 1e6),
                        "working_set": "activations of one step (> L2) are rewritten every step", "cuda_graph": not args.no_graph},
             "gpu_launches": int(ops.launch_count() - n0), "final_loss": float(total)}))
@@ -228,6 +239,7 @@ def main():
     ap.add_argument("--cpu-faces", type=int, default=6, help="faces in the bounded CPU-baseline sample")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--lanes", type=int, default=3, help="runner lanes the e2e (host-buffer) path rotates over")
+    ap.add_argument("--no-gan", action="store_true", help="train workload without the PatchGAN terms")
     ap.add_argument("--workload", default="forward", choices=["forward", "train"],
                     help="forward = configs[1] (the default bench line); train = configs[2]/[3]: generator training step, "
                          "B=16 per GPU, one flat-gradient all-reduce per step")

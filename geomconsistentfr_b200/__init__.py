@@ -9,6 +9,7 @@ andrewhou1/GeomConsistentFR: ray-march shadow mask, Lambertian shading/render, R
 from . import _lib, ops  # noqa: F401
 from .relightnet import RelightNet, intrinsic_matrix  # noqa: F401
 from .runner import RelightRunner  # noqa: F401
+from .patchgan import PatchGAN  # noqa: F401
 from .autograd import ShadowMarch, ShadeRender, SSIMPlanes, MaskedLosses, FlatAdam, dssim_loss  # noqa: F401
 
 __version__ = "0.1.0"

@@ -40,6 +40,12 @@ _PROTOS = {
     "gfr_pw_conv16_bwd": [_c_void_p] * 7 + [_c_int] * 6 + [_c_float, _c_void_p],
     "gfr_stem_conv_train_fwd": [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p],
     "gfr_stem_conv_wgrad": [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p],
+    # PatchGAN support
+    "gfr_space_to_depth": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_depth_to_space": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_lrelu_bwd_c4": [_c_void_p, _c_void_p, _c_void_p, ctypes.c_longlong, _c_void_p],
+    "gfr_conv4x4s1_to1_fwd": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
+    "gfr_conv4x4s1_to1_bwd": [_c_void_p] * 6 + [_c_int] * 4 + [_c_void_p],
     # tensor-core path (C4 layout)
     "gfr_nchw_to_c4": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_c4_to_nchw": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],

@@ -129,11 +129,14 @@ class ConvBNAct(torch.autograd.Function):
             else:                                   # the layer read only the leading channels of a wider tensor (TRAIN:225)
                 g_x = torch.zeros_like(x)
                 g_x[:, :g_in.shape[1]] = g_in
-        g_w = torch.zeros_like(w)
-        g_b4 = torch.zeros(((Cout + 3) // 4) * 4, dtype=torch.float32, device=x.device)
-        _chk(_lib.load().gfr_conv3x3_wgrad(_ptr(x), _ptr(g_raw), _ptr(g_w), _ptr(g_b4), int(deconv), N, cin, G, Cout, H, W, _stream()),
-             "gfr_conv3x3_wgrad", 2)
-        return g_x, g_w, g_b4[:Cout].contiguous(), g_gamma, g_beta, g_res, g_post, None
+        g_w = g_b = None
+        if ctx.needs_input_grad[1]:          # frozen weights (the generator's pass through the discriminator) skip the wgrad
+            g_w = torch.zeros_like(w)
+            g_b4 = torch.zeros(((Cout + 3) // 4) * 4, dtype=torch.float32, device=x.device)
+            _chk(_lib.load().gfr_conv3x3_wgrad(_ptr(x), _ptr(g_raw), _ptr(g_w), _ptr(g_b4), int(deconv), N, cin, G, Cout, H, W,
+                                               _stream()), "gfr_conv3x3_wgrad", 2)
+            g_b = g_b4[:Cout].contiguous()
+        return g_x, g_w, g_b, g_gamma, g_beta, g_res, g_post, None
 
 
 class StemBNAct(torch.autograd.Function):

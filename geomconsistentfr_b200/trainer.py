@@ -3,10 +3,12 @@
     forward (RelightNet in train mode) -> masked recon / depth / albedo losses (K5) + ambient L1 + light cosine +
     DSSIM (K4) -> backward (K2b, K1b, BN / conv backward) -> ONE flat-buffer gradient all-reduce -> fused Adam.
 
-The PatchGAN discriminator (TRAIN:15-35) and its two loss terms (`0.01*BCE(D(composite), 1)` in the generator loss,
-TRAIN:641-642, and the discriminator update, TRAIN:619-631) are NOT built yet: `GeneratorStep` trains the remaining six
-terms of TRAIN:645 and reports which terms it used.  TRAIN = train_raytracing_relighting_CelebAHQ_DSSIM_8x.py."""
+`GeneratorStep` trains the six non-adversarial terms of TRAIN:645; `TrainStep` is the reference's full iteration
+(TRAIN:617-656): discriminator loss on (composite, real) with an Adam step every GD_ratio-th iteration, then the
+generator loss with the 0.01*BCE(D(composite), 1) term (TRAIN:641-642) and its Adam step.
+TRAIN = train_raytracing_relighting_CelebAHQ_DSSIM_8x.py."""
 import torch
+import torch.nn.functional as F
 
 from .autograd import FlatAdam, MaskedLosses, dssim_loss
 
@@ -74,3 +76,79 @@ class GeneratorStep:
         scale = self.opt.all_reduce_grads(self.group)                                     # data parallel: one collective
         self.opt.step(grad_scale=scale)                                                   # TRAIN:656
         return total.detach(), {k: v.detach() for k, v in terms.items()}
+
+
+class TrainStep(GeneratorStep):
+    """The reference's training iteration with the PatchGAN (TRAIN:617-656).  Two equivalences are used to skip work
+    whose results the reference throws away: (1) `d_loss.backward(retain_graph=True)` (TRAIN:625) also back-propagates
+    into the generator, but `optimizer.zero_grad()` (TRAIN:631) clears those gradients before they are used — here the
+    discriminator sees `composite.detach()`; (2) `total_loss.backward()` (TRAIN:655) also fills the discriminator's
+    parameter gradients, which `optimizer_patchgan.zero_grad()` (TRAIN:617) discards — here the discriminator's weights
+    are frozen for that pass (its input gradient still flows).  Parameter updates are identical."""
+
+    def __init__(self, net, patchgan, intrinsic_matrix, lr=None, group=None):
+        super().__init__(net, intrinsic_matrix, lr, group)
+        self.D = patchgan.train()
+        self.opt_d = FlatAdam(list(patchgan.parameters()), lr=net.lr if lr is None else lr)      # TRAIN:590
+        self.GD_ratio = net.GD_ratio
+
+    def step(self, img, epoch, masks_fill, masks, depth_gt, albedo_gt, lighting_gt, j=0):
+        """Iteration j of an epoch.  Returns (total, terms) with the reference's loss names (TRAIN:672-682)."""
+        B, H, W, _ = img.shape
+        update_d = (j % self.GD_ratio) == 0                                               # TRAIN:624
+        self.opt_d.zero_grad()                                                            # TRAIN:617
+        out = self.net(img, epoch, self.K, masks_fill.reshape(B, H, W, 1))                # TRAIN:618
+        rendered = out[5]
+        target = img.permute(0, 3, 1, 2).contiguous()
+        m3 = masks_fill.float()[:, None]
+        composite = rendered * m3 + (1.0 - m3) * target
+        logits_fake = self.D(composite.detach())                                          # TRAIN:619
+        logits_real = self.D(target)                                                      # TRAIN:620
+        d_fake = 0.01 * F.binary_cross_entropy_with_logits(logits_fake, torch.zeros_like(logits_fake))   # TRAIN:621
+        d_real = 0.01 * F.binary_cross_entropy_with_logits(logits_real, torch.ones_like(logits_real))    # TRAIN:622
+        d_loss = d_fake + d_real
+        if update_d:
+            d_loss.backward()                                                             # TRAIN:625
+            self.opt_d.step(grad_scale=self.opt_d.all_reduce_grads(self.group))           # TRAIN:626
+        self.opt.zero_grad()                                                              # TRAIN:631
+        total, terms = self.losses(out, img, masks_fill, masks, depth_gt, albedo_gt, lighting_gt)
+        for p in self.D.parameters():
+            p.requires_grad_(False)
+        try:
+            logits_fake2 = self.D(composite)                                              # TRAIN:641 (after the D update)
+        finally:
+            for p in self.D.parameters():
+                p.requires_grad_(True)
+        g_loss = 0.01 * F.binary_cross_entropy_with_logits(logits_fake2, torch.ones_like(logits_fake2))  # TRAIN:642
+        total = total + g_loss
+        total.backward()                                                                  # TRAIN:655
+        self.opt.step(grad_scale=self.opt.all_reduce_grads(self.group))                   # TRAIN:656
+        terms = dict(terms, generator=g_loss, discriminator=d_loss, discriminator_real=d_real, discriminator_fake=d_fake)
+        return total.detach(), {k: v.detach() for k, v in terms.items()}
+
+    # two graphs: iterations that update the discriminator and iterations that do not
+    def capture(self, img, epoch, masks_fill, masks, depth_gt, albedo_gt, lighting_gt, warmup=2):
+        self._static = [t.clone() for t in (img, masks_fill, masks, depth_gt, albedo_gt, lighting_gt)]
+        self._stream = torch.cuda.Stream(device=img.device)
+        self._stream.wait_stream(torch.cuda.current_stream())
+        self._graphs, self._outs = {}, {}
+        with torch.cuda.stream(self._stream):
+            for _ in range(warmup):
+                for j in (0, 1):
+                    self.step(self._static[0], epoch, *self._static[1:], j=j)
+            self._stream.synchronize()
+            for j in (0, 1):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._stream):
+                    self._outs[j] = self.step(self._static[0], epoch, *self._static[1:], j=j)
+                self._graphs[j] = g
+        torch.cuda.current_stream().wait_stream(self._stream)
+        return self
+
+    def step_graphed(self, img, masks_fill, masks, depth_gt, albedo_gt, lighting_gt, j=0):
+        k = 0 if (j % self.GD_ratio) == 0 else 1
+        with torch.cuda.stream(self._stream):
+            for dst, src in zip(self._static, (img, masks_fill, masks, depth_gt, albedo_gt, lighting_gt)):
+                dst.copy_(src, non_blocking=True)
+            self._graphs[k].replay()
+        return self._outs[k]

@@ -195,6 +195,23 @@ int gfr_stem_conv_train_fwd(const float* img, const float* w, const float* bias,
                             void* stream);
 int gfr_stem_conv_wgrad(const float* img, const float* g_out, float* g_w, float* g_bias, int N, int H, int W, void* stream);
 
+/* ---- PatchGAN discriminator support (TRAIN:15-35) ---------------------------------------------------------------
+ * conv1..conv4 (4x4, stride 2, pad 1) run as 3x3 / stride 1 convolutions on the tensor cores over a space-to-depth of
+ * their input: out[n][c][y][x][2dy+dx] = in[n, c, 2y+dy, 2x+dx] (channel c becomes one C4 group holding its four
+ * phases; H, W even).  in: NCHW planes (in_is_nchw 1, e.g. the [N,3,H,W] image) or C4; out: C4 [N,4C,H/2,W/2].
+ * gfr_depth_to_space is the inverse (= the backward). */
+int gfr_space_to_depth(const float* in, float* out, int N, int C, int H, int W, int in_is_nchw, void* stream);
+int gfr_depth_to_space(const float* g, float* out, int N, int C, int H, int W, int out_is_nchw, void* stream);
+
+/* g_pre = g_y * (y > 0 ? 1 : 0.2): backward of y = LeakyReLU(pre, 0.2) from the forward OUTPUT (n_floats % 4 == 0). */
+int gfr_lrelu_bwd_c4(const float* y, const float* g_y, float* g_pre, long long n_floats, void* stream);
+
+/* conv5 of the PatchGAN: 4x4, stride 1, pad 1, C -> 1 (TRAIN:33).  in C4 [N,C,H,W] (C % 4 == 0); w [1,C,4,4]; bias [1];
+ * out [N,1,H-1,W-1].  Backward: g_in C4 (written, may be NULL), g_w / g_bias (+=, may both be NULL). */
+int gfr_conv4x4s1_to1_fwd(const float* in, const float* w, const float* bias, float* out, int N, int C, int H, int W, void* stream);
+int gfr_conv4x4s1_to1_bwd(const float* in, const float* w, const float* g_out, float* g_in, float* g_w, float* g_bias, int N, int C,
+                          int H, int W, void* stream);
+
 /* fp32 convolution with fused epilogue (exact-fp32 CNN path).  Replaces one
  * Conv2d / ConvTranspose2d(stride 1) + BatchNorm2d(eval, folded into w/bias by the caller) + residual add +
  * LeakyReLU(0.2) / sigmoid + skip add + nearest x2 upsample step of RelightNet (TRAIN:197-350, TEST1:170-323):

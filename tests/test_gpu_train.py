@@ -174,3 +174,88 @@ def test_generator_step_losses_and_all_gradients_vs_oracle():
     bad = {k: v for k, v in worst.items() if v > 3e-2}
     assert not bad, bad
     assert np.median(list(worst.values())) <= 5e-3
+
+
+def test_patchgan_forward_backward_vs_oracle():
+    """PatchGAN (TRAIN:15-35) in train() mode on the library kernels (space-to-depth + tcgen05 3x3, conv5 on CUDA cores) vs
+    the torch oracle: logits, input gradient (what flows back into the generator, TRAIN:641-642) and all parameter gradients."""
+    from geomconsistentfr_b200 import PatchGAN
+    from oracle import relight_oracle as O
+    torch.manual_seed(0)
+    ref = O.PatchGANOracle().cuda().train()
+    mine = PatchGAN().cuda().train()
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    img = torch.rand(4, 3, 256, 256, device="cuda", generator=g)
+    Gl = torch.randn(4, 1, 15, 15, device="cuda", generator=g)
+    xr = img.clone().requires_grad_()
+    lr_ = ref(xr)
+    (lr_ * Gl).sum().backward()
+    xm = img.clone().requires_grad_()
+    lm = mine(xm)
+    assert lm.shape == (4, 1, 15, 15)
+    assert _rel(lm.detach(), lr_.detach()) <= 2e-4
+    (lm * Gl).sum().backward()
+    assert _rel(xm.grad, xr.grad) <= 5e-3
+    for (n1, p1), (n2, p2) in zip(mine.named_parameters(), ref.named_parameters()):
+        assert n1 == n2
+        if n1 in ("conv2.bias", "conv3.bias", "conv4.bias"):
+            continue                                   # bias before a train-mode BN: zero gradient up to rounding
+        assert _rel(p1.grad, p2.grad) <= 1e-2, (n1, _rel(p1.grad, p2.grad))
+    for b1, b2 in zip(mine.buffers(), ref.buffers()):
+        assert (b1.float() - b2.float()).abs().max() <= 1e-4
+
+
+def test_full_train_iteration_losses_vs_oracle():
+    """One iteration of TRAIN:617-656 (j = 0: the discriminator is updated before the generator loss is evaluated):
+    all ten loss terms vs the CPU oracle driven exactly like the reference (torch.optim.Adam on the oracle PatchGAN)."""
+    import torch.nn.functional as F
+    from geomconsistentfr_b200 import PatchGAN, RelightNet, intrinsic_matrix
+    from geomconsistentfr_b200.trainer import TrainStep
+    from oracle import relight_oracle as O
+    f = np.load(os.path.join(G, "ffhq.npz"))
+    sel = [3, 6]
+    B = len(sel)
+    sd = torch.load(os.path.join(G, "model_epoch99.pth"), map_location="cpu")
+    img = torch.from_numpy(f["q"][sel] / 1020.0).float()
+    mf = torch.from_numpy((f["masks"][sel] > 128).astype(np.float32))
+    depth_gt = torch.stack([O.synthetic_face(seed=s)[0] for s in (3, 4)]) * 0.5
+    albedo_gt = torch.rand(B, 256, 256, generator=torch.Generator().manual_seed(2))
+    light_gt = torch.tensor([[0.45, 0.5145, 0.0, 0.8575], [0.55, -0.5843, 0.0, 0.8115]])
+    torch.manual_seed(5)
+    d_ref = O.PatchGANOracle().train()
+    d_sd = {k: v.clone() for k, v in d_ref.state_dict().items()}
+
+    # ---- oracle, the reference's order of operations
+    ref = O.RelightNetOracle(); ref.load_state_dict(sd); ref.train()
+    opt_d = torch.optim.Adam(d_ref.parameters(), lr=1e-4)
+    opt_d.zero_grad()
+    out = ref.forward_train(img, 200, O.intrinsic_matrix(), mf.double().view(B, 256, 256, 1))
+    albedo, depth, _, _, _, rendered, unit_l, amb_v = out
+    m3 = mf[:, None].repeat(1, 3, 1, 1); target = img.permute(0, 3, 1, 2)
+    comp = rendered * m3 + (1.0 - m3) * target
+    lf, lr_ = d_ref(comp), d_ref(target)
+    t_ref = dict(discriminator_fake=0.01 * F.binary_cross_entropy_with_logits(lf, torch.zeros_like(lf)),
+                 discriminator_real=0.01 * F.binary_cross_entropy_with_logits(lr_, torch.ones_like(lr_)))
+    (t_ref["discriminator_fake"] + t_ref["discriminator_real"]).backward(retain_graph=True)
+    opt_d.step()
+    lf2 = d_ref(comp)
+    t_ref["generator"] = 0.01 * F.binary_cross_entropy_with_logits(lf2, torch.ones_like(lf2))
+    t_ref["recon"] = 20.0 * ((rendered * m3.double() - target * m3.double()) ** 2).sum() / m3.double().sum()
+    t_ref["DSSIM"] = 8.0 * (1 - O.ssim(comp, target, data_range=1.0, size_average=True, nonnegative_ssim=True)) / 2.0
+
+    # ---- library
+    net = RelightNet(batch_size=B); net.load_state_dict(sd, strict=True); net = net.float().cuda().train()
+    D = PatchGAN(); D.load_state_dict(d_sd, strict=True); D = D.cuda().train()
+    step = TrainStep(net, D, intrinsic_matrix().cuda())
+    c = lambda t: t.cuda()
+    total, terms = step.step(c(img), 200, c(mf), c(mf), c(depth_gt), c(albedo_gt), c(light_gt), j=0)
+    assert set(terms) == {"recon", "depth", "ambient", "lighting", "albedo", "DSSIM", "generator", "discriminator",
+                          "discriminator_real", "discriminator_fake"}                       # TRAIN:672-682
+    for k, v in t_ref.items():
+        a, b = float(terms[k]), float(v)
+        assert abs(a - b) <= 2e-3 * max(abs(b), 1e-4), (k, a, b)
+    # the discriminator really moved (Adam step on every parameter that has a gradient) and stayed finite
+    moved = sum(float((p.detach().cpu() - d_sd[n]).abs().max()) > 0 for n, p in D.named_parameters())
+    assert moved >= 10 and all(torch.isfinite(p).all() for p in D.parameters())
+    assert torch.isfinite(total)
