@@ -12,6 +12,9 @@
 // The face mask is 1 bit/pixel in shared memory (8 KB for 256x256).
 #include "gfr_common.cuh"
 
+#include <math.h>
+#include <stdlib.h>
+
 namespace {
 
 struct SampleTable { double t[GFR_MAX_SAMPLES]; };
@@ -26,6 +29,7 @@ struct MarchArgs {
   int mask_stride;           // words
   int B, H, W, n;
   int lpf;                   // lights per face: (face, light) pair b reads depth / mask of face b / lpf
+  float t0, inv_dt;          // uniform sample table t_k = t0 + k*dt (inv_dt = 0: not uniform, no sample-range culling)
   float bonus;
 };
 
@@ -190,10 +194,36 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
   const float bcx = __fsub_rn(Lx, x), bcy = __fsub_rn(Ly, y), bcz = __fsub_rn(Lz, z); // BC, TRAIN:507
   const int cW = W >> 1, cH = H >> 1;
 
+  // Sample-range culling (exact): a sample can only pass the face-mask test if its nearest pixel lies in the bounding box
+  // of the mask, i.e. for t in an interval that is solved here in fp32 with a 0.01-pixel / one-sample safety margin; the
+  // warp walks the union of its 32 intervals (uniform bounds, uniform table loads), everything outside is 1e6 anyway.
+  int k_begin = 0, k_end = a.n - 1;
+  if (a.inv_dt != 0.f) {
+    const int* bb = reinterpret_cast<const int*>(a.mask_bits + (size_t)f * a.mask_stride + words);
+    const int c_lo = __ldg(bb), c_hi = -__ldg(bb + 1), r_lo = __ldg(bb + 2), r_hi = -__ldg(bb + 3);
+    float tlo = 0.f, thi = 1.f;
+    bool none = c_lo > c_hi;
+    const float xa = (float)(c_lo - cW) - 0.51f, xb = (float)(c_hi - cW) + 0.51f;
+    const float ya = (float)(cH - r_hi) - 0.51f, yb = (float)(cH - r_lo) + 0.51f;
+    const float dxf = __fsub_rn(ex, x), dyf = __fsub_rn(ey, y);
+    if (fabsf(dxf) > 1e-6f) {
+      const float t1 = (xa - x) / dxf, t2 = (xb - x) / dxf;
+      tlo = fmaxf(tlo, fminf(t1, t2)); thi = fminf(thi, fmaxf(t1, t2));
+    } else if (x < xa || x > xb) none = true;
+    if (fabsf(dyf) > 1e-6f) {
+      const float t1 = (ya - y) / dyf, t2 = (yb - y) / dyf;
+      tlo = fmaxf(tlo, fminf(t1, t2)); thi = fminf(thi, fmaxf(t1, t2));
+    } else if (y < ya || y > yb) none = true;
+    int kl = (int)floorf((tlo - a.t0) * a.inv_dt) - 1, kh = (int)ceilf((thi - a.t0) * a.inv_dt) + 1;
+    if (none || tlo > thi) { kl = a.n; kh = -1; }
+    k_begin = max(__reduce_min_sync(0xffffffffu, kl), 0);
+    k_end = min(__reduce_max_sync(0xffffffffu, kh), a.n - 1);
+  }
+
   float qmin = __int_as_float(0x7f800000);   // +inf == "outside the face"
   int kmin = 255;
 #pragma unroll 2
-  for (int k = 0; k < a.n; ++k) {
+  for (int k = k_begin; k <= k_end; ++k) {
     const double t = tab.t[k];
     const double px = __dadd_rn(xd, __dmul_rn(t, dx));                                // TRAIN:472,480
     const double py = __dadd_rn(yd, __dmul_rn(t, dy));
@@ -254,11 +284,26 @@ __global__ void widen_depth_kernel(const float4* __restrict__ in, double* __rest
 // mask packing
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void mask_pack_kernel(const T* __restrict__ mask, uint32_t* __restrict__ bits, size_t n_pixels) {
+__global__ void mask_pack_kernel(const T* __restrict__ mask, uint32_t* __restrict__ bits, size_t n_pixels, int H, int W) {
+  // row of mask m in `bits`: H*W/32 bitmap words, then GFR_MASK_EXTRA_WORDS = 4 words {c_lo, -c_hi, r_lo, -r_hi}: the bounding
+  // box of the non-zero pixels, kept with atomicMin (the buffer is pre-filled with 0x7f bytes)
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool nz = i < n_pixels ? (mask[i] != (T)0) : false;
   const uint32_t w = __ballot_sync(0xffffffffu, nz);
-  if ((threadIdx.x & 31) == 0 && i < n_pixels) bits[i >> 5] = w;
+  const size_t hw = (size_t)H * W;
+  const size_t m = i / hw, p = i % hw;
+  const size_t row_words = hw / 32 + GFR_MASK_EXTRA_WORDS;
+  if ((threadIdx.x & 31) == 0 && i < n_pixels) bits[m * row_words + (p >> 5)] = w;
+  if (w != 0u) {                     // hw % 32 == 0: the 32 pixels of a warp belong to one mask
+    const int r = (int)(p / W), c = (int)(p % W);
+    const int big = 0x7f7f7f7f;
+    const int c_lo = __reduce_min_sync(0xffffffffu, nz ? c : big), c_hi_n = __reduce_min_sync(0xffffffffu, nz ? -c : big);
+    const int r_lo = __reduce_min_sync(0xffffffffu, nz ? r : big), r_hi_n = __reduce_min_sync(0xffffffffu, nz ? -r : big);
+    if ((threadIdx.x & 31) == 0) {
+      int* bb = reinterpret_cast<int*>(bits + m * row_words + hw / 32);
+      atomicMin(bb + 0, c_lo); atomicMin(bb + 1, c_hi_n); atomicMin(bb + 2, r_lo); atomicMin(bb + 3, r_hi_n);
+    }
+  }
 }
 
 }  // namespace
@@ -270,10 +315,12 @@ extern "C" int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int 
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   cudaStream_t s = (cudaStream_t)stream;
+  const cudaError_t e = cudaMemsetAsync(bits, 0x7f, (size_t)n_masks * ((size_t)H * W / 32 + GFR_MASK_EXTRA_WORDS) * 4, s);
+  if (e != cudaSuccess) return (int)e;
   switch (mask_dtype) {
-    case GFR_MASK_U8: mask_pack_kernel<uint8_t><<<blocks, threads, 0, s>>>((const uint8_t*)mask, bits, n); break;
-    case GFR_MASK_F32: mask_pack_kernel<float><<<blocks, threads, 0, s>>>((const float*)mask, bits, n); break;
-    case GFR_MASK_F64: mask_pack_kernel<double><<<blocks, threads, 0, s>>>((const double*)mask, bits, n); break;
+    case GFR_MASK_U8: mask_pack_kernel<uint8_t><<<blocks, threads, 0, s>>>((const uint8_t*)mask, bits, n, H, W); break;
+    case GFR_MASK_F32: mask_pack_kernel<float><<<blocks, threads, 0, s>>>((const float*)mask, bits, n, H, W); break;
+    case GFR_MASK_F64: mask_pack_kernel<double><<<blocks, threads, 0, s>>>((const double*)mask, bits, n, H, W); break;
     default: return GFR_E_ARG;
   }
   return gfr_launch_status();
@@ -287,13 +334,21 @@ extern "C" int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bit
   GFR_RETURN_IF_NULL(t_host); GFR_RETURN_IF_NULL(d_min);
   if (B <= 0 || H <= 0 || W <= 0 || (W % TILE_W) || (H % TILE_H) || H > 512 || W > 512 || B > 65535) return GFR_E_SHAPE;
   if (n <= 0 || n > 255) return GFR_E_ARG;     // 255 is the "no sample inside the face" argmin code
-  if (mask_batch_stride != 0 && mask_batch_stride != (H * W) / 32) return GFR_E_ARG;
+  if (mask_batch_stride != 0 && mask_batch_stride != (H * W) / 32 + GFR_MASK_EXTRA_WORDS) return GFR_E_ARG;
   if (variant < 0 || variant > 1) return GFR_E_ARG;
   if (lights_per_face < 1 || B % lights_per_face) return GFR_E_ARG;
   const int faces = B / lights_per_face;
   SampleTable tab;
   for (int k = 0; k < GFR_MAX_SAMPLES; ++k) tab.t[k] = k < n ? t_host[k] : 0.0;
-  MarchArgs a{depth, mask_bits, light_pt, d_min, argmin, shadow, mask_batch_stride, B, H, W, n, lights_per_face, inside_bonus};
+    // culling needs t_k = t0 + k*dt (true for the reference's np.arange table); any other table marches every sample
+  float t0 = (float)t_host[0], inv_dt = 0.f;
+  if (n >= 2) {
+    const double dt = (t_host[n - 1] - t_host[0]) / (n - 1);
+    bool uniform = dt > 0.0;
+    for (int k = 0; k < n && uniform; ++k) uniform = fabs(t_host[k] - (t_host[0] + k * dt)) <= 1e-9;
+    if (uniform && getenv("GFR_MARCH_NO_CULL") == nullptr) inv_dt = (float)(1.0 / dt);
+  }
+  MarchArgs a{depth, mask_bits, light_pt, d_min, argmin, shadow, mask_batch_stride, B, H, W, n, lights_per_face, t0, inv_dt, inside_bonus};
   const dim3 grid(W / TILE_W, H / TILE_H, B), block(TILE_W, TILE_H);
   const size_t smem = (size_t)(H * W / 32) * sizeof(uint32_t);
   if (variant == 0 && depth64_scratch != nullptr && ((size_t)faces * H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0) {

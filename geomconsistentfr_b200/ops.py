@@ -49,15 +49,18 @@ def _need(t, dtype, name):
     return t if t.is_contiguous() else t.contiguous()
 
 
+MASK_EXTRA_WORDS = 4      # GFR_MASK_EXTRA_WORDS: the bounding box of the mask rides behind its bitmap
+
+
 def mask_pack(mask):
-    """mask [n,H,W] (u8/bool/f32/f64, CUDA) -> bits [n, H*W/32] int32 (bit set iff mask != 0; TRAIN:510)."""
+    """mask [n,H,W] (u8/bool/f32/f64, CUDA) -> bits [n, H*W/32 + 4] int32 (bit set iff mask != 0, TRAIN:510; + bbox)."""
     if not (torch.is_tensor(mask) and mask.is_cuda):
         raise RuntimeError("mask must be a CUDA tensor")
     if mask.dtype not in _MASK_DTYPES:
         raise RuntimeError("unsupported mask dtype %s" % mask.dtype)
     mask = mask.contiguous()
     n, H, W = mask.shape
-    bits = torch.empty((n, H * W // 32), dtype=torch.int32, device=mask.device)
+    bits = torch.empty((n, H * W // 32 + MASK_EXTRA_WORDS), dtype=torch.int32, device=mask.device)
     rc = _lib.load().gfr_mask_pack(_ptr(mask), _MASK_DTYPES[mask.dtype], n, H, W, _ptr(bits), _stream())
     _lib.check(rc, "gfr_mask_pack"); _count()
     return bits
@@ -74,13 +77,13 @@ def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0,
     B = light_pt.shape[0]
     if light_pt.dim() != 2 or light_pt.shape[1] != 3 or B % F:
         raise RuntimeError("light_pt must be [F*L,3]")
-    if mask_bits.shape[0] not in (1, F) or mask_bits.shape[1] != H * W // 32:
-        raise RuntimeError("mask_bits must be [1|F, H*W/32]")
+    if mask_bits.shape[0] not in (1, F) or mask_bits.shape[1] != H * W // 32 + MASK_EXTRA_WORDS:
+        raise RuntimeError("mask_bits must be [1|F, H*W/32 + 4] (from mask_pack)")
     t = reference_samples() if samples is None else np.ascontiguousarray(samples, dtype=np.float64)
     dmin = torch.empty((B, H, W), dtype=torch.float32, device=depth.device)
     arg = torch.empty((B, H, W), dtype=torch.uint8, device=depth.device) if want_argmin else None
     shadow = torch.empty((B, H, W), dtype=torch.float32, device=depth.device) if want_shadow else None
-    stride = 0 if mask_bits.shape[0] == 1 else H * W // 32
+    stride = 0 if mask_bits.shape[0] == 1 else H * W // 32 + MASK_EXTRA_WORDS
     scratch = torch.empty((F, H, W), dtype=torch.float64, device=depth.device) if variant == 0 else None
     rc = _lib.load().gfr_shadow_march_fwd(
         _ptr(depth), _ptr(mask_bits), stride, _ptr(light_pt), t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]),

@@ -39,17 +39,21 @@ const char* gfr_error_string(int code);
 #define GFR_MASK_F32 1
 #define GFR_MASK_F64 2
 
+#define GFR_MASK_EXTRA_WORDS 4
+
 /* Face-mask bit packing.  The march only ever tests `mask[r, c] == 0` (TRAIN:510, TEST1:488), so the
  * mask travels as 1 bit per pixel: bit (r*W + c) & 31 of word (r*W + c) >> 5 is set iff mask != 0.
- * mask: [n_masks, H, W] of the given dtype; bits: [n_masks, H*W/32] uint32.  H*W must be a multiple of 32. */
+ * mask: [n_masks, H, W] of the given dtype; bits: [n_masks, H*W/32 + GFR_MASK_EXTRA_WORDS] uint32 — each row is the
+ * bitmap followed by the bounding box of the non-zero pixels as int32 {c_lo, -c_hi, r_lo, -r_hi} (the march uses it to
+ * skip samples that cannot lie on the face).  H*W must be a multiple of 32. */
 int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int H, int W, uint32_t* bits, void* stream);
 
 /* Ray-march forward: minimum point-to-ray distance over the samples, per pixel.
  * Replaces TRAIN:374-515 / TEST1:351-496 (end points, 160 fp64 sample positions, bilinear depth,
  * point-to-line distance, face-mask reject, min, optional "+5 when the light projects inside the image").
  *   depth      [B,1,H,W]   raw depth (100 x the depth head), fp32
- *   mask_bits  [1|B, H*W/32] from gfr_mask_pack; mask_batch_stride = 0 (one mask for the batch,
- *              TEST1:488) or H*W/32 (one per image, TRAIN:510), in uint32 words
+ *   mask_bits  [1|B, H*W/32 + 4] from gfr_mask_pack; mask_batch_stride = 0 (one mask for the batch,
+ *              TEST1:488) or H*W/32 + GFR_MASK_EXTRA_WORDS (one per image, TRAIN:510), in uint32 words
  *   light_pt   [B,3]       light_distance * unit(L)   (TRAIN:360-363)
  *   t_host     [n] HOST doubles: the sample parameters, exactly np.arange(0.025, 0.825, 0.005) for the
  *              reference configuration (TRAIN:468); n <= GFR_MAX_SAMPLES

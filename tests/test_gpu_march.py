@@ -86,9 +86,33 @@ def test_mask_pack_dtypes(ops, march):
     for t in (m.float() / 255.0, m.double() / 255.0, m > 0):
         assert torch.equal(ops.mask_pack(t.cuda()), ref)
     flat = (m.view(-1) != 0).numpy()
-    words = ref.cpu().numpy().view(np.uint32).reshape(-1)
+    row = ref.cpu().numpy()[0]
+    words = row[:256 * 256 // 32].view(np.uint32)
     bits = ((words[:, None] >> np.arange(32, dtype=np.uint32)[None]) & 1).astype(bool).reshape(-1)
     assert np.array_equal(bits, flat)
+    rr, cc = np.nonzero(march["mask_u8"])                       # the 4 extra words: bounding box {c_lo, -c_hi, r_lo, -r_hi}
+    assert list(row[-4:]) == [cc.min(), -cc.max(), rr.min(), -rr.max()]
+    empty = ops.mask_pack(torch.zeros(1, 64, 64, dtype=torch.uint8, device="cuda")).cpu().numpy()[0]
+    assert not empty[:-4].any() and empty[-4] > -empty[-3]       # empty mask: c_lo > c_hi
+
+
+def test_march_culling_is_exact_on_offcentre_masks(ops):
+    """Sample-range culling against the mask bounding box (variant 0) vs the cull-free literal kernel (variant 1):
+    bit-identical d_min / argmin for small, off-centre, ragged and empty masks and lights on every side."""
+    H = W = 128
+    g = torch.Generator().manual_seed(21)
+    depth = (torch.rand(4, 1, H, W, generator=g) * 40.0).cuda()
+    masks = torch.zeros(4, H, W, dtype=torch.uint8)
+    masks[0, 10:30, 90:120] = 1
+    masks[1, 100:128, 0:25] = 255
+    masks[2] = (torch.rand(H, W, generator=g) > 0.97).to(torch.uint8)
+    bits = ops.mask_pack(masks.cuda())                                                       # mask 3 stays empty
+    L = torch.tensor([(0.7, 0.1, 0.7), (-0.6, -0.5, 0.62), (0.004, 0.003, 1.0), (0.0, 0.7071, 0.7071)])
+    P_L = (4013.0 * torch.nn.functional.normalize(L, dim=1)).cuda()
+    d0, a0, _ = ops.shadow_march_fwd(depth, bits, P_L, inside_bonus=5.0, want_argmin=True, variant=0)
+    d1, a1, _ = ops.shadow_march_fwd(depth, bits, P_L, inside_bonus=5.0, want_argmin=True, variant=1)
+    assert torch.equal(d0, d1) and torch.equal(a0, a1)
+    assert float(d0[3].min()) >= 1e6                                                         # empty mask: every ray misses
 
 
 def test_shade_render_vs_oracle(ops, march):
