@@ -16,6 +16,8 @@ _PROTOS = {
     "gfr_shadow_march_fwd": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_float,
                              _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_shade_render_fwd": [_c_void_p] * 11 + [_c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_march_shade_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_float] + [_c_void_p] * 9
+                           + [_c_int] * 4 + [_c_void_p],
     "gfr_shadow_march_bwd": [_c_void_p] * 5 + [_c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_shade_render_bwd": [_c_void_p] * 16 + [_c_int, _c_int, _c_int, _c_void_p],
     "gfr_conv2d_fwd": [_c_void_p] * 7 + [_c_int] * 9 + [_c_float, _c_void_p],

@@ -11,6 +11,7 @@
 // ~1e-4 of the pixels.  Everything after `.float()` in the reference (TRAIN:502) is fp32 here too.
 // The face mask is 1 bit/pixel in shared memory (8 KB for 256x256).
 #include "gfr_common.cuh"
+#include "shade_device.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -30,6 +31,8 @@ struct MarchArgs {
   int B, H, W, n;
   int lpf;                   // lights per face: (face, light) pair b reads depth / mask of face b / lpf
   float t0, inv_dt;          // uniform sample table t_k = t0 + k*dt (inv_dt = 0: not uniform, no sample-range culling)
+  int fuse_shade;            // 1: normals + Lambert + blend + render of the pixel follow in the same thread (shade)
+  gfr_shade::ShadeArgs shade;
   float bonus;
 };
 
@@ -266,9 +269,10 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
   }
   if (a.bonus != 0.0f && Lx >= xmin && Lx <= xmax && Ly >= ymin && Ly <= ymax) d = __fadd_rn(d, a.bonus);   // TEST1:495-496
   const size_t o = (size_t)b * H * W + row * W + col;
-  a.dmin[o] = d;
+  if (a.dmin) a.dmin[o] = d;
   if (a.argmin) a.argmin[o] = (uint8_t)kmin;
-  if (a.shadow) a.shadow[o] = shadow_weight(d);
+  if (a.fuse_shade) gfr_shade::shade_pixel(a.shade, b, row, col, d);       // TRAIN:353-369, 517-522: d_min never leaves the SM
+  else if (a.shadow) a.shadow[o] = shadow_weight(d);
 }
 
 __global__ void widen_depth_kernel(const float4* __restrict__ in, double* __restrict__ out, size_t n4) {
@@ -326,12 +330,14 @@ extern "C" int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int 
   return gfr_launch_status();
 }
 
-extern "C" int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
-                                    const float* light_pt, const double* t_host, int n, float inside_bonus,
-                                    float* d_min, uint8_t* argmin, float* shadow, double* depth64_scratch, int B, int H,
-                                    int W, int lights_per_face, int variant, void* stream) {
+static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_batch_stride, const float* light_pt,
+                      const double* t_host, int n, float inside_bonus, float* d_min, uint8_t* argmin, float* shadow,
+                      double* depth64_scratch, int B, int H, int W, int lights_per_face, int variant,
+                      const gfr_shade::ShadeArgs* fuse, void* stream) {
   GFR_RETURN_IF_NULL(depth); GFR_RETURN_IF_NULL(mask_bits); GFR_RETURN_IF_NULL(light_pt);
-  GFR_RETURN_IF_NULL(t_host); GFR_RETURN_IF_NULL(d_min);
+  GFR_RETURN_IF_NULL(t_host);
+  if (fuse == nullptr) GFR_RETURN_IF_NULL(d_min);
+  if (fuse != nullptr && (variant != 0 || depth64_scratch == nullptr)) return GFR_E_ARG;
   if (B <= 0 || H <= 0 || W <= 0 || (W % TILE_W) || (H % TILE_H) || H > 512 || W > 512 || B > 65535) return GFR_E_SHAPE;
   if (n <= 0 || n > 255) return GFR_E_ARG;     // 255 is the "no sample inside the face" argmin code
   if (mask_batch_stride != 0 && mask_batch_stride != (H * W) / 32 + GFR_MASK_EXTRA_WORDS) return GFR_E_ARG;
@@ -348,10 +354,16 @@ extern "C" int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bit
     for (int k = 0; k < n && uniform; ++k) uniform = fabs(t_host[k] - (t_host[0] + k * dt)) <= 1e-9;
     if (uniform && getenv("GFR_MARCH_NO_CULL") == nullptr) inv_dt = (float)(1.0 / dt);
   }
-  MarchArgs a{depth, mask_bits, light_pt, d_min, argmin, shadow, mask_batch_stride, B, H, W, n, lights_per_face, t0, inv_dt, inside_bonus};
+  MarchArgs a = {};
+  a.depth = depth; a.mask_bits = mask_bits; a.light = light_pt; a.dmin = d_min; a.argmin = argmin; a.shadow = shadow;
+  a.mask_stride = mask_batch_stride; a.B = B; a.H = H; a.W = W; a.n = n; a.lpf = lights_per_face; a.t0 = t0; a.inv_dt = inv_dt;
+  a.bonus = inside_bonus;
+  if (fuse != nullptr) { a.fuse_shade = 1; a.shade = *fuse; }
   const dim3 grid(W / TILE_W, H / TILE_H, B), block(TILE_W, TILE_H);
   const size_t smem = (size_t)(H * W / 32) * sizeof(uint32_t);
-  if (variant == 0 && depth64_scratch != nullptr && ((size_t)faces * H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0) {
+  const bool fast_ok = ((size_t)faces * H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
+  if (fuse != nullptr && !fast_ok) return GFR_E_SHAPE;
+  if (variant == 0 && depth64_scratch != nullptr && fast_ok) {
     const size_t n4 = (size_t)faces * H * W / 4;
     widen_depth_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch, n4);
     shadow_march_fwd_fast<<<grid, block, smem, (cudaStream_t)stream>>>(a, depth64_scratch, tab);
@@ -359,4 +371,25 @@ extern "C" int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bit
     shadow_march_fwd_l1<<<grid, block, smem, (cudaStream_t)stream>>>(a, tab);
   }
   return gfr_launch_status();
+}
+
+extern "C" int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
+                                    const float* light_pt, const double* t_host, int n, float inside_bonus,
+                                    float* d_min, uint8_t* argmin, float* shadow, double* depth64_scratch, int B, int H,
+                                    int W, int lights_per_face, int variant, void* stream) {
+  return march_impl(depth, mask_bits, mask_batch_stride, light_pt, t_host, n, inside_bonus, d_min, argmin, shadow, depth64_scratch,
+                    B, H, W, lights_per_face, variant, nullptr, stream);
+}
+
+extern "C" int gfr_march_shade_fwd(const float* albedo, const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
+                                   const float* light_pt, const float* ambient, const double* t_host, int n, float inside_bonus,
+                                   const float* intr_host, double* depth64_scratch, float* d_min, uint8_t* argmin, float* shadow,
+                                   float* full, float* final_shading, float* rendered, float* normals, int B, int H, int W,
+                                   int lights_per_face, void* stream) {
+  GFR_RETURN_IF_NULL(ambient); GFR_RETURN_IF_NULL(intr_host); GFR_RETURN_IF_NULL(depth64_scratch);
+  if (rendered != nullptr && albedo == nullptr) return GFR_E_NULL;
+  gfr_shade::ShadeArgs sh{albedo, depth, nullptr, light_pt, ambient, shadow, full, final_shading, rendered, normals, B, H, W,
+                          lights_per_face, intr_host[0], intr_host[1], intr_host[2], intr_host[3], intr_host[4], intr_host[5]};
+  return march_impl(depth, mask_bits, mask_batch_stride, light_pt, t_host, n, inside_bonus, d_min, argmin, nullptr, depth64_scratch,
+                    B, H, W, lights_per_face, 0, &sh, stream);
 }

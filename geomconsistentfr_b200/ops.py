@@ -121,6 +121,41 @@ def shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx=1570.0, fy=1570
     return out
 
 
+def march_shade_fwd(albedo, depth, mask_bits, light_pt, ambient, inside_bonus=0.0, fx=1570.0, fy=1570.0, cx=None, cy=None,
+                    depth_offset=1610.0, intensity=0.5, want=("shadow", "full", "final", "rendered", "normals")):
+    """shadow_march_fwd + shade_render_fwd in one launch (d_min stays on the SM).  Same arguments / outputs as the pair;
+    returns the dict of the requested outputs ([B,...], B = F * lights per face)."""
+    depth = _need(depth, torch.float32, "depth")
+    light_pt = _need(light_pt, torch.float32, "light_pt")
+    mask_bits = _need(mask_bits, torch.int32, "mask_bits")
+    ambient = _need(ambient.reshape(-1), torch.float32, "ambient")
+    F, _, H, W = depth.shape
+    B = light_pt.shape[0]
+    if light_pt.dim() != 2 or light_pt.shape[1] != 3 or B % F or ambient.shape[0] != F:
+        raise RuntimeError("march_shade_fwd: light_pt must be [F*L,3], ambient [F]")
+    if mask_bits.shape[0] not in (1, F) or mask_bits.shape[1] != H * W // 32 + MASK_EXTRA_WORDS:
+        raise RuntimeError("mask_bits must be [1|F, H*W/32 + 4] (from mask_pack)")
+    if "rendered" in want:
+        albedo = _need(albedo, torch.float32, "albedo")
+    t = reference_samples()
+    intr = np.array([fx, fy, W / 2.0 if cx is None else cx, H / 2.0 if cy is None else cy, depth_offset, intensity],
+                    dtype=np.float32)
+    dev = depth.device
+    out = {}
+    for k, shape in (("shadow", (B, H, W)), ("full", (B, H, W)), ("final", (B, H, W)), ("rendered", (B, 3, H, W)),
+                     ("normals", (B, 3, H, W)), ("d_min", (B, H, W))):
+        out[k] = torch.empty(shape, dtype=torch.float32, device=dev) if k in want else None
+    stride = 0 if mask_bits.shape[0] == 1 else H * W // 32 + MASK_EXTRA_WORDS
+    scratch = torch.empty((F, H, W), dtype=torch.float64, device=dev)
+    rc = _lib.load().gfr_march_shade_fwd(
+        _ptr(albedo) if "rendered" in want else None, _ptr(depth), _ptr(mask_bits), stride, _ptr(light_pt), _ptr(ambient),
+        t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]), float(inside_bonus), intr.ctypes.data_as(ctypes.c_void_p),
+        _ptr(scratch), _ptr(out["d_min"]), None, _ptr(out["shadow"]), _ptr(out["full"]), _ptr(out["final"]),
+        _ptr(out["rendered"]), _ptr(out["normals"]), B, H, W, B // F, _stream())
+    _lib.check(rc, "gfr_march_shade_fwd"); _count(2)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # CNN building blocks (fp32 direct path)
 # ---------------------------------------------------------------------------------------------------

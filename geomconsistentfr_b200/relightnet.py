@@ -357,11 +357,14 @@ class RelightNet(nn.Module):
             L = torch.cat((L[:, 0:2], torch.clamp(L[:, 2:3], min=0.0)), 1)
         unit = torch.nn.functional.normalize(L, p=2, dim=1)                 # TRAIN:360
         light_pt = (self.light_distance * unit).contiguous()                # TRAIN:362
-        d_min, _, _ = ops.shadow_march_fwd(depth, mask_bits, light_pt, inside_bonus=inside_bonus,
-                                           variant=self.march_variant)
         fx, fy, cx, cy = self._intrinsics(intrinsic_matrix)
-        o = ops.shade_render_fwd(albedo, depth, d_min, light_pt, ambient_values, fx, fy, cx, cy,
-                                 self.depth_offset, self.directional_intensity)
+        if self.march_variant == 0:          # one launch: every thread shades its pixel right after its ray march
+            o = ops.march_shade_fwd(albedo, depth, mask_bits, light_pt, ambient_values, inside_bonus, fx, fy, cx, cy,
+                                    self.depth_offset, self.directional_intensity)
+        else:
+            d_min, _, _ = ops.shadow_march_fwd(depth, mask_bits, light_pt, inside_bonus=inside_bonus, variant=self.march_variant)
+            o = ops.shade_render_fwd(albedo, depth, d_min, light_pt, ambient_values, fx, fy, cx, cy,
+                                     self.depth_offset, self.directional_intensity)
         ambient_light = ambient_values.view(B, 1, 1).expand(B, H, W)        # TRAIN:368 (`.repeat` there; a view here)
         return o, ambient_light, unit.view(B, 3, 1, 1)
 
@@ -418,10 +421,9 @@ class RelightNet(nn.Module):
         ambient = (sl[:, 0] - 0.1).contiguous()                                          # TEST1:342
         unit = torch.nn.functional.normalize(lights.reshape(F_ * L, 3), p=2, dim=1)
         light_pt = (self.light_distance * unit).contiguous()
-        d_min, _, _ = ops.shadow_march_fwd(depth, bits, light_pt, inside_bonus=5.0, variant=self.march_variant)
         fx, fy, cx, cy = self._intrinsics(intrinsic_matrix)
-        o = ops.shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx, fy, cx, cy, self.depth_offset,
-                                 self.directional_intensity, want=("shadow", "final", "rendered"))
+        o = ops.march_shade_fwd(albedo, depth, bits, light_pt, ambient, 5.0, fx, fy, cx, cy, self.depth_offset,
+                                self.directional_intensity, want=("shadow", "final", "rendered"))
         return dict(rendered=o["rendered"].view(F_, L, 3, H, W), shadow=o["shadow"].view(F_, L, H, W),
                     final=o["final"].view(F_, L, H, W), albedo=albedo, depth=depth, ambient=ambient,
                     unit_light=unit.view(F_, L, 3))

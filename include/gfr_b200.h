@@ -91,6 +91,16 @@ int gfr_shade_render_fwd(const float* albedo, const float* depth, const float* d
                          float* final_shading, float* rendered, float* normals, int B, int H, int W,
                          int lights_per_face, void* stream);
 
+/* gfr_shadow_march_fwd and gfr_shade_render_fwd fused into one launch (+ the depth-widening pre-pass): every thread
+ * shades its pixel right after its ray march, d_min never makes the round trip through memory.  Arguments as in the
+ * two functions; d_min / argmin / shadow / full / final_shading / rendered / normals may each be NULL;
+ * depth64_scratch is required.  Bit-identical to the two-launch sequence. */
+int gfr_march_shade_fwd(const float* albedo, const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
+                        const float* light_pt, const float* ambient, const double* t_host, int n, float inside_bonus,
+                        const float* intr_host, double* depth64_scratch, float* d_min, uint8_t* argmin, float* shadow,
+                        float* full, float* final_shading, float* rendered, float* normals, int B, int H, int W,
+                        int lights_per_face, void* stream);
+
 /* Ray-march backward (what autograd does for TRAIN:374-517): the min over samples routes the gradient to the arg-min
  * sample, which is re-evaluated with the forward's arithmetic; gradients flow to the pixel's depth, the four bilinear
  * corners of the sample, and the light point — directly (BC = P_L - P) and through the sample position (end point <-

@@ -139,3 +139,21 @@ def test_ops_reject_cpu_tensors(ops):
         ops.mask_pack(torch.zeros(1, 256, 256, dtype=torch.uint8))
     with pytest.raises(RuntimeError):
         ops.shadow_march_fwd(torch.zeros(1, 1, 256, 256), torch.zeros(1, 2048, dtype=torch.int32), torch.zeros(1, 3))
+
+
+def test_fused_march_shade_equals_two_launches(ops, march):
+    """gfr_march_shade_fwd (shading in the ray-march kernel's epilogue) == gfr_shadow_march_fwd + gfr_shade_render_fwd, bit
+    for bit, also with several lights per face."""
+    F_, L = 2, 3
+    depth = torch.from_numpy(march["depth"]).view(1, 1, 256, 256).repeat(F_, 1, 1, 1).cuda()
+    depth[1] += 5.0
+    bits = ops.mask_pack(torch.from_numpy(march["mask_u8"]).view(1, 256, 256).cuda())
+    P_L = _light_pt([march["light_" + t] for t in TAGS[:F_ * L]]).cuda()
+    albedo = torch.rand(F_, 3, 256, 256, generator=torch.Generator().manual_seed(3)).cuda()
+    amb = torch.tensor([0.3, 0.45]).cuda()
+    d, _, _ = ops.shadow_march_fwd(depth, bits, P_L, inside_bonus=5.0)
+    two = ops.shade_render_fwd(albedo, depth, d, P_L, amb)
+    one = ops.march_shade_fwd(albedo, depth, bits, P_L, amb, inside_bonus=5.0, want=("shadow", "full", "final", "rendered", "normals", "d_min"))
+    assert torch.equal(one["d_min"], d)
+    for k in ("shadow", "full", "final", "rendered", "normals"):
+        assert torch.equal(one[k], two[k]), k

@@ -40,19 +40,25 @@ def test_conv_bn_act_unit_vs_torch_autograd(deconv, cin, cout, S, res, post):
     r = torch.randn(N, cout, S, S, device="cuda", generator=g) if res else None
     p = torch.randn(N, cout, S // 2, S // 2, device="cuda", generator=g) if post else None
     Gy = torch.randn(N, cout, S, S, device="cuda", generator=g)
-    # torch reference
-    xr = x.clone().requires_grad_()
-    rr = r.clone().requires_grad_() if res else None
-    pr = p.clone().requires_grad_() if post else None
-    pre = bn(mod(xr[:, :cin]))
+    # torch reference in float64 (cuDNN's fp32 backward-filter algorithms are neither deterministic nor equally accurate)
+    mod64 = (torch.nn.ConvTranspose2d if deconv else torch.nn.Conv2d)(cin, cout, 3, padding=1).cuda().double()
+    bn64 = torch.nn.BatchNorm2d(cout).cuda().double()
+    with torch.no_grad():
+        mod64.weight.copy_(mod.weight); mod64.bias.copy_(mod.bias); bn64.weight.copy_(bn.weight); bn64.bias.copy_(bn.bias)
+    xr = x.double().requires_grad_()
+    rr = r.double().requires_grad_() if res else None
+    pr = p.double().requires_grad_() if post else None
+    pre = bn64(mod64(xr[:, :cin]))
     y_ref = F.leaky_relu(pre + rr if res else pre, 0.2)
     if post:
         y_ref = y_ref + F.interpolate(pr, scale_factor=2, mode="nearest")
-    (y_ref * Gy).sum().backward()
-    ref = dict(w=mod.weight.grad.clone(), b=mod.bias.grad.clone(), gamma=bn.weight.grad.clone(), beta=bn.bias.grad.clone(),
-               x=xr.grad.clone())
-    for q in (mod.weight, mod.bias, bn.weight, bn.bias):
-        q.grad = None
+    (y_ref * Gy.double()).sum().backward()
+    ref = dict(w=mod64.weight.grad.float(), b=mod64.bias.grad.float(), gamma=bn64.weight.grad.float(), beta=bn64.bias.grad.float(),
+               x=xr.grad.float())
+    y_ref = y_ref.float()
+    bn = bn64
+    rr_grad = rr.grad.float() if res else None
+    pr_grad = pr.grad.float() if post else None
     bn2 = torch.nn.BatchNorm2d(cout).cuda()
     # ours
     xc = ops.nchw_to_c4(x).data.requires_grad_()
@@ -63,16 +69,16 @@ def test_conv_bn_act_unit_vs_torch_autograd(deconv, cin, cout, S, res, post):
     y = T.ConvBNAct.apply(xc, mod.weight, mod.bias, bn2.weight, bn2.bias, rc, pc, meta)
     got_y = ops.c4_to_nchw(ops.C4(y.detach(), cout))
     assert (got_y - y_ref.detach()).abs().max() <= 2e-4
-    assert (bn2.running_mean - bn.running_mean).abs().max() <= 1e-5 and (bn2.running_var - bn.running_var).abs().max() <= 1e-4
+    assert (bn2.running_mean - bn.running_mean.float()).abs().max() <= 1e-5 and (bn2.running_var - bn.running_var.float()).abs().max() <= 1e-4
     (y * ops.nchw_to_c4(Gy).data).sum().backward()
     assert _rel(mod.weight.grad, ref["w"]) <= 2e-3
     assert _rel(bn2.weight.grad, ref["gamma"]) <= 2e-3 and _rel(bn2.bias.grad, ref["beta"]) <= 2e-3
     assert mod.bias.grad.abs().max() <= 1e-3 * max(1.0, float(ref["w"].abs().max()))      # exactly 0 in exact arithmetic (BN removes the mean)
     assert _rel(ops.c4_to_nchw(ops.C4(xc.grad, ctot)), ref["x"]) <= 2e-3
     if res:
-        assert _rel(ops.c4_to_nchw(ops.C4(rc.grad, cout)), rr.grad) <= 1e-4
+        assert _rel(ops.c4_to_nchw(ops.C4(rc.grad, cout)), rr_grad) <= 1e-4
     if post:
-        assert _rel(ops.c4_to_nchw(ops.C4(pc.grad, cout)), pr.grad) <= 1e-4
+        assert _rel(ops.c4_to_nchw(ops.C4(pc.grad, cout)), pr_grad) <= 1e-4
 
 
 @pytest.fixture(scope="module")
