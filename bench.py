@@ -33,6 +33,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 B_PER_GPU = 8
 H = W = 256
 MARCH_BYTES_PER_FACE = 786432          # depth f32 + mask f32 + d_min f32
+# the fused march+shade launch: depth + mask in (d_min stays on the SM), + albedo in, + shadow/full/final + rendered + normals out
+FUSED_BYTES_PER_FACE = 2 * 262144 + 786432 + 3 * 262144 + 2 * 786432
 MARCH_SAMPLES_PER_FACE = 160 * H * W
 CNN_FLOP_PER_FACE = 4.54e9
 METRIC = "relit faces/sec @256x256 (shadow+CNN)"
@@ -48,13 +50,8 @@ def peaks():
 
 def synthetic_batch(B, seed):
     """Synthetic 256x256 faces: image U(0,1) (seeded), elliptical face mask, one of the 18 light directions."""
-    from oracle.relight_oracle import LIGHTS_18, synthetic_face
-    g = torch.Generator().manual_seed(seed)
-    img = torch.rand(B, H, W, 3, generator=g)
-    _, m = synthetic_face(seed=seed)
-    mask = (m * 255).to(torch.uint8).view(1, H, W)
-    light = torch.tensor([LIGHTS_18[(seed + i) % 18] for i in range(B)], dtype=torch.float32).view(B, 3, 1, 1)
-    return img, mask, light
+    from geomconsistentfr_b200.synthetic import synthetic_batch as sb
+    return sb(B, seed, H, W)
 
 
 class ClockSampler(threading.Thread):
@@ -160,7 +157,7 @@ def run_train(args, rank, world, local, dist):
     from geomconsistentfr_b200 import RelightNet, intrinsic_matrix, ops
     from geomconsistentfr_b200 import PatchGAN
     from geomconsistentfr_b200.trainer import GeneratorStep, TrainStep
-    from oracle.relight_oracle import LIGHTS_18, synthetic_face
+    from geomconsistentfr_b200.synthetic import LIGHTS_18, synthetic_face
     B = 16
     net = RelightNet(batch_size=B)
     net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"), strict=True)
@@ -238,6 +235,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-faces", type=int, default=6, help="faces in the bounded CPU-baseline sample")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-gpu-port", action="store_true", help="skip the informational torch-eager GPU run of the oracle port "
+                                                               "(~50k tiny launches; always skip it under ncu)")
     ap.add_argument("--lanes", type=int, default=3, help="runner lanes the e2e (host-buffer) path rotates over")
     ap.add_argument("--no-gan", action="store_true", help="train workload without the PatchGAN terms")
     ap.add_argument("--workload", default="forward", choices=["forward", "train"],
@@ -353,21 +352,48 @@ def main():
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     d2h = B * 3 * H * W * 4
 
-    # ---- roofline: the ray-march kernel on the depth maps of the last forward, CUDA events on the same stream
-    depth = runner.out[1]
+    # ---- roofline: the kernel of the step that does the ray march.  In the forward it is ONE fused launch
+    # (march_shade_fwd_kernel: every thread marches its ray, then shades its pixel; d_min never leaves the SM), timed
+    # here on the depth / albedo maps of the last forward with CUDA events on the launching stream, L2 flushed between
+    # launches.  The host is allowed to run ahead of the device (a device-side sleep is queued first), so the event
+    # pairs bracket device time only.  The stand-alone march kernel (the operator ShadowMarch uses) is timed beside it.
+    albedo, depth = runner.out[0], runner.out[1]
     bits = ops.mask_pack(dev[0][1].view(1, H, W))
     light_pt = (net.light_distance * torch.nn.functional.normalize(dev[0][2].view(B, 3), dim=1)).contiguous()
+    amb = torch.full((B,), 0.4, device="cuda")
+
+    def step_fused(i):
+        ops.march_shade_fwd(albedo, depth, bits, light_pt, amb, inside_bonus=5.0)
 
     def step_march(i):
-        ops.shadow_march_fwd(depth, bits, light_pt, inside_bonus=5.0, variant=net.march_variant)
+        ops.shadow_march_fwd(depth, bits, light_pt, inside_bonus=5.0, variant=0)
 
-    march_ms = timed(step_march, max(args.steps, 20), 3) / max(args.steps, 20)
+    def timed_kernel(fn, steps):
+        for i in range(3):
+            fn(i)
+        barrier()
+        pairs = []
+        with torch.cuda.stream(stream):
+            torch.cuda._sleep(40_000_000)                 # ~20 ms: the whole loop below is enqueued before it ends
+            for i in range(steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn(i)
+                e1.record(stream)
+                pairs.append((e0, e1))
+        barrier()
+        return statistics.median(a.elapsed_time(b) for a, b in pairs)
+
+    n_k = max(args.steps, 20)
+    fused_ms = timed_kernel(step_fused, n_k)
+    march_ms = timed_kernel(step_march, n_k)
     hbm_peak, peak_src = peaks()
-    achieved = MARCH_BYTES_PER_FACE * B / (march_ms * 1e-3) / 1e9
-    traffic = None
+    achieved = FUSED_BYTES_PER_FACE * B / (fused_ms * 1e-3) / 1e9
+    traffic = {}
     tp = os.path.join(ROOT, "profiles", "march_traffic.json")
     if os.path.isfile(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        traffic = json.load(open(tp))
 
     line = {
         "metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -384,20 +410,31 @@ def main():
                         "steps pipelined over the runner lanes, one event pair around all K steps"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "shadow_march_fwd", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                     "ms_per_launch": march_ms, "share_of_step": march_ms / ms_per_step,
-                     "note": "algorithmic bytes 786432 B/face; the kernel is instruction-issue bound (81 % issue-active, ~90 "
-                             "instructions per in-mask sample), not HBM bound - see DESIGN.md 3/K1",
-                     "gsamples_per_s": MARCH_SAMPLES_PER_FACE * B / (march_ms * 1e-3) / 1e9},
+        "roofline": {"kernel": "march_shade_fwd_kernel (ray march + normals + Lambert + render, one launch)", "bound": "hbm",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic.get("fused_dram_bytes_per_launch"), "peak_source": peak_src,
+                     "ms_per_launch": fused_ms, "share_of_step": fused_ms / ms_per_step,
+                     "algorithmic_bytes_per_face": FUSED_BYTES_PER_FACE,
+                     "note": "the kernel is instruction-issue bound by construction (160 samples x ~90 instructions per "
+                             "in-mask pixel against 56 algorithmic bytes per pixel), not HBM bound - DESIGN.md 3/K1; "
+                             "gsamples_per_s counts the reference's 160 samples for every pixel",
+                     "gsamples_per_s": MARCH_SAMPLES_PER_FACE * B / (fused_ms * 1e-3) / 1e9,
+                     "march_only": {"kernel": "shadow_march_fwd_fast", "ms_per_launch": march_ms,
+                                    "algorithmic_bytes_per_face": MARCH_BYTES_PER_FACE,
+                                    "achieved": MARCH_BYTES_PER_FACE * B / (march_ms * 1e-3) / 1e9,
+                                    "frac": MARCH_BYTES_PER_FACE * B / (march_ms * 1e-3) / 1e9 / hbm_peak,
+                                    "traffic": traffic.get("dram_bytes_per_launch"),
+                                    "gsamples_per_s": MARCH_SAMPLES_PER_FACE * B / (march_ms * 1e-3) / 1e9}},
     }
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
-        t = cpu_forward_faces_per_s(args.cpu_faces, threads)[1:]
+        t = cpu_forward_faces_per_s(max(args.cpu_faces, 2), threads)[1:]
         line["cpu_baseline"] = {"value": len(t) / sum(t), "unit": "faces/s", "cores": threads, "kind": "port",
                                 "sample": "%d faces (1 warm-up dropped), B=1 each, torch CPU oracle port of TEST1:169-505"
                                           % len(t)}
         try:
+            if args.no_gpu_port:
+                raise RuntimeError("skipped (--no-gpu-port)")
             tg = gpu_port_faces_per_s(8)
             line["reference_gpu_port"] = {"value": len(tg) / sum(tg), "unit": "faces/s", "kind": "port",
                                           "sample": "%d faces, B=1 each, the torch oracle port (TEST1:169-505) run eagerly on cuda:0" % len(tg)}

@@ -159,6 +159,42 @@ class FlatAdam:
     def zero_grad(self):
         self.grad.zero_()
 
+    # ---- checkpointing, in torch.optim.Adam's own state_dict layout (per-parameter step / exp_avg / exp_avg_sq), so a
+    # checkpoint written here resumes under the reference's `torch.optim.Adam` (TRAIN:589-590) and vice versa
+    def state_dict(self):
+        step = float(self.state[0].item())
+        st, o = {}, 0
+        for i, p in enumerate(self.params):
+            k = p.numel()
+            st[i] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[o:o + k].view_as(p).detach().cpu().clone(),
+                     "exp_avg_sq": self.exp_avg_sq[o:o + k].view_as(p).detach().cpu().clone()}
+            o += k
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+        return {"state": st if step > 0 else {}, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        g = sd["param_groups"][0]
+        if len(g["params"]) != len(self.params):
+            raise ValueError("optimizer state holds %d parameters, this optimiser %d" % (len(g["params"]), len(self.params)))
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+        steps, o = set(), 0
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                k = p.numel()
+                e = sd["state"].get(i)
+                if e is None:
+                    self.exp_avg[o:o + k].zero_(); self.exp_avg_sq[o:o + k].zero_(); steps.add(0.0)
+                else:
+                    self.exp_avg[o:o + k].copy_(e["exp_avg"].reshape(-1)); self.exp_avg_sq[o:o + k].copy_(e["exp_avg_sq"].reshape(-1))
+                    steps.add(float(e["step"]))
+                o += k
+            if len(steps) != 1:
+                raise ValueError("per-parameter step counts differ: %s" % sorted(steps))
+            t = steps.pop()
+            self.state.copy_(torch.tensor([t, 1.0 - self.betas[0] ** t, (1.0 - self.betas[1] ** t) ** 0.5], dtype=torch.float64).float())
+
     def all_reduce_grads(self, group=None):
         """ONE collective per optimiser step over the flat gradient buffer (sum); returns the 1/world factor."""
         import torch.distributed as dist

@@ -368,3 +368,75 @@ def light_head_c4_fwd(feat, c_first, w1, b1, w2, b2):
                                            _ptr(_need(b2, torch.float32, "b2")), _ptr(out), N, _stream())
     _lib.check(rc, "gfr_light_head_c4_fwd"); _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# output stage of the inference drivers (csrc/postprocess.cu): TEST1:590-620, TESTB:589-608, the MATLAB border fix
+def _mask_u8(mask, B, H, W):
+    if not (torch.is_tensor(mask) and mask.is_cuda and mask.dtype == torch.uint8):
+        raise RuntimeError("mask must be a CUDA uint8 tensor holding the skin-mask values (0..255)")
+    mask = mask.contiguous()
+    if mask.numel() == H * W:
+        return mask, 0
+    if mask.numel() == B * H * W:
+        return mask, H * W
+    raise RuntimeError("mask must be [H,W] (shared) or [B,H,W]")
+
+
+def composite_bgr_u8(image, rendered, mask):
+    """image [B,H,W,3] RGB in [0,1] (CUDA f64 like the reference's `training_images`, or f32), rendered [B,3,H,W] f32,
+    mask u8 [H,W] | [B,H,W] -> [B,H,W,3] u8 BGR: the array cv2.imwrite stores at TEST1:620."""
+    rendered = _need(rendered, torch.float32, "rendered")
+    if not (torch.is_tensor(image) and image.is_cuda and image.dtype in (torch.float32, torch.float64)):
+        raise RuntimeError("image must be a CUDA f32/f64 tensor")
+    image = image.contiguous()
+    B, _, H, W = rendered.shape
+    if tuple(image.shape) != (B, H, W, 3):
+        raise RuntimeError("image must be [B,H,W,3]")
+    mask, stride = _mask_u8(mask, B, H, W)
+    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=rendered.device)
+    rc = _lib.load().gfr_composite_bgr_u8(_ptr(image), int(image.dtype == torch.float64), _ptr(rendered), _ptr(mask), stride,
+                                          _ptr(out), B, H, W, _stream())
+    _lib.check(rc, "gfr_composite_bgr_u8"); _count()
+    return out
+
+
+def export_planes_u8(albedo, depth, shadow, final_shading, normals, mask,
+                     want=("shadow_mask", "albedo", "depth", "shading", "surface_normals")):
+    """TESTB:590-608: the five auxiliary images as u8 (BGR for the 3-channel ones).  Returns a dict."""
+    depth = _need(depth, torch.float32, "depth")
+    B, _, H, W = depth.shape
+    mask, stride = _mask_u8(mask, B, H, W)
+    dev = depth.device
+    src = {"shadow_mask": shadow, "albedo": albedo, "depth": depth, "shading": final_shading, "surface_normals": normals}
+    for k in want:
+        src[k] = _need(src[k], torch.float32, k)
+    out = {k: (torch.empty((B, H, W, 3) if k in ("albedo", "surface_normals") else (B, H, W), dtype=torch.uint8, device=dev)
+               if k in want else None) for k in src}
+    keys = None
+    lib = _lib.load()
+    if "depth" in want:
+        keys = torch.empty(2, dtype=torch.int32, device=dev)
+        rc = lib.gfr_neg_depth_range(_ptr(depth), depth.numel(), _ptr(keys), _stream())
+        _lib.check(rc, "gfr_neg_depth_range"); _count(2)
+    g = lambda k: _ptr(src[k]) if k in want else None
+    rc = lib.gfr_export_planes_u8(g("albedo"), g("depth"), g("shadow_mask"), g("shading"), g("surface_normals"), _ptr(mask),
+                                  stride, _ptr(keys), _ptr(out["shadow_mask"]), _ptr(out["albedo"]), _ptr(out["depth"]),
+                                  _ptr(out["shading"]), _ptr(out["surface_normals"]), B, H, W, _stream())
+    _lib.check(rc, "gfr_export_planes_u8"); _count()
+    return {k: v for k, v in out.items() if v is not None}
+
+
+def border_median_fix_u8(img, mask, max_sum=30):
+    """fix_border_artifacts_CVPR2022.m on a u8 image batch [B,H,W,C] (or [B,H,W]); mask u8 [H,W] | [B,H,W]."""
+    if not (torch.is_tensor(img) and img.is_cuda and img.dtype == torch.uint8):
+        raise RuntimeError("img must be a CUDA uint8 tensor")
+    img = img.contiguous()
+    shape = img.shape
+    B, H, W = shape[:3]
+    C = shape[3] if img.dim() == 4 else 1
+    mask, stride = _mask_u8(mask, B, H, W)
+    out = torch.empty_like(img)
+    rc = _lib.load().gfr_border_median_fix_u8(_ptr(img), _ptr(mask), stride, _ptr(out), B, H, W, C, int(max_sum), _stream())
+    _lib.check(rc, "gfr_border_median_fix_u8"); _count()
+    return out

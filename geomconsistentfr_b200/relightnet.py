@@ -384,7 +384,9 @@ class RelightNet(nn.Module):
         with torch.no_grad():
             albedo, depth, sl = self._cnn_eval(img, epoch)
             if test_mode:                                                   # TEST1:169-505
-                m = mask.to(dev, non_blocking=True).reshape(1, H, W)
+                m = mask.to(dev, non_blocking=True).reshape(-1, H, W)   # (H,W,1) like the reference, or one mask per face
+                if m.shape[0] not in (1, B):
+                    raise RuntimeError("mask must be [H,W,1] (TEST1:488) or [B,H,W,1]")
                 bits = ops.mask_pack(m)
                 ambient_values = (sl[:, 0] - 0.1).contiguous()              # TEST1:342
                 light = target_lighting.to(dev, torch.float32, non_blocking=True)

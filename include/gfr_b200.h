@@ -320,6 +320,38 @@ int gfr_upsample2_fwd(const float* in, const float* add, float* out, int NC, int
 int gfr_light_head_fwd(const float* feat, long long feat_batch_stride, int c_first, int HW, const float* w1,
                        const float* b1, const float* w2, const float* b2, float* out, int N, void* stream);
 
+/* ---- output stage of the inference drivers (csrc/postprocess.cu) --------------------------------------------------
+ * The reference copies every fp32 plane to the host and quantises there in numpy; these entry points produce the
+ * 8-bit images cv2.imwrite would store, on the device.  Arithmetic = numpy's promotion in the reference expressions
+ * (fp32 product with 255, fp64 product with mask/255, round-half-to-even, saturate).  masks are the skin masks as
+ * stored (u8, values {0,64,128,255}); mask_batch_stride = 0 (one mask for the batch) or H*W. */
+
+/* TEST1:613-620 / TESTB:596-601: out[b,r,c,:] (BGR) = 255 * rendered[b,2-ch,r,c] * mask/255 where mask > 0, else
+ * 255 * image[b,r,c,2-ch].  image [B,H,W,3] RGB in [0,1], fp64 (the reference's dtype; image_is_f64 = 1) or fp32;
+ * rendered [B,3,H,W] fp32; out_bgr [B,H,W,3] u8. */
+int gfr_composite_bgr_u8(const void* image, int image_is_f64, const float* rendered, const uint8_t* mask,
+                         int mask_batch_stride, uint8_t* out_bgr, int B, int H, int W, void* stream);
+
+/* TESTB:595-597: range of -depth over all n elements, as two order-preserving uint32 keys {min, max} that
+ * gfr_export_planes_u8 decodes (2 launches: init + reduce). */
+int gfr_neg_depth_range(const float* depth, long long n, uint32_t* range_keys, void* stream);
+
+/* TESTB:590-608: the five auxiliary images.  albedo/normals [B,3,H,W], depth [B,1,H,W], shadow/final_shading [B,H,W];
+ * outputs (any may be NULL, its source may then be NULL too): out_shadow/out_depth/out_shading [B,H,W] u8,
+ * out_albedo/out_normals [B,H,W,3] u8 BGR.  depth is written as 255 * (-d - min)/(max - min) * mask/255 with the
+ * range from gfr_neg_depth_range; normals as 255 * (n + 1) / 2 * mask/255. */
+int gfr_export_planes_u8(const float* albedo, const float* depth, const float* shadow, const float* final_shading,
+                         const float* normals, const uint8_t* mask, int mask_batch_stride, const uint32_t* range_keys,
+                         uint8_t* out_shadow, uint8_t* out_albedo, uint8_t* out_depth, uint8_t* out_shading,
+                         uint8_t* out_normals, int B, int H, int W, void* stream);
+
+/* fix_border_artifacts_CVPR2022.m:1-18: face = (mask >= 128) (MATLAB's uint8 `imread(mask)/255.0`), s = 7x7 box sum of
+ * face with zero padding; pixels with 0 < s <= max_sum take the 3x3 median (zero padded, per channel) of img.
+ * max_sum = 30 reproduces the shipped FFHQ_relighting_results/ PNGs on every pixel; 29 is the .m file as written
+ * (`convolved < 30`).  img/out [B,H,W,C] u8, C <= 4, out != img. */
+int gfr_border_median_fix_u8(const uint8_t* img, const uint8_t* mask, int mask_batch_stride, uint8_t* out, int B, int H,
+                             int W, int C, int max_sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,3 +34,26 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError):
         net(torch.zeros(1, 256, 256, 3), 200, intrinsic_matrix(), torch.ones(256, 256, 1),
             torch.ones(1, 3, 1, 1), torch.ones(1, 1, 1), None)
+
+
+def test_bench_workload_generator_matches_the_oracle_generator():
+    """bench.py's product arm builds its inputs from the package (no oracle import); both arms must see the same faces."""
+    from geomconsistentfr_b200 import synthetic as S
+    assert S.LIGHTS_18 == O.LIGHTS_18
+    for seed, H, W in ((0, 256, 256), (5, 64, 64), (17, 48, 80)):
+        d0, m0 = S.synthetic_face(seed, H, W, noise=2.0)
+        d1, m1 = O.synthetic_face(seed, H, W, noise=2.0)
+        assert torch.equal(d0, d1) and torch.equal(m0, m1)
+    L = torch.tensor(S.LIGHTS_18)
+    assert torch.equal(S.light_point(L)[1], O.light_point(L)[1])
+
+
+def test_product_code_never_imports_the_oracle():
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "geomconsistentfr_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f

@@ -2,7 +2,7 @@
 import sys, os, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from geomconsistentfr_b200 import ops
-from oracle import relight_oracle as O
+from geomconsistentfr_b200 import synthetic as O
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 depth = torch.zeros(B, 1, 256, 256); masks = torch.zeros(B, 256, 256, dtype=torch.uint8)
