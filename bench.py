@@ -6,11 +6,13 @@ batch 8 per GPU, full relight forward, fp32, eval mode, epoch-99 weights, synthe
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One JSON line on stdout (rank 0).  A "step" is one forward over one batch of 8 faces per GPU.
-  value      faces/s, whole job, inputs resident in HBM, device-timed (CUDA events per step on the launching
-             stream, L2 flushed between steps, max over ranks)
+  value      faces/s, whole job, inputs resident in HBM: the K steps rotate over the runner lanes and a 151 MB pool of
+             distinct device batches (> L2), one CUDA-event pair around all K steps, max over ranks
+  latency    the same forward on one lane, CUDA events per step, L2 flushed between steps
   e2e        faces/s through RelightRunner.relight_host: pinned host image/mask/light -> H2D -> forward -> D2H of
              rendered_images, all inside the timed region
-  roofline   the ray-march kernel (the metric BASELINE.json names): algorithmic bytes / CUDA-event duration
+  roofline   the kernel of the step that does the ray march (one fused launch: march + normals + Lambert + render):
+             algorithmic bytes / CUDA-event duration, L2 flushed between launches; the stand-alone march beside it
   cpu_baseline / --impl reference: the CPU oracle port of the reference forward (oracle/relight_oracle.py, torch
              CPU, all host threads) on a bounded sample
 """
@@ -270,9 +272,10 @@ def main():
     stream = runner.stream
 
     # distinct synthetic batches, host-pinned (for e2e) and device-resident (for value)
-    n_pool = 4
-    host = [tuple(t.pin_memory() for t in synthetic_batch(B, 1000 * rank + i)) for i in range(n_pool)]
-    dev = [tuple(t.cuda() for t in h) for h in host]
+    n_pool = 24                                                          # 24 x 6.3 MB of images = 151 MB > L2 (126 MB)
+    batches = [synthetic_batch(B, 1000 * rank + i) for i in range(n_pool)]
+    host = [tuple(t.pin_memory() for t in b) for b in batches[:4]]
+    dev = [tuple(t.cuda() for t in b) for b in batches]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
     def barrier():
@@ -303,28 +306,18 @@ def main():
             total_ms = float(t.item())
         return total_ms
 
-    # ---- value: inputs resident in HBM
+    # ---- value: whole-job throughput, inputs resident in HBM.  The K steps rotate over the runner lanes (the latency-
+    # bound low-resolution layers of one forward overlap the machine-filling layers of another) and over a pool of
+    # distinct device-resident batches that is larger than L2 (24 x 6.3 MB = 151 MB > 126 MB), so no step finds its
+    # inputs cached; one event pair brackets all K steps (start on lane 0, every lane waits for it; end = last lane).
+    # `latency` is the same forward on ONE lane, one event pair per step, L2 flushed (untimed) between steps.
     def step_device(i):
         runner.set_inputs(*dev[i % n_pool])
         runner.run()
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    n0 = ops.launch_count()
-    total_ms = timed(step_device, args.steps, args.warmup)
-    launches = runner.launches_per_run * args.steps if runner.graph is not None else \
-        (ops.launch_count() - n0) * args.steps // (args.steps + args.warmup)
-    ms_per_step = total_ms / args.steps
-    value = world * B * 1e3 / ms_per_step
-
-    # ---- e2e: host buffers through the public runner API (RelightRunner.relight_host), copies inside the timed
-    # region.  The runner rotates over its lanes, so the H2D of step i+1 / D2H of step i-1 overlap the kernels of step
-    # i; the K steps are bracketed by one event pair (start on lane 0, every lane waits for it; end = the last lane to
-    # finish).  Every step streams a different host batch; the per-step working set (~1.1 GB of activations) exceeds L2.
-    def timed_pipelined(steps, warmup):
+    def timed_lanes(submit, steps, warmup):
         for i in range(warmup):
-            runner.relight_host(*host[i % n_pool])
+            submit(i)
         runner.synchronize()
         barrier()
         start = torch.cuda.Event(enable_timing=True)
@@ -332,7 +325,7 @@ def main():
         for lane in runner.lanes[1:]:
             lane.stream.wait_event(start)
         for i in range(steps):
-            runner.relight_host(*host[i % n_pool])
+            submit(warmup + i)
         ends = []
         for lane in runner.lanes:
             e = torch.cuda.Event(enable_timing=True)
@@ -347,7 +340,21 @@ def main():
             total_ms = float(t.item())
         return total_ms
 
-    e2e_ms = timed_pipelined(args.steps, args.warmup) / args.steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    n0 = ops.launch_count()
+    latency_ms = timed(step_device, args.steps, args.warmup) / args.steps
+    ms_per_step = timed_lanes(lambda i: runner.relight_resident(*dev[i % n_pool]), args.steps, args.warmup) / args.steps
+    launches = runner.launches_per_run * args.steps if runner.graph is not None else \
+        (ops.launch_count() - n0) * args.steps // (2 * (args.steps + args.warmup))
+    value = world * B * 1e3 / ms_per_step
+
+    # ---- e2e: host buffers through the public runner API (RelightRunner.relight_host), copies inside the timed
+    # region.  The runner rotates over its lanes, so the H2D of step i+1 / D2H of step i-1 overlap the kernels of step
+    # i; the K steps are bracketed by one event pair (start on lane 0, every lane waits for it; end = the last lane to
+    # finish).  Every step streams a different host batch; the per-step working set (~1.1 GB of activations) exceeds L2.
+    e2e_ms = timed_lanes(lambda i: runner.relight_host(*host[i % len(host)]), args.steps, args.warmup) / args.steps
     clocks = sampler.stop()
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     d2h = B * 3 * H * W * 4
@@ -402,18 +409,22 @@ def main():
         "config": {"workload": "configs[1]: batch 8 per GPU, full relight forward 256x256 fp32 "
                                "(RelightNet CNN + normals + 160-sample ray-march + Lambert render), eval, epoch-99 weights",
                    "global_batch": world * B, "parallelism": "dp%d (faces sharded, no collective)" % world,
-                   "l2": "256 MiB flush written between timed steps (untimed)", "cnn": net.cnn_impl,
+                   "l2": "value/e2e: every step reads a different batch of a 151 MB device pool (> 126 MB L2) / streams it from "
+                         "the host, and rewrites ~1.1 GB of activations; latency + roofline: 256 MiB flush written between "
+                         "timed launches (untimed)", "lanes": len(runner.lanes), "cnn": net.cnn_impl,
                    "cuda_graph": runner.graph is not None},
         "e2e": {"value": world * B * 1e3 / e2e_ms, "unit": "faces/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "lanes": len(runner.lanes),
                 "note": "RelightRunner.relight_host: pinned host image/mask/light -> H2D -> forward -> D2H rendered, "
                         "steps pipelined over the runner lanes, one event pair around all K steps"},
+        "latency": {"ms_per_step": latency_ms, "faces_per_s": world * B * 1e3 / latency_ms,
+                    "note": "one forward of 8 faces on ONE lane, CUDA events per step, L2 flushed between steps"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "march_shade_fwd_kernel (ray march + normals + Lambert + render, one launch)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic.get("fused_dram_bytes_per_launch"), "peak_source": peak_src,
-                     "ms_per_launch": fused_ms, "share_of_step": fused_ms / ms_per_step,
+                     "ms_per_launch": fused_ms, "share_of_step": fused_ms / latency_ms,
                      "algorithmic_bytes_per_face": FUSED_BYTES_PER_FACE,
                      "note": "the kernel is instruction-issue bound by construction (160 samples x ~90 instructions per "
                              "in-mask pixel against 56 algorithmic bytes per pixel), not HBM bound - DESIGN.md 3/K1; "

@@ -121,6 +121,17 @@ class RelightRunner:
             rendered_host.copy_(lane.out[5], non_blocking=True)
         return rendered_host, lane.stream
 
+    def relight_resident(self, img, mask, light):
+        """Device buffers in, device buffers out, rotating over the lanes like `relight_host` (no host copies): the
+        inputs are copied into the next lane's static buffers and its forward is enqueued on its stream.  Returns
+        (the lane's output tuple, lane stream); outputs are overwritten `lanes` calls later."""
+        lane = self.lanes[self._next]
+        self._next = (self._next + 1) % len(self.lanes)
+        self._last = lane
+        lane.set_inputs(img, mask, light)
+        lane.run()
+        return lane.out, lane.stream
+
     def synchronize(self):
         for lane in self.lanes:
             lane.stream.synchronize()

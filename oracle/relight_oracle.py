@@ -33,6 +33,8 @@ DIRECTIONAL_INTENSITY = 0.5      # TRAIN:46
 NUM_SAMPLES = 160                # TRAIN:48
 T0, DT = 0.025, 0.005            # TRAIN:468  np.arange(0.025, 0.825, 0.005)
 FOCAL, DEPTH_OFFSET = 1570.0, 1610.0   # TRAIN:353,572-573
+# lighting-transfer variant (TEST_LT = test_relight_single_image_lighting_transfer.py): TEST_LT:20,22,325,451,530-531,332
+LT = dict(directional_intensity=0.41, num_samples=159, t0=0.03, depth_offset=1410.0, focal=700.0, z_floor=0.16)
 
 
 # --------------------------------------------------------------------------------------
@@ -145,17 +147,24 @@ def ray_endpoints(xx, yy, Lx, Ly):
     return torch.stack((ex, ey), 0)
 
 
-def light_inside_image(Lx, Ly, H=IMG, W=IMG):
-    """TEST1:495."""
+def light_inside_image(Lx, Ly, H=IMG, W=IMG, rule="image"):
+    """TEST1:495 (rule "image": the light projects inside the image rectangle) / TEST_LT:503 (rule "wide": inside
+    +-4 image sizes)."""
     lx, ly = float(Lx.detach()) if torch.is_tensor(Lx) else float(Lx), float(Ly.detach()) if torch.is_tensor(Ly) else float(Ly)
+    if rule == "wide":
+        return (-4 * W <= lx <= 4 * W) and (4 * (1 - H) <= ly <= 4 * H)
     return (-(W / 2.0) <= lx <= W - W / 2.0 - 1) and (1 - H / 2.0 <= ly <= H / 2.0)
 
 
 def sample_increments(t0=T0, dt=DT, n=NUM_SAMPLES):
-    """TRAIN:468: exactly np.arange's fp64 values start + k*step."""
+    """TRAIN:468 / TEST_LT:451: exactly np.arange's fp64 values start + k*step."""
     if (t0, dt, n) == (T0, DT, NUM_SAMPLES):
         t = np.arange(0.025, 0.825, 0.005)
         assert t.shape[0] == NUM_SAMPLES
+        return torch.from_numpy(t)
+    if (t0, dt, n) == (LT["t0"], DT, LT["num_samples"]):
+        t = np.arange(0.03, 0.825, 0.005)
+        assert t.shape[0] == LT["num_samples"]
         return torch.from_numpy(t)
     return torch.from_numpy(t0 + dt * np.arange(n, dtype=np.float64))
 
@@ -163,7 +172,7 @@ def sample_increments(t0=T0, dt=DT, n=NUM_SAMPLES):
 # --------------------------------------------------------------------------------------
 # the ray-march: minimum point-to-ray distance over the samples
 # --------------------------------------------------------------------------------------
-def _march_one(depth, mask2d, P_L, xx, yy, t, inside_bonus, chunk):
+def _march_one(depth, mask2d, P_L, xx, yy, t, inside_bonus, chunk, inside_rule="image"):
     """One image.  depth (H,W) f32; mask2d (H,W) any dtype (tested ==0); P_L (3,) f32."""
     H, W = depth.shape
     end = ray_endpoints(xx, yy, P_L[0], P_L[1])
@@ -203,13 +212,13 @@ def _march_one(depth, mask2d, P_L, xx, yy, t, inside_bonus, chunk):
     allmin = torch.stack(mins, 0)
     dmin, which = torch.min(allmin, dim=0)
     arg = torch.gather(torch.stack(args, 0), 0, which[None])[0]
-    if inside_bonus != 0.0 and light_inside_image(P_L[0], P_L[1], H, W):
+    if inside_bonus != 0.0 and light_inside_image(P_L[0], P_L[1], H, W, inside_rule):
         dmin = dmin + inside_bonus                         # TEST1:495-496
     return dmin, arg
 
 
 def shadow_march(depth, mask, light_pt, t0=T0, dt=DT, n=NUM_SAMPLES, inside_bonus=0.0, chunk=32,
-                 return_argmin=False):
+                 return_argmin=False, inside_rule="image"):
     """depth (B,1,H,W) f32; mask (B|1,H,W) (any dtype; ==0 means outside the face);
     light_pt (B,3) f32 = 4013*unit(L).  Returns d_min (B,H,W) f32 (TRAIN:374-515)."""
     B, _, H, W = depth.shape
@@ -218,7 +227,7 @@ def shadow_march(depth, mask, light_pt, t0=T0, dt=DT, n=NUM_SAMPLES, inside_bonu
     outs, args = [], []
     for i in range(B):
         m = mask[i if mask.shape[0] > 1 else 0]
-        d, a = _march_one(depth[i, 0], m, light_pt[i], xx, yy, t, inside_bonus, chunk)
+        d, a = _march_one(depth[i, 0], m, light_pt[i], xx, yy, t, inside_bonus, chunk, inside_rule)
         outs.append(d)
         args.append(a)
     d = torch.stack(outs, 0)
@@ -244,18 +253,18 @@ def intrinsic_matrix(H=IMG, W=IMG, focal=FOCAL):
     return torch.from_numpy(K)
 
 
-def shade(depth, K, light_pt, ambient_values):
+def shade(depth, K, light_pt, ambient_values, depth_offset=DEPTH_OFFSET, intensity=DIRECTIONAL_INTENSITY):
     """TRAIN:353-369.  depth (B,1,H,W); light_pt (B,3); ambient_values (B,).
     Returns normals (B,3,H,W) [after the y flip and 2nd normalise], directional (B,H,W),
     ambient_light (B,H,W), full_shading (B,H,W)."""
     B, _, H, W = depth.shape
     xx, yy = pixel_grid(H, W, depth.device)
-    n = depth_to_normals(depth + DEPTH_OFFSET, K.to(depth.device))
+    n = depth_to_normals(depth + depth_offset, K.to(depth.device))
     n = torch.cat((n[:, 0:1], -n[:, 1:2], n[:, 2:3]), 1)                  # TRAIN:354
     P = torch.cat((xx.expand(B, 1, H, W), yy.expand(B, 1, H, W), depth), 1)
     l = F.normalize(light_pt.view(B, 3, 1, 1) - P, p=2, dim=1)            # TRAIN:364
     n = F.normalize(n, p=2, dim=1)                                        # TRAIN:365
-    directional = DIRECTIONAL_INTENSITY * torch.clamp(torch.sum(n * l, dim=1), min=0.0)
+    directional = intensity * torch.clamp(torch.sum(n * l, dim=1), min=0.0)
     ambient_light = ambient_values.view(B, 1, 1).expand(B, H, W)
     return n, directional, ambient_light, ambient_light + directional
 
@@ -267,13 +276,14 @@ def render(albedo, shadow, full_shading, ambient_light):
 
 
 def relight_from_maps(albedo, depth, mask, light_dir, ambient_values, K=None, inside_bonus=5.0,
-                      clamp_z=False, t0=T0, dt=DT, n=NUM_SAMPLES):
+                      clamp_z=False, t0=T0, dt=DT, n=NUM_SAMPLES, depth_offset=DEPTH_OFFSET,
+                      intensity=DIRECTIONAL_INTENSITY, inside_rule="image"):
     """Everything after the CNN (TEST1:325-505): maps -> dict of outputs."""
     if K is None:
         K = intrinsic_matrix(depth.shape[2], depth.shape[3])
     unit, P_L = light_point(light_dir, clamp_z)
-    normals, directional, amb, full = shade(depth, K, P_L, ambient_values)
-    d_min = shadow_march(depth, mask, P_L, t0, dt, n, inside_bonus)
+    normals, directional, amb, full = shade(depth, K, P_L, ambient_values, depth_offset, intensity)
+    d_min = shadow_march(depth, mask, P_L, t0, dt, n, inside_bonus, inside_rule=inside_rule)
     s = shadow_weight(d_min)
     final, rendered = render(albedo, s, full, amb)
     return dict(d_min=d_min, shadow=s, ambient_light=amb, full_shading=full, final_shading=final,
@@ -318,17 +328,27 @@ class RelightNetOracle(nn.Module):
     """RelightNet (TRAIN:38-350 / TEST1:12-323) in plain torch; strict state_dict compatibility
     with model/model_epoch99.pth."""
 
-    def __init__(self):
+    def __init__(self, variant="default"):
+        """variant "lighting_transfer": the nine shortcut (de)convs are 1x1 and bias-free (TEST_LT:36-42,66-76,119-129;
+        strict state_dict compatibility with model_lighting_transfer/model_epoch106.pth, 391 tensors)."""
         super().__init__()
+        assert variant in ("default", "lighting_transfer")
+        self.variant = variant
+        lt = variant == "lighting_transfer"
+
+        def make(mod, name, cin, cout, k):
+            if lt and "shortcut" in name:
+                return mod(cin, cout, 1, bias=False)
+            return mod(cin, cout, k, padding=(k // 2, k // 2))
+
         for name, cin, cout, k in ENCODER_LAYERS:
-            setattr(self, name, nn.Conv2d(cin, cout, k, padding=(k // 2, k // 2)))
+            setattr(self, name, make(nn.Conv2d, name, cin, cout, k))
             setattr(self, _bn_name(name), nn.BatchNorm2d(cout))
         self.linear_SL1 = nn.Linear(27, 128)
         self.linear_SL2 = nn.Linear(128, 4)
         for p in ("albedo", "depth"):
             for name, kind, cin, cout, k, has_bn in decoder_layers(p):
-                mod = nn.ConvTranspose2d if kind == "deconv" else nn.Conv2d
-                setattr(self, name, mod(cin, cout, k, padding=(k // 2, k // 2)))
+                setattr(self, name, make(nn.ConvTranspose2d if kind == "deconv" else nn.Conv2d, name, cin, cout, k))
                 if has_bn:
                     setattr(self, _bn_name(name), nn.BatchNorm2d(cout))
 
@@ -395,6 +415,21 @@ class RelightNetOracle(nn.Module):
         o = relight_from_maps(albedo, depth, m, target_lighting.reshape(B, 3), amb, K, inside_bonus)
         return (albedo, depth, o["shadow"], o["ambient_light"], o["full_shading"], o["rendered"],
                 o["unit_light"], amb.view(B, 1, 1), o["final_shading"], o["normals"])
+
+    def forward_lighting_transfer(self, img, epoch, K, mask, target_lighting, target_ambient_values):
+        """TEST_LT:169-514 semantics (variant "lighting_transfer").  mask (H,W,1); target_lighting (B,3,1,1);
+        target_ambient_values (B,1,1) — USED here (TEST_LT:348), unlike TEST1.  Returns the 12-tuple: TEST1's ten +
+        estimated_unit_light_direction (B,3,1,1) [z floored at 0.16, TEST_LT:332-334] + estimated_ambient_light (B,1,1)."""
+        albedo, depth, sl = self.cnn(img, epoch)
+        B = img.shape[0]
+        est = torch.cat((sl[:, 1:3], torch.maximum(sl[:, 3:4], torch.tensor(LT["z_floor"]))), 1)
+        est_unit = F.normalize(est, p=2, dim=1).view(B, 3, 1, 1)
+        amb = target_ambient_values.reshape(B).float()
+        m = mask.reshape(1, mask.shape[0], mask.shape[1])
+        o = relight_from_maps(albedo, depth, m, target_lighting.reshape(B, 3), amb, K, 5.0, t0=LT["t0"], n=LT["num_samples"],
+                              depth_offset=LT["depth_offset"], intensity=LT["directional_intensity"], inside_rule="wide")
+        return (albedo, depth, o["shadow"], o["ambient_light"], o["full_shading"], o["rendered"], o["unit_light"],
+                amb.view(B, 1, 1), o["final_shading"], o["normals"], est_unit, sl[:, 0].view(B, 1, 1))
 
     def forward_train(self, img, epoch, K, masks):
         """TRAIN:196-524 semantics.  masks (B,H,W,1).  Returns the 8-tuple."""
