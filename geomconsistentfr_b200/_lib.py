@@ -13,10 +13,10 @@ _PROTOS = {
     "gfr_version": [],
     "gfr_error_string": [_c_int],
     "gfr_mask_pack": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p],
-    "gfr_shadow_march_fwd": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_float,
+    "gfr_shadow_march_fwd": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_float, _c_void_p,
                              _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_shade_render_fwd": [_c_void_p] * 11 + [_c_int, _c_int, _c_int, _c_int, _c_void_p],
-    "gfr_march_shade_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_float] + [_c_void_p] * 9
+    "gfr_march_shade_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_float] + [_c_void_p] * 10
                            + [_c_int] * 4 + [_c_void_p],
     "gfr_shadow_march_bwd": [_c_void_p] * 5 + [_c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_shade_render_bwd": [_c_void_p] * 16 + [_c_int, _c_int, _c_int, _c_void_p],

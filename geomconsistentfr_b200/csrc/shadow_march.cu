@@ -34,6 +34,7 @@ struct MarchArgs {
   int fuse_shade;            // 1: normals + Lambert + blend + render of the pixel follow in the same thread (shade)
   gfr_shade::ShadeArgs shade;
   float bonus;
+  float bx0, bx1, by0, by1;   // the light must project into [bx0,bx1] x [by0,by1] for the bonus (TEST1:495 / TEST_LT:503)
 };
 
 constexpr int TILE_W = 32, TILE_H = 8;
@@ -143,7 +144,7 @@ shadow_march_fwd_l1(const MarchArgs a, const __grid_constant__ SampleTable tab) 
     const float den = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bcx, bcx), __fmul_rn(bcy, bcy)), __fmul_rn(bcz, bcz)), 1e-4f));
     d = __fdiv_rn(sqrtf(__fadd_rn(qmin, 1e-4f)), den);
   }
-  if (a.bonus != 0.0f && Lx >= xmin && Lx <= xmax && Ly >= ymin && Ly <= ymax) d = __fadd_rn(d, a.bonus);   // TEST1:495-496
+  if (a.bonus != 0.0f && Lx >= a.bx0 && Lx <= a.bx1 && Ly >= a.by0 && Ly <= a.by1) d = __fadd_rn(d, a.bonus);   // TEST1:495-496
   const size_t o = (size_t)b * H * W + row * W + col;
   a.dmin[o] = d;
   if (a.argmin) a.argmin[o] = (uint8_t)kmin;
@@ -267,7 +268,7 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
     const float den = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bcx, bcx), __fmul_rn(bcy, bcy)), __fmul_rn(bcz, bcz)), 1e-4f));
     d = __fdiv_rn(sqrtf(__fadd_rn(qmin, 1e-4f)), den);
   }
-  if (a.bonus != 0.0f && Lx >= xmin && Lx <= xmax && Ly >= ymin && Ly <= ymax) d = __fadd_rn(d, a.bonus);   // TEST1:495-496
+  if (a.bonus != 0.0f && Lx >= a.bx0 && Lx <= a.bx1 && Ly >= a.by0 && Ly <= a.by1) d = __fadd_rn(d, a.bonus);   // TEST1:495-496
   const size_t o = (size_t)b * H * W + row * W + col;
   if (a.dmin) a.dmin[o] = d;
   if (a.argmin) a.argmin[o] = (uint8_t)kmin;
@@ -331,7 +332,7 @@ extern "C" int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int 
 }
 
 static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_batch_stride, const float* light_pt,
-                      const double* t_host, int n, float inside_bonus, float* d_min, uint8_t* argmin, float* shadow,
+                      const double* t_host, int n, float inside_bonus, const float* bonus_rect_host, float* d_min, uint8_t* argmin, float* shadow,
                       double* depth64_scratch, int B, int H, int W, int lights_per_face, int variant,
                       const gfr_shade::ShadeArgs* fuse, void* stream) {
   GFR_RETURN_IF_NULL(depth); GFR_RETURN_IF_NULL(mask_bits); GFR_RETURN_IF_NULL(light_pt);
@@ -358,6 +359,11 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
   a.depth = depth; a.mask_bits = mask_bits; a.light = light_pt; a.dmin = d_min; a.argmin = argmin; a.shadow = shadow;
   a.mask_stride = mask_batch_stride; a.B = B; a.H = H; a.W = W; a.n = n; a.lpf = lights_per_face; a.t0 = t0; a.inv_dt = inv_dt;
   a.bonus = inside_bonus;
+  if (bonus_rect_host != nullptr) {
+    a.bx0 = bonus_rect_host[0]; a.bx1 = bonus_rect_host[1]; a.by0 = bonus_rect_host[2]; a.by1 = bonus_rect_host[3];
+  } else {                                   // the image rectangle, TEST1:495
+    a.bx0 = -0.5f * W; a.bx1 = W - 0.5f * W - 1.0f; a.by0 = 1.0f - 0.5f * H; a.by1 = 0.5f * H;
+  }
   if (fuse != nullptr) { a.fuse_shade = 1; a.shade = *fuse; }
   const dim3 grid(W / TILE_W, H / TILE_H, B), block(TILE_W, TILE_H);
   const size_t smem = (size_t)(H * W / 32) * sizeof(uint32_t);
@@ -375,21 +381,22 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
 
 extern "C" int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
                                     const float* light_pt, const double* t_host, int n, float inside_bonus,
-                                    float* d_min, uint8_t* argmin, float* shadow, double* depth64_scratch, int B, int H,
-                                    int W, int lights_per_face, int variant, void* stream) {
-  return march_impl(depth, mask_bits, mask_batch_stride, light_pt, t_host, n, inside_bonus, d_min, argmin, shadow, depth64_scratch,
+                                    const float* bonus_rect_host, float* d_min, uint8_t* argmin, float* shadow,
+                                    double* depth64_scratch, int B, int H, int W, int lights_per_face, int variant,
+                                    void* stream) {
+  return march_impl(depth, mask_bits, mask_batch_stride, light_pt, t_host, n, inside_bonus, bonus_rect_host, d_min, argmin, shadow, depth64_scratch,
                     B, H, W, lights_per_face, variant, nullptr, stream);
 }
 
 extern "C" int gfr_march_shade_fwd(const float* albedo, const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
                                    const float* light_pt, const float* ambient, const double* t_host, int n, float inside_bonus,
-                                   const float* intr_host, double* depth64_scratch, float* d_min, uint8_t* argmin, float* shadow,
+                                   const float* bonus_rect_host, const float* intr_host, double* depth64_scratch, float* d_min, uint8_t* argmin, float* shadow,
                                    float* full, float* final_shading, float* rendered, float* normals, int B, int H, int W,
                                    int lights_per_face, void* stream) {
   GFR_RETURN_IF_NULL(ambient); GFR_RETURN_IF_NULL(intr_host); GFR_RETURN_IF_NULL(depth64_scratch);
   if (rendered != nullptr && albedo == nullptr) return GFR_E_NULL;
   gfr_shade::ShadeArgs sh{albedo, depth, nullptr, light_pt, ambient, shadow, full, final_shading, rendered, normals, B, H, W,
                           lights_per_face, intr_host[0], intr_host[1], intr_host[2], intr_host[3], intr_host[4], intr_host[5]};
-  return march_impl(depth, mask_bits, mask_batch_stride, light_pt, t_host, n, inside_bonus, d_min, argmin, nullptr, depth64_scratch,
+  return march_impl(depth, mask_bits, mask_batch_stride, light_pt, t_host, n, inside_bonus, bonus_rect_host, d_min, argmin, nullptr, depth64_scratch,
                     B, H, W, lights_per_face, 0, &sh, stream);
 }

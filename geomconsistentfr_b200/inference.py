@@ -83,6 +83,34 @@ def relight(model, images, masks, lights, ambient=0.5, epoch=200, fix_border=Fal
     return host
 
 
+@torch.no_grad()
+def lighting_transfer(model, input_image, reference_image, mask, epoch=200, planes=True):
+    """`main()` of test_relight_single_image_lighting_transfer.py (TEST_LT:516-579): pass 1 runs the REFERENCE image with a
+    zero target light to estimate its light direction (z floored at 0.16) and ambient; pass 2 relights the INPUT image
+    with them (f = 700, TEST_LT:530-531).  `model` is RelightNet(variant="lighting_transfer") in eval mode; images
+    [256,256,3] RGB in [0,1] (f64 like the reference, or f32); mask uint8 [256,256] (the input's).
+    Returns (dict of host uint8 images as `relight`, estimated unit light [3], estimated ambient)."""
+    if getattr(model, "variant", "default") != "lighting_transfer":
+        raise RuntimeError("lighting_transfer() needs RelightNet(variant='lighting_transfer')")
+    if model.training:
+        raise RuntimeError("lighting_transfer() is an inference path: call model.eval() first (TEST_LT:521)")
+    dev = model.device
+    img, m, _ = _as_batch(input_image, mask, (0.0, 0.0, 1.0))
+    ref, _, _ = _as_batch(reference_image, mask, (0.0, 0.0, 1.0))
+    B, H, W, _ = img.shape
+    K = intrinsic_matrix(H, W, focal=model.focal_length)
+    img_d, ref_d, m_d = img.to(dev), ref.to(dev), m.to(dev)
+    mk = m_d.view(-1, H, W, 1)[0]
+    zero = torch.zeros(B, 4, device=dev)
+    r1 = model(ref_d.float(), epoch, K, mk, zero[:, 1:4].view(B, 3, 1, 1), zero[:, 0].view(B, 1, 1))            # TEST_LT:543
+    est_l, est_a = r1[10], r1[11]
+    o = model(img_d.float(), epoch, K, mk, est_l.view(B, 3, 1, 1), est_a.view(B, 1, 1))                          # TEST_LT:545
+    res = {"rendered_image": ops.composite_bgr_u8(img_d, o[5], m_d[0])}
+    if planes:
+        res.update(ops.export_planes_u8(o[0], o[1], o[2], o[8], o[9], m_d[0]))                                   # TEST_LT:574-579
+    return {k: v.cpu().numpy() for k, v in res.items()}, est_l.reshape(B, 3)[0].cpu().numpy(), float(est_a.reshape(B)[0])
+
+
 def relight_single_image(model, image, mask, light, **kw):
     """TEST1 `main()` for one image: image [256,256,3] RGB in [0,1], mask uint8 [256,256], light (x,y,z).
     Returns the [256,256,3] uint8 BGR array the reference writes to FFHQ_relighting_results/<name>_rendered_image.png."""

@@ -66,8 +66,16 @@ def mask_pack(mask):
     return bits
 
 
+def _bonus_rect(rect):
+    """None -> NULL (the image rectangle, TEST1:495); else 4 host floats {x_min, x_max, y_min, y_max} (TEST_LT:503)."""
+    if rect is None:
+        return None, None
+    r = np.ascontiguousarray(rect, dtype=np.float32).reshape(4)
+    return r, r.ctypes.data_as(ctypes.c_void_p)
+
+
 def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0, want_argmin=False,
-                     want_shadow=False, variant=0):
+                     want_shadow=False, variant=0, bonus_rect=None):
     """depth [F,1,H,W] f32; mask_bits [1|F, H*W/32] i32; light_pt [B,3] f32 with B = F * L (L lights per face, pair b
     uses face b // L) -> d_min [B,H,W] (+ argmin u8, + shadow).  TRAIN:374-517."""
     depth = _need(depth, torch.float32, "depth")
@@ -85,9 +93,10 @@ def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0,
     shadow = torch.empty((B, H, W), dtype=torch.float32, device=depth.device) if want_shadow else None
     stride = 0 if mask_bits.shape[0] == 1 else H * W // 32 + MASK_EXTRA_WORDS
     scratch = torch.empty((F, H, W), dtype=torch.float64, device=depth.device) if variant == 0 else None
+    _keep, rect = _bonus_rect(bonus_rect)
     rc = _lib.load().gfr_shadow_march_fwd(
         _ptr(depth), _ptr(mask_bits), stride, _ptr(light_pt), t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]),
-        float(inside_bonus), _ptr(dmin), _ptr(arg), _ptr(shadow), _ptr(scratch), B, H, W, B // F, int(variant), _stream())
+        float(inside_bonus), rect, _ptr(dmin), _ptr(arg), _ptr(shadow), _ptr(scratch), B, H, W, B // F, int(variant), _stream())
     _lib.check(rc, "gfr_shadow_march_fwd"); _count(2 if variant == 0 else 1)
     return dmin, arg, shadow
 
@@ -122,7 +131,8 @@ def shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx=1570.0, fy=1570
 
 
 def march_shade_fwd(albedo, depth, mask_bits, light_pt, ambient, inside_bonus=0.0, fx=1570.0, fy=1570.0, cx=None, cy=None,
-                    depth_offset=1610.0, intensity=0.5, want=("shadow", "full", "final", "rendered", "normals")):
+                    depth_offset=1610.0, intensity=0.5, want=("shadow", "full", "final", "rendered", "normals"),
+                    samples=None, bonus_rect=None):
     """shadow_march_fwd + shade_render_fwd in one launch (d_min stays on the SM).  Same arguments / outputs as the pair;
     returns the dict of the requested outputs ([B,...], B = F * lights per face)."""
     depth = _need(depth, torch.float32, "depth")
@@ -137,7 +147,8 @@ def march_shade_fwd(albedo, depth, mask_bits, light_pt, ambient, inside_bonus=0.
         raise RuntimeError("mask_bits must be [1|F, H*W/32 + 4] (from mask_pack)")
     if "rendered" in want:
         albedo = _need(albedo, torch.float32, "albedo")
-    t = reference_samples()
+    t = reference_samples() if samples is None else np.ascontiguousarray(samples, dtype=np.float64)
+    _keep, rect = _bonus_rect(bonus_rect)
     intr = np.array([fx, fy, W / 2.0 if cx is None else cx, H / 2.0 if cy is None else cy, depth_offset, intensity],
                     dtype=np.float32)
     dev = depth.device
@@ -149,7 +160,7 @@ def march_shade_fwd(albedo, depth, mask_bits, light_pt, ambient, inside_bonus=0.
     scratch = torch.empty((F, H, W), dtype=torch.float64, device=dev)
     rc = _lib.load().gfr_march_shade_fwd(
         _ptr(albedo) if "rendered" in want else None, _ptr(depth), _ptr(mask_bits), stride, _ptr(light_pt), _ptr(ambient),
-        t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]), float(inside_bonus), intr.ctypes.data_as(ctypes.c_void_p),
+        t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]), float(inside_bonus), rect, intr.ctypes.data_as(ctypes.c_void_p),
         _ptr(scratch), _ptr(out["d_min"]), None, _ptr(out["shadow"]), _ptr(out["full"]), _ptr(out["final"]),
         _ptr(out["rendered"]), _ptr(out["normals"]), B, H, W, B // F, _stream())
     _lib.check(rc, "gfr_march_shade_fwd"); _count(2)

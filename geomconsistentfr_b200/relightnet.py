@@ -37,27 +37,36 @@ def _bn_name(layer):
 
 
 class RelightNet(nn.Module):
-    def __init__(self, batch_size=1):
+    def __init__(self, batch_size=1, variant="default"):
+        """variant "default": TRAIN / TEST1 / TESTB.  variant "lighting_transfer": the network and constants of
+        test_relight_single_image_lighting_transfer.py (TEST_LT) — the nine shortcut (de)convs are 1x1 and bias-free
+        (TEST_LT:36-42,66-76,119-129; loads model_lighting_transfer/model_epoch106.pth strictly), directional intensity
+        0.41, 159 samples from t = 0.03, depth offset 1410 (TEST_LT:20,22,325,451); inference only."""
         super().__init__()
+        if variant not in ("default", "lighting_transfer"):
+            raise ValueError("variant must be 'default' or 'lighting_transfer'")
+        self.variant = variant
+        lt = variant == "lighting_transfer"
         self.batch_size = batch_size          # TRAIN:41 (3) / TEST1:15 (1); here only a default — B comes from the input
         self.img_height = 256
         self.img_width = 256
         self.lr = 0.0001
         self.df_dim = 64
-        self.directional_intensity = 0.5
+        self.directional_intensity = 0.41 if lt else 0.5          # TEST_LT:20 / TRAIN:46
         self.light_distance = 4013.0
-        self.num_sample_points = 160
+        self.num_sample_points = 159 if lt else 160               # TEST_LT:22 / TRAIN:48
+        self.sample_start = 0.03 if lt else 0.025                 # TEST_LT:451 / TRAIN:468 (np.arange(start, 0.825, 0.005))
         self.GD_ratio = 5
-        self.focal_length = 1570.0            # TRAIN:572-573 (read back from intrinsic_matrix at call time)
-        self.depth_offset = 1610.0            # TRAIN:353
+        self.focal_length = 700.0 if lt else 1570.0               # TEST_LT:530-531 / TRAIN:572-573 (read back from intrinsic_matrix at call time)
+        self.depth_offset = 1410.0 if lt else 1610.0              # TEST_LT:325 / TRAIN:353
+        self.light_z_floor = 0.16                                 # TEST_LT:332 (estimated light of the reference image)
         self.march_variant = 0
         self.cnn_impl = "tc"                  # "tc": tcgen05 3xTF32 convs on C4 activations; "direct": exact-fp32 CUDA-core convs
         self.tc_precision = 2                 # eval-mode convs: 2 = fp16 pair split (~22-bit products, half the operand bytes; needs
                                               # |activation| < 4095 — an overflow shows up as inf/NaN, not silently), 3 = 3xTF32, 1 = TF32
 
         for name, cin, cout, k in ENCODER_LAYERS:
-            setattr(self, name, nn.Conv2d(cin, cout, k, padding=(k // 2, k // 2)))
-            setattr(self, _bn_name(name), nn.BatchNorm2d(cout))
+            self._add(name, nn.Conv2d, cin, cout, k)
         self.linear_SL1 = nn.Linear(27, 128)
         self.linear_SL2 = nn.Linear(128, 4)
         for p in ("albedo", "depth"):
@@ -81,8 +90,18 @@ class RelightNet(nn.Module):
         self._tc_key = None
 
     def _add(self, name, mod, cin, cout, k):
-        setattr(self, name, mod(cin, cout, k, padding=(k // 2, k // 2)))
+        if self.variant == "lighting_transfer" and "shortcut" in name:
+            setattr(self, name, mod(cin, cout, 1, bias=False))
+        else:
+            setattr(self, name, mod(cin, cout, k, padding=(k // 2, k // 2)))
         setattr(self, _bn_name(name), nn.BatchNorm2d(cout))
+
+    def sample_table(self):
+        """The reference's sample parameters, bit for bit: np.arange(0.025, 0.825, 0.005) (TRAIN:468) or
+        np.arange(0.03, 0.825, 0.005) (TEST_LT:451)."""
+        t = np.arange(self.sample_start, 0.825, 0.005)
+        assert t.shape[0] == self.num_sample_points
+        return t
 
     # ------------------------------------------------------------------ reference-compatible attributes
     @property
@@ -117,7 +136,11 @@ class RelightNet(nn.Module):
             w = mod.weight.detach().float()
             if isinstance(mod, nn.ConvTranspose2d):          # stride-1 deconv == conv with swapped, flipped kernel
                 w = w.transpose(0, 1).flip(2, 3)
-            b = mod.bias.detach().float()
+            if w.shape[2] == 1 and "shortcut" in name:       # lighting-transfer 1x1 shortcut: the centre tap of a 3x3 kernel,
+                w3 = w.new_zeros(w.shape[0], w.shape[1], 3, 3)   # so it runs on the same tcgen05 kernel (and fuses as the residual)
+                w3[:, :, 1, 1] = w[:, :, 0, 0]
+                w = w3
+            b = mod.bias.detach().float() if mod.bias is not None else w.new_zeros(w.shape[0])
             bn = getattr(self, _bn_name(name), None)
             if bn is not None:
                 scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
@@ -358,11 +381,16 @@ class RelightNet(nn.Module):
         unit = torch.nn.functional.normalize(L, p=2, dim=1)                 # TRAIN:360
         light_pt = (self.light_distance * unit).contiguous()                # TRAIN:362
         fx, fy, cx, cy = self._intrinsics(intrinsic_matrix)
+        samples = self.sample_table()
+        rect = None                                                         # TEST1:495: the image rectangle
+        if self.variant == "lighting_transfer":                            # TEST_LT:503: +-4 image sizes
+            rect = (-4.0 * W, 4.0 * W, 4.0 * (1 - H), 4.0 * H)
         if self.march_variant == 0:          # one launch: every thread shades its pixel right after its ray march
             o = ops.march_shade_fwd(albedo, depth, mask_bits, light_pt, ambient_values, inside_bonus, fx, fy, cx, cy,
-                                    self.depth_offset, self.directional_intensity)
+                                    self.depth_offset, self.directional_intensity, samples=samples, bonus_rect=rect)
         else:
-            d_min, _, _ = ops.shadow_march_fwd(depth, mask_bits, light_pt, inside_bonus=inside_bonus, variant=self.march_variant)
+            d_min, _, _ = ops.shadow_march_fwd(depth, mask_bits, light_pt, samples=samples, inside_bonus=inside_bonus,
+                                               variant=self.march_variant, bonus_rect=rect)
             o = ops.shade_render_fwd(albedo, depth, d_min, light_pt, ambient_values, fx, fy, cx, cy,
                                      self.depth_offset, self.directional_intensity)
         ambient_light = ambient_values.view(B, 1, 1).expand(B, H, W)        # TRAIN:368 (`.repeat` there; a view here)
@@ -375,6 +403,8 @@ class RelightNet(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("RelightNet (geomconsistentfr_b200) runs on CUDA only; call .cuda() first")
         if self.training:
+            if self.variant == "lighting_transfer":
+                raise NotImplementedError("the lighting-transfer variant is inference-only here (TEST_LT); call .eval()")
             if target_lighting is not None:
                 raise NotImplementedError("the TEST1 signature (given target lighting) is an inference call: use .eval()")
             return self._forward_train(img, epoch, intrinsic_matrix, mask)
@@ -388,11 +418,23 @@ class RelightNet(nn.Module):
                 if m.shape[0] not in (1, B):
                     raise RuntimeError("mask must be [H,W,1] (TEST1:488) or [B,H,W,1]")
                 bits = ops.mask_pack(m)
+                if self.variant == "lighting_transfer":                    # TEST_LT:169-514
+                    if target_ambient_values is None:
+                        raise RuntimeError("the lighting-transfer forward uses target_ambient_values (TEST_LT:348)")
+                    ambient_values = target_ambient_values.to(dev, torch.float32).reshape(B).contiguous()
+                    light = target_lighting.to(dev, torch.float32, non_blocking=True)
+                    o, amb_l, unit = self._render(albedo, depth, bits, light, ambient_values, intrinsic_matrix, 5.0, False)
+                    est = torch.cat((sl[:, 1:3], torch.clamp(sl[:, 3:4], min=self.light_z_floor)), 1)       # TEST_LT:329-332
+                    est_unit = torch.nn.functional.normalize(est, p=2, dim=1).view(B, 3, 1, 1)              # TEST_LT:334
+                    return (albedo, depth, o["shadow"], amb_l, o["full"], o["rendered"], unit, ambient_values.view(B, 1, 1),
+                            o["final"], o["normals"], est_unit, sl[:, 0].reshape(B, 1, 1).contiguous())
                 ambient_values = (sl[:, 0] - 0.1).contiguous()              # TEST1:342
                 light = target_lighting.to(dev, torch.float32, non_blocking=True)
                 o, amb_l, unit = self._render(albedo, depth, bits, light, ambient_values, intrinsic_matrix, 5.0, False)
                 return (albedo, depth, o["shadow"], amb_l, o["full"], o["rendered"], unit,
                         ambient_values.view(B, 1, 1), o["final"], o["normals"])
+            if self.variant == "lighting_transfer":
+                raise NotImplementedError("the lighting-transfer variant needs target_lighting / target_ambient_values (TEST_LT:169)")
             m = mask.to(dev, non_blocking=True).reshape(B, H, W)            # TRAIN:196-524
             bits = ops.mask_pack(m)
             ambient_values = sl[:, 0].contiguous()                          # TRAIN:367

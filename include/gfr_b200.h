@@ -58,6 +58,9 @@ int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int H, int W, u
  *   t_host     [n] HOST doubles: the sample parameters, exactly np.arange(0.025, 0.825, 0.005) for the
  *              reference configuration (TRAIN:468); n <= GFR_MAX_SAMPLES
  *   inside_bonus  0 (train) or 5 (test, TEST1:495-496)
+ *   bonus_rect_host  NULL: the bonus applies when the light projects inside the image rectangle (TEST1:495); else HOST
+ *              floats {x_min, x_max, y_min, y_max} the projected light point must lie in (the lighting-transfer script
+ *              uses +-4 image sizes: {-4W, 4W, 4(1-H), 4H}, TEST_LT:503)
  *   d_min      [B,H,W] out
  *   argmin     [B,H,W] out, uint8 index of the minimising sample (255 = every sample was outside the
  *              face); may be NULL.  Needed by the backward.
@@ -72,7 +75,7 @@ int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int H, int W, u
  */
 int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
                          const float* light_pt, const double* t_host, int n, float inside_bonus,
-                         float* d_min, uint8_t* argmin, float* shadow, double* depth64_scratch, int B, int H, int W,
+                         const float* bonus_rect_host, float* d_min, uint8_t* argmin, float* shadow, double* depth64_scratch, int B, int H, int W,
                          int lights_per_face, int variant, void* stream);
 
 /* Normals + Lambertian shading + shadow blend + albedo render.  Replaces TRAIN:353-369 and 517-522
@@ -97,6 +100,7 @@ int gfr_shade_render_fwd(const float* albedo, const float* depth, const float* d
  * depth64_scratch is required.  Bit-identical to the two-launch sequence. */
 int gfr_march_shade_fwd(const float* albedo, const float* depth, const uint32_t* mask_bits, int mask_batch_stride,
                         const float* light_pt, const float* ambient, const double* t_host, int n, float inside_bonus,
+                        const float* bonus_rect_host,
                         const float* intr_host, double* depth64_scratch, float* d_min, uint8_t* argmin, float* shadow,
                         float* full, float* final_shading, float* rendered, float* normals, int B, int H, int W,
                         int lights_per_face, void* stream);

@@ -51,6 +51,6 @@ def test_argument_errors_without_gpu():
     assert lib.gfr_error_string(0) == b"ok"
     # NULL pointers are rejected before any CUDA call
     assert lib.gfr_mask_pack(None, 0, 1, 256, 256, None, None) == -1
-    assert lib.gfr_shadow_march_fwd(None, None, 0, None, None, 160, 0.0, None, None, None, None, 1, 256, 256, 1, 0, None) == -1
+    assert lib.gfr_shadow_march_fwd(None, None, 0, None, None, 160, 0.0, None, None, None, None, None, 1, 256, 256, 1, 0, None) == -1
     assert lib.gfr_shadow_march_bwd(None, None, None, None, None, 160, None, None, 1, 256, 256, None) == -1
     assert lib.gfr_conv_tc_pack_size(16, 16, 16) == 2 * 9 * 4 * 16 * 4 and lib.gfr_conv_tc_pack_size(16, 16, 24) < 0

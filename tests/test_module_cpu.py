@@ -57,3 +57,26 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_lighting_transfer_variant_loads_the_reference_weights_strictly():
+    """TEST_LT:36-42,66-76,119-129: nine 1x1 bias-free shortcuts; model_lighting_transfer/model_epoch106.pth has 391 tensors."""
+    sd = torch.load(os.path.join(G, "model_epoch106.pth"), map_location="cpu")
+    net = RelightNet(variant="lighting_transfer")
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected and len(sd) == 391 == len(net.state_dict())
+    assert net.conv_shortcut_h3_out.weight.shape == (155, 64, 1, 1) and net.conv_shortcut_h3_out.bias is None
+    assert net.deconv_depth_shortcut_all_features.weight.shape == (128, 64, 1, 1)
+    assert (net.directional_intensity, net.num_sample_points, net.depth_offset, net.focal_length) == (0.41, 159, 1410.0, 700.0)
+    import numpy as np
+    assert np.array_equal(net.sample_table(), np.arange(0.03, 0.825, 0.005))              # TEST_LT:451
+    assert np.array_equal(RelightNet().sample_table(), np.arange(0.025, 0.825, 0.005))    # TRAIN:468
+    assert set(net.state_dict()) == set(O.RelightNetOracle(variant="lighting_transfer").state_dict())
+    with pytest.raises(ValueError):
+        RelightNet(variant="nope")
+    # folded eval weights: the 1x1 shortcut becomes the centre tap of a 3x3 kernel with a zero bias
+    f = net.eval()._folded_weights()
+    w, b = f["conv_shortcut_h1_out"]
+    assert w.shape == (32, 16, 3, 3) and float(w[:, :, 0, 0].abs().max()) == 0.0 and float(w[:, :, 1, 1].abs().max()) > 0.0
+    w, b = f["deconv_albedo_shortcut_h5_out"]
+    assert w.shape == (32, 64, 3, 3) and float(w[:, :, 2, 1].abs().max()) == 0.0
