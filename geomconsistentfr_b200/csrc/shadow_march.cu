@@ -34,6 +34,7 @@ struct MarchArgs {
   int fuse_shade;            // 1: normals + Lambert + blend + render of the pixel follow in the same thread (shade)
   gfr_shade::ShadeArgs shade;
   float bonus;
+  double hWd, hHd, neg_eps;   // W/2, H/2 and -1e-4 as fp64 kernel parameters: constant-bank operands of the per-sample DADDs
   float bx0, bx1, by0, by1;   // the light must project into [bx0,bx1] x [by0,by1] for the bonus (TEST1:495 / TEST_LT:503)
 };
 
@@ -101,7 +102,7 @@ shadow_march_fwd_l1(const MarchArgs a, const __grid_constant__ SampleTable tab) 
   ray_end(x, y, Lx, Ly, xmin, xmax, ymin, ymax, ex, ey);
   const double dx = (double)__fsub_rn(ex, x), dy = (double)__fsub_rn(ey, y);          // TRAIN:467
   const double xd = (double)x, yd = (double)y;
-  const double hW = (double)halfW, hH = (double)halfH;
+  const double hW = (double)halfW, hH = (double)halfH, neg_eps = -0.0001;
   const float bcx = __fsub_rn(Lx, x), bcy = __fsub_rn(Ly, y), bcz = __fsub_rn(Lz, z); // BC, TRAIN:507
 
   float qmin = __int_as_float(0x7f800000);   // +inf == "outside the face"
@@ -116,8 +117,8 @@ shadow_march_fwd_l1(const MarchArgs a, const __grid_constant__ SampleTable tab) 
     const int mi = ri * W + ci;
     const bool inside = (s_mask[mi >> 5] >> (mi & 31)) & 1u;                          // TRAIN:510
     if (!inside) continue;        // the reference computes the sample and then overwrites it with 1e6 (TRAIN:510-512)
-    const double u = __dadd_rn(__dadd_rn(px, hW), -0.0001);                           // TRAIN:481,483
-    const double v = __dadd_rn(__dsub_rn(hH, py), -0.0001);                           // TRAIN:482,483
+    const double u = __dadd_rn(__dadd_rn(px, hW), neg_eps);                           // TRAIN:481,483
+    const double v = __dadd_rn(__dsub_rn(hH, py), neg_eps);                           // TRAIN:482,483
     const int uf = __double2int_rd(u), uc = __double2int_ru(u);                       // TRAIN:486-487
     const int vf = __double2int_rd(v), vc = __double2int_ru(v);
     const int ufi = uf < 0 ? uf + W : uf, vfi = vf < 0 ? vf + H : vf;                 // python negative index
@@ -181,7 +182,8 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
 
   const int col = blockIdx.x * TILE_W + threadIdx.x;
   const int row = blockIdx.y * TILE_H + threadIdx.y;
-  const double* __restrict__ D = depth64 + (size_t)f * H * W;
+  const double* D = depth64 + (size_t)f * H * W;
+  asm volatile("" : "+l"(D));               // one 64-bit base register pair: every gather address is then a single IMAD.WIDE
   const float halfW = 0.5f * W, halfH = 0.5f * H;
   const float xmin = -halfW, xmax = W - halfW - 1.0f, ymin = 1.0f - halfH, ymax = halfH;
   const float x = (float)col - halfW;            // TRAIN:52
@@ -194,7 +196,7 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
   const double dx = (double)__fsub_rn(ex, x), dy = (double)__fsub_rn(ey, y);          // TRAIN:467
   double xd = (double)x, yd = (double)y;
   asm volatile("" : "+d"(xd), "+d"(yd));     // keep them in registers: ptxas otherwise re-converts x, y every sample (2 XU ops)
-  const double hW = (double)halfW, hH = (double)halfH;
+  const double hW = a.hWd, hH = a.hHd, neg_eps = a.neg_eps;   // (ptxas re-derived (double)(0.5f*W) per sample: 2 I2F + 2 F2F)
   const float bcx = __fsub_rn(Lx, x), bcy = __fsub_rn(Ly, y), bcz = __fsub_rn(Lz, z); // BC, TRAIN:507
   const int cW = W >> 1, cH = H >> 1;
 
@@ -235,8 +237,8 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
     const int ri = cH - __double2loint(__dadd_rn(py, kMagic));
     const int mi = ri * W + ci;
     if (!((s_mask[mi >> 5] >> (mi & 31)) & 1u)) continue;                             // TRAIN:510-512
-    const double u = __dadd_rn(__dadd_rn(px, hW), -0.0001);                           // TRAIN:481,483
-    const double v = __dadd_rn(__dsub_rn(hH, py), -0.0001);                           // TRAIN:482,483
+    const double u = __dadd_rn(__dadd_rn(px, hW), neg_eps);                           // TRAIN:481,483
+    const double v = __dadd_rn(__dsub_rn(hH, py), neg_eps);                           // TRAIN:482,483
     // floor / ceil: the same magic add in round-down / round-up mode (TRAIN:486-487)
     const double sfu = __dadd_rd(u, kMagic), scu = __dadd_ru(u, kMagic);
     const double sfv = __dadd_rd(v, kMagic), scv = __dadd_ru(v, kMagic);
@@ -247,9 +249,12 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
     const unsigned ufi = uf < 0 ? uf + W : uf, vfi = vf < 0 ? vf + H : vf;            // python negative index
     const double wu0 = __dsub_rn(ucd, u), wu1 = __dsub_rn(u, ufd);
     const double wv0 = __dsub_rn(vcd, v), wv1 = __dsub_rn(v, vfd);
-    const unsigned r0 = vfi * (unsigned)W, r1 = (unsigned)vc * (unsigned)W;
-    const double ul = __ldg(D + (r0 + ufi)), ur = __ldg(D + (r0 + (unsigned)uc));
-    const double ll = __ldg(D + (r1 + ufi)), lr = __ldg(D + (r1 + (unsigned)uc));
+    // four corners from ONE 64-bit address: the other three are 32-bit element offsets (one IMAD.WIDE each)
+    const double* p00 = D + (vfi * (unsigned)W + ufi);
+    const int du = uc - (int)ufi, dv = (vc - (int)vfi) * W;                           // +1 / 0, or -(W-1) / -(H-1)*W on a wrap
+    const double* p10 = p00 + dv;
+    const double ul = __ldg(p00), ur = __ldg(p00 + du);
+    const double ll = __ldg(p10), lr = __ldg(p10 + du);
     const double up = __dadd_rn(__dmul_rn(ul, wu0), __dmul_rn(ur, wu1));              // TRAIN:492
     const double lo = __dadd_rn(__dmul_rn(ll, wu0), __dmul_rn(lr, wu1));              // TRAIN:493
     const double zi = __dadd_rn(__dmul_rn(up, wv0), __dmul_rn(lo, wv1));              // TRAIN:494
@@ -359,6 +364,7 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
   a.depth = depth; a.mask_bits = mask_bits; a.light = light_pt; a.dmin = d_min; a.argmin = argmin; a.shadow = shadow;
   a.mask_stride = mask_batch_stride; a.B = B; a.H = H; a.W = W; a.n = n; a.lpf = lights_per_face; a.t0 = t0; a.inv_dt = inv_dt;
   a.bonus = inside_bonus;
+  a.hWd = (double)(0.5f * W); a.hHd = (double)(0.5f * H); a.neg_eps = -0.0001;
   if (bonus_rect_host != nullptr) {
     a.bx0 = bonus_rect_host[0]; a.bx1 = bonus_rect_host[1]; a.by0 = bonus_rect_host[2]; a.by1 = bonus_rect_host[3];
   } else {                                   // the image rectangle, TEST1:495

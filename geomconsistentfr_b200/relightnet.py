@@ -174,7 +174,10 @@ class RelightNet(nn.Module):
         return t
 
     # ------------------------------------------------------------------ CNN (eval mode) on the tensor cores, TRAIN:197-350
-    def _cnn_eval_tc(self, img, epoch):
+    def _cnn_eval_tc(self, img, epoch, after_encoder=None):
+        """-> albedo, depth, sl, after_encoder(sl).  The light head and `after_encoder` (light / ambient / mask preparation
+        for the render stage) run on an auxiliary stream as soon as the encoder is done, beside the two decoders, so they
+        are off the critical path (a third parallel branch under graph capture)."""
         t = self._tc_weights()
         prec = self.tc_precision
 
@@ -190,8 +193,13 @@ class RelightNet(nn.Module):
         h3_og = conv("conv_h3_2", conv("conv_h3_1", h2), res=conv("conv_shortcut_h2_out", h2, act=None))
         h3 = ops.maxpool2_c4_fwd(h3_og)
         h4 = conv("conv_h4_2", conv("conv_h4_1", h3), res=conv("conv_shortcut_h3_out", h3, act=None))
-        sl = ops.light_head_c4_fwd(h4, 128, self.linear_SL1.weight, self.linear_SL1.bias,
-                                   self.linear_SL2.weight, self.linear_SL2.bias)        # [B,4]  TRAIN:225-232
+        cur = torch.cuda.current_stream()
+        side, aux = self._side_stream(), self._side_stream("_aux")
+        aux.wait_stream(cur)
+        with torch.cuda.stream(aux):
+            sl = ops.light_head_c4_fwd(h4, 128, self.linear_SL1.weight, self.linear_SL1.bias,
+                                       self.linear_SL2.weight, self.linear_SL2.bias)    # [B,4]  TRAIN:225-232
+            prep = after_encoder(sl) if after_encoder is not None else None
         skips = {"s1": h3_og, "s2": h2_og, "s3": h1_og, "s4": c1_og}
 
         def decoder(p):
@@ -214,21 +222,22 @@ class RelightNet(nn.Module):
 
         # the two decoders are independent (TRAIN:235-290 / 293-350): the depth decoder runs on a side stream so the
         # small low-resolution layers of one overlap those of the other (under graph capture: two parallel branches)
-        cur = torch.cuda.current_stream()
-        side = self._side_stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             depth = decoder("depth")
         albedo = decoder("albedo")
         cur.wait_stream(side)
+        cur.wait_stream(aux)
         depth.record_stream(cur)
-        return albedo, depth, sl
+        for tns in [sl] + [v for v in (prep or {}).values() if torch.is_tensor(v)]:
+            tns.record_stream(cur)
+        return albedo, depth, sl, prep
 
-    def _side_stream(self):
+    def _side_stream(self, name="_side"):
         dev = self.device
-        if getattr(self, "_side", None) is None or self._side.device != dev:
-            self._side = torch.cuda.Stream(device=dev)
-        return self._side
+        if getattr(self, name, None) is None or getattr(self, name).device != dev:
+            setattr(self, name, torch.cuda.Stream(device=dev))
+        return getattr(self, name)
 
     @staticmethod
     def _up_and_skip_tc(conv, p, skip, t, enc, epoch):
@@ -311,9 +320,13 @@ class RelightNet(nn.Module):
         return (albedo, depth, shadow, ambient_light, full, rendered, unit.view(B, 3, 1, 1), ambient_values.view(B, 1, 1))
 
     # ------------------------------------------------------------------ CNN (eval mode), exact fp32 on CUDA cores
-    def _cnn_eval(self, img, epoch):
+    def _cnn_eval(self, img, epoch, after_encoder=None):
         if self.cnn_impl == "tc":
-            return self._cnn_eval_tc(img.contiguous(), epoch)
+            return self._cnn_eval_tc(img.contiguous(), epoch, after_encoder)
+        albedo, depth, sl = self._cnn_eval_direct(img, epoch)
+        return albedo, depth, sl, (after_encoder(sl) if after_encoder is not None else None)
+
+    def _cnn_eval_direct(self, img, epoch):
         f = self._folded_weights()
 
         def conv(name, x, **kw):
@@ -373,13 +386,18 @@ class RelightNet(nn.Module):
             self._intr_cache = (key, (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])))
         return self._intr_cache[1]
 
-    def _render(self, albedo, depth, mask_bits, light_dir, ambient_values, intrinsic_matrix, inside_bonus, clamp_z):
-        B, _, H, W = depth.shape
-        L = light_dir.reshape(B, 3)
+    def _light_prep(self, light_dir, n_pairs, clamp_z):
+        """unit light direction and point light of every (face, light) pair — TRAIN:357-362 / TEST1:332-335."""
+        L = light_dir.reshape(n_pairs, 3)
         if clamp_z:                                                         # TRAIN:357-359
             L = torch.cat((L[:, 0:2], torch.clamp(L[:, 2:3], min=0.0)), 1)
         unit = torch.nn.functional.normalize(L, p=2, dim=1)                 # TRAIN:360
-        light_pt = (self.light_distance * unit).contiguous()                # TRAIN:362
+        return unit, (self.light_distance * unit).contiguous()              # TRAIN:362
+
+    def _render(self, albedo, depth, prep, intrinsic_matrix, inside_bonus, want=("shadow", "full", "final", "rendered", "normals")):
+        """prep: dict(bits, ambient [F], unit [B,3], light_pt [B,3]) made by the forward's after-encoder hook."""
+        F_, _, H, W = depth.shape
+        mask_bits, ambient_values, light_pt = prep["bits"], prep["ambient"], prep["light_pt"]
         fx, fy, cx, cy = self._intrinsics(intrinsic_matrix)
         samples = self.sample_table()
         rect = None                                                         # TEST1:495: the image rectangle
@@ -387,14 +405,14 @@ class RelightNet(nn.Module):
             rect = (-4.0 * W, 4.0 * W, 4.0 * (1 - H), 4.0 * H)
         if self.march_variant == 0:          # one launch: every thread shades its pixel right after its ray march
             o = ops.march_shade_fwd(albedo, depth, mask_bits, light_pt, ambient_values, inside_bonus, fx, fy, cx, cy,
-                                    self.depth_offset, self.directional_intensity, samples=samples, bonus_rect=rect)
+                                    self.depth_offset, self.directional_intensity, want=want, samples=samples, bonus_rect=rect)
         else:
             d_min, _, _ = ops.shadow_march_fwd(depth, mask_bits, light_pt, samples=samples, inside_bonus=inside_bonus,
                                                variant=self.march_variant, bonus_rect=rect)
             o = ops.shade_render_fwd(albedo, depth, d_min, light_pt, ambient_values, fx, fy, cx, cy,
-                                     self.depth_offset, self.directional_intensity)
-        ambient_light = ambient_values.view(B, 1, 1).expand(B, H, W)        # TRAIN:368 (`.repeat` there; a view here)
-        return o, ambient_light, unit.view(B, 3, 1, 1)
+                                     self.depth_offset, self.directional_intensity, want=want)
+        ambient_light = ambient_values.view(F_, 1, 1).expand(F_, H, W)      # TRAIN:368 (`.repeat` there; a view here)
+        return o, ambient_light, prep["unit"].view(-1, 3, 1, 1)
 
     # ------------------------------------------------------------------ forward: both reference signatures
     def forward(self, img, epoch, intrinsic_matrix, mask, target_lighting=None, target_ambient_values=None,
@@ -411,39 +429,39 @@ class RelightNet(nn.Module):
         img = img.to(dev, torch.float32, non_blocking=True)
         B, H, W, _ = img.shape
         test_mode = target_lighting is not None
+        lt = self.variant == "lighting_transfer"
+        if lt and not test_mode:
+            raise NotImplementedError("the lighting-transfer variant needs target_lighting / target_ambient_values (TEST_LT:169)")
+        if lt and target_ambient_values is None:
+            raise RuntimeError("the lighting-transfer forward uses target_ambient_values (TEST_LT:348)")
+        m = mask.to(dev, non_blocking=True).reshape(-1, H, W)      # (H,W,1) like TEST1:488, or one mask per face (TRAIN:510)
+        if m.shape[0] != B and not (test_mode and m.shape[0] == 1):
+            raise RuntimeError("mask must be [B,H,W,1] (TRAIN:510)" + (" or [H,W,1] (TEST1:488)" if test_mode else ""))
+
+        def prep(sl):                     # runs on the auxiliary stream, beside the decoders
+            if lt:                                                          # TEST_LT:348: the given ambient is used
+                ambient = target_ambient_values.to(dev, torch.float32).reshape(B).contiguous()
+            elif test_mode:
+                ambient = (sl[:, 0] - 0.1).contiguous()                     # TEST1:342
+            else:
+                ambient = sl[:, 0].contiguous()                             # TRAIN:367
+            light = target_lighting.to(dev, torch.float32, non_blocking=True) if test_mode else sl[:, 1:4]
+            unit, light_pt = self._light_prep(light, B, clamp_z=not test_mode)
+            return dict(bits=ops.mask_pack(m), ambient=ambient, unit=unit, light_pt=light_pt)
+
         with torch.no_grad():
-            albedo, depth, sl = self._cnn_eval(img, epoch)
-            if test_mode:                                                   # TEST1:169-505
-                m = mask.to(dev, non_blocking=True).reshape(-1, H, W)   # (H,W,1) like the reference, or one mask per face
-                if m.shape[0] not in (1, B):
-                    raise RuntimeError("mask must be [H,W,1] (TEST1:488) or [B,H,W,1]")
-                bits = ops.mask_pack(m)
-                if self.variant == "lighting_transfer":                    # TEST_LT:169-514
-                    if target_ambient_values is None:
-                        raise RuntimeError("the lighting-transfer forward uses target_ambient_values (TEST_LT:348)")
-                    ambient_values = target_ambient_values.to(dev, torch.float32).reshape(B).contiguous()
-                    light = target_lighting.to(dev, torch.float32, non_blocking=True)
-                    o, amb_l, unit = self._render(albedo, depth, bits, light, ambient_values, intrinsic_matrix, 5.0, False)
-                    est = torch.cat((sl[:, 1:3], torch.clamp(sl[:, 3:4], min=self.light_z_floor)), 1)       # TEST_LT:329-332
-                    est_unit = torch.nn.functional.normalize(est, p=2, dim=1).view(B, 3, 1, 1)              # TEST_LT:334
-                    return (albedo, depth, o["shadow"], amb_l, o["full"], o["rendered"], unit, ambient_values.view(B, 1, 1),
-                            o["final"], o["normals"], est_unit, sl[:, 0].reshape(B, 1, 1).contiguous())
-                ambient_values = (sl[:, 0] - 0.1).contiguous()              # TEST1:342
-                light = target_lighting.to(dev, torch.float32, non_blocking=True)
-                o, amb_l, unit = self._render(albedo, depth, bits, light, ambient_values, intrinsic_matrix, 5.0, False)
-                return (albedo, depth, o["shadow"], amb_l, o["full"], o["rendered"], unit,
-                        ambient_values.view(B, 1, 1), o["final"], o["normals"])
-            if self.variant == "lighting_transfer":
-                raise NotImplementedError("the lighting-transfer variant needs target_lighting / target_ambient_values (TEST_LT:169)")
-            m = mask.to(dev, non_blocking=True).reshape(B, H, W)            # TRAIN:196-524
-            bits = ops.mask_pack(m)
-            ambient_values = sl[:, 0].contiguous()                          # TRAIN:367
-            o, amb_l, unit = self._render(albedo, depth, bits, sl[:, 1:4], ambient_values, intrinsic_matrix, 0.0, True)
-            return (albedo, depth, o["shadow"], amb_l, o["full"], o["rendered"], unit, ambient_values.view(B, 1, 1))
+            albedo, depth, sl, pr = self._cnn_eval(img, epoch, prep)
+            o, amb_l, unit = self._render(albedo, depth, pr, intrinsic_matrix, 5.0 if test_mode else 0.0)
+            out = (albedo, depth, o["shadow"], amb_l, o["full"], o["rendered"], unit, pr["ambient"].view(B, 1, 1))
+            if not test_mode:                                               # TRAIN:196-524 (8-tuple)
+                return out
+            out = out + (o["final"], o["normals"])                          # TEST1:169-505 (10-tuple)
+            if lt:                                                          # TEST_LT:169-514 (12-tuple)
+                est = torch.cat((sl[:, 1:3], torch.clamp(sl[:, 3:4], min=self.light_z_floor)), 1)       # TEST_LT:329-332
+                est_unit = torch.nn.functional.normalize(est, p=2, dim=1).view(B, 3, 1, 1)              # TEST_LT:334
+                out = out + (est_unit, sl[:, 0].reshape(B, 1, 1).contiguous())
+            return out
 
-
-    # ------------------------------------------------------------------ one CNN pass, many lights (TESTB:565-583 sweep)
-    @torch.no_grad()
     def relight_sweep(self, img, epoch, intrinsic_matrix, mask, lights):
         """Relight F faces under L lights with ONE CNN pass per face (the reference re-runs the whole network for every
         light of its 18-direction Multi-PIE sweep, TESTB:565-583).  img [F,H,W,3]; mask [H,W,1] (shared) or [F,H,W,1];
@@ -459,15 +477,16 @@ class RelightNet(nn.Module):
         if lights.dim() == 2:
             lights = lights.unsqueeze(0).expand(F_, -1, -1)
         L = lights.shape[1]
-        albedo, depth, sl = self._cnn_eval(img, epoch)
-        m = mask.to(dev, non_blocking=True)
-        bits = ops.mask_pack(m.reshape(-1, H, W))
-        ambient = (sl[:, 0] - 0.1).contiguous()                                          # TEST1:342
-        unit = torch.nn.functional.normalize(lights.reshape(F_ * L, 3), p=2, dim=1)
-        light_pt = (self.light_distance * unit).contiguous()
-        fx, fy, cx, cy = self._intrinsics(intrinsic_matrix)
-        o = ops.march_shade_fwd(albedo, depth, bits, light_pt, ambient, 5.0, fx, fy, cx, cy, self.depth_offset,
-                                self.directional_intensity, want=("shadow", "final", "rendered"))
+        m = mask.to(dev, non_blocking=True).reshape(-1, H, W)
+
+        def prep(sl):
+            unit, light_pt = self._light_prep(lights, F_ * L, clamp_z=False)
+            return dict(bits=ops.mask_pack(m), ambient=(sl[:, 0] - 0.1).contiguous(), unit=unit, light_pt=light_pt)   # TEST1:342
+
+        with torch.no_grad():
+            albedo, depth, sl, pr = self._cnn_eval(img, epoch, prep)
+            o, _, _ = self._render(albedo, depth, pr, intrinsic_matrix, 5.0, want=("shadow", "final", "rendered"))
+        ambient, unit = pr["ambient"], pr["unit"]
         return dict(rendered=o["rendered"].view(F_, L, 3, H, W), shadow=o["shadow"].view(F_, L, H, W),
                     final=o["final"].view(F_, L, H, W), albedo=albedo, depth=depth, ambient=ambient,
                     unit_light=unit.view(F_, L, 3))
