@@ -168,8 +168,14 @@ __device__ __forceinline__ void round_parts(double v, int& r, double& rd) {
   rd = __dsub_rn(s, kMagic);
 }
 
-__global__ void __launch_bounds__(TILE_W * TILE_H, 4)
+// TH = rows of the CTA tile (32 x TH pixels, TH warps).  TH = 8: 256-thread CTAs, 4 per SM.  TH = 4: 128-thread CTAs (8 per
+// SM) that also fit beside two resident tcgen05 conv CTAs (2 x 320 threads x 84 registers + 175 KB shared memory leave
+// room for 128 x 62 registers + 8 KB), so the issue-bound march of one runner lane can share SMs with the shared-memory /
+// tensor-bound convolutions of another.
+template <int TH>
+__global__ void __launch_bounds__(TILE_W * TH, 1024 / (TILE_W * TH))
 shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, const __grid_constant__ SampleTable tab) {
+  constexpr int TILE_H = TH;
   extern __shared__ uint32_t s_mask[];
   const int b = blockIdx.z, f = b / a.lpf;
   const int H = a.H, W = a.W;
@@ -371,14 +377,20 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
     a.bx0 = -0.5f * W; a.bx1 = W - 0.5f * W - 1.0f; a.by0 = 1.0f - 0.5f * H; a.by1 = 0.5f * H;
   }
   if (fuse != nullptr) { a.fuse_shade = 1; a.shade = *fuse; }
-  const dim3 grid(W / TILE_W, H / TILE_H, B), block(TILE_W, TILE_H);
+  dim3 grid(W / TILE_W, H / TILE_H, B), block(TILE_W, TILE_H);
   const size_t smem = (size_t)(H * W / 32) * sizeof(uint32_t);
+  static const int fast_th = [] { const char* e = getenv("GFR_MARCH_TILE_H"); return (e && atoi(e) == 8) ? 8 : 4; }();
   const bool fast_ok = ((size_t)faces * H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
   if (fuse != nullptr && !fast_ok) return GFR_E_SHAPE;
   if (variant == 0 && depth64_scratch != nullptr && fast_ok) {
     const size_t n4 = (size_t)faces * H * W / 4;
     widen_depth_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch, n4);
-    shadow_march_fwd_fast<<<grid, block, smem, (cudaStream_t)stream>>>(a, depth64_scratch, tab);
+    if (fast_th == 4 && H % 4 == 0) {
+      grid.y = H / 4; block.y = 4;
+      shadow_march_fwd_fast<4><<<grid, block, smem, (cudaStream_t)stream>>>(a, depth64_scratch, tab);
+    } else {
+      shadow_march_fwd_fast<8><<<grid, block, smem, (cudaStream_t)stream>>>(a, depth64_scratch, tab);
+    }
   } else {
     shadow_march_fwd_l1<<<grid, block, smem, (cudaStream_t)stream>>>(a, tab);
   }

@@ -321,10 +321,13 @@ class RelightNet(nn.Module):
 
     # ------------------------------------------------------------------ CNN (eval mode), exact fp32 on CUDA cores
     def _cnn_eval(self, img, epoch, after_encoder=None):
+        """-> (albedo, depth, sl), plus after_encoder(sl) as a fourth item when a hook is given."""
         if self.cnn_impl == "tc":
-            return self._cnn_eval_tc(img.contiguous(), epoch, after_encoder)
-        albedo, depth, sl = self._cnn_eval_direct(img, epoch)
-        return albedo, depth, sl, (after_encoder(sl) if after_encoder is not None else None)
+            r = self._cnn_eval_tc(img.contiguous(), epoch, after_encoder)
+        else:
+            albedo, depth, sl = self._cnn_eval_direct(img, epoch)
+            r = (albedo, depth, sl, after_encoder(sl) if after_encoder is not None else None)
+        return r if after_encoder is not None else r[:3]
 
     def _cnn_eval_direct(self, img, epoch):
         f = self._folded_weights()
