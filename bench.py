@@ -402,6 +402,16 @@ def main():
     if os.path.isfile(tp):
         traffic = json.load(open(tp))
 
+    # the bound that actually binds: warp-instruction issue (ncu instruction count of the same launch / live duration
+    # against 148 SMs x 4 schedulers x SM clock)
+    issue = None
+    if traffic.get("fused_inst_executed") and B == 8:
+        peak_ginst = 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e-3
+        ach = traffic["fused_inst_executed"] / (fused_ms * 1e-3) / 1e9
+        issue = {"bound": "warp-instruction issue", "warp_inst_per_launch": traffic["fused_inst_executed"],
+                 "achieved": ach, "peak": peak_ginst, "unit": "G warp-inst/s", "frac": ach / peak_ginst,
+                 "source": "smsp__inst_executed.sum from profiles/r01_ncu_march_shade_full.csv"}
+
     line = {
         "metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -430,6 +440,7 @@ def main():
                              "in-mask pixel against 56 algorithmic bytes per pixel), not HBM bound - DESIGN.md 3/K1; "
                              "gsamples_per_s counts the reference's 160 samples for every pixel",
                      "gsamples_per_s": MARCH_SAMPLES_PER_FACE * B / (fused_ms * 1e-3) / 1e9,
+                     "issue": issue,
                      "march_only": {"kernel": "shadow_march_fwd_fast", "ms_per_launch": march_ms,
                                     "algorithmic_bytes_per_face": MARCH_BYTES_PER_FACE,
                                     "achieved": MARCH_BYTES_PER_FACE * B / (march_ms * 1e-3) / 1e9,
