@@ -223,10 +223,15 @@ def run_train(args, rank, world, local, dist):
                                                                "; PatchGAN terms skipped (--no-gan)"), "global_batch": world * B,
                        "parallelism": "dp%d, one all_reduce of %.1f MB per step" % (world, step.opt.grad.numel() * 4 / 1e6),
                        "working_set": "activations of one step (> L2) are rewritten every step", "cuda_graph": not args.no_graph},
-            "gpu_launches": int(ops.launch_count() - n0), "final_loss": float(total)}))
+            "gpu_launches": int(ops.launch_count() - n0), "final_loss": float(total)}), flush=True)
     if dist is not None:
+        # the step graphs hold captured NCCL kernels: tearing the communicator down under them was observed to hang at
+        # interpreter exit on 2 GPUs, so synchronise, agree that everybody is done, and leave without finalisers
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
