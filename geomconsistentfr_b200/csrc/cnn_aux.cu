@@ -8,8 +8,6 @@
 //   * light  — global average pool of the 27 lighting channels + the 2-layer MLP (TRAIN:225-232) on a C4 feature map.
 #include "gfr_common.cuh"
 
-#include <stdlib.h>
-
 namespace {
 
 // ------------------------------------------------------------------------------------------------- stem
@@ -25,21 +23,9 @@ struct StemArgs {
 constexpr int ST_TW = 32, ST_TH = 16;                          // CTA tile (pixels); thread = 2x2 pixels
 constexpr int ST_IW = ST_TW + 4, ST_IH = ST_TH + 4;
 
-// SW = true: the 1216 weights are copied from the kernel parameter into shared memory once per CTA and reach the FFMAs as
-// LDS.128 broadcasts (register operands).  SW = false: they are FFMA uniform-register operands fed by LDCU loads of the
-// constant bank - 287 LDCU for 3517 FFMA with ~60 uniform registers to hide their latency in, which left the kernel at
-// 23 % of its issue rate.
-template <bool SW>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const StemArgs a, const __grid_constant__ StemWeights wt) {
   __shared__ __align__(16) float s_in[3][ST_IH][ST_IW];
-  __shared__ __align__(16) float s_w[SW ? 75 : 1][16];
-  __shared__ float s_b[16];
   const int tid = threadIdx.x;
-  if (SW) {
-    const float* wp = &wt.w[0][0][0];
-    for (int i = tid; i < 75 * 16; i += 128) s_w[i >> 4][i & 15] = wp[i];
-    if (tid < 16) s_b[tid] = wt.b[tid];
-  }
   const int tiles_x = gfr_ceil_div(a.W, ST_TW);
   const int x0 = (blockIdx.x % tiles_x) * ST_TW, y0 = (blockIdx.x / tiles_x) * ST_TH;
   const int n = blockIdx.y;
@@ -61,7 +47,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemArgs a, const 
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[p][c] = SW ? s_b[c] : wt.b[c];
+    for (int c = 0; c < 16; ++c) acc[p][c] = wt.b[c];
 
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci) {
@@ -79,7 +65,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemArgs a, const 
       for (int kx = 0; kx < 5; ++kx)
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          const float w = SW ? s_w[(ky * 5 + kx) * 3 + ci][c] : wt.w[ky * 5 + kx][ci][c];
+          const float w = wt.w[ky * 5 + kx][ci][c];
           acc[0][c] = fmaf(w, win[ky][kx], acc[0][c]);
           acc[1][c] = fmaf(w, win[ky][kx + 1], acc[1][c]);
           acc[2][c] = fmaf(w, win[ky + 1][kx], acc[2][c]);
@@ -210,9 +196,7 @@ extern "C" int gfr_stem_conv_fwd(const float* img, const float* w_host, const fl
   }
   StemArgs a{img, out, pooled, N, H, W};
   const dim3 grid(gfr_ceil_div(W, ST_TW) * gfr_ceil_div(H, ST_TH), N);
-  static const bool ldcu = [] { const char* e = getenv("GFR_STEM_WEIGHTS"); return e && e[0] == 'c'; }();   // "const": the old path (A/B)
-  if (ldcu) stem_conv_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a, wt);
-  else stem_conv_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a, wt);
+  stem_conv_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, wt);
   return gfr_launch_status();
 }
 
