@@ -121,21 +121,26 @@ def test_full_size_properties_without_an_oracle(ops):
     P_L = _lp(LIGHTS_18[4:4 + B])
     bits = ops.mask_pack(masks.cuda())
     d, a, s = ops.shadow_march_fwd(depth.cuda(), bits, P_L.cuda(), want_argmin=True, want_shadow=True)
-    assert float(s.min()) >= 0.0 and float(s.max()) <= 1.0 and bool((s[a == 255] == 1.0).all()) and bool((d[a == 255] == 1e6).all())
+    # (s = 1 - 4e/(1+e)^2 in fp32 can come out one ulp below 0 where d_min ~ 1e-6: the reference's formula does the same)
+    assert float(s.min()) >= -2e-7, float(s.min())
+    assert float(s.max()) <= 1.0, float(s.max())
+    assert bool((s[a == 255] == 1.0).all()) and bool((d[a == 255] == 1e6).all())
     grown = torch.nn.functional.max_pool2d(masks.float()[:, None], 9, 1, 4)[:, 0].to(torch.uint8)
     d2, _, _ = ops.shadow_march_fwd(depth.cuda(), ops.mask_pack(grown.cuda()), P_L.cuda())
-    assert bool((d2 <= d).all()) and bool((d2 < d).any())
+    assert bool((d2 <= d).all()), int((d2 > d).sum())
+    assert bool((d2 < d).any())
     for b in (0, 5):
         db, _, _ = ops.shadow_march_fwd(depth[b:b + 1].cuda(), ops.mask_pack(masks[b:b + 1].cuda()), P_L[b:b + 1].cuda())
-        assert torch.equal(db[0], d[b])
+        assert torch.equal(db[0], d[b]), b
     dl, _, _ = ops.shadow_march_fwd(depth[:2].cuda(), ops.mask_pack(masks[:2].cuda()), P_L.cuda())      # 2 faces x 4 lights
     for f in range(2):
         for l in range(4):
             one, _, _ = ops.shadow_march_fwd(depth[f:f + 1].cuda(), ops.mask_pack(masks[f:f + 1].cuda()), P_L[4 * f + l:4 * f + l + 1].cuda())
-            assert torch.equal(one[0], dl[4 * f + l])
+            assert torch.equal(one[0], dl[4 * f + l]), (f, l)
     d1, _, _ = ops.shadow_march_fwd(depth.cuda(), bits, P_L.cuda(), variant=1)
-    assert torch.equal(d1, d)
+    assert torch.equal(d1, d), "variant 1 != variant 0"
     amb = torch.full((B,), 0.3, device="cuda")
     o = ops.march_shade_fwd(torch.rand(B, 3, 256, 256, device="cuda"), depth.cuda(), bits, P_L.cuda(), amb,
                             want=("shadow", "d_min"))
-    assert torch.equal(o["d_min"], d) and torch.equal(o["shadow"], s)
+    assert torch.equal(o["d_min"], d), "fused d_min"
+    assert torch.equal(o["shadow"], s), "fused shadow"
