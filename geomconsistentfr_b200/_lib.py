@@ -54,6 +54,7 @@ _PROTOS = {
     "gfr_conv_tc_pack_size": [_c_int, _c_int, _c_int],
     "gfr_conv_tc_pack_weights": [_c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_conv3x3_tc_fwd": [_c_void_p] * 6 + [_c_int] * 9 + [_c_float, _c_int, _c_int, _c_float, _c_float, _c_void_p],
+    "gfr_conv3x3_tc_head_fwd": [_c_void_p] * 5 + [_c_int] * 7 + [_c_float, _c_int, _c_int, _c_float, _c_float, _c_void_p],
     "gfr_conv_tc_pack_size_f16": [_c_int, _c_int, _c_int],
     "gfr_conv_tc_pack_weights_f16": [_c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
     "gfr_stem_conv_fwd": [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p],

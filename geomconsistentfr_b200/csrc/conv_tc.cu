@@ -62,6 +62,12 @@ struct ConvTcArgs {
   int static_w;        // 1: the packed weights were not written by the preceding kernel: fetch them before griddepcontrol.wait
   float out_scale;
   float x_scale, inv_scale;   // F16 kind: activations are multiplied by x_scale before the fp16 split, the sum by 1/(x_scale*w_scale)
+  // HEAD variant (decoder tail fused into the epilogue of c2_1, TRAIN:284-290 / 344-350): the 16 activated channels of a pixel
+  // go through c2_2, c2_3 (1x1, 16 -> 16, BN folded, LeakyReLU) and c2_o (1x1, 16 -> head_n) in the pixel's own thread
+  const float* head;   // [w2 16x16 | b2 16 | w3 16x16 | b3 16 | wo 3x16 | bo 4] floats ([co][ci] rows), device
+  float* head_out;     // NCHW [N][head_n][H][W]
+  int head_n, head_act;
+  float head_scale;
 };
 
 constexpr int KIND_TF32 = 0, KIND_F16 = 1;
@@ -78,9 +84,10 @@ struct Smem {
   static constexpr uint32_t TMEM_COLS = 4 * NT <= 32 ? 32 : (4 * NT <= 64 ? 64 : (4 * NT <= 128 ? 128 : 256));
 };
 
-template <int NT, int KIND>
+template <int NT, int KIND, bool HEAD = false>
 __global__ void __launch_bounds__(NUM_THREADS, NT <= 32 ? 2 : 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a) {
+  static_assert(!HEAD || NT == 16, "the fused decoder tail needs the pixel's 16 channels in one thread");
   using S = Smem<NT, KIND>;
   constexpr int STAGES = S::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -266,7 +273,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
       const size_t o_base = (((size_t)n * C4out * a.H + y) * a.W + x) * 4;            // + cq * H*W*4
       const size_t o_plane = (size_t)a.H * a.W * 4;
       // NT <= 16: into registers; wider tiles: an L2 prefetch (no registers), the loads themselves come after the MMAs
-      constexpr bool PREF_REGS = NT <= 16;
+      constexpr bool PREF_REGS = NT <= 16 && !HEAD;      // (the HEAD variant has no residual / post operands)
       float4 rres[PREF_REGS ? NT / 4 : 1], rpost[PREF_REGS ? NT / 4 : 1];
 #pragma unroll
       for (int c0 = 0; c0 < NT; c0 += 4) {
@@ -275,7 +282,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
           rres[c0 / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
           rpost[c0 / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (ok && cq < C4out) {
+        if (!HEAD && ok && cq < C4out) {
           const size_t po = ((((size_t)n * C4out + cq) * pH + (y >> a.post_shift)) * pW + (x >> a.post_shift)) * 4;
           if (PREF_REGS) {
             if (a.res) rres[c0 / 4] = __ldg(reinterpret_cast<const float4*>(a.res + o_base + (size_t)cq * o_plane));
@@ -306,6 +313,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
         tc_fence_before_sync();
         mbar_arrive(bar_accempty + 8 * p);
       }
+      [[maybe_unused]] float yv[HEAD ? NT : 1];
       if (ok) {
 #pragma unroll
         for (int c0 = 0; c0 < NT; c0 += 4) {
@@ -318,7 +326,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
           float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), pp = rr;
           if (PREF_REGS) {
             rr = rres[c0 / 4]; pp = rpost[c0 / 4];
-          } else {
+          } else if (!HEAD) {
             if (a.res) rr = __ldg(reinterpret_cast<const float4*>(a.res + o_base + (size_t)cq * o_plane));
             if (a.post) pp = __ldg(reinterpret_cast<const float4*>(a.post + ((((size_t)n * C4out + cq) * pH + (y >> a.post_shift)) * pW + (x >> a.post_shift)) * 4));
           }
@@ -331,8 +339,58 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
             for (int e = 0; e < 4; ++e) v[e] = 1.0f / (1.0f + expf(-v[e]));
           }
           v[0] += pp.x; v[1] += pp.y; v[2] += pp.z; v[3] += pp.w;
-          *reinterpret_cast<float4*>(a.out + o_base + (size_t)cq * o_plane) =
-              make_float4(v[0] * a.out_scale, v[1] * a.out_scale, v[2] * a.out_scale, v[3] * a.out_scale);
+          if constexpr (HEAD) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) yv[c0 + e] = v[e] * a.out_scale;
+          } else {
+            *reinterpret_cast<float4*>(a.out + o_base + (size_t)cq * o_plane) =
+                make_float4(v[0] * a.out_scale, v[1] * a.out_scale, v[2] * a.out_scale, v[3] * a.out_scale);
+          }
+        }
+        if constexpr (HEAD) {
+          // c2_2 -> c2_3 -> c2_o per pixel; weight rows are warp-uniform 16-byte loads (L1-resident, 2.4 KB in all),
+          // accumulation order = the stand-alone head_1x1_kernel's (bias first, ci ascending)
+          const float4* hw = reinterpret_cast<const float4*>(a.head);
+          float h2[16];
+#pragma unroll
+          for (int o = 0; o < 16; ++o) {
+            float acc = __ldg(a.head + 256 + o);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 w = __ldg(hw + o * 4 + c4);
+              acc = fmaf(w.x, yv[4 * c4], acc); acc = fmaf(w.y, yv[4 * c4 + 1], acc);
+              acc = fmaf(w.z, yv[4 * c4 + 2], acc); acc = fmaf(w.w, yv[4 * c4 + 3], acc);
+            }
+            h2[o] = acc > 0.f ? acc : 0.2f * acc;
+            if ((o & 3) == 3) asm volatile("" ::: "memory");     // keep the weight loads from being hoisted 150 deep (spills)
+          }
+#pragma unroll
+          for (int o = 0; o < 16; ++o) {
+            float acc = __ldg(a.head + 528 + o);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 w = __ldg(hw + 68 + o * 4 + c4);
+              acc = fmaf(w.x, h2[4 * c4], acc); acc = fmaf(w.y, h2[4 * c4 + 1], acc);
+              acc = fmaf(w.z, h2[4 * c4 + 2], acc); acc = fmaf(w.w, h2[4 * c4 + 3], acc);
+            }
+            yv[o] = acc > 0.f ? acc : 0.2f * acc;
+            if ((o & 3) == 3) asm volatile("" ::: "memory");
+          }
+          const size_t hw_px = (size_t)a.H * a.W;
+          float* op = a.head_out + (size_t)n * a.head_n * hw_px + (size_t)y * a.W + x;
+#pragma unroll
+          for (int o = 0; o < 3; ++o) {
+            if (o >= a.head_n) break;
+            float acc = __ldg(a.head + 592 + o);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 w = __ldg(hw + 136 + o * 4 + c4);
+              acc = fmaf(w.x, yv[4 * c4], acc); acc = fmaf(w.y, yv[4 * c4 + 1], acc);
+              acc = fmaf(w.z, yv[4 * c4 + 2], acc); acc = fmaf(w.w, yv[4 * c4 + 3], acc);
+            }
+            if (a.head_act == 2) acc = 1.0f / (1.0f + expf(-acc));
+            op[(size_t)o * hw_px] = acc * a.head_scale;
+          }
         }
       }
     }
@@ -385,13 +443,13 @@ int make_c4_map(CUtensorMap* tm, const float* base, int N, int C4, int C4_alloc,
   return r == CUDA_SUCCESS ? GFR_OK : GFR_E_ARG;
 }
 
-template <int NT, int KIND>
+template <int NT, int KIND, bool HEAD = false>
 int launch_tc(const CUtensorMap& tm, const ConvTcArgs& a, cudaStream_t s) {
   using S = Smem<NT, KIND>;
   static bool attr_done = false;
   if (!attr_done) {
     const uint32_t mx = S::BYTES_RES > S::BYTES_STR ? S::BYTES_RES : S::BYTES_STR;
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<NT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<NT, KIND, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
@@ -418,7 +476,7 @@ int launch_tc(const CUtensorMap& tm, const ConvTcArgs& a, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NT, KIND>, tm, a);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NT, KIND, HEAD>, tm, a);
   return e == cudaSuccess ? gfr_launch_status() : (int)e;
 }
 
@@ -577,6 +635,7 @@ extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const 
   a.single_pass = precision == 1;
   a.x_scale = x_scale; a.inv_scale = precision == 2 ? 1.0f / (x_scale * w_scale) : 1.0f;
   a.static_w = weights_static ? 1 : 0;
+  a.head = nullptr; a.head_out = nullptr; a.head_n = 0; a.head_act = 0; a.head_scale = 1.0f;
   CUtensorMap tm;
   const int rc = make_c4_map(&tm, in, N, (Cin + 3) / 4, in_groups, H, W, HALO_W, HALO_H);
   if (rc != GFR_OK) return rc;
@@ -587,6 +646,34 @@ extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const 
     case 64: return precision == 2 ? launch_tc<64, KIND_F16>(tm, a, s) : launch_tc<64, KIND_TF32>(tm, a, s);
     default: return GFR_E_ARG;
   }
+}
+
+extern "C" int gfr_conv3x3_tc_head_fwd(const float* in, const float* w_packed, const float* bias, const float* head, float* out,
+                                       int N, int Cin, int in_groups, int H, int W, int n_out, int head_act, float head_scale,
+                                       int precision, int weights_static, float x_scale, float w_scale, void* stream) {
+  GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w_packed); GFR_RETURN_IF_NULL(bias); GFR_RETURN_IF_NULL(head); GFR_RETURN_IF_NULL(out);
+  if (N <= 0 || Cin <= 0 || H <= 0 || W <= 0 || n_out < 1 || n_out > 3) return GFR_E_SHAPE;
+  if ((head_act != 0 && head_act != 2) || precision < 2 || precision > 3) return GFR_E_ARG;
+  if (precision == 2 && !(x_scale > 0.f && w_scale > 0.f)) return GFR_E_ARG;
+  if (in_groups == 0) in_groups = (Cin + 3) / 4;
+  if (in_groups < (Cin + 3) / 4) return GFR_E_ARG;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(head)) & 15) return GFR_E_ARG;
+  ConvTcArgs a;
+  a.wpk = w_packed; a.bias = bias; a.res = nullptr; a.post = nullptr; a.out = nullptr;
+  a.N = N; a.Cin = Cin; a.Cout = 16; a.H = H; a.W = W;
+  a.ncb = gfr_ceil_div(Cin, CB);
+  a.tiles_x = gfr_ceil_div(W, TILE_PX_W); a.tiles_y = gfr_ceil_div(H, TILE_PX_H);
+  a.m_tiles = N * a.tiles_x * a.tiles_y;
+  a.post_shift = 0; a.act = 1; a.out_scale = 1.0f;
+  a.single_pass = 0;
+  a.x_scale = x_scale; a.inv_scale = precision == 2 ? 1.0f / (x_scale * w_scale) : 1.0f;
+  a.static_w = weights_static ? 1 : 0;
+  a.head = head; a.head_out = out; a.head_n = n_out; a.head_act = head_act; a.head_scale = head_scale;
+  CUtensorMap tm;
+  const int rc = make_c4_map(&tm, in, N, (Cin + 3) / 4, in_groups, H, W, HALO_W, HALO_H);
+  if (rc != GFR_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  return precision == 2 ? launch_tc<16, KIND_F16, true>(tm, a, s) : launch_tc<16, KIND_TF32, true>(tm, a, s);
 }
 
 extern "C" int gfr_nchw_to_c4(const float* in, float* out, int N, int C, int H, int W, void* stream) {

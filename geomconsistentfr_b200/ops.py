@@ -329,6 +329,37 @@ def conv3x3_tc_fwd(x, w_packed, bias, Cout, NT, res=None, post=None, post_shift=
     return C4(out, Cout)
 
 
+def pack_head_weights(w2, b2, w3, b3, wo, bo, device):
+    """The decoder tail's six (BN-folded) tensors as the 600-float device operand of gfr_conv3x3_tc_head_fwd:
+    [w2 16x16 | b2 16 | w3 16x16 | b3 16 | wo 3x16 | bo 4], rows [co][ci]."""
+    n_out = wo.shape[0]
+    buf = torch.zeros(600, dtype=torch.float32)
+    buf[0:256] = w2.reshape(16, 16).reshape(-1)
+    buf[256:272] = b2
+    buf[272:528] = w3.reshape(16, 16).reshape(-1)
+    buf[528:544] = b3
+    buf[544:544 + 16 * n_out] = wo.reshape(n_out, 16).reshape(-1)
+    buf[592:592 + n_out] = bo
+    return buf.to(device)
+
+
+def conv3x3_tc_head_fwd(x, w_packed, bias, head, n_out, act=None, out_scale=1.0, precision=2, w_scale=1.0):
+    """c2_1 (3x3, 16 -> 16, BN folded, LeakyReLU) with the 1x1 tail c2_2 -> c2_3 -> c2_o fused into its epilogue
+    (TRAIN:284-290 / 344-350).  x: C4 [N,16,H,W]; head from pack_head_weights -> NCHW [N,n_out,H,W]."""
+    N, Cin, H, W = x.shape
+    if not x.data.is_cuda:
+        raise RuntimeError("conv3x3_tc_head_fwd: x must be on CUDA")
+    w_packed, bias, head = _need(w_packed, torch.float32, "w_packed"), _need(bias, torch.float32, "bias"), _need(head, torch.float32, "head")
+    if head.numel() != 600:
+        raise RuntimeError("head must come from pack_head_weights (600 floats)")
+    out = torch.empty((N, n_out, H, W), dtype=torch.float32, device=x.data.device)
+    rc = _lib.load().gfr_conv3x3_tc_head_fwd(_ptr(x.data), _ptr(w_packed), _ptr(bias), _ptr(head), _ptr(out), N, Cin,
+                                             x.data.shape[1], H, W, int(n_out), _ACT[act], float(out_scale), int(precision), 1,
+                                             X_SCALE_F16, float(w_scale), _stream())
+    _lib.check(rc, "gfr_conv3x3_tc_head_fwd"); _count()
+    return out
+
+
 def maxpool2_c4_fwd(x):
     N, C, H, W = x.shape
     out = _c4_empty(N, C, H // 2, W // 2, x.data.device)

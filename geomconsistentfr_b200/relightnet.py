@@ -62,6 +62,7 @@ class RelightNet(nn.Module):
         self.light_z_floor = 0.16                                 # TEST_LT:332 (estimated light of the reference image)
         self.march_variant = 0
         self.cnn_impl = "tc"                  # "tc": tcgen05 3xTF32 convs on C4 activations; "direct": exact-fp32 CUDA-core convs
+        self.fuse_head = True                 # c2_1 + the 1x1 tail (c2_2, c2_3, c2_o) in one tcgen05 launch per decoder
         self.tc_precision = 2                 # eval-mode convs: 2 = fp16 pair split (~22-bit products, half the operand bytes; needs
                                               # |activation| < 4095 — an overflow shows up as inf/NaN, not silently), 3 = 3xTF32, 1 = TF32
 
@@ -170,6 +171,8 @@ class RelightNet(nn.Module):
                     t[name] = (ops.conv_tc_pack_weights(w, NT), b, Cout, NT, 1.0)
             else:
                 t[name] = (w.cpu().contiguous(), b.cpu().contiguous())
+        for p in ("albedo", "depth"):          # the fused decoder tail's operand (gfr_conv3x3_tc_head_fwd)
+            t["head_" + p] = ops.pack_head_weights(*t["conv_%s_c2_2" % p], *t["conv_%s_c2_3" % p], *t["conv_%s_c2_o" % p], self.device)
         self._tc, self._tc_key = t, key
         return t
 
@@ -212,6 +215,11 @@ class RelightNet(nn.Module):
             a = conv("deconv_%s_h8_1" % p, h)
             tt = conv("deconv_%s_h8_2" % p, a, res=h)
             h = self._up_and_skip_tc(conv, p, "s4", tt, skips["s4"], epoch)
+            act, scale = ("sigmoid", 1.0) if p == "albedo" else (None, 100.0)                   # TRAIN:290 / 350
+            if self.fuse_head and prec >= 2:
+                wp, b, _, _, w_scale = t["conv_%s_c2_1" % p]
+                return ops.conv3x3_tc_head_fwd(h, wp, b, t["head_" + p], 3 if p == "albedo" else 1, act=act, out_scale=scale,
+                                               precision=prec, w_scale=w_scale)
             h = conv("conv_%s_c2_1" % p, h)
             w2, b2 = t["conv_%s_c2_2" % p]
             w3, b3 = t["conv_%s_c2_3" % p]

@@ -289,6 +289,15 @@ int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const float* bias
                        int act, float out_scale, int precision, int weights_static, float x_scale, float w_scale,
                        void* stream);
 
+/* gfr_conv3x3_tc_fwd for a 16-output-channel layer with LeakyReLU, with the decoder tail fused into its epilogue: the
+ * 16 channels of every pixel go straight through c2_2, c2_3 (1x1, 16 -> 16, BN folded, LeakyReLU) and c2_o (1x1,
+ * 16 -> n_out; head_act 0 = none | 2 = sigmoid; x head_scale) — TRAIN:284-290 (albedo) / 344-350 (depth) — without a
+ * round trip of the 16-channel map through memory.  head: DEVICE floats [w2 16x16 | b2 16 | w3 16x16 | b3 16 |
+ * wo 3x16 | bo 4] ([co][ci] rows, 600 floats, 16-byte aligned); out: NCHW [N, n_out, H, W].  precision 2 | 3. */
+int gfr_conv3x3_tc_head_fwd(const float* in, const float* w_packed, const float* bias, const float* head, float* out,
+                            int N, int Cin, int in_groups, int H, int W, int n_out, int head_act, float head_scale,
+                            int precision, int weights_static, float x_scale, float w_scale, void* stream);
+
 /* Stem: conv_c1_og (5x5, 3 -> 16, padding 2) + BatchNorm(eval, folded) + LeakyReLU(0.2) on the NHWC image, with the
  * first 2x2 max pool fused (TRAIN:197-201).  img [N,H,W,3]; w_host [16,3,5,5] and bias_host [16] are HOST pointers
  * (they travel as kernel parameters); out C4 [N,16,H,W]; pooled C4 [N,16,H/2,W/2] or NULL. */

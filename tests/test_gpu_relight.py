@@ -136,3 +136,23 @@ def test_relight_sweep_equals_per_light_forward(net, ffhq):
         o = net(x, 200, K, m, tl, torch.full((2, 1, 1), 0.5).cuda(), None)
         assert torch.equal(sw["rendered"][:, j], o[5])
         assert torch.equal(sw["shadow"][:, j], o[2])
+
+
+@pytest.mark.parametrize("precision", [2, 3])
+def test_fused_decoder_tail_equals_the_two_launch_tail(net, ffhq, precision):
+    """gfr_conv3x3_tc_head_fwd (c2_1 with c2_2 -> c2_3 -> c2_o in its epilogue) against gfr_conv3x3_tc_fwd followed by
+    gfr_head_1x1_fwd: same accumulation order, so albedo and depth agree to the last bit or two."""
+    x = _inputs(ffhq, [1, 4, 7]).cuda()
+    net.tc_precision = precision
+    try:
+        with torch.no_grad():
+            net.fuse_head = True
+            a1, d1, sl1 = net._cnn_eval(x, 200)
+            net.fuse_head = False
+            a0, d0, sl0 = net._cnn_eval(x, 200)
+    finally:
+        net.fuse_head, net.tc_precision = True, 2
+    assert a1.shape == a0.shape == (3, 3, 256, 256) and d1.shape == d0.shape == (3, 1, 256, 256)
+    assert float((a1 - a0).abs().max()) <= 2e-7
+    assert float((d1 - d0).abs().max()) <= 2e-5          # 100 x a value of order 1
+    assert torch.equal(sl1, sl0)
