@@ -84,6 +84,25 @@ struct Smem {
   static constexpr uint32_t TMEM_COLS = 4 * NT <= 32 ? 32 : (4 * NT <= 64 ? 64 : (4 * NT <= 128 ? 128 : 256));
 };
 
+// y[o] = lrelu(b[o] + sum_ci w[o][ci] x[ci]) for 16 -> 16, weights in shared memory ([co][ci] rows)
+__device__ __forceinline__ void head_dense16(const float* w, const float* b, const float (&x)[16], float (&y)[16]) {
+#pragma unroll
+  for (int o = 0; o < 16; o += 4) {
+    float acc[4] = {b[o], b[o + 1], b[o + 2], b[o + 3]};
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(w + (o + r) * 16 + 4 * c4);
+        acc[r] = fmaf(v.x, x[4 * c4], acc[r]); acc[r] = fmaf(v.y, x[4 * c4 + 1], acc[r]);
+        acc[r] = fmaf(v.z, x[4 * c4 + 2], acc[r]); acc[r] = fmaf(v.w, x[4 * c4 + 3], acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) y[o + r] = acc[r] > 0.f ? acc[r] : 0.2f * acc[r];
+  }
+}
+
 template <int NT, int KIND, bool HEAD = false>
 __global__ void __launch_bounds__(NUM_THREADS, NT <= 32 ? 2 : 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a) {
@@ -115,6 +134,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
     tma_prefetch_desc(&tm_in);
   }
   if (warp == 1) tmem_alloc(bars + 104, S::TMEM_COLS);
+  [[maybe_unused]] float* s_head = nullptr;
+  if constexpr (HEAD) {                                       // static operand: not written by the preceding kernel
+    __shared__ __align__(16) float s_head_buf[600];
+    s_head = s_head_buf;
+    for (int i = tid; i < 600; i += NUM_THREADS) s_head[i] = __ldg(a.head + i);
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -348,43 +373,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
           }
         }
         if constexpr (HEAD) {
-          // c2_2 -> c2_3 -> c2_o per pixel; weight rows are warp-uniform 16-byte loads (L1-resident, 2.4 KB in all),
-          // accumulation order = the stand-alone head_1x1_kernel's (bias first, ci ascending)
-          const float4* hw = reinterpret_cast<const float4*>(a.head);
+          // c2_2 -> c2_3 -> c2_o per pixel.  Weights come from shared memory as LDS.128 broadcasts; four outputs are
+          // accumulated side by side (independent FMA chains); per accumulator the order is the stand-alone
+          // head_1x1_kernel's (bias first, ci ascending), so the result is bit-identical to the two-launch tail.
           float h2[16];
-#pragma unroll
-          for (int o = 0; o < 16; ++o) {
-            float acc = __ldg(a.head + 256 + o);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const float4 w = __ldg(hw + o * 4 + c4);
-              acc = fmaf(w.x, yv[4 * c4], acc); acc = fmaf(w.y, yv[4 * c4 + 1], acc);
-              acc = fmaf(w.z, yv[4 * c4 + 2], acc); acc = fmaf(w.w, yv[4 * c4 + 3], acc);
-            }
-            h2[o] = acc > 0.f ? acc : 0.2f * acc;
-            if ((o & 3) == 3) asm volatile("" ::: "memory");     // keep the weight loads from being hoisted 150 deep (spills)
-          }
-#pragma unroll
-          for (int o = 0; o < 16; ++o) {
-            float acc = __ldg(a.head + 528 + o);
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const float4 w = __ldg(hw + 68 + o * 4 + c4);
-              acc = fmaf(w.x, h2[4 * c4], acc); acc = fmaf(w.y, h2[4 * c4 + 1], acc);
-              acc = fmaf(w.z, h2[4 * c4 + 2], acc); acc = fmaf(w.w, h2[4 * c4 + 3], acc);
-            }
-            yv[o] = acc > 0.f ? acc : 0.2f * acc;
-            if ((o & 3) == 3) asm volatile("" ::: "memory");
-          }
+          head_dense16(s_head, s_head + 256, yv, h2);
+          head_dense16(s_head + 272, s_head + 528, h2, yv);
           const size_t hw_px = (size_t)a.H * a.W;
           float* op = a.head_out + (size_t)n * a.head_n * hw_px + (size_t)y * a.W + x;
 #pragma unroll
           for (int o = 0; o < 3; ++o) {
             if (o >= a.head_n) break;
-            float acc = __ldg(a.head + 592 + o);
+            float acc = s_head[592 + o];
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
-              const float4 w = __ldg(hw + 136 + o * 4 + c4);
+              const float4 w = *reinterpret_cast<const float4*>(s_head + 544 + o * 16 + 4 * c4);
               acc = fmaf(w.x, yv[4 * c4], acc); acc = fmaf(w.y, yv[4 * c4 + 1], acc);
               acc = fmaf(w.z, yv[4 * c4 + 2], acc); acc = fmaf(w.w, yv[4 * c4 + 3], acc);
             }
