@@ -62,7 +62,10 @@ class RelightNet(nn.Module):
         self.light_z_floor = 0.16                                 # TEST_LT:332 (estimated light of the reference image)
         self.march_variant = 0
         self.cnn_impl = "tc"                  # "tc": tcgen05 3xTF32 convs on C4 activations; "direct": exact-fp32 CUDA-core convs
-        self.fuse_head = True                 # c2_1 + the 1x1 tail (c2_2, c2_3, c2_o) in one tcgen05 launch per decoder
+        self.fuse_head = False                # True: c2_1 + the 1x1 tail (c2_2, c2_3, c2_o) in one tcgen05 launch per decoder
+                                              # (gfr_conv3x3_tc_head_fwd; bit-identical).  Measured neutral-to-slower (11.0k vs
+                                              # 11.15k faces/s): the 4 epilogue warps pay for the tail what the stand-alone
+                                              # head kernel paid, so the two-launch tail stays the default
         self.tc_precision = 2                 # eval-mode convs: 2 = fp16 pair split (~22-bit products, half the operand bytes; needs
                                               # |activation| < 4095 — an overflow shows up as inf/NaN, not silently), 3 = 3xTF32, 1 = TF32
 

@@ -151,7 +151,7 @@ def test_fused_decoder_tail_equals_the_two_launch_tail(net, ffhq, precision):
             net.fuse_head = False
             a0, d0, sl0 = net._cnn_eval(x, 200)
     finally:
-        net.fuse_head, net.tc_precision = True, 2
+        net.fuse_head, net.tc_precision = False, 2
     assert a1.shape == a0.shape == (3, 3, 256, 256) and d1.shape == d0.shape == (3, 1, 256, 256)
     assert float((a1 - a0).abs().max()) <= 2e-7
     assert float((d1 - d0).abs().max()) <= 2e-5          # 100 x a value of order 1
