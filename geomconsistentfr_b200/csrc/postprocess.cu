@@ -154,7 +154,51 @@ __global__ void __launch_bounds__(BT_W * BT_H) border_median_fix_kernel(const ui
   }
 }
 
+// ---- MSE_MP.m:15-25: per-image masked MSE between two 8-bit images, sums in fp64
+__global__ void __launch_bounds__(256) masked_mse_kernel(const uint8_t* __restrict__ recon, const uint8_t* __restrict__ gt,
+                                                         const uint8_t* __restrict__ mask, long long mask_stride,
+                                                         double* __restrict__ sums, int HW, int C) {
+  const int b = blockIdx.y;
+  double num = 0.0, den = 0.0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    const double m = __ddiv_rn((double)__ldg(mask + (long long)b * mask_stride + p), 255.0);
+    den += m;
+    const uint8_t* r = recon + ((long long)b * HW + p) * C;
+    const uint8_t* g = gt + ((long long)b * HW + p) * C;
+    for (int c = 0; c < C; ++c) {
+      const double d = __dsub_rn(__dmul_rn(__ddiv_rn((double)r[c], 255.0), m), __dmul_rn(__ddiv_rn((double)g[c], 255.0), m));
+      num += d * d;
+    }
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    num += __shfl_xor_sync(0xFFFFFFFFu, num, s);
+    den += __shfl_xor_sync(0xFFFFFFFFu, den, s);
+  }
+  __shared__ double sn[8], sd[8];
+  if ((threadIdx.x & 31) == 0) { sn[threadIdx.x >> 5] = num; sd[threadIdx.x >> 5] = den; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int w = 0; w < 8; ++w) { a += sn[w]; c += sd[w]; }
+    atomicAdd(sums + 2 * b, a);
+    atomicAdd(sums + 2 * b + 1, c);
+  }
+}
+
 }  // namespace
+
+extern "C" int gfr_masked_mse_u8(const uint8_t* recon, const uint8_t* gt, const uint8_t* mask, int mask_batch_stride,
+                                 double* sums, int B, int H, int W, int C, void* stream) {
+  GFR_RETURN_IF_NULL(recon); GFR_RETURN_IF_NULL(gt); GFR_RETURN_IF_NULL(mask); GFR_RETURN_IF_NULL(sums);
+  if (B <= 0 || B > 65535 || H <= 0 || W <= 0 || C < 1 || C > 4) return GFR_E_SHAPE;
+  if (mask_batch_stride != 0 && mask_batch_stride != H * W) return GFR_E_ARG;
+  const cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)B * 2 * sizeof(double), (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  const dim3 grid((unsigned)min(64, gfr_ceil_div(H * W, 256)), B);
+  masked_mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(recon, gt, mask, mask_batch_stride, sums, H * W, C);
+  return gfr_launch_status();
+}
 
 extern "C" int gfr_composite_bgr_u8(const void* image, int image_is_f64, const float* rendered, const uint8_t* mask,
                                     int mask_batch_stride, uint8_t* out_bgr, int B, int H, int W, void* stream) {

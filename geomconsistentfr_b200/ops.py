@@ -482,3 +482,19 @@ def border_median_fix_u8(img, mask, max_sum=30):
     rc = _lib.load().gfr_border_median_fix_u8(_ptr(img), _ptr(mask), stride, _ptr(out), B, H, W, C, int(max_sum), _stream())
     _lib.check(rc, "gfr_border_median_fix_u8"); _count()
     return out
+
+
+def masked_mse_u8(recon, gt, mask):
+    """MSE_MP.m:15-25: per-image masked MSE of two uint8 image batches [B,H,W,C]; mask u8 [H,W] | [B,H,W] -> [B] f64."""
+    for t, n in ((recon, "recon"), (gt, "gt")):
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.uint8 and t.dim() == 4):
+            raise RuntimeError("%s must be a CUDA uint8 tensor [B,H,W,C]" % n)
+    if recon.shape != gt.shape:
+        raise RuntimeError("recon and gt must have the same shape")
+    recon, gt = recon.contiguous(), gt.contiguous()
+    B, H, W, C = recon.shape
+    mask, stride = _mask_u8(mask, B, H, W)
+    sums = torch.empty((B, 2), dtype=torch.float64, device=recon.device)
+    rc = _lib.load().gfr_masked_mse_u8(_ptr(recon), _ptr(gt), _ptr(mask), stride, _ptr(sums), B, H, W, C, _stream())
+    _lib.check(rc, "gfr_masked_mse_u8"); _count()
+    return sums[:, 0] / (C * sums[:, 1])

@@ -365,6 +365,12 @@ int gfr_export_planes_u8(const float* albedo, const float* depth, const float* s
 int gfr_border_median_fix_u8(const uint8_t* img, const uint8_t* mask, int mask_batch_stride, uint8_t* out, int B, int H,
                              int W, int C, int max_sum, void* stream);
 
+/* MSE_MP.m:15-25 (the reference's Multi-PIE evaluation metric): per image b, sums[2b] = sum over pixels and channels of
+ * (recon/255 * m - gt/255 * m)^2 and sums[2b+1] = sum of m, with m = mask/255, in fp64; the metric is
+ * sums[2b] / (C * sums[2b+1]).  recon, gt [B,H,W,C] u8; mask [1|B,H,W] u8; sums [B,2] doubles (zeroed by the call). */
+int gfr_masked_mse_u8(const uint8_t* recon, const uint8_t* gt, const uint8_t* mask, int mask_batch_stride, double* sums,
+                      int B, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

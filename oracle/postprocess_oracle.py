@@ -5,7 +5,7 @@ __graft_entry__.smoke() and bench.py's baseline leg may import this module; the 
 geomconsistentfr_b200/csrc/postprocess.cu.
 
 Pinned: composite + border fix applied to the (pinned) oracle forward reproduce all 10 shipped
-FFHQ_relighting_results/*.png on EVERY pixel to <= 1 grey level (tests/test_oracle_postprocess.py) — with the border
+FFHQ_relighting_results/*.png on EVERY pixel to <= 1 grey level (tests/test_oracle_golden.py) — with the border
 rule `0 < boxsum <= 30`.  The shipped .m file reads `convolved < 30`; with that literal rule 45-130 pixels per image
 (all with boxsum == 30 exactly) keep their unfiltered value and differ from the shipped PNGs by up to 77 grey levels,
 so the shipped files were evidently produced with `<= 30`.  The threshold is therefore a parameter (`max_sum`):
@@ -84,3 +84,11 @@ def border_fix_u8(img_u8, mask_u8, max_sum=30):
     for c in range(img_u8.shape[2]):
         out[:, :, c][b] = medfilt3_zero(img_u8[:, :, c])[b]
     return out
+
+
+def masked_mse(recon_u8, gt_u8, mask_u8):
+    """MSE_MP.m:15-25 for one image: sum(|recon.*m - gt.*m|.^2) / (3 * sum(m)), everything / 255 in double."""
+    m = mask_u8.astype(np.float64) / 255.0
+    m3 = np.repeat(m[:, :, None], recon_u8.shape[2], axis=2)
+    r, g = recon_u8.astype(np.float64) / 255.0, gt_u8.astype(np.float64) / 255.0
+    return np.sum(np.abs(r * m3 - g * m3) ** 2) / (recon_u8.shape[2] * np.sum(m))

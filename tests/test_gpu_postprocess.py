@@ -130,3 +130,21 @@ def test_driver_rejects_cpu_and_train_mode(net):
         relight(RelightNet().eval(), np.zeros((256, 256, 3)), np.zeros((256, 256), np.uint8), (0, 0, 1))
     with pytest.raises(RuntimeError):
         relight(net, np.zeros((256, 256, 3)), np.zeros((256, 256), np.float64), (0, 0, 1))   # /255 float masks are refused
+
+
+def test_masked_mse_metric_matches_the_matlab_expression(ffhq):
+    """MSE_MP.m:15-25 on the device vs its numpy restatement (fp64 sums; tolerance = summation order only)."""
+    from geomconsistentfr_b200 import ops
+    from oracle import postprocess_oracle as P
+    g = np.random.default_rng(5)
+    recon = ffhq["pngs_bgr"][:4]
+    gt = np.clip(recon.astype(np.int32) + g.integers(-20, 21, recon.shape), 0, 255).astype(np.uint8)
+    masks = ffhq["masks"][:4]
+    c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    got = ops.masked_mse_u8(c(recon), c(gt), c(masks)).cpu().numpy()
+    for b in range(4):
+        want = P.masked_mse(recon[b], gt[b], masks[b])
+        assert abs(got[b] - want) <= 1e-10 * want, b
+    shared = ops.masked_mse_u8(c(recon), c(gt), c(masks[0])).cpu().numpy()
+    assert abs(shared[2] - P.masked_mse(recon[2], gt[2], masks[0])) <= 1e-10 * shared[2]
+    assert float(ops.masked_mse_u8(c(recon), c(recon), c(masks))[0]) == 0.0
