@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(CSRC, "libgfr_b200.so")
+LIB = os.environ.get("GFR_LIB_PATH") or os.path.join(CSRC, "libgfr_b200.so")      # GFR_LIB_PATH: an alternative build (A/B runs)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -74,13 +74,23 @@ constexpr int KIND_TF32 = 0, KIND_F16 = 1;
 
 template <int NT, int KIND>
 struct Smem {
-  static constexpr int STAGES = NT <= 32 ? 3 : 2;
+  // ring depth, measured on the whole forward (B = 8, 3 lanes): 3/3 slots (weights resident / streamed) 11 190 faces/s,
+  // 3/2 11 800, 4/2 11 810, 2/2 11 990.  With streamed weights (Cin > 16) a third slot makes the CTA 124 KB and it runs
+  // alone on its SM, with two slots (83 KB) two CTAs share it - the low-resolution layers are latency-bound and gain most.
+#ifndef GFR_CONV_STAGES_RES
+#define GFR_CONV_STAGES_RES 2
+#endif
+#ifndef GFR_CONV_STAGES_STR
+#define GFR_CONV_STAGES_STR 2
+#endif
+  static constexpr int STAGES_RES = NT <= 32 ? GFR_CONV_STAGES_RES : 2, STAGES_STR = NT <= 32 ? GFR_CONV_STAGES_STR : 2;
+  static constexpr int MAX_STAGES = STAGES_RES > STAGES_STR ? STAGES_RES : STAGES_STR;
   // TF32: [tap][4-ch group (4)][hi|lo][n][4 floats];  F16: [tap][8-ch chunk (2)][w1|w2][n][8 halfs]  — of one 16-channel step
   static constexpr uint32_t W_STEP = 9 * (KIND == KIND_TF32 ? CB / 4 : CB / 8) * 2 * NT * 16;
   // resident-weights mode (Cin <= 16): [W][slot: A_hi, A_lo] ; streaming mode: [slot: A_hi, A_lo, W]
   static constexpr uint32_t SLOT_RES = 2 * A_BYTES, SLOT_STR = 2 * A_BYTES + W_STEP;
-  static constexpr uint32_t BYTES_RES = W_STEP + STAGES * SLOT_RES + 128;
-  static constexpr uint32_t BYTES_STR = STAGES * SLOT_STR + 128;
+  static constexpr uint32_t BYTES_RES = W_STEP + STAGES_RES * SLOT_RES + 256;
+  static constexpr uint32_t BYTES_STR = STAGES_STR * SLOT_STR + 256;
   static constexpr uint32_t TMEM_COLS = 4 * NT <= 32 ? 32 : (4 * NT <= 64 ? 64 : (4 * NT <= 128 ? 128 : 256));
 };
 
@@ -108,16 +118,17 @@ __global__ void __launch_bounds__(NUM_THREADS, NT <= 32 ? 2 : 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a) {
   static_assert(!HEAD || NT == 16, "the fused decoder tail needs the pixel's 16 channels in one thread");
   using S = Smem<NT, KIND>;
-  constexpr int STAGES = S::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool resident = a.ncb == 1;
+  const int STAGES = resident ? S::STAGES_RES : S::STAGES_STR;
   const uint32_t smem0 = smem_u32(smem);
   const uint32_t slot_bytes = resident ? S::SLOT_RES : S::SLOT_STR;
   const uint32_t slots0 = smem0 + (resident ? S::W_STEP : 0u);
   const uint32_t bars = slots0 + STAGES * slot_bytes;               // 8-byte aligned (all sizes are multiples of 128)
-  // barrier map: full[s] = bars + 8 s, ready[s] = +24, empty[s] = +48, accfull[p] = +72, accempty[p] = +88, tmem slot +104
-  const uint32_t bar_full = bars, bar_ready = bars + 24, bar_empty = bars + 48, bar_accfull = bars + 72, bar_accempty = bars + 88;
+  // barrier map: full[s] = bars + 8 s, ready[s], empty[s] (STAGES each), accfull[p], accempty[p] (2 each), then the TMEM slot
+  constexpr uint32_t SB = 8 * S::MAX_STAGES, TMEM_SLOT = 3 * SB + 32;
+  const uint32_t bar_full = bars, bar_ready = bars + SB, bar_empty = bars + 2 * SB, bar_accfull = bars + 3 * SB, bar_accempty = bars + 3 * SB + 16;
   uint8_t* gen_bars = smem + (bars - smem0);
 
   if (tid == 0) {
@@ -133,7 +144,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
     fence_mbar_init();
     tma_prefetch_desc(&tm_in);
   }
-  if (warp == 1) tmem_alloc(bars + 104, S::TMEM_COLS);
+  if (warp == 1) tmem_alloc(bars + TMEM_SLOT, S::TMEM_COLS);
   [[maybe_unused]] float* s_head = nullptr;
   if constexpr (HEAD) {                                       // static operand: not written by the preceding kernel
     __shared__ __align__(16) float s_head_buf[600];
@@ -143,7 +154,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_bars + 104);
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_bars + TMEM_SLOT);
 
   const int n_my_tiles = (a.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int n_steps = n_my_tiles * a.ncb;
