@@ -114,7 +114,10 @@ __device__ __forceinline__ void head_dense16(const float* w, const float* b, con
 }
 
 template <int NT, int KIND, bool HEAD = false>
-__global__ void __launch_bounds__(NUM_THREADS, NT <= 32 ? 2 : 1)
+#ifndef GFR_CONV_OCC
+#define GFR_CONV_OCC 2
+#endif
+__global__ void __launch_bounds__(NUM_THREADS, NT <= 32 ? (NT <= 16 ? GFR_CONV_OCC : 2) : 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a) {
   static_assert(!HEAD || NT == 16, "the fused decoder tail needs the pixel's 16 channels in one thread");
   using S = Smem<NT, KIND>;
@@ -470,7 +473,7 @@ int launch_tc(const CUtensorMap& tm, const ConvTcArgs& a, cudaStream_t s) {
   const uint32_t bytes = a.ncb == 1 ? S::BYTES_RES : S::BYTES_STR;
   const int n_tiles = gfr_ceil_div(a.Cout, NT);
   int occ = (int)(225u * 1024u / (bytes + 1024u));
-  const int occ_max = NT <= 32 ? 2 : 1;
+  const int occ_max = NT <= 32 ? (NT <= 16 ? GFR_CONV_OCC : 2) : 1;
   if (occ > occ_max) occ = occ_max;
   if (occ < 1) occ = 1;
   int gx = (sm_count() * occ) / n_tiles;

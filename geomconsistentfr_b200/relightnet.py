@@ -13,6 +13,8 @@ All compute runs in libgfr_b200.so (CUDA, sm_100a) through geomconsistentfr_b200
 parameters and the device memory.  There is no CPU path: CPU inputs are copied to the module's device.
 The nn.Conv2d / nn.BatchNorm2d members are parameter containers only — their forward is never called.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -62,6 +64,7 @@ class RelightNet(nn.Module):
         self.light_z_floor = 0.16                                 # TEST_LT:332 (estimated light of the reference image)
         self.march_variant = 0
         self.cnn_impl = "tc"                  # "tc": tcgen05 3xTF32 convs on C4 activations; "direct": exact-fp32 CUDA-core convs
+        self.parallel_shortcuts = os.environ.get("GFR_PARALLEL_SHORTCUTS", "1") != "0"   # shortcut convs of the residual blocks on a helper stream beside conv 1
         self.fuse_head = False                # True: c2_1 + the 1x1 tail (c2_2, c2_3, c2_o) in one tcgen05 launch per decoder
                                               # (gfr_conv3x3_tc_head_fwd; bit-identical).  Measured neutral-to-slower (11.0k vs
                                               # 11.15k faces/s): the 4 epilogue warps pay for the tail what the stand-alone
@@ -191,14 +194,30 @@ class RelightNet(nn.Module):
             wp, b, Cout, NT, w_scale = t[name]
             return ops.conv3x3_tc_fwd(x, wp, b, Cout, NT, precision=prec, w_scale=w_scale, **kw)
 
+        def res_block(n1, n2, nsc, x, cin=None):
+            """lrelu(bn(conv_sc(x)) + bn(conv2(lrelu(bn(conv1(x)))))) — TRAIN:203-223, 235-239.  The shortcut conv only
+            feeds the residual operand of conv2, so it runs on a helper stream beside conv1 (a parallel graph branch):
+            one launch less on the critical path of each of the 9 blocks."""
+            if not self.parallel_shortcuts:
+                return conv(n2, conv(n1, x, cin=cin), res=conv(nsc, x, cin=cin, act=None))
+            here = torch.cuda.current_stream()
+            helper = self._side_stream("_sc_%d" % here.cuda_stream)
+            helper.wait_stream(here)
+            with torch.cuda.stream(helper):
+                sc = conv(nsc, x, cin=cin, act=None)
+            a = conv(n1, x, cin=cin)
+            here.wait_stream(helper)
+            sc.data.record_stream(here)
+            return conv(n2, a, res=sc)
+
         c1_og, c1 = ops.stem_conv_fwd(img, *t["conv_c1_og"])                # TRAIN:197-201 (conv + BN + LReLU + pool)
         h1_og = conv("conv_h1_2", conv("conv_h1_1", c1), res=c1)
         h1 = ops.maxpool2_c4_fwd(h1_og)
-        h2_og = conv("conv_h2_2", conv("conv_h2_1", h1), res=conv("conv_shortcut_h1_out", h1, act=None))
+        h2_og = res_block("conv_h2_1", "conv_h2_2", "conv_shortcut_h1_out", h1)
         h2 = ops.maxpool2_c4_fwd(h2_og)
-        h3_og = conv("conv_h3_2", conv("conv_h3_1", h2), res=conv("conv_shortcut_h2_out", h2, act=None))
+        h3_og = res_block("conv_h3_1", "conv_h3_2", "conv_shortcut_h2_out", h2)
         h3 = ops.maxpool2_c4_fwd(h3_og)
-        h4 = conv("conv_h4_2", conv("conv_h4_1", h3), res=conv("conv_shortcut_h3_out", h3, act=None))
+        h4 = res_block("conv_h4_1", "conv_h4_2", "conv_shortcut_h3_out", h3)
         cur = torch.cuda.current_stream()
         side, aux = self._side_stream(), self._side_stream("_aux")
         aux.wait_stream(cur)
@@ -211,9 +230,7 @@ class RelightNet(nn.Module):
         def decoder(p):
             h, cin = h4, 128                                                # TRAIN:225: the first 128 channels, in place
             for blk, sc, _, cout, skip in _UP_BLOCKS:
-                a = conv("deconv_%s_%s_1" % (p, blk), h, cin=cin)
-                s = conv("deconv_%s_%s" % (p, sc), h, cin=cin, act=None)
-                tt = conv("deconv_%s_%s_2" % (p, blk), a, res=s)
+                tt = res_block("deconv_%s_%s_1" % (p, blk), "deconv_%s_%s_2" % (p, blk), "deconv_%s_%s" % (p, sc), h, cin=cin)
                 h, cin = self._up_and_skip_tc(conv, p, skip, tt, skips[skip], epoch), None
             a = conv("deconv_%s_h8_1" % p, h)
             tt = conv("deconv_%s_h8_2" % p, a, res=h)
