@@ -114,6 +114,8 @@ __device__ __forceinline__ void head_dense16(const float* w, const float* b, con
 }
 
 template <int NT, int KIND, bool HEAD = false>
+// CTAs per SM of the NT = 16 kernel: 3 would fit shared memory and TMEM but caps the kernel at 64 registers (256 B of
+// spills in the epilogue): measured 10 550 vs 12 020 faces/s, so 2
 #ifndef GFR_CONV_OCC
 #define GFR_CONV_OCC 2
 #endif
