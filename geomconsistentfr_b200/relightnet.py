@@ -42,8 +42,9 @@ class RelightNet(nn.Module):
     def __init__(self, batch_size=1, variant="default"):
         """variant "default": TRAIN / TEST1 / TESTB.  variant "lighting_transfer": the network and constants of
         test_relight_single_image_lighting_transfer.py (TEST_LT) — the nine shortcut (de)convs are 1x1 and bias-free
-        (TEST_LT:36-42,66-76,119-129; loads model_lighting_transfer/model_epoch106.pth strictly), directional intensity
-        0.41, 159 samples from t = 0.03, depth offset 1410 (TEST_LT:20,22,325,451); inference only."""
+        (TEST_LT:36-42,66-76,119-129; loads model_lighting_transfer/model_epoch106.pth strictly); in eval mode
+        directional intensity 0.41, 159 samples from t = 0.03, depth offset 1410 (TEST_LT:20,22,325,451); in train mode
+        it is train_lighting_transfer.py's forward (TRAIN_LT = TRAIN with those shortcuts: 0.5, 160 samples, +1610)."""
         super().__init__()
         if variant not in ("default", "lighting_transfer"):
             raise ValueError("variant must be 'default' or 'lighting_transfer'")
@@ -285,7 +286,12 @@ class RelightNet(nn.Module):
             mod, bn = getattr(self, name), getattr(self, _bn_name(name))
             meta = dict(cin=mod.in_channels, cout=mod.out_channels, deconv=isinstance(mod, nn.ConvTranspose2d), act=act,
                         post_shift=post_shift, bn=bn)
-            return T.ConvBNAct.apply(x, mod.weight, mod.bias, bn.weight, bn.bias, res, post, meta)
+            w, b = mod.weight, mod.bias
+            if w.shape[-1] == 1:          # lighting-transfer 1x1 shortcut (TRAIN_LT:63-69,93-103,146-156): the centre tap of a 3x3
+                w = torch.nn.functional.pad(w, (1, 1, 1, 1))        # kernel, differentiably (its gradient is the centre of the 3x3 one)
+            if b is None:                 # bias=False: a constant zero (a bias in front of batch-stat BN has no effect anyway)
+                b = w.new_zeros(mod.out_channels)
+            return T.ConvBNAct.apply(x, w, b, bn.weight, bn.bias, res, post, meta)
 
         def up_and_skip(p, skip, t, enc):
             if epoch > _EPOCH_GATES[skip]:
@@ -342,7 +348,9 @@ class RelightNet(nn.Module):
         light_pt = self.light_distance * unit                                                      # TRAIN:362
         d_min = ShadowMarch.apply(depth, bits, light_pt, 0.0)
         fx, fy, cx, cy = self._intrinsics(intrinsic_matrix)
-        intr = (fx, fy, cx, cy, self.depth_offset, self.directional_intensity)
+        # the training scripts' constants (TRAIN:46,353 = TRAIN_LT:46,353): both variants train with +1610 and 0.5; the
+        # lighting-transfer TEST script's 0.41 / +1410 / 159 samples are inference-only
+        intr = (fx, fy, cx, cy, 1610.0, 0.5)
         shadow, full, _, rendered, _ = ShadeRender.apply(albedo, depth, d_min, light_pt, ambient_values, intr)
         ambient_light = ambient_values.view(B, 1, 1).expand(B, H, W)
         return (albedo, depth, shadow, ambient_light, full, rendered, unit.view(B, 3, 1, 1), ambient_values.view(B, 1, 1))
@@ -452,8 +460,6 @@ class RelightNet(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("RelightNet (geomconsistentfr_b200) runs on CUDA only; call .cuda() first")
         if self.training:
-            if self.variant == "lighting_transfer":
-                raise NotImplementedError("the lighting-transfer variant is inference-only here (TEST_LT); call .eval()")
             if target_lighting is not None:
                 raise NotImplementedError("the TEST1 signature (given target lighting) is an inference call: use .eval()")
             return self._forward_train(img, epoch, intrinsic_matrix, mask)

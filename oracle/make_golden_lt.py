@@ -57,8 +57,38 @@ def main():
             out[tag + "_shadow"] = r[2].numpy().astype(np.float32)
             print(tag, "light point", (4013 * torch.nn.functional.normalize(tl, dim=1)).view(3).tolist())
     np.savez_compressed(os.path.join(OUT, "lt.npz"), **out)
+
+    # ---- lt_train.npz: the UNMODIFIED train_lighting_transfer.py (TRAIN_LT) model, train() mode, B = 3 (hard-coded at
+    # TRAIN_LT:359), forward + autograd gradients of the recon + DSSIM terms (TRAIN_LT:640,650), epoch-106 weights
+    from oracle import relight_oracle as O
+    tnet = ref_shims.reference_model("TRAIN_LT")                       # stays in train() mode like TRAIN_LT:568-570
+    sel = [names.index(n) for n in ("00104", "00322", "00508")]
+    x = torch.from_numpy(f["q"][sel] / 1020.0).float()
+    mk = (f["masks"][sel] > 128).astype(np.float64).reshape(3, 256, 256, 1)
+    mt = torch.from_numpy(mk)
+    r = tnet(x, 200, O.intrinsic_matrix(), mt)
+    albedo, depth_t, shadow, _, _, rendered, unit_l, amb_v = r
+    depth_t.retain_grad()
+    m3 = mt.permute(0, 3, 1, 2).repeat(1, 3, 1, 1).float()
+    target = x.permute(0, 3, 1, 2)
+    comp = rendered * m3 + (1.0 - m3) * target
+    loss = 20.0 * torch.sum((rendered * m3 - target * m3) ** 2) / torch.sum(m3) \
+        + 8.0 * (1 - O.ssim(comp, target, data_range=1.0, size_average=True, nonnegative_ssim=True)) / 2.0
+    loss.backward()
+    np.savez_compressed(
+        os.path.join(OUT, "lt_train.npz"), sel=np.array(sel), masks01=mk.astype(np.uint8)[..., 0],
+        depth=depth_t.detach().numpy(), shadow=shadow.detach().numpy().astype(np.float16),
+        rendered=rendered.detach().numpy().astype(np.float16), unit_light=unit_l.detach().numpy().reshape(3, 3),
+        ambient=amb_v.detach().numpy().reshape(3), loss=np.float64(loss.item()),
+        albedo_mean=albedo.detach().numpy().mean(axis=(2, 3)),
+        grad_depth=depth_t.grad.numpy().astype(np.float16),
+        grad_shortcut_h1=tnet.conv_shortcut_h1_out.weight.grad.numpy(),
+        grad_shortcut_h3=tnet.conv_shortcut_h3_out.weight.grad.numpy(),
+        grad_deconv_depth_shortcut_h6=tnet.deconv_depth_shortcut_h6_out.weight.grad.numpy(),
+        grad_sl2_w=tnet.linear_SL2.weight.grad.numpy(), grad_depth_head_w=tnet.conv_depth_c2_o.weight.grad.numpy())
+    print("train_lt done, loss", loss.item())
     print("est light", out["est_light"], "est ambient", out["est_ambient"])
-    for fn in ("lt.npz", "model_epoch106.pth"):
+    for fn in ("lt.npz", "lt_train.npz", "model_epoch106.pth"):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 
 

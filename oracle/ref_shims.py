@@ -34,6 +34,7 @@ _SCRIPTS = {
     "TEST1": "test_relight_single_image.py",
     "TESTB": "test_raytracing_relighting_CelebAHQ_DSSIM_8x.py",
     "TEST_LT": "test_relight_single_image_lighting_transfer.py",
+    "TRAIN_LT": "train_lighting_transfer.py",
 }
 
 
@@ -112,7 +113,7 @@ def reference_model(short="TEST1", batch_size=None, weights=True):
         net.xx = net.xx[:1].repeat(batch_size, 1, 1)
         net.yy = net.yy[:1].repeat(batch_size, 1, 1)
     if weights:
-        rel = ("model_lighting_transfer", "model_epoch106.pth") if short == "TEST_LT" else ("model", "model_epoch99.pth")
+        rel = ("model_lighting_transfer", "model_epoch106.pth") if short in ("TEST_LT", "TRAIN_LT") else ("model", "model_epoch99.pth")
         sd = torch.load(os.path.join(REFERENCE_ROOT, *rel), map_location="cpu")
         net.load_state_dict(sd)
     return net.float()
