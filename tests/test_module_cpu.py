@@ -80,3 +80,19 @@ def test_lighting_transfer_variant_loads_the_reference_weights_strictly():
     assert w.shape == (32, 16, 3, 3) and float(w[:, :, 0, 0].abs().max()) == 0.0 and float(w[:, :, 1, 1].abs().max()) > 0.0
     w, b = f["deconv_albedo_shortcut_h5_out"]
     assert w.shape == (32, 64, 3, 3) and float(w[:, :, 2, 1].abs().max()) == 0.0
+
+
+def test_inference_driver_argument_shapes():
+    """inference._as_batch: one image or a batch, shared or per-face uint8 masks, one light or one per face."""
+    import numpy as np
+    from geomconsistentfr_b200.inference import _as_batch
+    img, m, L = _as_batch(np.zeros((256, 256, 3)), np.zeros((256, 256), np.uint8), (0.0, 0.6, 0.8))
+    assert img.shape == (1, 256, 256, 3) and img.dtype == torch.float64 and m.shape == (1, 256, 256) and L.shape == (1, 3)
+    img, m, L = _as_batch(np.zeros((4, 64, 96, 3), np.float32), np.zeros((4, 64, 96), np.uint8), (0.0, 0.6, 0.8))
+    assert img.shape == (4, 64, 96, 3) and m.shape == (4, 64, 96) and L.shape == (4, 3) and L.is_contiguous()
+    with pytest.raises(RuntimeError):
+        _as_batch(np.zeros((2, 64, 96, 3)), np.zeros((3, 64, 96), np.uint8), (0.0, 0.6, 0.8))        # 3 masks for 2 faces
+    with pytest.raises(RuntimeError):
+        _as_batch(np.zeros((2, 64, 96, 3)), np.zeros((64, 96), np.float32), (0.0, 0.6, 0.8))           # /255 float mask
+    with pytest.raises(RuntimeError):
+        _as_batch(np.zeros((2, 64, 96, 3)), np.zeros((64, 96), np.uint8), np.zeros((3, 3)))            # 3 lights for 2 faces
