@@ -234,6 +234,68 @@ def run_train(args, rank, world, local, dist):
         os._exit(0)
 
 
+def run_sweep(args, rank, world, local, dist):
+    """configs[4]: the 18-light Multi-PIE sweep (TESTB:565-583) - every face relit under 18 light directions with ONE CNN
+    pass per face (`RelightNet.relight_sweep`, lights_per_face = 18 in the march/shade launch); faces are sharded over the
+    ranks with no collective.  One step = 8 faces x 18 lights = 144 relit images per GPU, captured in a CUDA graph."""
+    from geomconsistentfr_b200 import RelightNet, intrinsic_matrix, ops
+    from geomconsistentfr_b200.synthetic import LIGHTS_18
+    net = RelightNet()
+    net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"), strict=True)
+    net = net.float().cuda().eval()
+    B, L = B_PER_GPU, 18
+    K = intrinsic_matrix()
+    lights = torch.tensor(LIGHTS_18, dtype=torch.float32).cuda()
+    pool = [tuple(t.cuda() for t in synthetic_batch(B, 2000 * rank + i)) for i in range(8)]
+    img, mask = pool[0][0].clone(), pool[0][1].clone()
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            n0 = ops.launch_count()
+            out = net.relight_sweep(img, 200, K, mask.view(H, W, 1), lights)
+            per_step = ops.launch_count() - n0
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            out = net.relight_sweep(img, 200, K, mask.view(H, W, 1), lights)
+
+        def one(i):
+            img.copy_(pool[i % len(pool)][0], non_blocking=True)
+            mask.copy_(pool[i % len(pool)][1], non_blocking=True)
+            graph.replay()
+
+        for i in range(max(args.warmup, 3)):
+            one(i)
+        stream.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            one(i)
+        e1.record(stream)
+        stream.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "relit images/sec @256x256, 18-light sweep (one CNN pass per face)", "value": world * B * L * args.steps * 1e3 / ms,
+            "unit": "images/s", "faces_per_s": world * B * args.steps * 1e3 / ms, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[4]: 18 Multi-PIE light directions x 8 faces per GPU per step (512 faces = 64 steps of one GPU "
+                                   "or 8 steps of eight), CNN once per face, march + shade for 144 (face, light) pairs in one launch",
+                       "global_batch": world * B, "lights": L, "parallelism": "dp%d (faces sharded, no collective)" % world,
+                       "working_set": "144 relit images = 170 MB of outputs per step (> L2)", "cuda_graph": True},
+            "gpu_launches": int(per_step * args.steps), "rendered_shape": list(out["rendered"].shape)}), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,7 +308,7 @@ def main():
                                                                "(~50k tiny launches; always skip it under ncu)")
     ap.add_argument("--lanes", type=int, default=3, help="runner lanes the e2e (host-buffer) path rotates over")
     ap.add_argument("--no-gan", action="store_true", help="train workload without the PatchGAN terms")
-    ap.add_argument("--workload", default="forward", choices=["forward", "train"],
+    ap.add_argument("--workload", default="forward", choices=["forward", "train", "sweep"],
                     help="forward = configs[1] (the default bench line); train = configs[2]/[3]: generator training step, "
                          "B=16 per GPU, one flat-gradient all-reduce per step")
     args = ap.parse_args()
@@ -267,6 +329,8 @@ def main():
 
     if args.workload == "train":
         return run_train(args, rank, world, local, dist)
+    if args.workload == "sweep":
+        return run_sweep(args, rank, world, local, dist)
 
     from geomconsistentfr_b200 import RelightNet, RelightRunner, ops
     net = RelightNet()
