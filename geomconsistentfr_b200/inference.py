@@ -125,3 +125,54 @@ def write_pngs(out_dir, names, result):
         stem = os.path.splitext(n)[0]
         for k, v in result.items():
             cv2.imwrite(os.path.join(out_dir, "%s_%s.png" % (stem, k)), v[i])
+
+
+def _main(argv=None):
+    """Command-line form of the two single-image scripts (file I/O through cv2, which the reference also uses to write):
+
+        python -m geomconsistentfr_b200.inference relight  MODEL.pth IMAGE MASK LX,LY,LZ OUT.png [--fix-border]
+        python -m geomconsistentfr_b200.inference transfer MODEL.pth INPUT REFERENCE MASK OUT_DIR
+
+    `relight` = test_relight_single_image.py main() (TEST1:507-620; the image is resized to 256x256 like TEST1:515);
+    `transfer` = test_relight_single_image_lighting_transfer.py main() (TEST_LT:516-579; 256x256 inputs, six PNGs)."""
+    import argparse
+    import cv2
+    from .relightnet import RelightNet
+    ap = argparse.ArgumentParser(prog="python -m geomconsistentfr_b200.inference", description=_main.__doc__,
+                                 formatter_class=argparse.RawDescriptionHelpFormatter)
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    r = sub.add_parser("relight")
+    r.add_argument("model"); r.add_argument("image"); r.add_argument("mask"); r.add_argument("light"); r.add_argument("out")
+    r.add_argument("--fix-border", action="store_true")
+    t = sub.add_parser("transfer")
+    t.add_argument("model"); t.add_argument("input"); t.add_argument("reference"); t.add_argument("mask"); t.add_argument("out_dir")
+    a = ap.parse_args(argv)
+
+    def read_rgb01(path):
+        img = cv2.imread(path, cv2.IMREAD_COLOR)
+        if img is None:
+            raise FileNotFoundError(path)
+        img = img[:, :, ::-1] / 255.0                               # imageio.imread(...)/255.0, RGB (TEST1:515)
+        return img if img.shape[:2] == (256, 256) else cv2.resize(img, (256, 256))
+
+    def read_mask(path):
+        m = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        if m is None:
+            raise FileNotFoundError(path)
+        return np.ascontiguousarray(m[:, :, 0] if m.ndim == 3 else m).astype(np.uint8)
+
+    net = RelightNet(variant="lighting_transfer" if a.cmd == "transfer" else "default")
+    net.load_state_dict(torch.load(a.model, map_location="cpu"), strict=True)
+    net = net.float().cuda().eval()
+    if a.cmd == "relight":
+        light = tuple(float(v) for v in a.light.split(","))
+        out = relight_single_image(net, read_rgb01(a.image), read_mask(a.mask), light, fix_border=a.fix_border)
+        cv2.imwrite(a.out, out)                                     # TEST1:620
+    else:
+        res, est_l, est_a = lighting_transfer(net, read_rgb01(a.input), read_rgb01(a.reference), read_mask(a.mask))
+        write_pngs(a.out_dir, [os.path.basename(a.input)], res)    # TEST_LT:574-579
+        print("estimated light", est_l.tolist(), "ambient", est_a)
+
+
+if __name__ == "__main__":
+    _main()
