@@ -65,7 +65,7 @@ class RelightNet(nn.Module):
         self.light_z_floor = 0.16                                 # TEST_LT:332 (estimated light of the reference image)
         self.march_variant = 0
         self.cnn_impl = "tc"                  # "tc": tcgen05 3xTF32 convs on C4 activations; "direct": exact-fp32 CUDA-core convs
-        self.parallel_shortcuts = os.environ.get("GFR_PARALLEL_SHORTCUTS", "0") != "0"   # shortcut convs of the residual blocks on a helper stream beside conv 1
+        self.parallel_shortcuts = os.environ.get("GFR_PARALLEL_SHORTCUTS", "1") != "0"   # shortcut convs of the residual blocks on a helper stream beside conv 1
         self.fuse_head = False                # True: c2_1 + the 1x1 tail (c2_2, c2_3, c2_o) in one tcgen05 launch per decoder
                                               # (gfr_conv3x3_tc_head_fwd; bit-identical).  Measured neutral-to-slower (11.0k vs
                                               # 11.15k faces/s): the 4 epilogue warps pay for the tail what the stand-alone
