@@ -8,6 +8,8 @@
 //   * light  — global average pool of the 27 lighting channels + the 2-layer MLP (TRAIN:225-232) on a C4 feature map.
 #include "gfr_common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------- stem
@@ -23,9 +25,19 @@ struct StemArgs {
 constexpr int ST_TW = 32, ST_TH = 16;                          // CTA tile (pixels); thread = 2x2 pixels
 constexpr int ST_IW = ST_TW + 4, ST_IH = ST_TH + 4;
 
+// ROLLED = false: everything unrolled, weights as FFMA uniform-register operands (LDCU from the constant bank): 27k SASS
+// instructions (430 KB) - ncu: the top stall is `no_instruction` (instruction-cache misses, 2.8 per issue), FMA pipe 42 %.
+// ROLLED = true: the (ci, ky) loops stay rolled (a ~400-instruction body), weights come from shared memory as LDS.128
+// broadcasts; same accumulation order (ci, ky, kx), so the result is bit-identical.
+template <bool ROLLED>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const StemArgs a, const __grid_constant__ StemWeights wt) {
   __shared__ __align__(16) float s_in[3][ST_IH][ST_IW];
+  __shared__ __align__(16) float s_w[ROLLED ? 75 : 1][16];
   const int tid = threadIdx.x;
+  if (ROLLED) {
+    const float* wp = &wt.w[0][0][0];
+    for (int i = tid; i < 75 * 16; i += 128) s_w[i >> 4][i & 15] = wp[i];
+  }
   const int tiles_x = gfr_ceil_div(a.W, ST_TW);
   const int x0 = (blockIdx.x % tiles_x) * ST_TW, y0 = (blockIdx.x / tiles_x) * ST_TH;
   const int n = blockIdx.y;
@@ -49,6 +61,37 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemArgs a, const 
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[p][c] = wt.b[c];
 
+  if constexpr (ROLLED) {
+#pragma unroll 1
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll 1
+      for (int ky = 0; ky < 5; ++ky) {
+        float r0[6], r1[6];
+#pragma unroll
+        for (int c = 0; c < 6; c += 2) {
+          const float2 u = *reinterpret_cast<const float2*>(&s_in[ci][2 * ty + ky][2 * tx + c]);
+          const float2 v = *reinterpret_cast<const float2*>(&s_in[ci][2 * ty + ky + 1][2 * tx + c]);
+          r0[c] = u.x; r0[c + 1] = u.y; r1[c] = v.x; r1[c + 1] = v.y;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          const float4* w4 = reinterpret_cast<const float4*>(&s_w[(ky * 5 + kx) * 3 + ci][0]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 w = w4[q];
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[0][4 * q + e] = fmaf(wv[e], r0[kx], acc[0][4 * q + e]);
+              acc[1][4 * q + e] = fmaf(wv[e], r0[kx + 1], acc[1][4 * q + e]);
+              acc[2][4 * q + e] = fmaf(wv[e], r1[kx], acc[2][4 * q + e]);
+              acc[3][4 * q + e] = fmaf(wv[e], r1[kx + 1], acc[3][4 * q + e]);
+            }
+          }
+        }
+      }
+    }
+  } else {
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci) {
     float win[6][6];
@@ -71,6 +114,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemArgs a, const 
           acc[2][c] = fmaf(w, win[ky + 1][kx], acc[2][c]);
           acc[3][c] = fmaf(w, win[ky + 1][kx + 1], acc[3][c]);
         }
+  }
   }
 
   const int oy = y0 + 2 * ty, ox = x0 + 2 * tx;
@@ -196,7 +240,9 @@ extern "C" int gfr_stem_conv_fwd(const float* img, const float* w_host, const fl
   }
   StemArgs a{img, out, pooled, N, H, W};
   const dim3 grid(gfr_ceil_div(W, ST_TW) * gfr_ceil_div(H, ST_TH), N);
-  stem_conv_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, wt);
+  static const bool rolled = [] { const char* e = getenv("GFR_STEM_ROLLED"); return e != nullptr && e[0] == '1'; }();
+  if (rolled) stem_conv_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a, wt);
+  else stem_conv_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a, wt);
   return gfr_launch_status();
 }
 
