@@ -240,7 +240,8 @@ extern "C" int gfr_stem_conv_fwd(const float* img, const float* w_host, const fl
   }
   StemArgs a{img, out, pooled, N, H, W};
   const dim3 grid(gfr_ceil_div(W, ST_TW) * gfr_ceil_div(H, ST_TH), N);
-  static const bool rolled = [] { const char* e = getenv("GFR_STEM_ROLLED"); return e != nullptr && e[0] == '1'; }();
+  // rolled is the default: 60.1 vs 62.8 us alone, +1.1 % value / +2 % e2e on the whole forward (GFR_STEM_ROLLED=0: the unrolled one)
+  static const bool rolled = [] { const char* e = getenv("GFR_STEM_ROLLED"); return !(e != nullptr && e[0] == '0'); }();
   if (rolled) stem_conv_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a, wt);
   else stem_conv_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a, wt);
   return gfr_launch_status();
