@@ -364,8 +364,7 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
     const double dt = (t_host[n - 1] - t_host[0]) / (n - 1);
     bool uniform = dt > 0.0;
     for (int k = 0; k < n && uniform; ++k) uniform = fabs(t_host[k] - (t_host[0] + k * dt)) <= 1e-9;
-    static const bool no_cull = getenv("GFR_MARCH_NO_CULL") != nullptr;      // A/B switch: march every sample
-    if (uniform && !no_cull) inv_dt = (float)(1.0 / dt);
+    if (uniform && getenv("GFR_MARCH_NO_CULL") == nullptr) inv_dt = (float)(1.0 / dt);
   }
   MarchArgs a = {};
   a.depth = depth; a.mask_bits = mask_bits; a.light = light_pt; a.dmin = d_min; a.argmin = argmin; a.shadow = shadow;
