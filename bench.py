@@ -40,6 +40,8 @@ FUSED_BYTES_PER_FACE = 2 * 262144 + 786432 + 3 * 262144 + 2 * 786432
 MARCH_SAMPLES_PER_FACE = 160 * H * W
 CNN_FLOP_PER_FACE = 4.54e9
 METRIC = "relit faces/sec @256x256 (shadow+CNN)"
+WORKLOAD = ("configs[1]: batch 8 per GPU, full relight forward 256x256 fp32 "
+            "(RelightNet CNN + normals + 160-sample ray-march + Lambert render), eval, epoch-99 weights")
 
 
 def peaks():
@@ -145,8 +147,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "faces/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: full relight forward 256x256 fp32 (CNN + normals + 160-sample ray-march + render)",
-                   "step": "bounded sample: 1 face per step (the reference's own batch size, TEST1:15)"},
+        "config": {"workload": WORKLOAD,
+                   "step": "bounded sample of that workload: 1 face per step (the reference's own batch size, TEST1:15), "
+                           "CPU oracle port on all host threads"},
         "cpu_baseline": {"value": v, "unit": "faces/s", "cores": threads, "kind": "port",
                          "sample": "%d faces, B=1 each, torch CPU oracle port of TEST1:169-505" % len(times)},
         "e2e": {"value": v, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -485,8 +488,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: batch 8 per GPU, full relight forward 256x256 fp32 "
-                               "(RelightNet CNN + normals + 160-sample ray-march + Lambert render), eval, epoch-99 weights",
+        "config": {"workload": WORKLOAD,
                    "global_batch": world * B, "parallelism": "dp%d (faces sharded, no collective)" % world,
                    "l2": "value/e2e: every step reads a different batch of a 151 MB device pool (> 126 MB L2) / streams it from "
                          "the host, and rewrites ~1.1 GB of activations; latency + roofline: 256 MiB flush written between "
