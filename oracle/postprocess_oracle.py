@@ -4,7 +4,9 @@ MATLAB border post-fix the shipped result PNGs went through (fix_border_artifact
 __graft_entry__.smoke() and bench.py's baseline leg may import this module; the product path is
 geomconsistentfr_b200/csrc/postprocess.cu.
 
-Pinned: composite + border fix applied to the (pinned) oracle forward reproduce all 10 shipped
+Pinned twice.  (1) tests/golden/planes.npz = what the UNMODIFIED export lines TESTB:584-608 hand to cv2.imwrite (through
+cv2's real 8-bit conversion) for synthetic forward outputs: composite and all five planes match bit for bit
+(tests/test_oracle_postprocess.py).  (2) composite + border fix applied to the (pinned) oracle forward reproduce all 10 shipped
 FFHQ_relighting_results/*.png on EVERY pixel to <= 1 grey level (tests/test_oracle_golden.py) — with the border
 rule `0 < boxsum <= 30`.  The shipped .m file reads `convolved < 30`; with that literal rule 45-130 pixels per image
 (all with boxsum == 30 exactly) keep their unfiltered value and differ from the shipped PNGs by up to 77 grey levels,
