@@ -9,12 +9,16 @@ One JSON line on stdout (rank 0).  A "step" is one forward over one batch of 8 f
   value      faces/s, whole job, inputs resident in HBM: the K steps rotate over the runner lanes and a 151 MB pool of
              distinct device batches (> L2), one CUDA-event pair around all K steps, max over ranks
   latency    the same forward on one lane, CUDA events per step, L2 flushed between steps
-  e2e        faces/s through RelightRunner.relight_host: pinned host image/mask/light -> H2D -> forward -> D2H of
-             rendered_images, all inside the timed region
+  e2e        faces/s through RelightRunner.relight_host: pinned host image/mask/light -> H2D -> forward -> composite ->
+             D2H of the 8-bit BGR images the reference's driver stores (TEST1:590-620), all inside the timed region
   roofline   the kernel of the step that does the ray march (one fused launch: march + normals + Lambert + render):
              algorithmic bytes / CUDA-event duration, L2 flushed between launches; the stand-alone march beside it
-  cpu_baseline / --impl reference: the CPU oracle port of the reference forward (oracle/relight_oracle.py, torch
-             CPU, all host threads) on a bounded sample
+  train      (sub-block of the same line) configs[2]/[3]: the reference's full training iteration TRAIN:617-656, B = 16
+             per GPU, ONE NCCL all-reduce of the flat generator gradient per step (+ the discriminator's every 5th)
+  sweep      (sub-block) configs[4]: 18 light directions x 8 faces per GPU per step, one CNN pass per face
+  cpu_baseline / --impl reference: the UNMODIFIED reference forward (TEST1.RelightNet.forward imported from
+             oracle/_ref through oracle/ref_shims.py, torch CPU, all host threads) on a bounded sample; the oracle port
+             when oracle/_ref is absent
 """
 import argparse
 import json
@@ -33,6 +37,7 @@ sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 B_PER_GPU = 8
+B_TRAIN = 16
 H = W = 256
 MARCH_BYTES_PER_FACE = 786432          # depth f32 + mask f32 + d_min f32
 # the fused march+shade launch: depth + mask in (d_min stays on the SM), + albedo in, + shadow/full/final + rendered + normals out
@@ -42,6 +47,14 @@ CNN_FLOP_PER_FACE = 4.54e9
 METRIC = "relit faces/sec @256x256 (shadow+CNN)"
 WORKLOAD = ("configs[1]: batch 8 per GPU, full relight forward 256x256 fp32 "
             "(RelightNet CNN + normals + 160-sample ray-march + Lambert render), eval, epoch-99 weights")
+
+
+def make_config(world):
+    """The `config` object of BOTH arms (ours and --impl reference): the workload, not how an arm executes it."""
+    return {"workload": WORKLOAD, "global_batch": world * B_PER_GPU,
+            "parallelism": "dp%d (faces sharded, no collective)" % world,
+            "l2": "every step reads a different batch of a 151 MB pool (> 126 MB L2); latency + roofline legs write a "
+                  "256 MiB flush between timed launches (untimed)"}
 
 
 def peaks():
@@ -92,81 +105,130 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_forward_faces_per_s(n_faces, threads):
-    """The CPU oracle port of the reference forward (TEST1:169-505), B=1 per call like the reference."""
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm (CPU) and the reference on one GPU — the only places that execute anything under oracle/
+# ----------------------------------------------------------------------------------------------------------------
+def _reference_forward_fn(device, ref_batch):
+    """-> (fn(img, mask01, light) running ONE forward of `ref_batch` faces, kind).  kind "reference": the unmodified
+    TEST1.RelightNet.forward from oracle/_ref (or /root/reference in the authoring container) through oracle/ref_shims;
+    "port": oracle/relight_oracle.py when no copy of the reference is present."""
+    from oracle import ref_shims as R
     from oracle import relight_oracle as O
-    torch.set_num_threads(threads)
-    net = O.RelightNetOracle()
-    net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"))
-    net.eval()
     K = O.intrinsic_matrix()
-    times = []
-    with torch.no_grad():
-        for i in range(n_faces):
-            img, mask, light = synthetic_batch(1, 100 + i)
-            m = mask.view(H, W, 1).double() / 255.0
-            t0 = time.perf_counter()
-            net.forward_test(img, 200, K, m, light[:1])
-            times.append(time.perf_counter() - t0)
-    return times
+    if R.reference_available():
+        net = R.reference_model("TEST1", batch_size=ref_batch, cuda_identity=(device == "cpu")).eval()
+        if device != "cpu":
+            net = net.cuda()                                  # TEST1:511
+            K = K.cuda()
 
-
-def gpu_port_faces_per_s(n_faces):
-    """The same oracle port on cuda:0 (torch eager: cuDNN convs + the per-sample tensor program of TEST1:351-498, with its
-    per-image host syncs), B = 1 per call like the reference: the closest stand-in for "the reference's 1-GPU PyTorch
-    throughput" that can run on this box (the reference itself cannot travel here)."""
-    from oracle import relight_oracle as O
+        def fn(img, m01, light):                              # the call at TEST1:588
+            B = img.shape[0]
+            if device != "cpu":
+                img, m01, light = img.cuda(), m01.cuda(), light.cuda()
+            return net(img, 200, K, m01, light.view(B, 3, 1, 1), torch.full((B, 1, 1), 0.5, device=img.device),
+                       m01.repeat(B, 1, 1, 1))
+        return fn, "reference"
     net = O.RelightNetOracle()
     net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"))
-    net = net.cuda().eval()
-    K = O.intrinsic_matrix().cuda()
+    net = net.eval()
+    if device != "cpu":
+        net, K = net.cuda(), K.cuda()
+
+    def fn(img, m01, light):
+        if device != "cpu":
+            img, m01, light = img.cuda(), m01.cuda(), light.cuda()
+        return net.forward_test(img, 200, K, m01, light)
+    return fn, "port"
+
+
+def reference_times(n_steps, faces_per_step, ref_batch, device="cpu"):
+    """Wall-clock seconds of each of `n_steps` steps; a step relights `faces_per_step` faces in forwards of `ref_batch`
+    (the reference bakes batch_size = 1 into its pixel grids, TEST1:15,25-26, so its B = 8 is 8 forwards)."""
+    fn, kind = _reference_forward_fn(device, ref_batch)
     times = []
     with torch.no_grad():
-        for i in range(n_faces + 2):
-            img, mask, light = synthetic_batch(1, 100 + i)
-            img, light = img.cuda(), light.cuda()
-            m = (mask.view(H, W, 1).double() / 255.0).cuda()
-            torch.cuda.synchronize()
+        for i in range(n_steps):
+            img, mask, light = synthetic_batch(faces_per_step, 100 + i)
+            m01 = mask.view(H, W, 1).double() / 255.0
+            if device != "cpu":
+                torch.cuda.synchronize()
             t0 = time.perf_counter()
-            net.forward_test(img, 200, K, m, light[:1])
-            torch.cuda.synchronize()
+            for b in range(0, faces_per_step, ref_batch):
+                out = fn(img[b:b + ref_batch], m01, light[b:b + ref_batch])
+                float(out[5].sum())                           # the reference's `.cpu().numpy()` read-back (TEST1:591)
+            if device != "cpu":
+                torch.cuda.synchronize()
             times.append(time.perf_counter() - t0)
-    return times[2:]
+    return times, kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port, kind 'port'), rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on all host threads, rank 0 only.  Each step is
+    a bounded sample of the workload (`--ref-faces` faces, default 1, relit one per forward like TEST1:15)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    gpu = args.impl == "reference-gpu"
     threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     total = args.warmup + args.steps
-    times = cpu_forward_faces_per_s(total, threads)[args.warmup:]
+    times, kind = reference_times(total, args.ref_faces, args.ref_batch, "cuda" if gpu else "cpu")
+    times = times[args.warmup:]
     ms = 1e3 * sum(times) / len(times)
-    v = 1e3 / ms
+    v = args.ref_faces * 1e3 / ms
+    what = ("the UNMODIFIED reference TEST1.RelightNet.forward (oracle/_ref via oracle/ref_shims.py)" if kind == "reference"
+            else "torch oracle port of TEST1:169-505 (oracle/_ref absent)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "faces/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "step": "bounded sample of that workload: 1 face per step (the reference's own batch size, TEST1:15), "
-                           "CPU oracle port on all host threads"},
-        "cpu_baseline": {"value": v, "unit": "faces/s", "cores": threads, "kind": "port",
-                         "sample": "%d faces, B=1 each, torch CPU oracle port of TEST1:169-505" % len(times)},
+        "dtype": "f32", "data": "synthetic", "config": make_config(max(1, args.gpus)),
+        "cpu_baseline": {"value": v, "unit": "faces/s", "cores": 0 if gpu else threads, "kind": kind,
+                         "device": "cuda:0 (torch eager, the reference's own .cuda() calls)" if gpu else "cpu",
+                         "sample": "%d steps x %d face(s), forwards of B=%d (the reference bakes batch_size = 1, TEST1:15): %s"
+                                   % (len(times), args.ref_faces, args.ref_batch, what)},
         "e2e": {"value": v, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0}), flush=True)
 
 
-def run_train(args, rank, world, local, dist):
-    """configs[2]/[3]: generator training step (TRAIN:618, 633-645 minus the PatchGAN terms, 655-656), B = 16 per GPU,
-    synthetic batch resident on the device, one NCCL all-reduce of the flat gradient buffer per step."""
+def reference_subprocess(impl, steps, warmup, extra=()):
+    """Runs `bench.py --impl reference[-gpu]` in a child process (the reference needs torch's `.cuda()` patched to the
+    identity on the CPU — that must not happen inside this process) and returns its parsed JSON line."""
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    if impl == "reference":
+        env["CUDA_VISIBLE_DEVICES"] = ""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", impl, "--steps", str(steps), "--warmup", str(warmup)] + list(extra)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise RuntimeError("reference arm failed: %s" % (r.stderr.strip()[-300:] or r.stdout.strip()[-300:]))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def _max_over_ranks(ms, dist):
+    if dist is None:
+        return ms
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_train(args, rank, world, dist):
+    """configs[2]/[3]: the reference's training iteration (TRAIN:617-656), B = 16 per GPU, synthetic batch resident on the
+    device: train-mode RelightNet forward, PatchGAN x3, all seven loss terms, backward, ONE NCCL all-reduce of the flat
+    generator gradient buffer per step (+ the discriminator's on every GD_ratio-th step, TRAIN:624), fused Adam; the whole
+    iteration replayed from two CUDA graphs (D-update and no-D-update iterations)."""
     from geomconsistentfr_b200 import RelightNet, intrinsic_matrix, ops
     from geomconsistentfr_b200 import PatchGAN
     from geomconsistentfr_b200.trainer import GeneratorStep, TrainStep
     from geomconsistentfr_b200.synthetic import LIGHTS_18, synthetic_face
-    B = 16
+    B = B_TRAIN
     net = RelightNet(batch_size=B)
     net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"), strict=True)
     net = net.float().cuda().train()
+    if args.train_precision:
+        net.train_precision = args.train_precision
     torch.manual_seed(0)
     full = not args.no_gan
     step = TrainStep(net, PatchGAN().cuda(), intrinsic_matrix().cuda()) if full else GeneratorStep(net, intrinsic_matrix().cuda())
@@ -177,12 +239,20 @@ def run_train(args, rank, world, local, dist):
     depth_gt = (torch.stack([f[0] for f in faces]) * 0.5).cuda()
     albedo_gt = torch.rand(B, H, W, generator=g).cuda()
     light_gt = torch.tensor([[0.5, *LIGHTS_18[(rank + i) % 18]] for i in range(B)], dtype=torch.float32).cuda()
-
     batch = (mf, mf, depth_gt, albedo_gt, light_gt)
+
+    opts = [step.opt] + ([step.opt_d] if full else [])
+    if world > 1:
+        for o in opts:                                       # CUDA events around the (captured) NCCL all-reduce node
+            o.ar_events = (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
     n_pre = ops.launch_count()
     step.step(img, 200, *batch)
-    launches_per_step = ops.launch_count() - n_pre
-    it = [0]                                             # iteration counter: the discriminator updates every GD_ratio-th (TRAIN:624)
+    launches_d_step = ops.launch_count() - n_pre
+    n_pre = ops.launch_count()
+    if full:
+        step.step(img, 200, *batch, j=1)
+    launches_g_step = ops.launch_count() - n_pre if full else launches_d_step
+    it = [0]                                                 # iteration counter: the discriminator updates every GD_ratio-th (TRAIN:624)
 
     def kw():
         it[0] += 1
@@ -195,13 +265,14 @@ def run_train(args, rank, world, local, dist):
         step.capture(img, 200, *batch)
         stream = step._stream
         one = lambda: step.step_graphed(img, *batch, **kw())
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         one()
     it[0] = 0
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    n0 = ops.launch_count() - launches_per_step * args.steps if not args.no_graph else ops.launch_count()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -210,34 +281,49 @@ def run_train(args, rank, world, local, dist):
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    if rank == 0:
-        print(json.dumps({
-            "metric": "training faces/sec @256x256 (%s)" % ("full iteration: generator + PatchGAN" if full else "generator step"), "value": world * B * args.steps * 1e3 / ms, "unit": "faces/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 convs)", "data": "synthetic",
-            "config": {"workload": "configs[2]/[3]: generator training step, batch 16 per GPU, 256x256: train-mode RelightNet fwd + "
-                                   "masked recon/depth/albedo + ambient + light + DSSIM losses + backward + flat-gradient "
-                                   "all-reduce + fused Adam" + ("; PatchGAN x3 passes, discriminator Adam step every 5th iteration (TRAIN:617-656)" if full else
-                                                               "; PatchGAN terms skipped (--no-gan)"), "global_batch": world * B,
-                       "parallelism": "dp%d, one all_reduce of %.1f MB per step" % (world, step.opt.grad.numel() * 4 / 1e6),
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1), dist)
+    n_d = len([j for j in range(args.steps) if j % 5 == 0]) if full else 0
+    launches = n_d * launches_d_step + (args.steps - n_d) * launches_g_step
+
+    ar = {"bytes_per_step_generator": step.opt.grad.numel() * 4,
+          "bytes_every_5th_step_discriminator": step.opt_d.grad.numel() * 4 if full else 0}
+    if world > 1:
+        def ar_us(o):
+            """CUDA-event time of the all-reduce inside the last replay; a stand-alone all-reduce of the same buffer when
+            event-record nodes of a graph cannot be read back."""
+            try:
+                return 1e3 * o.ar_events[0].elapsed_time(o.ar_events[1]), "events around the NCCL node inside the last replayed step graph"
+            except Exception:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(o.grad)
+                    a.record(stream)
+                    for _ in range(10):
+                        dist.all_reduce(o.grad)
+                    b.record(stream)
+                stream.synchronize()
+                return 1e2 * a.elapsed_time(b), "10 back-to-back all-reduces of the same buffer (stand-alone)"
+        gus, how = ar_us(step.opt)
+        ar.update(generator_us=_max_over_ranks(gus, dist), how=how, backend="nccl", world=world)
+        if full:
+            ar["discriminator_us"] = _max_over_ranks(ar_us(step.opt_d)[0], dist)
+    prec = getattr(net, "train_precision", 3)
+    return {"metric": "training faces/sec @256x256 (%s)" % ("full iteration TRAIN:617-656: generator + PatchGAN" if full else "generator step"),
+            "value": world * B * args.steps * 1e3 / ms, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "dtype": {3: "f32 (3xTF32 convs)", 1: "tf32 convs, fp32 march", 4: "bf16 CNN / fp32 ray-march"}.get(prec, str(prec)),
+            "data": "synthetic",
+            "config": {"workload": "configs[2]/[3]: training iteration, batch 16 per GPU, 256x256: train-mode RelightNet fwd + masked "
+                                   "recon/depth/albedo + ambient + light + DSSIM losses + backward + flat-gradient all-reduce + fused Adam"
+                                   + ("; PatchGAN x3 passes, discriminator Adam step every 5th iteration (TRAIN:617-656)" if full
+                                      else "; PatchGAN terms skipped (--no-gan)"),
+                       "global_batch": world * B, "parallelism": "dp%d, one all_reduce of %.1f MB per step" % (world, step.opt.grad.numel() * 4 / 1e6),
                        "working_set": "activations of one step (> L2) are rewritten every step", "cuda_graph": not args.no_graph},
-            "gpu_launches": int(ops.launch_count() - n0), "final_loss": float(total)}), flush=True)
-    if dist is not None:
-        # the step graphs hold captured NCCL kernels: tearing the communicator down under them was observed to hang at
-        # interpreter exit on 2 GPUs, so synchronise, agree that everybody is done, and leave without finalisers
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        os._exit(0)
+            "allreduce": ar, "gpu_launches": int(launches), "final_loss": float(total)}
 
 
-def run_sweep(args, rank, world, local, dist):
+def bench_sweep(args, rank, world, dist):
     """configs[4]: the 18-light Multi-PIE sweep (TESTB:565-583) - every face relit under 18 light directions with ONE CNN
     pass per face (`RelightNet.relight_sweep`, lights_per_face = 18 in the march/shade launch); faces are sharded over the
     ranks with no collective.  One step = 8 faces x 18 lights = 144 relit images per GPU, captured in a CUDA graph."""
@@ -252,6 +338,7 @@ def run_sweep(args, rank, world, local, dist):
     pool = [tuple(t.cuda() for t in synthetic_batch(B, 2000 * rank + i)) for i in range(8)]
     img, mask = pool[0][0].clone(), pool[0][1].clone()
     stream = torch.cuda.Stream()
+    warm = max(args.warmup, 3)
     with torch.cuda.stream(stream):
         for _ in range(2):
             n0 = ops.launch_count()
@@ -267,7 +354,7 @@ def run_sweep(args, rank, world, local, dist):
             mask.copy_(pool[i % len(pool)][1], non_blocking=True)
             graph.replay()
 
-        for i in range(max(args.warmup, 3)):
+        for i in range(warm):
             one(i)
         stream.synchronize()
         if dist is not None:
@@ -278,63 +365,21 @@ def run_sweep(args, rank, world, local, dist):
             one(i)
         e1.record(stream)
         stream.synchronize()
-    ms = e0.elapsed_time(e1)
     if dist is not None:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    if rank == 0:
-        print(json.dumps({
-            "metric": "relit images/sec @256x256, 18-light sweep (one CNN pass per face)", "value": world * B * L * args.steps * 1e3 / ms,
+        dist.barrier()
+    ms = _max_over_ranks(e0.elapsed_time(e1), dist)
+    return {"metric": "relit images/sec @256x256, 18-light sweep (one CNN pass per face)", "value": world * B * L * args.steps * 1e3 / ms,
             "unit": "images/s", "faces_per_s": world * B * args.steps * 1e3 / ms, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "dtype": "f32",
+            "data": "synthetic",
             "config": {"workload": "configs[4]: 18 Multi-PIE light directions x 8 faces per GPU per step (512 faces = 64 steps of one GPU "
                                    "or 8 steps of eight), CNN once per face, march + shade for 144 (face, light) pairs in one launch",
                        "global_batch": world * B, "lights": L, "parallelism": "dp%d (faces sharded, no collective)" % world,
                        "working_set": "144 relit images = 170 MB of outputs per step (> L2)", "cuda_graph": True},
-            "gpu_launches": int(per_step * args.steps), "rendered_shape": list(out["rendered"].shape)}), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+            "gpu_launches": int(per_step * args.steps), "rendered_shape": list(out["rendered"].shape)}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-faces", type=int, default=6, help="faces in the bounded CPU-baseline sample")
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-gpu-port", action="store_true", help="skip the informational torch-eager GPU run of the oracle port "
-                                                               "(~50k tiny launches; always skip it under ncu)")
-    ap.add_argument("--lanes", type=int, default=3, help="runner lanes the e2e (host-buffer) path rotates over")
-    ap.add_argument("--no-gan", action="store_true", help="train workload without the PatchGAN terms")
-    ap.add_argument("--workload", default="forward", choices=["forward", "train", "sweep"],
-                    help="forward = configs[1] (the default bench line); train = configs[2]/[3]: generator training step, "
-                         "B=16 per GPU, one flat-gradient all-reduce per step")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    args.warmup = max(args.warmup, 3)
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU baseline")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    if args.workload == "train":
-        return run_train(args, rank, world, local, dist)
-    if args.workload == "sweep":
-        return run_sweep(args, rank, world, local, dist)
-
+def bench_forward(args, rank, world, local, dist):
     from geomconsistentfr_b200 import RelightNet, RelightRunner, ops
     net = RelightNet()
     net.load_state_dict(torch.load(os.path.join(GOLDEN, "model_epoch99.pth"), map_location="cpu"), strict=True)
@@ -371,12 +416,7 @@ def main():
                 e1.record(stream)
                 pairs.append((e0, e1))
         barrier()
-        total_ms = sum(a.elapsed_time(b) for a, b in pairs)
-        if dist is not None:
-            t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms
+        return _max_over_ranks(sum(a.elapsed_time(b) for a, b in pairs), dist)
 
     # ---- value: whole-job throughput, inputs resident in HBM.  The K steps rotate over the runner lanes (the latency-
     # bound low-resolution layers of one forward overlap the machine-filling layers of another) and over a pool of
@@ -405,12 +445,7 @@ def main():
             ends.append(e)
         runner.synchronize()
         barrier()
-        total_ms = max(start.elapsed_time(e) for e in ends)
-        if dist is not None:
-            t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms
+        return _max_over_ranks(max(start.elapsed_time(e) for e in ends), dist)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -426,10 +461,12 @@ def main():
     # region.  The runner rotates over its lanes, so the H2D of step i+1 / D2H of step i-1 overlap the kernels of step
     # i; the K steps are bracketed by one event pair (start on lane 0, every lane waits for it; end = the last lane to
     # finish).  Every step streams a different host batch; the per-step working set (~1.1 GB of activations) exceeds L2.
-    e2e_ms = timed_lanes(lambda i: runner.relight_host(*host[i % len(host)]), args.steps, args.warmup) / args.steps
+    # The result read back is what the reference's driver keeps of a forward: the 8-bit BGR composite (TEST1:590-620).
+    out_kind = "rendered_f32" if args.e2e_f32 else "bgr_u8"
+    e2e_ms = timed_lanes(lambda i: runner.relight_host(*host[i % len(host)], output=out_kind), args.steps, args.warmup) / args.steps
     clocks = sampler.stop()
     h2d = sum(t.numel() * t.element_size() for t in host[0])
-    d2h = B * 3 * H * W * 4
+    d2h = B * 3 * H * W * (4 if args.e2e_f32 else 1)
 
     # ---- roofline: the kernel of the step that does the ray march.  In the forward it is ONE fused launch
     # (march_shade_fwd_kernel: every thread marches its ray, then shades its pixel; d_min never leaves the SM), timed
@@ -482,22 +519,20 @@ def main():
         ach = traffic["fused_inst_executed"] / (fused_ms * 1e-3) / 1e9
         issue = {"bound": "warp-instruction issue", "warp_inst_per_launch": traffic["fused_inst_executed"],
                  "achieved": ach, "peak": peak_ginst, "unit": "G warp-inst/s", "frac": ach / peak_ginst,
-                 "source": "smsp__inst_executed.sum from profiles/r01_ncu_march_shade_full.csv"}
+                 "source": traffic.get("source", "smsp__inst_executed.sum, profiles/march_traffic.json")}
 
+    cfg = make_config(world)
     line = {
         "metric": METRIC, "value": value, "unit": "faces/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "global_batch": world * B, "parallelism": "dp%d (faces sharded, no collective)" % world,
-                   "l2": "value/e2e: every step reads a different batch of a 151 MB device pool (> 126 MB L2) / streams it from "
-                         "the host, and rewrites ~1.1 GB of activations; latency + roofline: 256 MiB flush written between "
-                         "timed launches (untimed)", "lanes": len(runner.lanes), "cnn": net.cnn_impl,
-                   "cuda_graph": runner.graph is not None},
+        "data": "synthetic", "config": cfg,
+        "execution": {"lanes": len(runner.lanes), "cnn": net.cnn_impl, "tc_precision": net.tc_precision,
+                      "cuda_graph": runner.graph is not None},
         "e2e": {"value": world * B * 1e3 / e2e_ms, "unit": "faces/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "lanes": len(runner.lanes),
-                "note": "RelightRunner.relight_host: pinned host image/mask/light -> H2D -> forward -> D2H rendered, "
-                        "steps pipelined over the runner lanes, one event pair around all K steps"},
+                "note": "RelightRunner.relight_host: pinned host image/mask/light -> H2D -> forward -> "
+                        + ("D2H rendered (fp32)" if args.e2e_f32 else "device composite -> D2H of the 8-bit BGR images the reference's "
+                           "driver stores (TEST1:590-620)") + ", steps pipelined over the runner lanes, one event pair around all K steps"},
         "latency": {"ms_per_step": latency_ms, "faces_per_s": world * B * 1e3 / latency_ms,
                     "note": "one forward of 8 faces on ONE lane, CUDA events per step, L2 flushed between steps"},
         "gpu_launches": int(launches),
@@ -518,26 +553,102 @@ def main():
                                     "frac": MARCH_BYTES_PER_FACE * B / (march_ms * 1e-3) / 1e9 / hbm_peak,
                                     "traffic": traffic.get("dram_bytes_per_launch"),
                                     "gsamples_per_s": MARCH_SAMPLES_PER_FACE * B / (march_ms * 1e-3) / 1e9}},
+        "cnn": {"flop_per_face": CNN_FLOP_PER_FACE,
+                "note": "tensor-pipe utilisation of the conv kernel: profiles/ (ncu sm__inst_executed_pipe_tensor / pipe_tensor cycles active)"},
     }
-    if rank == 0 and world == 1:
-        threads = os.cpu_count() or 1
-        t = cpu_forward_faces_per_s(max(args.cpu_faces, 2), threads)[1:]
-        line["cpu_baseline"] = {"value": len(t) / sum(t), "unit": "faces/s", "cores": threads, "kind": "port",
-                                "sample": "%d faces (1 warm-up dropped), B=1 each, torch CPU oracle port of TEST1:169-505"
-                                          % len(t)}
-        try:
-            if args.no_gpu_port:
-                raise RuntimeError("skipped (--no-gpu-port)")
-            tg = gpu_port_faces_per_s(8)
-            line["reference_gpu_port"] = {"value": len(tg) / sum(tg), "unit": "faces/s", "kind": "port",
-                                          "sample": "%d faces, B=1 each, the torch oracle port (TEST1:169-505) run eagerly on cuda:0" % len(tg)}
-        except Exception as e:                      # informational only
-            line["reference_gpu_port"] = {"unavailable": str(e)[:200]}
+    del runner, dev, flush
+    torch.cuda.empty_cache()
+    return line
+
+
+def pin_rank_cores(local, world):
+    """N > 1: every rank keeps to its own slice of the host cores (the box's GPUs all report the same CPU affinity, so 8
+    ranks x (launch thread + copy threads + NCCL proxy) otherwise migrate over the same cores)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if per >= 2:
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+            return per
+    except Exception:
+        pass
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--cpu-faces", type=int, default=5, help="faces in the bounded CPU-baseline sample")
+    ap.add_argument("--ref-faces", type=int, default=1, help="--impl reference: faces relit per step (bounded sample of the 8-face batch)")
+    ap.add_argument("--ref-batch", type=int, default=1, help="--impl reference: faces per forward (the reference bakes 1; 8 patches its grids)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-gpu-ref", action="store_true", help="skip the informational run of the reference on cuda:0 "
+                                                              "(~50k tiny launches; always skip it under ncu)")
+    ap.add_argument("--lanes", type=int, default=3, help="runner lanes the e2e (host-buffer) path rotates over")
+    ap.add_argument("--e2e-f32", action="store_true", help="e2e reads back fp32 rendered_images (6.3 MB) instead of the 8-bit BGR composite")
+    ap.add_argument("--no-gan", action="store_true", help="train workload without the PatchGAN terms")
+    ap.add_argument("--train-precision", type=int, default=0, help="train-mode conv operand precision (3 = 3xTF32, 1 = TF32, 4 = bf16)")
+    ap.add_argument("--no-pin", action="store_true", help="do not pin each rank to its own host cores")
+    ap.add_argument("--workload", default="all", choices=["all", "forward", "train", "sweep"],
+                    help="all (default) = the configs[1] forward line with `train` (configs[2]/[3]) and `sweep` (configs[4]) "
+                         "sub-blocks; forward / train / sweep = that leg alone")
+    args = ap.parse_args()
+    if args.impl != "ours":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local)
+    dist = None
+    pinned = None
+    if world > 1:
+        if not args.no_pin:
+            pinned = pin_rank_cores(local, world)
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    if args.workload == "train":
+        line = bench_train(args, rank, world, dist)
+    elif args.workload == "sweep":
+        line = bench_sweep(args, rank, world, dist)
+    else:
+        line = bench_forward(args, rank, world, local, dist)
+        if pinned:
+            line["execution"]["host_cores_per_rank"] = pinned
+        if args.workload == "all":
+            line["sweep"] = bench_sweep(args, rank, world, dist)
+            line["train"] = bench_train(args, rank, world, dist)
+        if rank == 0 and world == 1:
+            try:
+                r = reference_subprocess("reference", max(args.cpu_faces, 2), 1)
+                line["cpu_baseline"] = r["cpu_baseline"]
+            except Exception as e:
+                line["cpu_baseline"] = {"unavailable": str(e)[:300]}
+            if not args.no_gpu_ref:
+                try:
+                    r = reference_subprocess("reference-gpu", 6, 2)
+                    line["reference_gpu"] = dict(r["cpu_baseline"], note="the reference's forward on cuda:0 (torch eager, cuDNN convs + the "
+                                                 "per-sample tensor program of TEST1:351-498 with its per-image host syncs): the "
+                                                 "north star's 'reference 1-GPU PyTorch throughput'")
+                except Exception as e:                      # informational only
+                    line["reference_gpu"] = {"unavailable": str(e)[:300]}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
+        # the step graphs hold captured NCCL kernels: tearing the communicator down under them was observed to hang at
+        # interpreter exit on 2 GPUs, so synchronise, agree that everybody is done, and leave without finalisers
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

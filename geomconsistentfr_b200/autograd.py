@@ -200,7 +200,12 @@ class FlatAdam:
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return 1.0
+        ev = getattr(self, "ar_events", None)         # optional (start, end) CUDA events (external=True under graph capture)
+        if ev is not None:
+            ev[0].record()
         dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+        if ev is not None:
+            ev[1].record()
         return 1.0 / dist.get_world_size(group)
 
     def step(self, grad_scale=1.0):

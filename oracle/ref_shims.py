@@ -27,7 +27,20 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("GFR_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(_HERE, "_ref")                 # byte copies made by oracle/fetch_ref.py (git-ignored; ships to the GPU box)
+_GOLDEN = os.path.join(_HERE, "..", "tests", "golden")
+
+
+def _default_root():
+    if os.environ.get("GFR_REFERENCE_ROOT"):
+        return os.environ["GFR_REFERENCE_ROOT"]
+    if os.path.isfile(os.path.join("/root/reference", "test_relight_single_image.py")):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _default_root()
 
 _SCRIPTS = {
     "TRAIN": "train_raytracing_relighting_CelebAHQ_DSSIM_8x.py",
@@ -42,12 +55,14 @@ def reference_available():
     return os.path.isfile(os.path.join(REFERENCE_ROOT, _SCRIPTS["TEST1"]))
 
 
-def _install_shims():
+def _install_shims(cuda_identity=True):
     from oracle import relight_oracle as spec
 
-    # 1. .cuda() -> identity
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    nn.Module.cuda = lambda self, *a, **k: self
+    # 1. .cuda() -> identity (CPU runs only; with cuda_identity=False the reference's own .cuda() calls stay real —
+    #    bench.py's `reference_gpu` leg on the GPU box)
+    if cuda_identity:
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        nn.Module.cuda = lambda self, *a, **k: self
     # 2. np.asscalar
     if not hasattr(np, "asscalar"):
         np.asscalar = lambda a: a.item()
@@ -88,13 +103,13 @@ def _install_shims():
 _loaded = {}
 
 
-def load_reference(short):
+def load_reference(short, cuda_identity=True):
     """Import one of the reference scripts (TRAIN / TEST1 / TESTB) unmodified."""
     if short in _loaded:
         return _loaded[short]
     if not reference_available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
-    _install_shims()
+    _install_shims(cuda_identity)
     path = os.path.join(REFERENCE_ROOT, _SCRIPTS[short])
     spec = importlib.util.spec_from_file_location("gfr_reference_" + short, path)
     mod = importlib.util.module_from_spec(spec)
@@ -103,10 +118,10 @@ def load_reference(short):
     return mod
 
 
-def reference_model(short="TEST1", batch_size=None, weights=True):
+def reference_model(short="TEST1", batch_size=None, weights=True, cuda_identity=True):
     """Instantiate the reference RelightNet (CPU).  `batch_size` patches the value the
     reference bakes into xx/yy at construction (TEST1:15,25-26 / TRAIN:41,52-53)."""
-    mod = load_reference(short)
+    mod = load_reference(short, cuda_identity)
     net = mod.RelightNet()
     if batch_size is not None and batch_size != net.batch_size:
         net.batch_size = batch_size
@@ -114,6 +129,9 @@ def reference_model(short="TEST1", batch_size=None, weights=True):
         net.yy = net.yy[:1].repeat(batch_size, 1, 1)
     if weights:
         rel = ("model_lighting_transfer", "model_epoch106.pth") if short in ("TEST_LT", "TRAIN_LT") else ("model", "model_epoch99.pth")
-        sd = torch.load(os.path.join(REFERENCE_ROOT, *rel), map_location="cpu")
+        path = os.path.join(REFERENCE_ROOT, *rel)
+        if not os.path.isfile(path):               # the staged copy carries no weights: tests/golden holds byte-identical files
+            path = os.path.join(_GOLDEN, rel[1])
+        sd = torch.load(path, map_location="cpu")
         net.load_state_dict(sd)
     return net.float()
