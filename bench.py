@@ -639,14 +639,15 @@ def main():
                                                  "north star's 'reference 1-GPU PyTorch throughput'")
                 except Exception as e:                      # informational only
                     line["reference_gpu"] = {"unavailable": str(e)[:300]}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if dist is not None:
         # the step graphs hold captured NCCL kernels: tearing the communicator down under them was observed to hang at
-        # interpreter exit on 2 GPUs, so synchronise, agree that everybody is done, and leave without finalisers
+        # interpreter exit on 2 GPUs, so synchronise, agree that everybody is done, print, and leave without finalisers
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
+    if rank == 0:
+        print(json.dumps(line), flush=True)          # the last thing on stdout (NCCL_DEBUG=INFO also writes there)
+    if dist is not None:
         sys.stdout.flush()
         os._exit(0)
 

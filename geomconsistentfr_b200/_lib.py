@@ -28,6 +28,8 @@ _PROTOS = {
     "gfr_ssim_bwd": [_c_void_p] * 5 + [_c_int, _c_int, _c_int, _c_void_p],
     "gfr_masked_losses": [_c_void_p] * 12 + [_c_int, _c_int, _c_int, _c_void_p],
     "gfr_adam_step": [_c_void_p] * 4 + [ctypes.c_longlong, _c_void_p, _c_float, _c_float, _c_float, _c_float, _c_float, _c_void_p],
+    "gfr_adam_step_segments": [_c_void_p] * 4 + [ctypes.c_longlong, _c_void_p, _c_void_p, _c_int, _c_float, _c_float, _c_float, _c_float,
+                               _c_float, _c_void_p],
     # train-mode CNN
     "gfr_conv_tc_pack_weights_dev": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p],
     "gfr_bn_train_stats": [_c_void_p] * 10 + [_c_int] * 4 + [_c_float, _c_float, _c_void_p],

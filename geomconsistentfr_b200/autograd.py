@@ -135,7 +135,13 @@ class MaskedLosses(torch.autograd.Function):
 class FlatAdam:
     """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8) over ONE flat fp32 buffer that the parameters are views of
     (TRAIN:589-590, 656) — a single fused kernel per step; `grad_scale` folds the 1/world_size of the data-parallel
-    gradient all-reduce."""
+    gradient all-reduce.
+
+    Like torch.optim.Adam the state is PER PARAMETER: every parameter tensor is a segment with its own step count and bias
+    correction (on the device, so a step replays from a CUDA graph), and a parameter that received no gradient is skipped
+    entirely — torch skips `p.grad is None` parameters, which is what the epoch-gated skip blocks are until their gate
+    opens (TRAIN:245,258,271,283); they then start at step 1 with a properly bias-corrected first update.  Here every
+    `.grad` is a view of the flat gradient buffer, so "has a gradient" is declared by the owner: `set_active(flags)`."""
 
     def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
         self.params = [p for p in params]
@@ -145,55 +151,67 @@ class FlatAdam:
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
-        o = 0
+        o, starts = 0, []
         with torch.no_grad():
             for p in self.params:                      # re-seat every parameter (and its .grad) as a view of the flat buffers
                 k = p.numel()
+                starts.append(o)
                 self.flat[o:o + k].copy_(p.reshape(-1))
                 p.data = self.flat[o:o + k].view_as(p)
                 p.grad = self.grad[o:o + k].view_as(p)
                 o += k
         self.lr, self.betas, self.eps = lr, betas, eps
-        self.state = torch.zeros(3, dtype=torch.float32, device=dev)       # {step, 1-b1^t, sqrt(1-b2^t)} advanced on the device
+        self.seg_start = torch.tensor(starts + [n], dtype=torch.int64, device=dev)
+        # per segment {step, 1-b1^t, sqrt(1-b2^t), active}, advanced on the device
+        self.seg_state = torch.zeros((len(self.params), 4), dtype=torch.float32, device=dev)
+        self.seg_state[:, 3] = 1.0
 
     def zero_grad(self):
         self.grad.zero_()
 
-    # ---- checkpointing, in torch.optim.Adam's own state_dict layout (per-parameter step / exp_avg / exp_avg_sq), so a
-    # checkpoint written here resumes under the reference's `torch.optim.Adam` (TRAIN:589-590) and vice versa
+    def set_active(self, flags):
+        """flags[i] False: parameter i gets no gradient in the coming steps (torch: `.grad is None`) — it is not updated and
+        its step count does not advance.  A plain device copy: call it between (not inside) graph replays."""
+        f = torch.as_tensor([1.0 if a else 0.0 for a in flags], dtype=torch.float32)
+        if f.numel() != len(self.params):
+            raise ValueError("set_active needs one flag per parameter")
+        self.seg_state[:, 3].copy_(f.to(self.seg_state.device))
+
+    # ---- checkpointing, in torch.optim.Adam's own state_dict layout (per-parameter step / exp_avg / exp_avg_sq; parameters
+    # that never had a gradient have no entry), so a checkpoint written here resumes under the reference's
+    # `torch.optim.Adam` (TRAIN:589-590) and vice versa
     def state_dict(self):
-        step = float(self.state[0].item())
+        steps = self.seg_state[:, 0].detach().cpu().tolist()
         st, o = {}, 0
         for i, p in enumerate(self.params):
             k = p.numel()
-            st[i] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[o:o + k].view_as(p).detach().cpu().clone(),
-                     "exp_avg_sq": self.exp_avg_sq[o:o + k].view_as(p).detach().cpu().clone()}
+            if steps[i] > 0:
+                st[i] = {"step": torch.tensor(float(steps[i])), "exp_avg": self.exp_avg[o:o + k].view_as(p).detach().cpu().clone(),
+                         "exp_avg_sq": self.exp_avg_sq[o:o + k].view_as(p).detach().cpu().clone()}
             o += k
         group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
-        return {"state": st if step > 0 else {}, "param_groups": [group]}
+        return {"state": st, "param_groups": [group]}
 
     def load_state_dict(self, sd):
         g = sd["param_groups"][0]
         if len(g["params"]) != len(self.params):
             raise ValueError("optimizer state holds %d parameters, this optimiser %d" % (len(g["params"]), len(self.params)))
         self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
-        steps, o = set(), 0
+        state, o = torch.zeros((len(self.params), 3), dtype=torch.float64), 0
         with torch.no_grad():
             for i, p in enumerate(self.params):
                 k = p.numel()
                 e = sd["state"].get(i)
-                if e is None:
-                    self.exp_avg[o:o + k].zero_(); self.exp_avg_sq[o:o + k].zero_(); steps.add(0.0)
+                if e is None:                      # never stepped (torch keeps no state for it)
+                    self.exp_avg[o:o + k].zero_(); self.exp_avg_sq[o:o + k].zero_()
                 else:
                     self.exp_avg[o:o + k].copy_(e["exp_avg"].reshape(-1)); self.exp_avg_sq[o:o + k].copy_(e["exp_avg_sq"].reshape(-1))
-                    steps.add(float(e["step"]))
+                    t = float(e["step"])
+                    state[i] = torch.tensor([t, 1.0 - self.betas[0] ** t, (1.0 - self.betas[1] ** t) ** 0.5], dtype=torch.float64)
                 o += k
-            if len(steps) != 1:
-                raise ValueError("per-parameter step counts differ: %s" % sorted(steps))
-            t = steps.pop()
-            self.state.copy_(torch.tensor([t, 1.0 - self.betas[0] ** t, (1.0 - self.betas[1] ** t) ** 0.5], dtype=torch.float64).float())
+            self.seg_state[:, :3].copy_(state.float())
 
     def all_reduce_grads(self, group=None):
         """ONE collective per optimiser step over the flat gradient buffer (sum); returns the 1/world factor."""
@@ -209,7 +227,8 @@ class FlatAdam:
         return 1.0 / dist.get_world_size(group)
 
     def step(self, grad_scale=1.0):
-        rc = _lib.load().gfr_adam_step(_ptr(self.flat), _ptr(self.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
-                                       self.flat.numel(), _ptr(self.state), self.lr, self.betas[0], self.betas[1], self.eps,
-                                       float(grad_scale), _stream())
-        _lib.check(rc, "gfr_adam_step"); ops._count(2)
+        rc = _lib.load().gfr_adam_step_segments(_ptr(self.flat), _ptr(self.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
+                                                self.flat.numel(), _ptr(self.seg_start), _ptr(self.seg_state), len(self.params),
+                                                self.lr, self.betas[0], self.betas[1], self.eps, float(grad_scale), _stream())
+        _lib.check(rc, "gfr_adam_step_segments"); ops._count(2)
+        ops.bump_param_generation()

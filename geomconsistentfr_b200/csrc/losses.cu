@@ -233,6 +233,40 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// Per-parameter step counts (torch.optim.Adam keeps `state[p]['step']` per parameter and skips parameters whose .grad is None):
+// seg_state[s] = {step, 1-beta1^step, sqrt(1-beta2^step), active}; only ACTIVE segments tick and are updated.
+__global__ void adam_tick_segments_kernel(float* __restrict__ seg_state, int n_seg, float beta1, float beta2) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  float* st = seg_state + 4 * s;
+  if (st[3] == 0.f) return;
+  const double t = (double)st[0] + 1.0;
+  st[0] = (float)t;
+  st[1] = (float)(1.0 - pow((double)beta1, t));
+  st[2] = (float)sqrt(1.0 - pow((double)beta2, t));
+}
+
+__global__ void adam_step_segments_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                          float* __restrict__ v, long long n, const long long* __restrict__ seg_start,
+                                          const float* __restrict__ seg_state, int n_seg, float lr, float beta1, float beta2,
+                                          float eps, float grad_scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lo = 0, hi = n_seg;                       // the segment with seg_start[lo] <= i < seg_start[lo + 1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(seg_start + mid) <= i) lo = mid; else hi = mid;
+  }
+  const float4 st = __ldg(reinterpret_cast<const float4*>(seg_state) + lo);
+  if (st.w == 0.f) return;                      // no gradient this step (torch: p.grad is None -> skipped, state untouched)
+  const float gi = g[i] * grad_scale;
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / st.z + eps;
+  p[i] -= (lr / st.y) * (mi / denom);
+}
+
 SsimWeights gaussian_window() {
   SsimWeights g;
   float s = 0.f;
@@ -298,5 +332,19 @@ extern "C" int gfr_adam_step(float* params, const float* grads, float* exp_avg, 
   adam_tick_kernel<<<1, 1, 0, s>>>(state3, beta1, beta2);
   adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, state3,
                                                               grad_scale);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_adam_step_segments(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                                      const long long* seg_start, float* seg_state, int n_seg, float lr, float beta1, float beta2,
+                                      float eps, float grad_scale, void* stream) {
+  GFR_RETURN_IF_NULL(params); GFR_RETURN_IF_NULL(grads); GFR_RETURN_IF_NULL(exp_avg); GFR_RETURN_IF_NULL(exp_avg_sq);
+  GFR_RETURN_IF_NULL(seg_start); GFR_RETURN_IF_NULL(seg_state);
+  if (n <= 0 || n_seg <= 0) return GFR_E_SHAPE;
+  if (reinterpret_cast<uintptr_t>(seg_state) & 15) return GFR_E_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  adam_tick_segments_kernel<<<(unsigned)((n_seg + 127) / 128), 128, 0, s>>>(seg_state, n_seg, beta1, beta2);
+  adam_step_segments_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, seg_start, seg_state,
+                                                                       n_seg, lr, beta1, beta2, eps, grad_scale);
   return gfr_launch_status();
 }

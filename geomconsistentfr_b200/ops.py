@@ -33,6 +33,20 @@ def _count(n=1):
     _launches += n
 
 
+_param_generation = 0    # bumped by everything that writes parameters / BatchNorm buffers through raw pointers (fused Adam, the
+                         # batch-statistics kernels, graph replays of a training step): torch's `_version` counters do not see
+                         # those writes, so caches of derived weights (BN-folded, packed) key on this as well
+
+
+def param_generation():
+    return _param_generation
+
+
+def bump_param_generation():
+    global _param_generation
+    _param_generation += 1
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 

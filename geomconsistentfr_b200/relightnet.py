@@ -92,6 +92,8 @@ class RelightNet(nn.Module):
             self._add("conv_%s_c2_2" % p, nn.Conv2d, 16, 16, 1)
             self._add("conv_%s_c2_3" % p, nn.Conv2d, 16, 16, 1)
             setattr(self, "conv_%s_c2_o" % p, nn.Conv2d(16, 3 if p == "albedo" else 1, 1))
+        self.track_gated_skip_stats = True    # train mode: run the encoder-skip blocks whose epoch gate is still closed (no gradient)
+                                              # so that their BN running statistics follow the reference's (TRAIN:240-246)
         self._folded = None
         self._folded_key = None
         self._tc = None
@@ -128,9 +130,23 @@ class RelightNet(nn.Module):
     def device(self):
         return self.conv_c1_og.weight.device
 
+    def active_parameter_flags(self, epoch):
+        """One bool per parameter (the order of `parameters()`): False for the encoder-skip blocks whose gate is closed at
+        `epoch` (TRAIN:245,258,271,283) — autograd gives them no gradient, so torch.optim.Adam leaves them and their step
+        count alone (FlatAdam.set_active)."""
+        import re
+        flags = []
+        for name, _ in self.named_parameters():
+            m = re.search(r"_skip_(s\d)_", name)
+            flags.append(not (m and epoch <= _EPOCH_GATES[m.group(1)]))
+        return flags
+
     # ------------------------------------------------------------------ eval-mode weights: BN folded into the conv
     def _fold_key(self):
-        return tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers()) + (str(self.device),)
+        # `_version` does not see raw-pointer writes (fused Adam on the flat buffer, BN running statistics, graph replays of
+        # a training step): ops.param_generation() counts those
+        return tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers()) \
+            + (str(self.device), ops.param_generation())
 
     @torch.no_grad()
     def _folded_weights(self):
@@ -297,6 +313,12 @@ class RelightNet(nn.Module):
             if epoch > _EPOCH_GATES[skip]:
                 s1 = unit("conv_%s_skip_%s_1" % (p, skip), enc)
                 return unit("conv_%s_skip_%s_2" % (p, skip), s1, res=enc, post=t, post_shift=1)
+            if self.track_gated_skip_stats:
+                # the reference evaluates the skip block in every forward and only gates the ADD (TRAIN:240-246 and the three
+                # like it), so its BatchNorm running statistics move from epoch 0 on: same here, outside autograd
+                with torch.no_grad():
+                    s1 = unit("conv_%s_skip_%s_1" % (p, skip), enc.detach())
+                    unit("conv_%s_skip_%s_2" % (p, skip), s1)
             return T.Upsample2.apply(t)
 
         bn0 = self.bn_c1_og
@@ -419,11 +441,21 @@ class RelightNet(nn.Module):
     def _intrinsics(self, intrinsic_matrix):
         """fx, fy, cx, cy as host floats.  The reference hands a CUDA tensor (TRAIN:618); reading it back is a
         device sync, so the values are cached per (storage, version)."""
-        key = (intrinsic_matrix.data_ptr(), intrinsic_matrix._version, str(intrinsic_matrix.device))
-        if getattr(self, "_intr_cache", (None,))[0] != key:
-            K = intrinsic_matrix.detach().to("cpu", torch.float64).reshape(-1, 3, 3)[0]
-            self._intr_cache = (key, (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])))
-        return self._intr_cache[1]
+        def read(K):
+            K = K.detach().to("cpu", torch.float64).reshape(-1, 3, 3)[0]
+            return (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]))
+
+        if not intrinsic_matrix.is_cuda:
+            return read(intrinsic_matrix)                      # host tensor: no sync to avoid, no cache
+        # device tensor: cached per tensor OBJECT (+ version).  A fresh temporary (`intrinsic_matrix.cuda()` inline, the
+        # reference's call style) may reuse a freed tensor's address, so the address is not an identity.
+        c = getattr(self, "_intr_cache", None)
+        if c is not None and c[0]() is intrinsic_matrix and c[1] == intrinsic_matrix._version:
+            return c[2]
+        import weakref
+        vals = read(intrinsic_matrix)
+        self._intr_cache = (weakref.ref(intrinsic_matrix), intrinsic_matrix._version, vals)
+        return vals
 
     def _light_prep(self, light_dir, n_pairs, clamp_z):
         """unit light direction and point light of every (face, light) pair — TRAIN:357-362 / TEST1:332-335."""

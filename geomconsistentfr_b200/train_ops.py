@@ -57,6 +57,7 @@ class _BN:
              "gfr_bn_train_stats", 2)
         if track:
             bn.num_batches_tracked += 1
+            ops.bump_param_generation()
         return mean, rstd, scale, shift
 
     @staticmethod

@@ -10,6 +10,7 @@ TRAIN = train_raytracing_relighting_CelebAHQ_DSSIM_8x.py."""
 import torch
 import torch.nn.functional as F
 
+from . import ops
 from .autograd import FlatAdam, MaskedLosses, dssim_loss
 
 LOSS_TERMS = ("recon", "depth", "ambient", "lighting", "albedo", "DSSIM")     # TRAIN:672-682 names, minus the GAN terms
@@ -21,6 +22,17 @@ class GeneratorStep:
         self.K = intrinsic_matrix
         self.opt = FlatAdam(list(net.parameters()), lr=net.lr if lr is None else lr)      # TRAIN:589: Adam(lr=0.0001)
         self.group = group
+        self._active_sig = None
+
+    def _declare_active(self, epoch):
+        """Parameters of encoder-skip blocks whose gate is closed get no gradient: tell the optimiser (torch.optim.Adam skips
+        `.grad is None`).  A host->device copy, so it only happens when the gate signature changes (never inside a capture:
+        the capture's eager warm-up steps have set it)."""
+        flags = self.net.active_parameter_flags(epoch)
+        sig = tuple(flags)
+        if sig != self._active_sig:
+            self.opt.set_active(flags)
+            self._active_sig = sig
 
     def losses(self, out, img, masks_fill, masks, depth_gt, albedo_gt, lighting_gt):
         """The reference's loss expressions (TRAIN:633-645).  img [B,H,W,3]; masks_fill / masks [B,H,W] in {0,1};
@@ -64,10 +76,12 @@ class GeneratorStep:
             for dst, src in zip(self._static, (img, masks_fill, masks, depth_gt, albedo_gt, lighting_gt)):
                 dst.copy_(src, non_blocking=True)
             self._graph.replay()
+        ops.bump_param_generation()                 # the replay wrote parameters and BN buffers behind torch's back
         return self._static_out
 
     def step(self, img, epoch, masks_fill, masks, depth_gt, albedo_gt, lighting_gt):
         """One optimiser step.  Returns (total, terms) as device tensors (no host sync)."""
+        self._declare_active(epoch)
         self.opt.zero_grad()                                                              # TRAIN:631
         B, H, W, _ = img.shape
         out = self.net(img, epoch, self.K, masks_fill.reshape(B, H, W, 1))                # TRAIN:618
@@ -96,6 +110,7 @@ class TrainStep(GeneratorStep):
         """Iteration j of an epoch.  Returns (total, terms) with the reference's loss names (TRAIN:672-682)."""
         B, H, W, _ = img.shape
         update_d = (j % self.GD_ratio) == 0                                               # TRAIN:624
+        self._declare_active(epoch)
         self.opt_d.zero_grad()                                                            # TRAIN:617
         out = self.net(img, epoch, self.K, masks_fill.reshape(B, H, W, 1))                # TRAIN:618
         rendered = out[5]
@@ -151,4 +166,5 @@ class TrainStep(GeneratorStep):
             for dst, src in zip(self._static, (img, masks_fill, masks, depth_gt, albedo_gt, lighting_gt)):
                 dst.copy_(src, non_blocking=True)
             self._graphs[k].replay()
+        ops.bump_param_generation()
         return self._outs[k]

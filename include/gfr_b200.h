@@ -154,6 +154,15 @@ int gfr_masked_losses(const float* rendered, const float* img_nchw, const float*
 int gfr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state3, float lr,
                   float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* The same step with torch.optim.Adam's PER-PARAMETER state (TRAIN:589-590, 656): the flat buffer is cut into n_seg
+ * segments (seg_start[0..n_seg], device int64, seg_start[n_seg] = n), one per parameter tensor.  seg_state: n_seg x 4 device
+ * floats {step, 1-beta1^step, sqrt(1-beta2^step), active}, 16-byte aligned; only segments with active != 0 tick and are
+ * updated — torch skips parameters whose .grad is None (the epoch-gated skip blocks before their gate opens,
+ * TRAIN:245,258,271,283) and starts their bias correction at their first gradient. */
+int gfr_adam_step_segments(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                           const long long* seg_start, float* seg_state, int n_seg, float lr, float beta1, float beta2,
+                           float eps, float grad_scale, void* stream);
+
 /* ---- train-mode CNN building blocks (the reference trains with BATCH-statistics BatchNorm: it never calls .eval(),
  * TRAIN:561-563) — all activations C4 -------------------------------------------------------------------------- */
 

@@ -1,0 +1,106 @@
+"""GPU: three consecutive iterations of the training loop (TRAIN:606-656; j = 0 updates the discriminator) on the library's
+TrainStep against the reference's OWN `main()` run on the same nine samples (tests/golden/train_iter.npz, made by
+oracle/make_golden_train_iter.py from the unmodified script): every printed loss term of every iteration, and after the
+third iteration the parameters of BOTH networks and the generator's BatchNorm running statistics — at epoch 0 (all
+encoder-skip gates closed: their parameters must not move, their BN buffers must) and at epoch 15 (all gates open).
+Also PatchGAN alone against the reference class's logits / gradients (tests/golden/patchgan.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+LR = 1e-4
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-20))
+
+
+def test_patchgan_vs_reference_class_outputs():
+    from geomconsistentfr_b200 import PatchGAN
+    from oracle.make_golden_train_iter import patchgan_case, patchgan_init
+    f = np.load(os.path.join(G, "patchgan.npz"))
+    D = patchgan_init(PatchGAN()).cuda().train()
+    img, gl = patchgan_case()
+    x = img.cuda().requires_grad_()
+    logits = D(x)
+    (logits * gl.cuda()).sum().backward()
+    assert _rel(logits.detach().cpu().numpy(), f["logits"]) <= 2e-4
+    assert _rel(x.grad.cpu().numpy()[:, :, ::2, ::2], f["grad_input_s2"]) <= 5e-3
+    for n, p in D.named_parameters():
+        if n in ("conv2.bias", "conv3.bias", "conv4.bias"):
+            continue                                   # bias before a train-mode BN: zero gradient up to rounding
+        g = p.grad.reshape(-1)
+        got = g[:: max(1, g.numel() // 4096)].cpu().numpy()
+        assert _rel(got, f["gsample_" + n]) <= 1e-2, (n, _rel(got, f["gsample_" + n]))
+    for n, b in D.named_buffers():
+        if "num_batches" not in n:
+            assert np.abs(b.cpu().numpy() - f["buf_" + n]).max() <= 1e-4, n
+
+
+@pytest.mark.parametrize("epoch", [0, 15])
+def test_three_iterations_vs_reference_main(epoch):
+    from geomconsistentfr_b200 import PatchGAN, RelightNet, intrinsic_matrix
+    from geomconsistentfr_b200.train_loop import LOSS_NAMES, TrainingArrays
+    from geomconsistentfr_b200.trainer import TrainStep
+    from oracle.make_golden_train_iter import D_STRIDE, inputs, patchgan_init
+    f = np.load(os.path.join(G, "train_iter.npz"))
+    assert tuple(f["loss_names"]) == LOSS_NAMES
+    data = TrainingArrays(*inputs())
+    sd0 = torch.load(os.path.join(G, "model_epoch99.pth"), map_location="cpu")
+    net = RelightNet(batch_size=3)
+    net.load_state_dict(sd0, strict=True)
+    net = net.float().cuda().train()
+    D = patchgan_init(PatchGAN()).cuda().train()
+    d0 = {k: v.detach().cpu().clone() for k, v in D.state_dict().items()}
+    step = TrainStep(net, D, intrinsic_matrix().cuda())
+    want = f["terms_e%d" % epoch]
+    for j in range(3):
+        b = [t.cuda() for t in data.batch(j, 3)]
+        total, terms = step.step(b[0], epoch, *b[1:], j=j)
+        got = dict(terms, total=total)
+        for i, k in enumerate(LOSS_NAMES):
+            a, w = float(got[k]), float(want[j, i])
+            # iteration 0 sees identical parameters; iterations 1, 2 also carry the +-lr sign noise of near-zero gradients
+            tol = (2e-3 if j == 0 else 5e-3) * max(abs(w), 1e-3)
+            assert abs(a - w) <= tol, (epoch, j, k, a, w)
+
+    # ---- generator parameters after three Adam steps: delta from epoch 99, in units of lr
+    names = [k for k in sd0 if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"))]
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    mine = torch.cat([((sd[k] - sd0[k]).double() / LR).reshape(-1) for k in names]).numpy()
+    ref = f["g_delta_e%d" % epoch].astype(np.float64)                     # stored as delta * 1e4 = delta / lr
+    assert mine.shape == ref.shape
+    d = np.abs(mine - ref)
+    # Adam's step is lr * m / sqrt(v): a parameter whose gradient is rounding noise (conv biases in front of a batch-statistics
+    # BatchNorm: analytically zero) moves by +-lr per step with a sign that differs from run to run in the reference itself
+    is_noise_bias = np.concatenate([np.full(sd0[k].numel(), k.endswith(".bias") and ("conv" in k) and not k.endswith("c2_o.bias")) for k in names])
+    real = ~is_noise_bias
+    assert d[real].max() <= 6.0 + 1e-3                                    # 3 steps x 2 lr at the very worst
+    frac = float((d[real] > 0.3).mean())                                 # > 0.3 lr off after three steps
+    assert frac < 0.03, (epoch, frac)
+    assert float(np.median(d[real])) <= 0.02, float(np.median(d[real]))
+    if epoch == 0:                                                        # gated skip blocks: no gradient, no update (torch: grad None)
+        for k in names:
+            if "_skip_s" in k:
+                assert torch.equal(sd[k], sd0[k]), k
+    # ---- BatchNorm running statistics (momentum 0.1, three updates), including the gated skip blocks at epoch 0
+    worst = 0.0
+    for k in sd0:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            r = f["g_e%d_%s" % (epoch, k)]
+            err = float(np.abs(sd[k].numpy() - r).max() / (np.abs(r).max() + 1e-6))
+            worst = max(worst, err)
+            assert err <= 5e-3, (k, err)
+    # ---- discriminator parameters (one Adam step at j = 0), every D_STRIDE-th element
+    dn = [k for k in d0 if not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"))]
+    dsd = {k: v.detach().cpu() for k, v in D.state_dict().items()}
+    mine_d = torch.cat([((dsd[k] - d0[k]).double() / LR).reshape(-1)[::D_STRIDE] for k in dn]).numpy()
+    ref_d = f["d_delta_e%d" % epoch].astype(np.float64)
+    noise_d = np.concatenate([np.full(len(range(0, d0[k].numel(), D_STRIDE)), k in ("conv2.bias", "conv3.bias", "conv4.bias")) for k in dn])
+    dd = np.abs(mine_d - ref_d)[~noise_d]
+    assert dd.max() <= 2.0 + 1e-3 and float((dd > 0.3).mean()) < 0.03 and float(np.median(dd)) <= 0.02, \
+        (float(dd.max()), float((dd > 0.3).mean()), float(np.median(dd)))

@@ -83,8 +83,8 @@ def test_flat_adam_state_dict_interchanges_with_torch_adam():
         ref.step()
     mine = FlatAdam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=3e-4)
     mine.load_state_dict(ref.state_dict())                            # the reference's optimiser state loads here
-    assert mine.lr == 1e-4 and float(mine.state[0]) == 3.0
-    assert abs(float(mine.state[1]) - (1 - 0.9 ** 3)) < 1e-6 and abs(float(mine.state[2]) - (1 - 0.999 ** 3) ** 0.5) < 1e-6
+    assert mine.lr == 1e-4 and mine.seg_state[:, 0].tolist() == [3.0, 3.0]
+    assert abs(float(mine.seg_state[0, 1]) - (1 - 0.9 ** 3)) < 1e-6 and abs(float(mine.seg_state[1, 2]) - (1 - 0.999 ** 3) ** 0.5) < 1e-6
     assert torch.equal(mine.exp_avg[:12].view(4, 3), ref.state[ps[0]]["exp_avg"])
     assert torch.equal(mine.exp_avg_sq[12:], ref.state[ps[1]]["exp_avg_sq"])
     back = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=1.0)
@@ -95,4 +95,21 @@ def test_flat_adam_state_dict_interchanges_with_torch_adam():
     fresh = FlatAdam([torch.nn.Parameter(torch.zeros(2))])
     assert fresh.state_dict()["state"] == {}                          # like an unstepped torch.optim.Adam
     fresh.load_state_dict(fresh.state_dict())
-    assert float(fresh.state[0]) == 0.0
+    assert float(fresh.seg_state[0, 0]) == 0.0
+    # per-parameter steps: a torch.optim.Adam in which one parameter started late (an epoch-gated skip block,
+    # TRAIN:245) loads, keeps its differing step counts, and goes back out unchanged
+    late = torch.optim.Adam(ps, lr=1e-4)
+    ps[1].grad = None
+    ps[0].grad = torch.randn_like(ps[0]); late.step(); late.step()
+    ps[1].grad = torch.randn_like(ps[1]); late.step()
+    mine2 = FlatAdam([torch.nn.Parameter(p.detach().clone()) for p in ps])
+    mine2.load_state_dict(late.state_dict())
+    assert mine2.seg_state[:, 0].tolist() == [3.0, 1.0]
+    out = mine2.state_dict()["state"]
+    assert float(out[0]["step"]) == 3.0 and float(out[1]["step"]) == 1.0
+    never = torch.optim.Adam(ps, lr=1e-4)
+    ps[1].grad = None
+    never.step()
+    mine3 = FlatAdam([torch.nn.Parameter(p.detach().clone()) for p in ps])
+    mine3.load_state_dict(never.state_dict())                          # parameter 1 has no state at all
+    assert mine3.seg_state[:, 0].tolist() == [1.0, 0.0] and set(mine3.state_dict()["state"]) == {0}
