@@ -186,13 +186,13 @@ class Trainer:
         """Graph capture runs warm-up steps that would move the parameters, BN buffers and Adam state: snapshot and
         restore them around it so that capturing is invisible to the training trajectory."""
         opt, opt_d = self.step.opt, self.step.opt_d
-        saved = [t.clone() for t in (opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.state, opt_d.flat, opt_d.exp_avg, opt_d.exp_avg_sq, opt_d.state)]
+        saved = [t.clone() for t in (opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.seg_state, opt_d.flat, opt_d.exp_avg, opt_d.exp_avg_sq, opt_d.seg_state)]
         bufs = [b for m in (self.net, self.D) for b in m.buffers()]
         saved_bufs = [b.clone() for b in bufs]
         self.step.capture(batch[0], epoch, *batch[1:])
         torch.cuda.synchronize()
         with torch.no_grad():
-            for dst, src in zip((opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.state, opt_d.flat, opt_d.exp_avg, opt_d.exp_avg_sq, opt_d.state), saved):
+            for dst, src in zip((opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.seg_state, opt_d.flat, opt_d.exp_avg, opt_d.exp_avg_sq, opt_d.seg_state), saved):
                 dst.copy_(src)
             for dst, src in zip(bufs, saved_bufs):
                 dst.copy_(src)
