@@ -64,6 +64,17 @@ _PROTOS = {
     "gfr_light_head_c4_fwd": [_c_void_p, _c_int, _c_int, _c_int] + [_c_void_p] * 5 + [_c_int, _c_void_p],
     "gfr_maxpool2_c4_fwd": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_upsample2_c4_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    # eval-mode CNN on pre-split fp16-pair activations (P16)
+    "gfr_conv_p16_pack_size": [_c_int, _c_int, _c_int, _c_int],
+    "gfr_conv_p16_pack_weights": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
+    "gfr_conv3x3_p16_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p]
+                           + [_c_int] * 12 + [_c_float, _c_float, _c_int, _c_void_p],
+    "gfr_nchw_to_p16": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_p16_to_nchw": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_maxpool2_p16_fwd": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_stem_conv_p16_fwd": [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p],
+    "gfr_head_1x1_p16_fwd": [_c_void_p] * 8 + [_c_int] * 5 + [_c_float, _c_void_p],
+    "gfr_light_head_p16_fwd": [_c_void_p, _c_int, _c_int, _c_int] + [_c_void_p] * 5 + [_c_int, _c_void_p],
     # output stage of the inference drivers
     "gfr_composite_bgr_u8": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_neg_depth_range": [_c_void_p, ctypes.c_longlong, _c_void_p, _c_void_p],
@@ -72,7 +83,7 @@ _PROTOS = {
     "gfr_border_median_fix_u8": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
 }
 _RESTYPES = {"gfr_error_string": ctypes.c_char_p, "gfr_conv_tc_pack_size": ctypes.c_longlong,
-             "gfr_conv_tc_pack_size_f16": ctypes.c_longlong}
+             "gfr_conv_tc_pack_size_f16": ctypes.c_longlong, "gfr_conv_p16_pack_size": ctypes.c_longlong}
 
 _lib = None
 

@@ -7,6 +7,7 @@
 //              x100) fused per pixel, C4 in, NCHW planes out (TRAIN:285-290, 345-350).
 //   * light  — global average pool of the 27 lighting channels + the 2-layer MLP (TRAIN:225-232) on a C4 feature map.
 #include "gfr_common.cuh"
+#include "p16.cuh"
 
 #include <stdlib.h>
 
@@ -20,6 +21,7 @@ struct StemArgs {
   float* out;         // C4 [N,4,H,W,4]
   float* pooled;      // C4 [N,4,H/2,W/2,4] or null
   int N, H, W;
+  int p16;            // 1: out / pooled are P16 tensors [N,2,2,H,W,8] halfs (pre-split fp16 pairs, p16.cuh) instead of C4
 };
 
 constexpr int ST_TW = 32, ST_TH = 16;                          // CTA tile (pixels); thread = 2x2 pixels
@@ -120,6 +122,39 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemArgs a, const 
   const int oy = y0 + 2 * ty, ox = x0 + 2 * tx;
   if (oy >= a.H || ox >= a.W) return;
   const size_t plane = (size_t)a.H * a.W;
+  if (a.p16) {
+    // P16: 8-channel chunks, hi and lo units one plane apart
+    __half* out = reinterpret_cast<__half*>(a.out);
+    __half* pooled = reinterpret_cast<__half*>(a.pooled);
+#pragma unroll
+    for (int c8 = 0; c8 < 2; ++c8) {
+      float v[4][8], mx[8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float z = acc[p][c8 * 8 + e]; v[p][e] = z > 0.f ? z : 0.2f * z; }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mx[e] = fmaxf(fmaxf(v[0][e], v[1][e]), fmaxf(v[2][e], v[3][e]));
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int yy = oy + (p >> 1), xx = ox + (p & 1);
+        if (yy >= a.H || xx >= a.W) continue;
+        uint4 hi, lo;
+        gfr_p16::split8(v[p], hi, lo);
+        __half* o = out + gfr_p16::unit_offset(n, 2, c8, a.H, a.W, yy, xx);
+        *reinterpret_cast<uint4*>(o) = hi;
+        *reinterpret_cast<uint4*>(o + plane * 8) = lo;
+      }
+      if (pooled) {
+        uint4 hi, lo;
+        gfr_p16::split8(mx, hi, lo);
+        __half* o = pooled + gfr_p16::unit_offset(n, 2, c8, a.H >> 1, a.W >> 1, oy >> 1, ox >> 1);
+        *reinterpret_cast<uint4*>(o) = hi;
+        *reinterpret_cast<uint4*>(o + (plane >> 2) * 8) = lo;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float4 v[4];
@@ -156,6 +191,7 @@ struct HeadArgs {
   int n_out;          // 1 or 3
   int act;            // 0 none, 2 sigmoid
   float scale;
+  int p16;            // 1: `in` is a P16 tensor [N,2,2,H,W,8] halfs
 };
 
 __global__ void __launch_bounds__(256) head_1x1_kernel(const HeadArgs a, const __grid_constant__ HeadWeights wt) {
@@ -164,10 +200,22 @@ __global__ void __launch_bounds__(256) head_1x1_kernel(const HeadArgs a, const _
   const long long n = i / a.hw, p = i % a.hw;
   const float4* src = reinterpret_cast<const float4*>(a.in) + n * 4 * a.hw + p;
   float x[16], h[16];
+  if (a.p16) {
+    const __half* hp = reinterpret_cast<const __half*>(a.in) + ((size_t)n * 4 * a.hw + p) * 8;      // [n][c8][part][hw][8]
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 v = __ldg(src + q * a.hw);
-    x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    for (int c8 = 0; c8 < 2; ++c8) {
+      float v[8];
+      gfr_p16::join8(__ldg(reinterpret_cast<const uint4*>(hp + (size_t)(2 * c8) * a.hw * 8)),
+                     __ldg(reinterpret_cast<const uint4*>(hp + (size_t)(2 * c8 + 1) * a.hw * 8)), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[c8 * 8 + e] = v[e];
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = __ldg(src + q * a.hw);
+      x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
   }
 #pragma unroll
   for (int o = 0; o < 16; ++o) {
@@ -195,6 +243,7 @@ __global__ void __launch_bounds__(256) head_1x1_kernel(const HeadArgs a, const _
 }
 
 // ------------------------------------------------------------------------------------------------- light head (C4)
+template <bool P16>
 __global__ void __launch_bounds__(128) light_head_c4_kernel(const float* __restrict__ feat, int C4, int c_first, int HW,
                                                              const float* __restrict__ w1, const float* __restrict__ b1,
                                                              const float* __restrict__ w2, const float* __restrict__ b2,
@@ -204,9 +253,15 @@ __global__ void __launch_bounds__(128) light_head_c4_kernel(const float* __restr
   const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int c = warp; c < 27; c += 4) {
     const int ch = c_first + c;
-    const float* f = feat + (((size_t)n * C4 + (ch >> 2)) * HW) * 4 + (ch & 3);
     float s = 0.f;
-    for (int i = lane; i < HW; i += 32) s += __ldg(f + (size_t)i * 4);
+    if (P16) {      // C4 counts 8-channel chunks here; feat is [N][C8][hi|lo][HW][8] halfs
+      const __half* f = reinterpret_cast<const __half*>(feat) + (((size_t)n * C4 + (ch >> 3)) * 2 * HW) * 8 + (ch & 7);
+      for (int i = lane; i < HW; i += 32)
+        s += (__half2float(f[(size_t)i * 8]) + __half2float(f[((size_t)HW + i) * 8])) * gfr_p16::X_INV;
+    } else {
+      const float* f = feat + (((size_t)n * C4 + (ch >> 2)) * HW) * 4 + (ch & 3);
+      for (int i = lane; i < HW; i += 32) s += __ldg(f + (size_t)i * 4);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) s_pool[c] = s / (float)HW;
@@ -227,8 +282,8 @@ __global__ void __launch_bounds__(128) light_head_c4_kernel(const float* __restr
 
 }  // namespace
 
-extern "C" int gfr_stem_conv_fwd(const float* img, const float* w_host, const float* bias_host, float* out, float* pooled,
-                                 int N, int H, int W, void* stream) {
+static int stem_launch(const float* img, const float* w_host, const float* bias_host, float* out, float* pooled, int N, int H, int W,
+                       int p16, void* stream) {
   GFR_RETURN_IF_NULL(img); GFR_RETURN_IF_NULL(w_host); GFR_RETURN_IF_NULL(bias_host); GFR_RETURN_IF_NULL(out);
   if (N <= 0 || N > 65535 || H <= 0 || W <= 0) return GFR_E_SHAPE;
   if (pooled && ((H | W) & 1)) return GFR_E_SHAPE;
@@ -238,7 +293,7 @@ extern "C" int gfr_stem_conv_fwd(const float* img, const float* w_host, const fl
     for (int ci = 0; ci < 3; ++ci)
       for (int t = 0; t < 25; ++t) wt.w[t][ci][co] = w_host[(co * 3 + ci) * 25 + t];
   }
-  StemArgs a{img, out, pooled, N, H, W};
+  StemArgs a{img, out, pooled, N, H, W, p16};
   const dim3 grid(gfr_ceil_div(W, ST_TW) * gfr_ceil_div(H, ST_TH), N);
   // rolled is the default: 60.1 vs 62.8 us alone, +1.1 % value / +2 % e2e on the whole forward (GFR_STEM_ROLLED=0: the unrolled one)
   static const bool rolled = [] { const char* e = getenv("GFR_STEM_ROLLED"); return !(e != nullptr && e[0] == '0'); }();
@@ -247,9 +302,19 @@ extern "C" int gfr_stem_conv_fwd(const float* img, const float* w_host, const fl
   return gfr_launch_status();
 }
 
-extern "C" int gfr_head_1x1_fwd(const float* in, const float* w2_host, const float* b2_host, const float* w3_host,
-                                const float* b3_host, const float* wo_host, const float* bo_host, float* out, int N, int H,
-                                int W, int n_out, int act, float out_scale, void* stream) {
+extern "C" int gfr_stem_conv_fwd(const float* img, const float* w_host, const float* bias_host, float* out, float* pooled,
+                                 int N, int H, int W, void* stream) {
+  return stem_launch(img, w_host, bias_host, out, pooled, N, H, W, 0, stream);
+}
+
+extern "C" int gfr_stem_conv_p16_fwd(const float* img, const float* w_host, const float* bias_host, void* out, void* pooled, int N,
+                                     int H, int W, void* stream) {
+  return stem_launch(img, w_host, bias_host, reinterpret_cast<float*>(out), reinterpret_cast<float*>(pooled), N, H, W, 1, stream);
+}
+
+static int head_launch(const float* in, const float* w2_host, const float* b2_host, const float* w3_host, const float* b3_host,
+                       const float* wo_host, const float* bo_host, float* out, int N, int H, int W, int n_out, int act, float out_scale,
+                       int p16, void* stream) {
   GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w2_host); GFR_RETURN_IF_NULL(b2_host); GFR_RETURN_IF_NULL(w3_host);
   GFR_RETURN_IF_NULL(b3_host); GFR_RETURN_IF_NULL(wo_host); GFR_RETURN_IF_NULL(bo_host); GFR_RETURN_IF_NULL(out);
   if (N <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
@@ -263,9 +328,22 @@ extern "C" int gfr_head_1x1_fwd(const float* in, const float* w2_host, const flo
     wt.bo[o] = o < n_out ? bo_host[o] : 0.f;
     for (int c = 0; c < 16; ++c) wt.wo[o][c] = o < n_out ? wo_host[o * 16 + c] : 0.f;
   }
-  HeadArgs a{in, out, (long long)H * W, (long long)N * H * W, n_out, act, out_scale};
+  HeadArgs a{in, out, (long long)H * W, (long long)N * H * W, n_out, act, out_scale, p16};
   head_1x1_kernel<<<(unsigned)((a.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, wt);
   return gfr_launch_status();
+}
+
+extern "C" int gfr_head_1x1_fwd(const float* in, const float* w2_host, const float* b2_host, const float* w3_host,
+                                const float* b3_host, const float* wo_host, const float* bo_host, float* out, int N, int H,
+                                int W, int n_out, int act, float out_scale, void* stream) {
+  return head_launch(in, w2_host, b2_host, w3_host, b3_host, wo_host, bo_host, out, N, H, W, n_out, act, out_scale, 0, stream);
+}
+
+extern "C" int gfr_head_1x1_p16_fwd(const void* in, const float* w2_host, const float* b2_host, const float* w3_host,
+                                    const float* b3_host, const float* wo_host, const float* bo_host, float* out, int N, int H,
+                                    int W, int n_out, int act, float out_scale, void* stream) {
+  return head_launch(reinterpret_cast<const float*>(in), w2_host, b2_host, w3_host, b3_host, wo_host, bo_host, out, N, H, W, n_out, act,
+                     out_scale, 1, stream);
 }
 
 extern "C" int gfr_light_head_c4_fwd(const float* feat, int C, int c_first, int HW, const float* w1, const float* b1,
@@ -273,6 +351,16 @@ extern "C" int gfr_light_head_c4_fwd(const float* feat, int C, int c_first, int 
   GFR_RETURN_IF_NULL(feat); GFR_RETURN_IF_NULL(w1); GFR_RETURN_IF_NULL(b1); GFR_RETURN_IF_NULL(w2);
   GFR_RETURN_IF_NULL(b2); GFR_RETURN_IF_NULL(out);
   if (N <= 0 || HW <= 0 || C <= 0 || c_first < 0 || c_first + 27 > C) return GFR_E_SHAPE;
-  light_head_c4_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(feat, (C + 3) / 4, c_first, HW, w1, b1, w2, b2, out);
+  light_head_c4_kernel<false><<<N, 128, 0, (cudaStream_t)stream>>>(feat, (C + 3) / 4, c_first, HW, w1, b1, w2, b2, out);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_light_head_p16_fwd(const void* feat, int groups, int c_first, int HW, const float* w1, const float* b1,
+                                      const float* w2, const float* b2, float* out, int N, void* stream) {
+  GFR_RETURN_IF_NULL(feat); GFR_RETURN_IF_NULL(w1); GFR_RETURN_IF_NULL(b1); GFR_RETURN_IF_NULL(w2);
+  GFR_RETURN_IF_NULL(b2); GFR_RETURN_IF_NULL(out);
+  if (N <= 0 || HW <= 0 || groups <= 0 || c_first < 0 || c_first + 27 > groups * 8) return GFR_E_SHAPE;
+  light_head_c4_kernel<true><<<N, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(feat), groups, c_first, HW, w1, b1, w2,
+                                                                 b2, out);
   return gfr_launch_status();
 }

@@ -427,6 +427,159 @@ def light_head_c4_fwd(feat, c_first, w1, b1, w2, b2):
 
 
 # ---------------------------------------------------------------------------------------------------
+# eval-mode tensor-core CNN on PRE-SPLIT fp16-pair activations: the P16 layout [N][ceil(C/8)][hi|lo][H][W][8] fp16
+# (csrc/p16.cuh, csrc/conv_p16.cu)
+# ---------------------------------------------------------------------------------------------------
+class P16:
+    """An activation tensor in the P16 layout: data [N, groups, 2, H, W, 8] fp16 CUDA + the logical channel count."""
+    __slots__ = ("data", "C")
+
+    def __init__(self, data, C):
+        self.data, self.C = data, C
+
+    @property
+    def shape(self):
+        N, _, _, H, W, _ = self.data.shape
+        return (N, self.C, H, W)
+
+    @property
+    def groups(self):
+        return self.data.shape[1]
+
+
+def _p16_empty(N, C, H, W, device):
+    return torch.empty((N, (C + 7) // 8, 2, H, W, 8), dtype=torch.float16, device=device)
+
+
+def nchw_to_p16(x):
+    x = _need(x, torch.float32, "x")
+    N, C, H, W = x.shape
+    out = _p16_empty(N, C, H, W, x.device)
+    _lib.check(_lib.load().gfr_nchw_to_p16(_ptr(x), _ptr(out), N, C, H, W, _stream()), "gfr_nchw_to_p16"); _count()
+    return P16(out, C)
+
+
+def p16_to_nchw(x, C=None, c_first=0):
+    """P16 -> NCHW fp32; `c_first` (a multiple of 8) / `C` select a channel range of a wider tensor."""
+    N, Cx, H, W = x.shape
+    C = Cx - c_first if C is None else C
+    assert c_first % 8 == 0
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.data.device)
+    base = x.data[:, c_first // 8:]
+    rc = _lib.load().gfr_p16_to_nchw(ctypes.c_void_p(base.data_ptr()), _ptr(out), N, C, x.groups, H, W, _stream())
+    _lib.check(rc, "gfr_p16_to_nchw"); _count()
+    return out
+
+
+def conv_p16_config(Cin, Cout, N, H, W):
+    """(NT, MH, KS) for a layer: 16-wide N tiles for <= 16 output channels, 16x16-pixel tiles when the image gives every
+    SM several of them, 32 input channels per pipeline step when there are that many."""
+    NT = 16 if Cout <= 16 else 32
+    MH = 2 if (N * ((H + 15) // 16) * ((W + 15) // 16)) * ((Cout + NT - 1) // NT) >= 2 * 148 else 1
+    KS = 4 if Cin >= 32 else 2
+    return NT, MH, KS
+
+
+def conv_p16_pack_weights(w, NT, KS):
+    """w [Cout,Cin,3,3] fp32 -> (packed fp16 tensor on w's device, w_scale): w * w_scale = w1 + w2 as an fp16 pair, w_scale =
+    the largest power of two with max|w| * w_scale <= 2^14 (host-side packing, model-load time)."""
+    wc = w.detach().to("cpu", torch.float32).contiguous()
+    Cout, Cin, K, _ = wc.shape
+    assert K == 3
+    mx = float(wc.abs().max())
+    w_scale = 2.0 ** min(12, int(np.floor(np.log2(16384.0 / max(mx, 1e-30)))))
+    n = _lib.load().gfr_conv_p16_pack_size(Cin, Cout, NT, KS)
+    if n < 0:
+        raise RuntimeError("gfr_conv_p16_pack_size: bad arguments")
+    packed = torch.empty(n, dtype=torch.float16)
+    rc = _lib.load().gfr_conv_p16_pack_weights(ctypes.c_void_p(wc.data_ptr()), Cin, Cout, NT, KS, ctypes.c_float(w_scale),
+                                               ctypes.c_void_p(packed.data_ptr()))
+    _lib.check(rc, "gfr_conv_p16_pack_weights")
+    return packed.to(w.device), w_scale
+
+
+def conv3x3_p16_fwd(x, w_packed, bias, Cout, cfg, w_scale, res=None, res_c=0, post=None, post_shift=0, act="lrelu",
+                    act_channels=0, out_scale=1.0, cin=None, flags=None):
+    """x: P16; w_packed / w_scale from conv_p16_pack_weights(w, NT, KS); cfg = (NT, MH, KS).
+    out = out_scale * (act(conv(x[:, :cin]) + bias + res[:, res_c:res_c+Cout]) + up(post)) as P16 (the activation only on
+    output channels < act_channels when given).  `flags`: int32[1] CUDA tensor that collects range overflows."""
+    N, Cin, H, W = x.shape
+    if cin is not None:
+        assert cin <= Cin
+        Cin = cin
+    NT, MH, KS = cfg
+    if not x.data.is_cuda:
+        raise RuntimeError("conv3x3_p16_fwd: x must be on CUDA")
+    w_packed = _need(w_packed, torch.float16, "w_packed")
+    bias = _need(bias, torch.float32, "bias")
+    out = _p16_empty(N, Cout, H, W, x.data.device)
+    if res is not None:
+        assert res.shape[0] == N and res.shape[2:] == (H, W) and res_c % 8 == 0 and res_c + Cout <= res.groups * 8
+    if post is not None:
+        assert post.shape == (N, Cout, H >> post_shift, W >> post_shift)
+    rc = _lib.load().gfr_conv3x3_p16_fwd(
+        _ptr(x.data), _ptr(w_packed), _ptr(bias), _ptr(res.data if res is not None else None), res_c // 8,
+        res.groups if res is not None else 0, _ptr(post.data if post is not None else None), post.groups if post is not None else 0,
+        _ptr(out), 0, _ptr(flags), N, Cin, x.groups, Cout, H, W, NT, MH, KS, int(post_shift), _ACT[act], int(act_channels),
+        float(out_scale), float(w_scale), 1, _stream())
+    _lib.check(rc, "gfr_conv3x3_p16_fwd"); _count()
+    return P16(out, Cout)
+
+
+def maxpool2_p16_fwd(x):
+    N, C, H, W = x.shape
+    out = _p16_empty(N, C, H // 2, W // 2, x.data.device)
+    _lib.check(_lib.load().gfr_maxpool2_p16_fwd(_ptr(x.data), _ptr(out), N * x.groups, H // 2, W // 2, _stream()),
+               "gfr_maxpool2_p16_fwd"); _count()
+    return P16(out, C)
+
+
+def upsample2_p16_fwd(x):
+    """nearest x2: the hi and lo planes are upsampled as independent planes of 16-byte units (the C4 kernel does that)."""
+    N, C, H, W = x.shape
+    out = _p16_empty(N, C, 2 * H, 2 * W, x.data.device)
+    _lib.check(_lib.load().gfr_upsample2_c4_fwd(_ptr(x.data), None, _ptr(out), N * x.groups * 2, 2 * H, 2 * W, _stream()),
+               "gfr_upsample2_c4_fwd"); _count()
+    return P16(out, C)
+
+
+def stem_conv_p16_fwd(img, w_host, b_host, pool=True):
+    """img [N,H,W,3] fp32 CUDA; w_host [16,3,5,5], b_host [16] CPU tensors (BN folded) -> (P16 [N,16,H,W], pooled P16)."""
+    img = _need(img, torch.float32, "img")
+    N, H, W, _ = img.shape
+    out = _p16_empty(N, 16, H, W, img.device)
+    pooled = _p16_empty(N, 16, H // 2, W // 2, img.device) if pool else None
+    rc = _lib.load().gfr_stem_conv_p16_fwd(_ptr(img), ctypes.c_void_p(w_host.data_ptr()), ctypes.c_void_p(b_host.data_ptr()),
+                                           _ptr(out), _ptr(pooled), N, H, W, _stream())
+    _lib.check(rc, "gfr_stem_conv_p16_fwd"); _count()
+    return P16(out, 16), (P16(pooled, 16) if pool else None)
+
+
+def head_1x1_p16_fwd(x, w2, b2, w3, b3, wo, bo, act=None, out_scale=1.0):
+    """x P16 [N,16,H,W]; weights are CPU tensors (BN folded) -> NCHW [N,n_out,H,W]."""
+    N, C, H, W = x.shape
+    assert C == 16 and x.groups == 2
+    n_out = wo.shape[0]
+    out = torch.empty((N, n_out, H, W), dtype=torch.float32, device=x.data.device)
+    hp = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = _lib.load().gfr_head_1x1_p16_fwd(_ptr(x.data), hp(w2), hp(b2), hp(w3), hp(b3), hp(wo), hp(bo), _ptr(out), N, H, W, n_out,
+                                          _ACT[act], float(out_scale), _stream())
+    _lib.check(rc, "gfr_head_1x1_p16_fwd"); _count()
+    return out
+
+
+def light_head_p16_fwd(feat, c_first, w1, b1, w2, b2):
+    """feat P16 [N,C,h,w]; channels [c_first, c_first+27) -> [N,4] (TRAIN:225-232)."""
+    N, C, h, w = feat.shape
+    out = torch.empty((N, 4), dtype=torch.float32, device=feat.data.device)
+    rc = _lib.load().gfr_light_head_p16_fwd(_ptr(feat.data), feat.groups, int(c_first), h * w, _ptr(_need(w1, torch.float32, "w1")),
+                                            _ptr(_need(b1, torch.float32, "b1")), _ptr(_need(w2, torch.float32, "w2")),
+                                            _ptr(_need(b2, torch.float32, "b2")), _ptr(out), N, _stream())
+    _lib.check(rc, "gfr_light_head_p16_fwd"); _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
 # output stage of the inference drivers (csrc/postprocess.cu): TEST1:590-620, TESTB:589-608, the MATLAB border fix
 def _mask_u8(mask, B, H, W):
     if not (torch.is_tensor(mask) and mask.is_cuda and mask.dtype == torch.uint8):

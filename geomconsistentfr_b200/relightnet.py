@@ -71,7 +71,15 @@ class RelightNet(nn.Module):
                                               # 11.15k faces/s): the 4 epilogue warps pay for the tail what the stand-alone
                                               # head kernel paid, so the two-launch tail stays the default
         self.tc_precision = 2                 # eval-mode convs: 2 = fp16 pair split (~22-bit products, half the operand bytes; needs
-                                              # |activation| < 4095 — an overflow shows up as inf/NaN, not silently), 3 = 3xTF32, 1 = TF32
+                                              # |activation| < 4094 — checked on the device, see range_check), 3 = 3xTF32, 1 = TF32
+        self.p16 = True                       # precision 2 on PRE-SPLIT fp16-pair activations (csrc/conv_p16.cu); False: the first-
+                                              # generation kernel that splits fp32 C4 tiles in shared memory (kept for A/B runs)
+        self.range_check = True               # precision 2: every conv output is range-checked on the device; an eager forward
+                                              # whose flag is set is re-run in 3xTF32 (full fp32 exponent range) instead of returning
+                                              # inf / NaN.  Under CUDA-graph capture the flag is left in `last_range_flags` for the
+                                              # owner of the graph (RelightRunner checks it at its synchronisation points)
+        self.last_range_flags = None
+        self.range_fallbacks = 0              # how many eager forwards were re-run in 3xTF32 because of the range flag
 
         for name, cin, cout, k in ENCODER_LAYERS:
             self._add(name, nn.Conv2d, cin, cout, k)
@@ -98,6 +106,8 @@ class RelightNet(nn.Module):
         self._folded_key = None
         self._tc = None
         self._tc_key = None
+        self._p16w = None
+        self._p16w_key = None
 
     def _add(self, name, mod, cin, cout, k):
         if self.variant == "lighting_transfer" and "shortcut" in name:
@@ -198,6 +208,112 @@ class RelightNet(nn.Module):
             t["head_" + p] = ops.pack_head_weights(*t["conv_%s_c2_2" % p], *t["conv_%s_c2_3" % p], *t["conv_%s_c2_o" % p], self.device)
         self._tc, self._tc_key = t, key
         return t
+
+    # ------------------------------------------------------------------ CNN (eval mode) on pre-split fp16-pair activations
+    @torch.no_grad()
+    def _p16_weights(self):
+        """Per-layer operands of the P16 path (csrc/conv_p16.cu).  A residual block's first conv and its shortcut conv read
+        the same input, so they are packed as ONE layer with concatenated output channels (the first part padded to a multiple
+        of 8 channels): name "cat:<conv1>" -> (packed, bias, Cout_total, (NT, KS), w_scale, Cpad, Cout)."""
+        key = self._fold_key()
+        if self._p16w is not None and self._p16w_key == key:
+            return self._p16w
+        f = self._folded_weights()
+        t = {}
+
+        def pack(w, b):
+            Cout, Cin = w.shape[0], w.shape[1]
+            NT, KS = (16 if Cout <= 16 else 32), (4 if Cin >= 32 else 2)
+            packed, w_scale = ops.conv_p16_pack_weights(w, NT, KS)
+            return (packed, b.contiguous(), Cout, (NT, KS), w_scale)
+
+        for name, (w, b) in f.items():
+            if w.shape[2] == 3 and w.shape[1] >= 16:
+                t[name] = pack(w, b)
+            else:
+                t[name] = (w.cpu().contiguous(), b.cpu().contiguous())
+        blocks = [("conv_h2_1", "conv_shortcut_h1_out"), ("conv_h3_1", "conv_shortcut_h2_out"), ("conv_h4_1", "conv_shortcut_h3_out")]
+        for p in ("albedo", "depth"):
+            blocks += [("deconv_%s_%s_1" % (p, blk), "deconv_%s_%s" % (p, sc)) for blk, sc, _, _, _ in _UP_BLOCKS]
+        for n1, nsc in blocks:
+            (w1, b1), (wsc, bsc) = f[n1], f[nsc]
+            Cout = w1.shape[0]
+            Cpad = (Cout + 7) // 8 * 8
+            wz, bz = w1.new_zeros((Cpad - Cout,) + tuple(w1.shape[1:])), b1.new_zeros(Cpad - Cout)
+            t["cat:" + n1] = pack(torch.cat([w1, wz, wsc]), torch.cat([b1, bz, bsc])) + (Cpad, Cout)
+        self._p16w, self._p16w_key = t, key
+        return t
+
+    def _cnn_eval_p16(self, img, epoch, after_encoder=None):
+        """TRAIN:197-350 in eval mode on the P16 layout -> albedo, depth, sl, after_encoder(sl).  Same stream structure as
+        `_cnn_eval_tc` (light head + render preparation on an auxiliary stream, the depth decoder on a side stream); the
+        shortcut convs need no helper stream any more — they ride in their block's first launch."""
+        t = self._p16w_for_forward = self._p16_weights()
+        N, H, W, _ = img.shape
+        flags = torch.zeros(1, dtype=torch.int32, device=img.device)
+        self.last_range_flags = flags
+
+        def conv(name, x, **kw):
+            wp, b, Cout, (NT, KS), w_scale = t[name][:5]
+            _, _, h, w = x.shape
+            MH = 2 if N * ((h + 15) // 16) * ((w + 15) // 16) * ((Cout + NT - 1) // NT) >= 296 else 1
+            return ops.conv3x3_p16_fwd(x, wp, b, Cout, (NT, MH, KS), w_scale, flags=flags, **kw)
+
+        def res_block(n1, n2, x, cin=None):
+            """lrelu(bn(conv_sc(x)) + bn(conv2(lrelu(bn(conv1(x)))))) — TRAIN:203-223, 235-239: conv1 and conv_sc in one launch."""
+            Cpad, Cout = t["cat:" + n1][5:7]
+            both = conv("cat:" + n1, x, cin=cin, act_channels=Cpad)
+            return conv(n2, both, cin=Cout, res=both, res_c=Cpad)
+
+        def up_and_skip(p, skip, tt, enc):
+            if epoch > _EPOCH_GATES[skip]:
+                s1 = conv("conv_%s_skip_%s_1" % (p, skip), enc)
+                return conv("conv_%s_skip_%s_2" % (p, skip), s1, res=enc, post=tt, post_shift=1)
+            return ops.upsample2_p16_fwd(tt)
+
+        c1_og, c1 = ops.stem_conv_p16_fwd(img, *t["conv_c1_og"])            # TRAIN:197-201 (conv + BN + LReLU + pool)
+        h1_og = conv("conv_h1_2", conv("conv_h1_1", c1), res=c1)
+        h1 = ops.maxpool2_p16_fwd(h1_og)
+        h2_og = res_block("conv_h2_1", "conv_h2_2", h1)
+        h2 = ops.maxpool2_p16_fwd(h2_og)
+        h3_og = res_block("conv_h3_1", "conv_h3_2", h2)
+        h3 = ops.maxpool2_p16_fwd(h3_og)
+        h4 = res_block("conv_h4_1", "conv_h4_2", h3)
+        cur = torch.cuda.current_stream()
+        side, aux = self._side_stream(), self._side_stream("_aux")
+        aux.wait_stream(cur)
+        with torch.cuda.stream(aux):
+            sl = ops.light_head_p16_fwd(h4, 128, self.linear_SL1.weight, self.linear_SL1.bias,
+                                        self.linear_SL2.weight, self.linear_SL2.bias)    # [B,4]  TRAIN:225-232
+            prep = after_encoder(sl) if after_encoder is not None else None
+        skips = {"s1": h3_og, "s2": h2_og, "s3": h1_og, "s4": c1_og}
+
+        def decoder(p):
+            h, cin = h4, 128                                                # TRAIN:225: the first 128 channels, in place
+            for blk, sc, _, cout, skip in _UP_BLOCKS:
+                tt = res_block("deconv_%s_%s_1" % (p, blk), "deconv_%s_%s_2" % (p, blk), h, cin=cin)
+                h, cin = up_and_skip(p, skip, tt, skips[skip]), None
+            a = conv("deconv_%s_h8_1" % p, h)
+            tt = conv("deconv_%s_h8_2" % p, a, res=h)
+            h = up_and_skip(p, "s4", tt, skips["s4"])
+            h = conv("conv_%s_c2_1" % p, h)
+            w2, b2 = t["conv_%s_c2_2" % p]
+            w3, b3 = t["conv_%s_c2_3" % p]
+            wo, bo = t["conv_%s_c2_o" % p]
+            if p == "albedo":
+                return ops.head_1x1_p16_fwd(h, w2, b2, w3, b3, wo, bo, act="sigmoid")              # TRAIN:285-290
+            return ops.head_1x1_p16_fwd(h, w2, b2, w3, b3, wo, bo, act=None, out_scale=100.0)      # TRAIN:345-350
+
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            depth = decoder("depth")
+        albedo = decoder("albedo")
+        cur.wait_stream(side)
+        cur.wait_stream(aux)
+        depth.record_stream(cur)
+        for tns in [sl] + [v for v in (prep or {}).values() if torch.is_tensor(v)]:
+            tns.record_stream(cur)
+        return albedo, depth, sl, prep
 
     # ------------------------------------------------------------------ CNN (eval mode) on the tensor cores, TRAIN:197-350
     def _cnn_eval_tc(self, img, epoch, after_encoder=None):
@@ -380,12 +496,36 @@ class RelightNet(nn.Module):
     # ------------------------------------------------------------------ CNN (eval mode), exact fp32 on CUDA cores
     def _cnn_eval(self, img, epoch, after_encoder=None):
         """-> (albedo, depth, sl), plus after_encoder(sl) as a fourth item when a hook is given."""
-        if self.cnn_impl == "tc":
+        if self.cnn_impl == "tc" and self.tc_precision == 2 and self.p16:
+            r = self._cnn_eval_p16(img.contiguous(), epoch, after_encoder)
+        elif self.cnn_impl == "tc":
             r = self._cnn_eval_tc(img.contiguous(), epoch, after_encoder)
         else:
             albedo, depth, sl = self._cnn_eval_direct(img, epoch)
             r = (albedo, depth, sl, after_encoder(sl) if after_encoder is not None else None)
         return r if after_encoder is not None else r[:3]
+
+    def _cnn_eval_checked(self, img, epoch, after_encoder):
+        """`_cnn_eval` + the range guard of the fp16 pair split: the device flag that the P16 convs raise for |x| >= 4094 (or
+        NaN) is read back, and the CNN is re-run in 3xTF32 when it is set — this path must never return inf / NaN where the
+        reference's fp32 cuDNN convs do not (TEST1:170-323).  The read-back is one 4-byte D2H sync per forward (the reference
+        syncs once per image for its light, TEST1:357-358); under stream capture there is no read-back: the flag stays in
+        `last_range_flags` for the graph's owner."""
+        self.last_range_flags = None
+        r = self._cnn_eval(img, epoch, after_encoder)
+        flags = self.last_range_flags
+        if flags is None or not self.range_check or torch.cuda.is_current_stream_capturing():
+            return r
+        if int(flags.item()) != 0:
+            self.range_fallbacks += 1
+            saved = self.tc_precision
+            self.tc_precision = 3
+            try:
+                r = self._cnn_eval(img, epoch, after_encoder)
+            finally:
+                self.tc_precision = saved
+                self.last_range_flags = flags
+        return r
 
     def _cnn_eval_direct(self, img, epoch):
         f = self._folded_weights()
@@ -519,7 +659,7 @@ class RelightNet(nn.Module):
             return dict(bits=ops.mask_pack(m), ambient=ambient, unit=unit, light_pt=light_pt)
 
         with torch.no_grad():
-            albedo, depth, sl, pr = self._cnn_eval(img, epoch, prep)
+            albedo, depth, sl, pr = self._cnn_eval_checked(img, epoch, prep)
             o, amb_l, unit = self._render(albedo, depth, pr, intrinsic_matrix, 5.0 if test_mode else 0.0)
             out = (albedo, depth, o["shadow"], amb_l, o["full"], o["rendered"], unit, pr["ambient"].view(B, 1, 1))
             if not test_mode:                                               # TRAIN:196-524 (8-tuple)
@@ -553,7 +693,7 @@ class RelightNet(nn.Module):
             return dict(bits=ops.mask_pack(m), ambient=(sl[:, 0] - 0.1).contiguous(), unit=unit, light_pt=light_pt)   # TEST1:342
 
         with torch.no_grad():
-            albedo, depth, sl, pr = self._cnn_eval(img, epoch, prep)
+            albedo, depth, sl, pr = self._cnn_eval_checked(img, epoch, prep)
             o, _, _ = self._render(albedo, depth, pr, intrinsic_matrix, 5.0, want=("shadow", "final", "rendered"))
         ambient, unit = pr["ambient"], pr["unit"]
         return dict(rendered=o["rendered"].view(F_, L, 3, H, W), shadow=o["shadow"].view(F_, L, H, W),

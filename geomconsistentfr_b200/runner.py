@@ -37,6 +37,8 @@ class _Lane:
         self.launches_per_run = 0
         self.pin_out = {}
         self.bgr = None
+        self.flags = None                                  # the forward's range flag (fp16 pair split), zeroed inside the graph
+        self.last_host = None
         with torch.cuda.stream(self.stream):
             for _ in range(2):                             # warm up (folds BN, packs weights, fills the allocator)
                 n0 = ops.launch_count()
@@ -47,6 +49,7 @@ class _Lane:
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph, stream=self.stream):
                     self.out = self._forward()
+                self.flags = self.net.last_range_flags
         self.stream.synchronize()
 
     def _forward(self):
@@ -69,6 +72,32 @@ class _Lane:
             else:
                 self.out = self._forward()
         return self.out
+
+    def check_range(self):
+        """After a synchronisation: if the replayed forward raised the range flag of the fp16 pair split (an activation
+        >= 4094 or NaN), recompute this lane's batch eagerly in 3xTF32 and overwrite the graph's static outputs (and the host
+        buffer of the last `relight_host` call).  Returns True when that happened."""
+        if self.graph is None or self.flags is None or int(self.flags.item()) == 0:
+            return False
+        net, saved = self.net, self.net.tc_precision
+        net.tc_precision = 3
+        try:
+            with torch.cuda.stream(self.stream):
+                static_out, static_bgr = self.out, self.bgr
+                fresh = self._forward()
+                for dst, src in zip(static_out, fresh):
+                    if dst.data_ptr() != src.data_ptr():
+                        dst.copy_(src)
+                static_bgr.copy_(self.bgr)
+                self.out, self.bgr = static_out, static_bgr
+                if self.last_host is not None:
+                    host, kind = self.last_host
+                    host.copy_(self.out[5] if kind == "rendered_f32" else self.bgr, non_blocking=True)
+            self.stream.synchronize()
+        finally:
+            net.tc_precision = saved
+        self.flags.zero_()
+        return True
 
 
 class RelightRunner:
@@ -128,6 +157,7 @@ class RelightRunner:
         lane.run()
         with torch.cuda.stream(lane.stream):
             rendered_host.copy_(lane.out[5] if output == "rendered_f32" else lane.bgr, non_blocking=True)
+        lane.last_host = (rendered_host, output)
         return rendered_host, lane.stream
 
     def relight_resident(self, img, mask, light):
@@ -142,5 +172,9 @@ class RelightRunner:
         return lane.out, lane.stream
 
     def synchronize(self):
+        """Wait for every lane; a lane whose last forward left the fp16 split's range is recomputed in 3xTF32 (see
+        _Lane.check_range).  NOTE: with more than `lanes` calls in flight between synchronisations only each lane's LAST
+        batch can be repaired — callers that may feed out-of-range checkpoints synchronise once per rotation."""
         for lane in self.lanes:
             lane.stream.synchronize()
+        self.range_fallbacks = getattr(self, "range_fallbacks", 0) + sum(1 for lane in self.lanes if lane.check_range())

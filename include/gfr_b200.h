@@ -307,6 +307,46 @@ int gfr_conv3x3_tc_head_fwd(const float* in, const float* w_packed, const float*
                             int N, int Cin, int in_groups, int H, int W, int n_out, int head_act, float head_scale,
                             int precision, int weights_static, float x_scale, float w_scale, void* stream);
 
+/* ---- eval-mode tensor-core CNN, second generation: PRE-SPLIT fp16-pair activations ("P16", csrc/p16.cuh) -------------
+ * Every activation x is stored as the fp16 pair the tensor cores consume: 16 x = hi + lo, layout
+ * [N][groups = ceil(C/8)][hi|lo][H][W][8 halfs] (4 bytes per element, |x| < 4094).  Replaces the same reference lines as
+ * gfr_conv3x3_tc_fwd (TRAIN:197-350 / TEST1:170-323: Conv2d / ConvTranspose2d(stride 1) + BatchNorm(eval, folded) +
+ * LeakyReLU + residual / skip adds + nearest x2 upsample). */
+
+/* HOST packing for gfr_conv3x3_p16_fwd.  w_host [Cout,Cin,3,3] (BN folded; ConvTranspose2d as w.transpose(0,1).flip(2,3));
+ * the buffer holds [n_tile][cin_step][tap][chunk 0..KS-1][w1|w2][n 0..NT-1][8 halfs] with w*w_scale = w1 + w2 as fp16.
+ * NT in {16,32}, KS in {2,4} (8*KS input channels per pipeline step).  gfr_conv_p16_pack_size returns HALFS. */
+long long gfr_conv_p16_pack_size(int Cin, int Cout, int NT, int KS);
+int gfr_conv_p16_pack_weights(const float* w_host, int Cin, int Cout, int NT, int KS, float w_scale, void* packed_host);
+
+/* out = out_scale * (act(conv3x3(in[:, :Cin]) + bias + res) + up(post)), all tensors P16.
+ *   in_groups / out_groups / res_groups / post_groups: 8-channel chunks ALLOCATED per image in that tensor (0 = exactly
+ *   ceil(C/8)); res_c8: first chunk of the residual operand inside its tensor.
+ *   act 0 none | 1 LeakyReLU(0.2) | 2 sigmoid, applied to output channels < act_channels only (0 = all): a residual block's
+ *   first conv and its shortcut conv (same input, TRAIN:203-223 / 235-239) run as ONE launch with concatenated output
+ *   channels, and the block's second conv reads the leading channels as input and the trailing ones as `res`, in place.
+ *   MH 1 | 2: 8x16- or 16x16-pixel CTA tile (one or two M = 128 MMAs over one TMA box).
+ *   flags (may be NULL): device int, bit 0 is OR-ed in when an output leaves the split's range (|x| >= 4094 or NaN).
+ *   Padding channels (>= Cout, up to 8*out_groups) are written as zeros. */
+int gfr_conv3x3_p16_fwd(const void* in, const void* w_packed, const float* bias, const void* res, int res_c8, int res_groups,
+                        const void* post, int post_groups, void* out, int out_groups, int* flags, int N, int Cin,
+                        int in_groups, int Cout, int H, int W, int NT, int MH, int KS, int post_shift, int act,
+                        int act_channels, float out_scale, float w_scale, int weights_static, void* stream);
+
+/* NCHW fp32 <-> P16, 2x2 max pool on P16 (compares the joined fp32 values), and the P16 forms of the stem (out / pooled
+ * P16 [N,16,H,W] / [N,16,H/2,W/2]), the fused 1x1 decoder tail (in P16 [N,16,H,W]) and the light head (feat P16 with
+ * `groups` chunks). */
+int gfr_nchw_to_p16(const float* in, void* out, int N, int C, int H, int W, void* stream);
+int gfr_p16_to_nchw(const void* in, float* out, int N, int C, int groups, int H, int W, void* stream);
+int gfr_maxpool2_p16_fwd(const void* in, void* out, int NC8, int Ho, int Wo, void* stream);
+int gfr_stem_conv_p16_fwd(const float* img, const float* w_host, const float* bias_host, void* out, void* pooled, int N,
+                          int H, int W, void* stream);
+int gfr_head_1x1_p16_fwd(const void* in, const float* w2_host, const float* b2_host, const float* w3_host,
+                         const float* b3_host, const float* wo_host, const float* bo_host, float* out, int N, int H, int W,
+                         int n_out, int act, float out_scale, void* stream);
+int gfr_light_head_p16_fwd(const void* feat, int groups, int c_first, int HW, const float* w1, const float* b1,
+                           const float* w2, const float* b2, float* out, int N, void* stream);
+
 /* Stem: conv_c1_og (5x5, 3 -> 16, padding 2) + BatchNorm(eval, folded) + LeakyReLU(0.2) on the NHWC image, with the
  * first 2x2 max pool fused (TRAIN:197-201).  img [N,H,W,3]; w_host [16,3,5,5] and bias_host [16] are HOST pointers
  * (they travel as kernel parameters); out C4 [N,16,H,W]; pooled C4 [N,16,H/2,W/2] or NULL. */
