@@ -80,6 +80,7 @@ _PROTOS = {
     "gfr_neg_depth_range": [_c_void_p, ctypes.c_longlong, _c_void_p, _c_void_p],
     "gfr_export_planes_u8": [_c_void_p] * 6 + [_c_int] + [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _c_void_p],
     "gfr_masked_mse_u8": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_masked_ssim_u8": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_border_median_fix_u8": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
 }
 _RESTYPES = {"gfr_error_string": ctypes.c_char_p, "gfr_conv_tc_pack_size": ctypes.c_longlong,

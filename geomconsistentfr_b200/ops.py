@@ -665,3 +665,20 @@ def masked_mse_u8(recon, gt, mask):
     rc = _lib.load().gfr_masked_mse_u8(_ptr(recon), _ptr(gt), _ptr(mask), stride, _ptr(sums), B, H, W, C, _stream())
     _lib.check(rc, "gfr_masked_mse_u8"); _count()
     return sums[:, 0] / (C * sums[:, 1])
+
+
+def masked_dssim_u8(recon, gt, mask, window_3d=True):
+    """DSSIM_MP_RGB.m:15-27: per-image masked DSSIM of two uint8 RGB image batches [B,H,W,3]; mask u8 [H,W] | [B,H,W]
+    -> [B] f64 = (1 - sum(ssimmap * mask3) / sum(mask3)) / 2 with MATLAB's volume-window `ssim` map."""
+    for t, n in ((recon, "recon"), (gt, "gt")):
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.uint8 and t.dim() == 4 and t.shape[3] == 3):
+            raise RuntimeError("%s must be a CUDA uint8 tensor [B,H,W,3]" % n)
+    if recon.shape != gt.shape:
+        raise RuntimeError("recon and gt must have the same shape")
+    recon, gt = recon.contiguous(), gt.contiguous()
+    B, H, W, _ = recon.shape
+    mask, stride = _mask_u8(mask, B, H, W)
+    sums = torch.empty((B, 2), dtype=torch.float64, device=recon.device)
+    rc = _lib.load().gfr_masked_ssim_u8(_ptr(recon), _ptr(gt), _ptr(mask), stride, _ptr(sums), B, H, W, int(bool(window_3d)), _stream())
+    _lib.check(rc, "gfr_masked_ssim_u8"); _count()
+    return (1.0 - sums[:, 0] / sums[:, 1]) / 2.0

@@ -420,6 +420,13 @@ int gfr_border_median_fix_u8(const uint8_t* img, const uint8_t* mask, int mask_b
 int gfr_masked_mse_u8(const uint8_t* recon, const uint8_t* gt, const uint8_t* mask, int mask_batch_stride, double* sums,
                       int B, int H, int W, int C, void* stream);
 
+/* DSSIM_MP_RGB.m:15-27 on the device: sums[b] = {sum(ssimmap .* mask3), sum(mask3)} of MATLAB's `ssim(recon/255, gt/255)` map
+ * (3-D 11x11x11 Gaussian window with replicate padding when window_3d != 0 — what MATLAB does for an M x N x 3 array — or the
+ * per-plane 11x11 window), fp64 like MATLAB; DSSIM_b = (1 - sums[b][0] / sums[b][1]) / 2.  recon / gt uint8 [B,H,W,3]; mask
+ * uint8 [H,W] (mask_batch_stride 0) or [B,H,W] (H*W), used as mask / 255. */
+int gfr_masked_ssim_u8(const uint8_t* recon, const uint8_t* gt, const uint8_t* mask, int mask_batch_stride, double* sums,
+                       int B, int H, int W, int window_3d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

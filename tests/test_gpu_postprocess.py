@@ -148,3 +148,22 @@ def test_masked_mse_metric_matches_the_matlab_expression(ffhq):
     shared = ops.masked_mse_u8(c(recon), c(gt), c(masks[0])).cpu().numpy()
     assert abs(shared[2] - P.masked_mse(recon[2], gt[2], masks[0])) <= 1e-10 * shared[2]
     assert float(ops.masked_mse_u8(c(recon), c(recon), c(masks))[0]) == 0.0
+
+
+@pytest.mark.parametrize("window_3d", [True, False])
+def test_masked_dssim_metric_vs_numpy_restatement(window_3d):
+    """gfr_masked_ssim_u8 (DSSIM_MP_RGB.m:15-27, MATLAB's volume-window ssim map, fp64) against oracle/metrics_oracle.py on
+    random 8-bit image pairs incl. a ragged size and per-image / shared masks."""
+    from geomconsistentfr_b200 import ops
+    from oracle import metrics_oracle as M
+    rs = np.random.RandomState(5)
+    for (B, H, W, shared) in ((3, 256, 256, True), (2, 70, 45, False)):
+        a = rs.randint(0, 256, (B, H, W, 3)).astype(np.uint8)
+        b = np.clip(a.astype(np.int32) + rs.randint(-40, 41, a.shape), 0, 255).astype(np.uint8)
+        m = (rs.uniform(size=(1 if shared else B, H, W)) < 0.6).astype(np.uint8) * rs.choice([64, 128, 255])
+        got = ops.masked_dssim_u8(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(m[0] if shared else m).cuda(),
+                                  window_3d=window_3d).cpu().numpy()
+        want = np.array([M.dssim_mp_rgb(a[i], b[i], m[0] if shared else m[i], window_3d) for i in range(B)])
+        assert np.abs(got - want).max() <= 1e-10, (got, want)
+    same = ops.masked_dssim_u8(torch.from_numpy(a).cuda(), torch.from_numpy(a).cuda(), torch.from_numpy(m).cuda(), window_3d=window_3d)
+    assert float(same.abs().max()) <= 1e-14
