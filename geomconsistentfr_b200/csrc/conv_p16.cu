@@ -118,7 +118,7 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const __half* wsrc = a.wpk + (size_t)blockIdx.y * a.nsteps * (C::W_STEP / 2);
       const int n_pre = n_steps < STAGES ? n_steps : STAGES;
       for (int g = 0; g < n_pre; ++g) {
@@ -149,14 +149,15 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t IDESC_2N = umma_idesc_f16(128, 2 * NT), IDESC_N = umma_idesc_f16(128, NT);
-      int s = 0, ph = 0;
-      for (int g = 0; g < n_steps; ++g) {
-        const int p = g & 1;
-        mbar_wait(bar_full + 8 * s, ph);
-        mbar_wait(bar_accempty + 8 * p, ((g >> 1) & 1) ^ 1);
-        tc_fence_after_sync();
+    // The whole warp walks the pipeline (uniform waits), ONE elected lane issues the step's MMAs and commits.
+    constexpr uint32_t IDESC_2N = umma_idesc_f16(128, 2 * NT), IDESC_N = umma_idesc_f16(128, NT);
+    int s = 0, ph = 0;
+    for (int g = 0; g < n_steps; ++g) {
+      const int p = g & 1;
+      mbar_wait(bar_full + 8 * s, ph);
+      mbar_wait(bar_accempty + 8 * p, ((g >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      if (elect_one_sync()) {
         const uint32_t slot = slots0 + s * slot_bytes;
         const uint32_t wbase = resident ? smem0 : slot + C::A_BYTES;
         const uint64_t dB0 = umma_desc_kmajor_noswz(wbase, C::B_LBO, 128u);
@@ -179,8 +180,9 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
         }
         umma_commit(bar_empty + 8 * s);       // the slot may be refilled once these MMAs have read it
         umma_commit(bar_accfull + 8 * p);     // and the accumulators of this step are complete
-        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else {
     // =============================== epilogue (thread = pixel = TMEM lane of its M-half) ===============================

@@ -167,7 +167,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const float* wsrc = a.wpk + (size_t)blockIdx.y * a.ncb * (S::W_STEP / 4);
       // PDL prologue: the first ring slots are armed and (static weights) their weight copies are in flight before the
       // previous layer has finished; the activation loads follow griddepcontrol.wait.
@@ -199,7 +199,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // The whole warp walks the pipeline (uniform waits); ONE elected lane issues the step's MMAs and commits: under
+    // `elect.sync` every tcgen05.mma is one uniform-datapath instruction (+ one 64-bit add), under `if (lane == 0)` ptxas
+    // wraps each of them in an ELECT / BRA.U.ANY loop (~10 instructions) and the issuing thread sets the pace.
+    {
       constexpr uint32_t IDESC_2N = KIND == KIND_TF32 ? umma_idesc_tf32(128, 2 * NT) : umma_idesc_f16(128, 2 * NT);
       constexpr uint32_t IDESC_N = KIND == KIND_TF32 ? umma_idesc_tf32(128, NT) : umma_idesc_f16(128, NT);
       constexpr uint32_t B_LBO = 2 * NT * 16, B_TAP = (KIND == KIND_TF32 ? CB / 4 : CB / 8) * B_LBO;
@@ -208,43 +211,46 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
         mbar_wait(bar_ready + 8 * s, (g / STAGES) & 1);
         mbar_wait(bar_accempty + 8 * p, ((g >> 1) & 1) ^ 1);
         tc_fence_after_sync();
-        const uint32_t slot = slots0 + s * slot_bytes;
-        const uint32_t wbase = resident ? smem0 : slot + 2 * A_BYTES;
-        const uint32_t d_main = tmem + (uint32_t)(p * 2 * NT), d_corr = d_main + NT;
-        const uint64_t dB0 = umma_desc_kmajor_noswz(wbase, B_LBO, 128u);
-        if (KIND == KIND_TF32) {
-          const uint64_t dA_hi0 = umma_desc_kmajor_noswz(slot, A_LBO, A_SBO);
-          const uint64_t dA_lo0 = umma_desc_kmajor_noswz(slot + A_BYTES, A_LBO, A_SBO);
+        if (elect_one_sync()) {
+          const uint32_t slot = slots0 + s * slot_bytes;
+          const uint32_t wbase = resident ? smem0 : slot + 2 * A_BYTES;
+          const uint32_t d_main = tmem + (uint32_t)(p * 2 * NT), d_corr = d_main + NT;
+          const uint64_t dB0 = umma_desc_kmajor_noswz(wbase, B_LBO, 128u);
+          if (KIND == KIND_TF32) {
+            const uint64_t dA_hi0 = umma_desc_kmajor_noswz(slot, A_LBO, A_SBO);
+            const uint64_t dA_lo0 = umma_desc_kmajor_noswz(slot + A_BYTES, A_LBO, A_SBO);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint32_t ao = ((uint32_t)((tap / 3) * HALO_W + (tap % 3)) * 16u + (uint32_t)j * 2u * A_LBO) >> 4;
-              const uint32_t bo = ((uint32_t)tap * B_TAP + (uint32_t)j * 2u * B_LBO) >> 4;
-              const uint32_t first = (tap == 0 && j == 0) ? 0u : 1u;
-              if (a.single_pass) {
-                umma_tf32(d_main, dA_hi0 + ao, dB0 + bo, IDESC_N, first);
-              } else {
-                umma_tf32(d_main, dA_hi0 + ao, dB0 + bo, IDESC_2N, first);      // main += hi*Whi ; corr += hi*Wlo
-                umma_tf32(d_corr, dA_lo0 + ao, dB0 + bo, IDESC_N, 1u);          // corr += lo*Whi
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t ao = ((uint32_t)((tap / 3) * HALO_W + (tap % 3)) * 16u + (uint32_t)j * 2u * A_LBO) >> 4;
+                const uint32_t bo = ((uint32_t)tap * B_TAP + (uint32_t)j * 2u * B_LBO) >> 4;
+                const uint32_t first = (tap == 0 && j == 0) ? 0u : 1u;
+                if (a.single_pass) {
+                  umma_tf32(d_main, dA_hi0 + ao, dB0 + bo, IDESC_N, first);
+                } else {
+                  umma_tf32(d_main, dA_hi0 + ao, dB0 + bo, IDESC_2N, first);      // main += hi*Whi ; corr += hi*Wlo
+                  umma_tf32(d_corr, dA_lo0 + ao, dB0 + bo, IDESC_N, 1u);          // corr += lo*Whi
+                }
               }
             }
-          }
-        } else {
-          // fp16 pair split: the two operand tiles [2 chunks of 8 ch][18][10][8 halfs] sit behind the raw fp32 tile;
-          // one K = 16 MMA covers the whole 16-channel step of a tap
-          const uint64_t dA_1 = umma_desc_kmajor_noswz(slot + A_BYTES, A_LBO, A_SBO);
-          const uint64_t dA_2 = umma_desc_kmajor_noswz(slot + A_BYTES + A_BYTES / 2, A_LBO, A_SBO);
+          } else {
+            // fp16 pair split: the two operand tiles [2 chunks of 8 ch][18][10][8 halfs] sit behind the raw fp32 tile;
+            // one K = 16 MMA covers the whole 16-channel step of a tap
+            const uint64_t dA_1 = umma_desc_kmajor_noswz(slot + A_BYTES, A_LBO, A_SBO);
+            const uint64_t dA_2 = umma_desc_kmajor_noswz(slot + A_BYTES + A_BYTES / 2, A_LBO, A_SBO);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t ao = ((uint32_t)((tap / 3) * HALO_W + (tap % 3)) * 16u) >> 4;
-            const uint32_t bo = ((uint32_t)tap * B_TAP) >> 4;
-            umma_f16(d_main, dA_1 + ao, dB0 + bo, IDESC_2N, tap == 0 ? 0u : 1u);   // main += h1*W1 ; corr += h1*W2
-            umma_f16(d_corr, dA_2 + ao, dB0 + bo, IDESC_N, 1u);                    // corr += h2*W1
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t ao = ((uint32_t)((tap / 3) * HALO_W + (tap % 3)) * 16u) >> 4;
+              const uint32_t bo = ((uint32_t)tap * B_TAP) >> 4;
+              umma_f16(d_main, dA_1 + ao, dB0 + bo, IDESC_2N, tap == 0 ? 0u : 1u);   // main += h1*W1 ; corr += h1*W2
+              umma_f16(d_corr, dA_2 + ao, dB0 + bo, IDESC_N, 1u);                    // corr += h2*W1
+            }
           }
+          umma_commit(bar_empty + 8 * s);       // the slot may be refilled once these MMAs have read it
+          umma_commit(bar_accfull + 8 * p);     // and the accumulators of this step are complete
         }
-        umma_commit(bar_empty + 8 * s);       // the slot may be refilled once these MMAs have read it
-        umma_commit(bar_accfull + 8 * p);     // and the accumulators of this step are complete
+        __syncwarp();
       }
     }
   } else if (warp < 6) {

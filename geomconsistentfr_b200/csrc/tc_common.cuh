@@ -43,6 +43,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if ((spins & 1023u) == 1023u && global_timer_ns() - t0 > 2000000000ull) __trap();
 }
 
+// ---- single-thread election --------------------------------------------------------------------------
+// Whole-warp call (all 32 lanes converged): exactly one lane gets true.  Code under `if (elect_one_sync())` is known to ptxas
+// to run in ONE thread, so tcgen05.mma / commit / TMA issue there compile to plain uniform-datapath instructions; under
+// `if (lane == 0)` every such instruction is wrapped in an ELECT + BRA.U.ANY "waterfall" loop (measured: ~10 instead of ~3
+// SASS instructions per MMA, and the MMA-issuing thread was the pace-setter of the P16 convolution).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- proxies / fences -------------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads of shared memory)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -87,7 +87,9 @@ class _Lane:
                 fresh = self._forward()
                 for dst, src in zip(static_out, fresh):
                     if dst.data_ptr() != src.data_ptr():
-                        dst.copy_(src)
+                        # expanded views (ambient_light is ambient_values broadcast over H x W): write the one real element
+                        idx = tuple(slice(None) if st != 0 or sz == 1 else 0 for sz, st in zip(dst.shape, dst.stride()))
+                        dst[idx].copy_(src[idx])
                 static_bgr.copy_(self.bgr)
                 self.out, self.bgr = static_out, static_bgr
                 if self.last_host is not None:
