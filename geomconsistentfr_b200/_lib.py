@@ -32,6 +32,9 @@ _PROTOS = {
                                _c_float, _c_void_p],
     # train-mode CNN
     "gfr_conv_tc_pack_weights_dev": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p],
+    "gfr_conv_tc_pack_size_ex": [_c_int] * 5,
+    "gfr_conv_tc_pack_weights_dev_ex": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p],
+    "gfr_conv_tc_fwd_ex": [_c_void_p] * 6 + [_c_int] * 13 + [_c_float, _c_int, _c_int, _c_void_p],
     "gfr_bn_train_stats": [_c_void_p] * 10 + [_c_int] * 4 + [_c_float, _c_float, _c_void_p],
     "gfr_bn_apply_fwd": [_c_void_p] * 6 + [_c_int] * 6 + [_c_void_p],
     "gfr_bn_apply_bwd": [_c_void_p] * 11 + [_c_int] * 5 + [_c_void_p],
@@ -47,6 +50,9 @@ _PROTOS = {
     # PatchGAN support
     "gfr_space_to_depth": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_depth_to_space": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_space_to_depth_pad": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_depth_to_space_pad": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_conv2x2_wgrad": [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p],
     "gfr_lrelu_bwd_c4": [_c_void_p, _c_void_p, _c_void_p, ctypes.c_longlong, _c_void_p],
     "gfr_conv4x4s1_to1_fwd": [_c_void_p] * 4 + [_c_int] * 4 + [_c_void_p],
     "gfr_conv4x4s1_to1_bwd": [_c_void_p] * 6 + [_c_int] * 4 + [_c_void_p],
@@ -84,7 +90,8 @@ _PROTOS = {
     "gfr_border_median_fix_u8": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
 }
 _RESTYPES = {"gfr_error_string": ctypes.c_char_p, "gfr_conv_tc_pack_size": ctypes.c_longlong,
-             "gfr_conv_tc_pack_size_f16": ctypes.c_longlong, "gfr_conv_p16_pack_size": ctypes.c_longlong}
+             "gfr_conv_tc_pack_size_f16": ctypes.c_longlong, "gfr_conv_p16_pack_size": ctypes.c_longlong,
+             "gfr_conv_tc_pack_size_ex": ctypes.c_longlong}
 
 _lib = None
 

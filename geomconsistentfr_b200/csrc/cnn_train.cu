@@ -14,6 +14,8 @@
 //   pools     — 2x2 max-pool backward, 2x2 sum (backward of the nearest x2 upsample), 27-channel global average pool
 #include "gfr_common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace {
 
 __device__ __forceinline__ float tf32_rna_dev(float x) {
@@ -23,9 +25,10 @@ __device__ __forceinline__ float tf32_rna_dev(float x) {
 }
 
 // ------------------------------------------------------------------------------------------------- pack
-// packed[n_tile][cin_step][tap][group][hi|lo][n][4]; value(o, i, tap) = w[o*so + i*si + (flip ? 8 - tap : tap)]
+// TF32 (kind 0): packed[n_tile][cin_step][tap][group][hi|lo][n][4 floats];  BF16 (kind 1): packed[n_tile][cin_step][tap][8-ch chunk][n][8 bf16]
+// value(o, i, tap) = w[o*so + i*si + (flip ? taps - 1 - tap : tap)]
 __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ packed, long long total, int O, int I,
-                                    int NT, long long so, long long si, int flip) {
+                                    int NT, long long so, long long si, int flip, int taps) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int e = (int)(idx & 3);
@@ -33,18 +36,36 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, float* __restri
   const int n = (int)(t % NT); t /= NT;
   const int part = (int)(t & 1); t >>= 1;
   const int kc = (int)(t & 3); t >>= 2;
-  const int tap = (int)(t % 9); t /= 9;
+  const int tap = (int)(t % taps); t /= taps;
   const int ncb = (I + 15) / 16;
   const int cb = (int)(t % ncb);
   const int nt = (int)(t / ncb);
   const int o = nt * NT + n, i = cb * 16 + kc * 4 + e;
   float v = 0.f;
   if (o < O && i < I) {
-    const float x = __ldg(w + o * so + i * si + (flip ? 8 - tap : tap));
+    const float x = __ldg(w + o * so + i * si + (flip ? taps - 1 - tap : tap));
     const float hi = tf32_rna_dev(x);
     v = part == 0 ? hi : tf32_rna_dev(x - hi);
   }
   packed[idx] = v;
+}
+
+__global__ void pack_weights_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed, long long total, int O, int I,
+                                         int NT, long long so, long long si, int flip, int taps) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [n_tile][cin_step][tap][chunk 2][n][8]
+  if (idx >= total) return;
+  const int e = (int)(idx & 7);
+  long long t = idx >> 3;
+  const int n = (int)(t % NT); t /= NT;
+  const int ch = (int)(t & 1); t >>= 1;
+  const int tap = (int)(t % taps); t /= taps;
+  const int ncb = (I + 15) / 16;
+  const int cb = (int)(t % ncb);
+  const int nt = (int)(t / ncb);
+  const int o = nt * NT + n, i = cb * 16 + ch * 8 + e;
+  float v = 0.f;
+  if (o < O && i < I) v = __ldg(w + o * so + i * si + (flip ? taps - 1 - tap : tap));
+  packed[idx] = __float2bfloat16_rn(v);
 }
 
 // ------------------------------------------------------------------------------------------------- BN statistics
@@ -229,24 +250,28 @@ constexpr int WG_IPLANE = (WG_TH + 2) * WG_IP + 4;        // 364: channel-plane 
 constexpr int WG_GPLANE = WG_TH * WG_TW;
 
 struct WgradArgs {
-  const float* in; const float* g;     // C4 [N][Cin4_alloc][H][W][4], C4 [N][Cout4][H][W][4]
-  float* dw;                           // element (co, ci, tap) at dw[co*so + ci*si + (flip ? 8 - tap : tap)]  +=
-  int N, Cin, Cout, in_groups, H, W;
+  const float* in; const float* g;     // C4 [N][Cin4_alloc][Hin][Win][4], C4 [N][Cout4][H][W][4]
+  float* dw;                           // element (co, ci, tap) at dw[co*so + ci*si + (flip ? KT*KT - 1 - tap : tap)]  +=
+  int N, Cin, Cout, in_groups, H, W;   // H, W: size of g (the conv OUTPUT)
+  int Hin, Win;                        // size of `in`
   long long so, si; int flip;
   int tiles_x, tiles_y, n_tiles;
 };
 
-__global__ void __launch_bounds__(256) wgrad3x3_kernel(const WgradArgs a) {
+// KT = 3: 3x3 / pad 1 (input pixel (y + ky - 1, x + kx - 1));  KT = 2: the 2x2-tap layers (input pixel (y + ky, x + kx))
+template <int KT>
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
+  constexpr int ORG = KT == 3 ? 1 : 0, NTAP = KT * KT;
   __shared__ __align__(16) float s_in[16 * WG_IPLANE];
   __shared__ __align__(16) float s_g[16 * WG_GPLANE];
   const int tid = threadIdx.x;
   const int co_l = tid >> 4, ci_l = tid & 15;
   const int cob = blockIdx.y * 16, cib = blockIdx.z * 16;
   const int C4out = (a.Cout + 3) >> 2;
-  const size_t plane4 = (size_t)a.H * a.W * 4;
-  float acc[9];
+  const size_t plane4 = (size_t)a.H * a.W * 4, iplane4 = (size_t)a.Hin * a.Win * 4;
+  float acc[NTAP];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  for (int t = 0; t < NTAP; ++t) acc[t] = 0.f;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int tx = tile % a.tiles_x, t2 = tile / a.tiles_x;
     const int ty = t2 % a.tiles_y, n = t2 / a.tiles_y;
@@ -254,10 +279,10 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const WgradArgs a) {
     __syncthreads();
     for (int i = tid; i < 4 * (WG_TH + 2) * (WG_TW + 2); i += 256) {          // input halo tile: 4 groups = 16 channels
       const int c = i % (WG_TW + 2), r = (i / (WG_TW + 2)) % (WG_TH + 2), q = i / ((WG_TW + 2) * (WG_TH + 2));
-      const int gy = y0 + r - 1, gx = x0 + c - 1, grp = (cib >> 2) + q;
+      const int gy = y0 + r - ORG, gx = x0 + c - ORG, grp = (cib >> 2) + q;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && grp * 4 < a.Cin)
-        v = __ldg(reinterpret_cast<const float4*>(a.in + ((size_t)n * a.in_groups + grp) * plane4 + ((size_t)gy * a.W + gx) * 4));
+      if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win && grp * 4 < a.Cin)
+        v = __ldg(reinterpret_cast<const float4*>(a.in + ((size_t)n * a.in_groups + grp) * iplane4 + ((size_t)gy * a.Win + gx) * 4));
       float* d = s_in + (q * 4) * WG_IPLANE + r * WG_IP + c;
       d[0] = v.x; d[WG_IPLANE] = v.y; d[2 * WG_IPLANE] = v.z; d[3 * WG_IPLANE] = v.w;
     }
@@ -277,13 +302,13 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const WgradArgs a) {
       for (int c = 0; c < WG_TW; c += 4) {
         const float4 gv = *reinterpret_cast<const float4*>(s_g + co_l * WG_GPLANE + r * WG_TW + c);
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+        for (int ky = 0; ky < KT; ++ky) {
           const float* row = s_in + ci_l * WG_IPLANE + (r + ky) * WG_IP + c;
           const float4 i4 = *reinterpret_cast<const float4*>(row);
           const float i5 = row[4], i6 = row[5];
-          acc[ky * 3 + 0] += gv.x * i4.x + gv.y * i4.y + gv.z * i4.z + gv.w * i4.w;
-          acc[ky * 3 + 1] += gv.x * i4.y + gv.y * i4.z + gv.z * i4.w + gv.w * i5;
-          acc[ky * 3 + 2] += gv.x * i4.z + gv.y * i4.w + gv.z * i5 + gv.w * i6;
+          acc[ky * KT + 0] += gv.x * i4.x + gv.y * i4.y + gv.z * i4.z + gv.w * i4.w;
+          acc[ky * KT + 1] += gv.x * i4.y + gv.y * i4.z + gv.z * i4.w + gv.w * i5;
+          if (KT == 3) acc[ky * KT + KT - 1] += gv.x * i4.z + gv.y * i4.w + gv.z * i5 + gv.w * i6;
         }
       }
     }
@@ -291,7 +316,7 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const WgradArgs a) {
   const int co = cob + co_l, ci = cib + ci_l;
   if (co < a.Cout && ci < a.Cin) {
 #pragma unroll
-    for (int t = 0; t < 9; ++t) atomicAdd(a.dw + co * a.so + ci * a.si + (a.flip ? 8 - t : t), acc[t]);
+    for (int t = 0; t < NTAP; ++t) atomicAdd(a.dw + co * a.so + ci * a.si + (a.flip ? NTAP - 1 - t : t), acc[t]);
   }
 }
 
@@ -648,18 +673,37 @@ int chunks_for(int N, int C4, int HW) {
 
 extern "C" int gfr_conv_tc_pack_weights_dev(const float* w, int is_transposed_conv, int for_dgrad, int Cin, int Cout, int NT,
                                             float* packed, void* stream) {
+  return gfr_conv_tc_pack_weights_dev_ex(w, is_transposed_conv, for_dgrad, Cin, Cout, NT, 9, 3, packed, stream);
+}
+
+extern "C" long long gfr_conv_tc_pack_size_ex(int Cin, int Cout, int NT, int taps, int precision) {
+  if (Cin <= 0 || Cout <= 0 || (NT != 16 && NT != 32 && NT != 64 && NT != 128) || (taps != 9 && taps != 4)) return GFR_E_ARG;
+  const long long steps = (long long)gfr_ceil_div(Cout, NT) * gfr_ceil_div(Cin, 16) * taps;
+  return precision == 4 ? steps * 2 * NT * 4 : steps * 4 * 2 * NT * 4;      // in floats (8 bf16 = 4 floats)
+}
+
+extern "C" int gfr_conv_tc_pack_weights_dev_ex(const float* w, int is_transposed_conv, int for_dgrad, int Cin, int Cout, int NT,
+                                               int taps, int precision, float* packed, void* stream) {
   GFR_RETURN_IF_NULL(w); GFR_RETURN_IF_NULL(packed);
-  if (Cin <= 0 || Cout <= 0 || (NT != 16 && NT != 32 && NT != 64)) return GFR_E_ARG;
+  if (Cin <= 0 || Cout <= 0 || (NT != 16 && NT != 32 && NT != 64 && NT != 128) || (taps != 9 && taps != 4)) return GFR_E_ARG;
+  if (precision != 1 && precision != 3 && precision != 4) return GFR_E_ARG;
   // Cin / Cout are those of the LAYER (forward direction).  The packed operand computes O outputs from I inputs:
   const int O = for_dgrad ? Cin : Cout, I = for_dgrad ? Cout : Cin;
   long long so, si; int flip;
-  if (!is_transposed_conv) {        // Conv2d parameter [Cout][Cin][3][3]
-    if (!for_dgrad) { so = (long long)Cin * 9; si = 9; flip = 0; } else { so = 9; si = (long long)Cin * 9; flip = 1; }
-  } else {                          // ConvTranspose2d parameter [Cin][Cout][3][3]; forward = conv with w.transpose(0,1).flip(2,3)
-    if (!for_dgrad) { so = 9; si = (long long)Cout * 9; flip = 1; } else { so = (long long)Cout * 9; si = 9; flip = 0; }
+  if (!is_transposed_conv) {        // Conv2d parameter [Cout][Cin][k][k]
+    if (!for_dgrad) { so = (long long)Cin * taps; si = taps; flip = 0; } else { so = taps; si = (long long)Cin * taps; flip = 1; }
+  } else {                          // ConvTranspose2d parameter [Cin][Cout][k][k]; forward = conv with w.transpose(0,1).flip(2,3)
+    if (!for_dgrad) { so = taps; si = (long long)Cout * taps; flip = 1; } else { so = (long long)Cout * taps; si = taps; flip = 0; }
   }
-  const long long total = (long long)gfr_ceil_div(O, NT) * gfr_ceil_div(I, 16) * 9 * 4 * 2 * NT * 4;
-  pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, packed, total, O, I, NT, so, si, flip);
+  const long long steps = (long long)gfr_ceil_div(O, NT) * gfr_ceil_div(I, 16) * taps;
+  if (precision == 4) {
+    const long long total = steps * 2 * NT * 8;
+    pack_weights_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), total,
+                                                                                                O, I, NT, so, si, flip, taps);
+  } else {
+    const long long total = steps * 4 * 2 * NT * 4;
+    pack_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, packed, total, O, I, NT, so, si, flip, taps);
+  }
   return gfr_launch_status();
 }
 
@@ -711,28 +755,40 @@ extern "C" int gfr_bn_apply_bwd(const float* x, const float* res, const float* g
   return gfr_launch_status();
 }
 
-extern "C" int gfr_conv3x3_wgrad(const float* in, const float* g_out, float* g_w, float* g_bias, int is_transposed_conv, int N,
-                                 int Cin, int in_groups, int Cout, int H, int W, void* stream) {
+static int wgrad_launch(const float* in, const float* g_out, float* g_w, float* g_bias, int is_transposed_conv, int N, int Cin,
+                        int in_groups, int Cout, int Hin, int Win, int H, int W, int taps, void* stream) {
   GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(g_out); GFR_RETURN_IF_NULL(g_w);
   if (N <= 0 || N > 65535 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
   if (in_groups == 0) in_groups = (Cin + 3) / 4;
   if (in_groups < (Cin + 3) / 4) return GFR_E_ARG;
   WgradArgs a;
   a.in = in; a.g = g_out; a.dw = g_w; a.N = N; a.Cin = Cin; a.Cout = Cout; a.in_groups = in_groups; a.H = H; a.W = W;
-  if (!is_transposed_conv) { a.so = (long long)Cin * 9; a.si = 9; a.flip = 0; }     // dW_param[co][ci][tap]
-  else { a.so = 9; a.si = (long long)Cout * 9; a.flip = 1; }                         // dW_param[ci][co][8 - tap]
+  a.Hin = Hin; a.Win = Win;
+  if (!is_transposed_conv) { a.so = (long long)Cin * taps; a.si = taps; a.flip = 0; }     // dW_param[co][ci][tap]
+  else { a.so = taps; a.si = (long long)Cout * taps; a.flip = 1; }                         // dW_param[ci][co][taps - 1 - tap]
   a.tiles_x = gfr_ceil_div(W, WG_TW); a.tiles_y = gfr_ceil_div(H, WG_TH); a.n_tiles = N * a.tiles_x * a.tiles_y;
   const int gy = gfr_ceil_div(Cout, 16), gz = gfr_ceil_div(Cin, 16);
   int gx = (148 * 2) / (gy * gz);
   if (gx < 1) gx = 1;
   if (gx > a.n_tiles) gx = a.n_tiles;
   cudaStream_t s = (cudaStream_t)stream;
-  wgrad3x3_kernel<<<dim3(gx, gy, gz), 256, 0, s>>>(a);
+  if (taps == 9) wgrad_kernel<3><<<dim3(gx, gy, gz), 256, 0, s>>>(a);
+  else wgrad_kernel<2><<<dim3(gx, gy, gz), 256, 0, s>>>(a);
   if (g_bias) {
     const int C4 = (Cout + 3) / 4, chunks = chunks_for(N, C4, H * W);
     channel_sum_kernel<<<dim3(chunks, C4, N), 256, 0, s>>>(reinterpret_cast<const float4*>(g_out), g_bias, C4, H * W, chunks);
   }
   return gfr_launch_status();
+}
+
+extern "C" int gfr_conv3x3_wgrad(const float* in, const float* g_out, float* g_w, float* g_bias, int is_transposed_conv, int N,
+                                 int Cin, int in_groups, int Cout, int H, int W, void* stream) {
+  return wgrad_launch(in, g_out, g_w, g_bias, is_transposed_conv, N, Cin, in_groups, Cout, H, W, H, W, 9, stream);
+}
+
+extern "C" int gfr_conv2x2_wgrad(const float* in, const float* g_out, float* g_w, float* g_bias, int N, int Cin, int in_groups,
+                                 int Cout, int H, int W, void* stream) {
+  return wgrad_launch(in, g_out, g_w, g_bias, 0, N, Cin, in_groups, Cout, H + 1, W + 1, H, W, 4, stream);
 }
 
 extern "C" int gfr_maxpool2_c4_bwd(const float* x, const float* g_y, float* g_x, int NC4, int Ho, int Wo, void* stream) {

@@ -31,6 +31,7 @@
 #include "gfr_common.cuh"
 #include "tc_common.cuh"
 
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <mutex>
 #include <math.h>
@@ -40,6 +41,10 @@
 using namespace gfr_tc;
 
 namespace {
+
+// halo-tile offset (in pixels) of filter tap `tap`: 3x3 taps (ky, kx) = (tap / 3, tap % 3), 2x2 taps (tap / 2, tap % 2)
+template <int TAPS>
+__host__ __device__ constexpr int tap_offset(int tap) { return TAPS == 9 ? (tap / 3) * 10 + (tap % 3) : (tap / 2) * 10 + (tap % 2); }
 
 constexpr int TILE_PX_W = 8, TILE_PX_H = 16;           // 128 output pixels = UMMA M
 constexpr int HALO_W = TILE_PX_W + 2, HALO_H = TILE_PX_H + 2;
@@ -55,7 +60,9 @@ struct ConvTcArgs {
   const float* res;    // C4 [N][C4out][H][W][4] or null   (added before the activation)
   const float* post;   // C4 [N][C4out][H>>ps][W>>ps][4] or null (added after the activation, nearest x2 when ps=1)
   float* out;          // C4 [N][C4out][H][W][4]
-  int N, Cin, Cout, H, W;
+  int N, Cin, Cout, H, W;   // H, W: OUTPUT size (= input size for the 3x3 / pad 1 layers)
+  int Hin, Win;             // input size (the 2x2-tap layers map (H+1)x(W+1) -> HxW or HxW -> (H+1)x(W+1))
+  int org;                  // the tile's TMA box starts at (x0 - org, y0 - org): 1 for 3x3 / pad 1, 0 | 1 for the 2x2 taps
   int ncb, tiles_x, tiles_y, m_tiles;
   int post_shift, act;
   int single_pass;     // 1: hi*Whi only (plain TF32)
@@ -70,9 +77,9 @@ struct ConvTcArgs {
   float head_scale;
 };
 
-constexpr int KIND_TF32 = 0, KIND_F16 = 1;
+constexpr int KIND_TF32 = 0, KIND_F16 = 1, KIND_BF16 = 2;      // BF16: one bf16 operand per side, no correction MMAs
 
-template <int NT, int KIND>
+template <int NT, int KIND, int TAPS = 9>
 struct Smem {
   // ring depth, measured on the whole forward (B = 8, 3 lanes): 3/3 slots (weights resident / streamed) 11 190 faces/s,
   // 3/2 11 800, 4/2 11 810, 2/2 11 990.  With streamed weights (Cin > 16) a third slot makes the CTA 124 KB and it runs
@@ -86,12 +93,14 @@ struct Smem {
   static constexpr int STAGES_RES = NT <= 32 ? GFR_CONV_STAGES_RES : 2, STAGES_STR = NT <= 32 ? GFR_CONV_STAGES_STR : 2;
   static constexpr int MAX_STAGES = STAGES_RES > STAGES_STR ? STAGES_RES : STAGES_STR;
   // TF32: [tap][4-ch group (4)][hi|lo][n][4 floats];  F16: [tap][8-ch chunk (2)][w1|w2][n][8 halfs]  — of one 16-channel step
-  static constexpr uint32_t W_STEP = 9 * (KIND == KIND_TF32 ? CB / 4 : CB / 8) * 2 * NT * 16;
+  //   BF16: [tap][8-ch chunk (2)][n][8 bf16].  TAPS = 9 (3x3) or 4 (2x2: PatchGAN's 4x4 / stride 2 layers over a space-to-depth)
+  static constexpr uint32_t W_STEP = TAPS * (KIND == KIND_TF32 ? CB / 4 : CB / 8) * (KIND == KIND_BF16 ? 1 : 2) * NT * 16;
   // resident-weights mode (Cin <= 16): [W][slot: A_hi, A_lo] ; streaming mode: [slot: A_hi, A_lo, W]
   static constexpr uint32_t SLOT_RES = 2 * A_BYTES, SLOT_STR = 2 * A_BYTES + W_STEP;
   static constexpr uint32_t BYTES_RES = W_STEP + STAGES_RES * SLOT_RES + 256;
   static constexpr uint32_t BYTES_STR = STAGES_STR * SLOT_STR + 256;
-  static constexpr uint32_t TMEM_COLS = 4 * NT <= 32 ? 32 : (4 * NT <= 64 ? 64 : (4 * NT <= 128 ? 128 : 256));
+  static constexpr uint32_t ACC = (KIND == KIND_BF16 ? 1 : 2) * NT;          // columns of one accumulator buffer
+  static constexpr uint32_t TMEM_COLS = 2 * ACC <= 32 ? 32 : (2 * ACC <= 64 ? 64 : (2 * ACC <= 128 ? 128 : (2 * ACC <= 256 ? 256 : 512)));
 };
 
 // y[o] = lrelu(b[o] + sum_ci w[o][ci] x[ci]) for 16 -> 16, weights in shared memory ([co][ci] rows)
@@ -113,7 +122,7 @@ __device__ __forceinline__ void head_dense16(const float* w, const float* b, con
   }
 }
 
-template <int NT, int KIND, bool HEAD = false>
+template <int NT, int KIND, bool HEAD = false, int TAPS = 9>
 // CTAs per SM of the NT = 16 kernel: 3 would fit shared memory and TMEM but caps the kernel at 64 registers (256 B of
 // spills in the epilogue): measured 10 550 vs 12 020 faces/s, so 2
 #ifndef GFR_CONV_OCC
@@ -122,7 +131,8 @@ template <int NT, int KIND, bool HEAD = false>
 __global__ void __launch_bounds__(NUM_THREADS, NT <= 32 ? (NT <= 16 ? GFR_CONV_OCC : 2) : 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a) {
   static_assert(!HEAD || NT == 16, "the fused decoder tail needs the pixel's 16 channels in one thread");
-  using S = Smem<NT, KIND>;
+  using S = Smem<NT, KIND, TAPS>;
+  constexpr bool CUT = KIND != KIND_BF16;      // accumulator chain cut at every pipeline step (fp32-grade kinds)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool resident = a.ncb == 1;
@@ -191,7 +201,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
             mbar_wait(bar_empty + 8 * s, ((g / STAGES) & 1) ^ 1);
             mbar_expect_tx(bar_full + 8 * s, A_BYTES + (load_w ? S::W_STEP : 0u));
           }
-          tma_load_4d(slot, &tm_in, bar_full + 8 * s, (tx * TILE_PX_W - 1) * 4, ty * TILE_PX_H - 1, cb * (CB / 4), n);
+          tma_load_4d(slot, &tm_in, bar_full + 8 * s, (tx * TILE_PX_W - a.org) * 4, ty * TILE_PX_H - a.org, cb * (CB / 4), n);
           if (load_w && (g >= n_pre || !a.static_w))
             bulk_load(resident ? smem0 : slot + 2 * A_BYTES, wsrc + (size_t)cb * (S::W_STEP / 4), S::W_STEP, bar_full + 8 * s);
         }
@@ -204,26 +214,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
     // wraps each of them in an ELECT / BRA.U.ANY loop (~10 instructions) and the issuing thread sets the pace.
     {
       constexpr uint32_t IDESC_2N = KIND == KIND_TF32 ? umma_idesc_tf32(128, 2 * NT) : umma_idesc_f16(128, 2 * NT);
-      constexpr uint32_t IDESC_N = KIND == KIND_TF32 ? umma_idesc_tf32(128, NT) : umma_idesc_f16(128, NT);
-      constexpr uint32_t B_LBO = 2 * NT * 16, B_TAP = (KIND == KIND_TF32 ? CB / 4 : CB / 8) * B_LBO;
+      constexpr uint32_t IDESC_N = KIND == KIND_TF32 ? umma_idesc_tf32(128, NT) : (KIND == KIND_BF16 ? umma_idesc_bf16(128, NT) : umma_idesc_f16(128, NT));
+      constexpr uint32_t B_LBO = (KIND == KIND_BF16 ? 1 : 2) * NT * 16, B_TAP = (KIND == KIND_TF32 ? CB / 4 : CB / 8) * B_LBO;
       for (int g = 0; g < n_steps; ++g) {
-        const int s = g % STAGES, p = g & 1;
+        // CUT kinds: accumulator buffer / parity per pipeline step; BF16: per tile (its steps accumulate in TMEM)
+        const int s = g % STAGES, cb = g % a.ncb, e_acc = CUT ? g : g / a.ncb, p = e_acc & 1;
+        const bool first_of_acc = CUT || cb == 0, last_of_acc = CUT || cb == a.ncb - 1;
         mbar_wait(bar_ready + 8 * s, (g / STAGES) & 1);
-        mbar_wait(bar_accempty + 8 * p, ((g >> 1) & 1) ^ 1);
+        if (first_of_acc) mbar_wait(bar_accempty + 8 * p, ((e_acc >> 1) & 1) ^ 1);
         tc_fence_after_sync();
         if (elect_one_sync()) {
           const uint32_t slot = slots0 + s * slot_bytes;
           const uint32_t wbase = resident ? smem0 : slot + 2 * A_BYTES;
-          const uint32_t d_main = tmem + (uint32_t)(p * 2 * NT), d_corr = d_main + NT;
+          const uint32_t d_main = tmem + (uint32_t)(p * S::ACC), d_corr = d_main + NT;
           const uint64_t dB0 = umma_desc_kmajor_noswz(wbase, B_LBO, 128u);
           if (KIND == KIND_TF32) {
             const uint64_t dA_hi0 = umma_desc_kmajor_noswz(slot, A_LBO, A_SBO);
             const uint64_t dA_lo0 = umma_desc_kmajor_noswz(slot + A_BYTES, A_LBO, A_SBO);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < TAPS; ++tap) {
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                const uint32_t ao = ((uint32_t)((tap / 3) * HALO_W + (tap % 3)) * 16u + (uint32_t)j * 2u * A_LBO) >> 4;
+                const uint32_t ao = ((uint32_t)tap_offset<TAPS>(tap) * 16u + (uint32_t)j * 2u * A_LBO) >> 4;
                 const uint32_t bo = ((uint32_t)tap * B_TAP + (uint32_t)j * 2u * B_LBO) >> 4;
                 const uint32_t first = (tap == 0 && j == 0) ? 0u : 1u;
                 if (a.single_pass) {
@@ -234,21 +246,30 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
                 }
               }
             }
-          } else {
+          } else if (KIND == KIND_F16) {
             // fp16 pair split: the two operand tiles [2 chunks of 8 ch][18][10][8 halfs] sit behind the raw fp32 tile;
             // one K = 16 MMA covers the whole 16-channel step of a tap
             const uint64_t dA_1 = umma_desc_kmajor_noswz(slot + A_BYTES, A_LBO, A_SBO);
             const uint64_t dA_2 = umma_desc_kmajor_noswz(slot + A_BYTES + A_BYTES / 2, A_LBO, A_SBO);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t ao = ((uint32_t)((tap / 3) * HALO_W + (tap % 3)) * 16u) >> 4;
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const uint32_t ao = ((uint32_t)tap_offset<TAPS>(tap) * 16u) >> 4;
               const uint32_t bo = ((uint32_t)tap * B_TAP) >> 4;
               umma_f16(d_main, dA_1 + ao, dB0 + bo, IDESC_2N, tap == 0 ? 0u : 1u);   // main += h1*W1 ; corr += h1*W2
               umma_f16(d_corr, dA_2 + ao, dB0 + bo, IDESC_N, 1u);                    // corr += h2*W1
             }
+          } else {
+            // bf16: one operand tile [2 chunks of 8 ch][18][10][8 bf16] behind the raw fp32 tile, one MMA per tap
+            const uint64_t dA = umma_desc_kmajor_noswz(slot + A_BYTES, A_LBO, A_SBO);
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const uint32_t ao = ((uint32_t)tap_offset<TAPS>(tap) * 16u) >> 4;
+              const uint32_t bo = ((uint32_t)tap * B_TAP) >> 4;
+              umma_f16(d_main, dA + ao, dB0 + bo, IDESC_N, (tap == 0 && first_of_acc) ? 0u : 1u);
+            }
           }
           umma_commit(bar_empty + 8 * s);       // the slot may be refilled once these MMAs have read it
-          umma_commit(bar_accfull + 8 * p);     // and the accumulators of this step are complete
+          if (last_of_acc) umma_commit(bar_accfull + 8 * p);     // and the accumulators of this step (BF16: tile) are complete
         }
         __syncwarp();
       }
@@ -271,6 +292,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
           l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
           hi4[i] = h;
           lo4[i] = l;
+        }
+      } else if (KIND == KIND_BF16) {
+        constexpr int PIX = HALO_H * HALO_W;
+        const float4* raw = reinterpret_cast<const float4*>(slot_g);
+        uint4* t1 = reinterpret_cast<uint4*>(slot_g + A_BYTES);
+        for (int i = st; i < 2 * PIX; i += 128) {
+          const int c = i >= PIX ? 1 : 0, pix = i - c * PIX;
+          const float4 va = raw[(2 * c) * PIX + pix], vb = raw[(2 * c + 1) * PIX + pix];
+          const __nv_bfloat162 b0 = __floats2bfloat162_rn(va.x, va.y), b1 = __floats2bfloat162_rn(va.z, va.w);
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(vb.x, vb.y), b3 = __floats2bfloat162_rn(vb.z, vb.w);
+          t1[i] = make_uint4(*reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1),
+                             *reinterpret_cast<const uint32_t*>(&b2), *reinterpret_cast<const uint32_t*>(&b3));
         }
       } else {
         // x*x_scale = h1 + h2 (+ ~2^-22 relative), both fp16: 8 channels of a pixel -> one 16-byte row of each operand tile
@@ -307,13 +340,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
     const int C4out = (a.Cout + 3) >> 2;
     const int pH = a.H >> a.post_shift, pW = a.W >> a.post_shift;
     griddep_wait();                                       // residual / skip operands and the output buffer belong to earlier kernels
-    int g = 0;
-    for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x) {
+    int g = 0, ti = 0;
+    for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x, ++ti) {
       const int tx = mt % a.tiles_x, t2 = mt / a.tiles_x;
       const int ty = t2 % a.tiles_y, n = t2 / a.tiles_y;
-      float sum[NT];
-#pragma unroll
-      for (int c = 0; c < NT; ++c) sum[c] = 0.f;
       // residual / skip operands are fetched before the accumulators are waited for: their L2 latency overlaps the MMAs
       const int y = ty * TILE_PX_H + (m >> 3), x = tx * TILE_PX_W + (m & 7);
       const bool ok = y < a.H && x < a.W;
@@ -340,61 +370,91 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
           }
         }
       }
-      for (int cb = 0; cb < a.ncb; ++cb, ++g) {
-        const int p = g & 1;
-        mbar_wait(bar_accfull + 8 * p, (g >> 1) & 1);
-        tc_fence_after_sync();
-        const uint32_t t_main = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 2 * NT);
+      // CUT kinds: every pipeline step has its own accumulator, summed here in fp32 registers (round-to-nearest);
+      // BF16: the steps of a tile accumulate in TMEM, read once per tile in 16-column groups (no register array: NT up to 128)
+      [[maybe_unused]] float sum[CUT ? NT : 1];
+      if constexpr (CUT) {
 #pragma unroll
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          uint32_t rm[16], rc[16];
-          tmem_ld16(t_main + c0, rm);
-          if (!a.single_pass) tmem_ld16(t_main + NT + c0, rc);
-          tmem_ld_wait();
+        for (int c = 0; c < NT; ++c) sum[c] = 0.f;
+        for (int cb = 0; cb < a.ncb; ++cb, ++g) {
+          const int p = g & 1;
+          mbar_wait(bar_accfull + 8 * p, (g >> 1) & 1);
+          tc_fence_after_sync();
+          const uint32_t t_main = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * S::ACC);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float part = a.single_pass ? __uint_as_float(rm[e]) : __uint_as_float(rm[e]) + __uint_as_float(rc[e]);
-            sum[c0 + e] += part;
+          for (int c0 = 0; c0 < NT; c0 += 16) {
+            uint32_t rm[16], rc[16];
+            tmem_ld16(t_main + c0, rm);
+            if (!a.single_pass) tmem_ld16(t_main + NT + c0, rc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float part = a.single_pass ? __uint_as_float(rm[e]) : __uint_as_float(rm[e]) + __uint_as_float(rc[e]);
+              sum[c0 + e] += part;
+            }
           }
+          tc_fence_before_sync();
+          mbar_arrive(bar_accempty + 8 * p);
         }
-        tc_fence_before_sync();
-        mbar_arrive(bar_accempty + 8 * p);
+      } else {
+        mbar_wait(bar_accfull + 8 * (ti & 1), (ti >> 1) & 1);
+        tc_fence_after_sync();
       }
       [[maybe_unused]] float yv[HEAD ? NT : 1];
-      if (ok) {
 #pragma unroll
-        for (int c0 = 0; c0 < NT; c0 += 4) {
-          const int co = n0 + c0, cq = co >> 2;
-          if (cq >= C4out) continue;
-          float v[4];
+      for (int cg = 0; cg < NT; cg += 16) {
+        float acc16[16];
+        if constexpr (CUT) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            v[e] = (KIND == KIND_F16 ? sum[c0 + e] * a.inv_scale : sum[c0 + e]) + (co + e < a.Cout ? __ldg(a.bias + co + e) : 0.f);
-          float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), pp = rr;
-          if (PREF_REGS) {
-            rr = rres[c0 / 4]; pp = rpost[c0 / 4];
-          } else if (!HEAD) {
-            if (a.res) rr = __ldg(reinterpret_cast<const float4*>(a.res + o_base + (size_t)cq * o_plane));
-            if (a.post) pp = __ldg(reinterpret_cast<const float4*>(a.post + ((((size_t)n * C4out + cq) * pH + (y >> a.post_shift)) * pW + (x >> a.post_shift)) * 4));
-          }
-          v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-          if (a.act == 1) {
+          for (int e = 0; e < 16; ++e) acc16[e] = sum[cg + e];
+        } else {
+          uint32_t rm[16];
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((ti & 1) * S::ACC + cg), rm);
+          tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : 0.2f * v[e];
-          } else if (a.act == 2) {
+          for (int e = 0; e < 16; ++e) acc16[e] = __uint_as_float(rm[e]);
+        }
+        if (ok) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = 1.0f / (1.0f + expf(-v[e]));
-          }
-          v[0] += pp.x; v[1] += pp.y; v[2] += pp.z; v[3] += pp.w;
-          if constexpr (HEAD) {
+          for (int c0 = cg; c0 < cg + 16; c0 += 4) {
+            const int co = n0 + c0, cq = co >> 2;
+            if (cq >= C4out) continue;
+            float v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) yv[c0 + e] = v[e] * a.out_scale;
-          } else {
-            *reinterpret_cast<float4*>(a.out + o_base + (size_t)cq * o_plane) =
-                make_float4(v[0] * a.out_scale, v[1] * a.out_scale, v[2] * a.out_scale, v[3] * a.out_scale);
+            for (int e = 0; e < 4; ++e)
+              v[e] = (KIND == KIND_F16 ? acc16[c0 - cg + e] * a.inv_scale : acc16[c0 - cg + e]) + (co + e < a.Cout ? __ldg(a.bias + co + e) : 0.f);
+            float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), pp = rr;
+            if (PREF_REGS) {
+              rr = rres[c0 / 4]; pp = rpost[c0 / 4];
+            } else if (!HEAD) {
+              if (a.res) rr = __ldg(reinterpret_cast<const float4*>(a.res + o_base + (size_t)cq * o_plane));
+              if (a.post) pp = __ldg(reinterpret_cast<const float4*>(a.post + ((((size_t)n * C4out + cq) * pH + (y >> a.post_shift)) * pW + (x >> a.post_shift)) * 4));
+            }
+            v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+            if (a.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : 0.2f * v[e];
+            } else if (a.act == 2) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = 1.0f / (1.0f + expf(-v[e]));
+            }
+            v[0] += pp.x; v[1] += pp.y; v[2] += pp.z; v[3] += pp.w;
+            if constexpr (HEAD) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) yv[c0 + e] = v[e] * a.out_scale;
+            } else {
+              *reinterpret_cast<float4*>(a.out + o_base + (size_t)cq * o_plane) =
+                  make_float4(v[0] * a.out_scale, v[1] * a.out_scale, v[2] * a.out_scale, v[3] * a.out_scale);
+            }
           }
         }
-        if constexpr (HEAD) {
+      }
+      if constexpr (!CUT) {
+        tc_fence_before_sync();
+        mbar_arrive(bar_accempty + 8 * (ti & 1));
+      }
+      if constexpr (HEAD) {
+        if (ok) {
           // c2_2 -> c2_3 -> c2_o per pixel.  Weights come from shared memory as LDS.128 broadcasts; four outputs are
           // accumulated side by side (independent FMA chains); per accumulator the order is the stand-alone
           // head_1x1_kernel's (bias first, ci ascending), so the result is bit-identical to the two-launch tail.
@@ -468,16 +528,16 @@ int make_c4_map(CUtensorMap* tm, const float* base, int N, int C4, int C4_alloc,
   return r == CUDA_SUCCESS ? GFR_OK : GFR_E_ARG;
 }
 
-template <int NT, int KIND, bool HEAD = false>
+template <int NT, int KIND, bool HEAD = false, int TAPS = 9>
 int launch_tc(const CUtensorMap& tm, const ConvTcArgs& a, cudaStream_t s) {
-  using S = Smem<NT, KIND>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  using S = Smem<NT, KIND, TAPS>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
     const uint32_t mx = S::BYTES_RES > S::BYTES_STR ? S::BYTES_RES : S::BYTES_STR;
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<NT, KIND, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
-    if (e != cudaSuccess) return (int)e;
-    attr_done = true;
-  }
+    attr_err = cudaFuncSetAttribute(conv3x3_tc_kernel<NT, KIND, HEAD, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+  });
+  if (attr_err != cudaSuccess) return (int)attr_err;
   const uint32_t bytes = a.ncb == 1 ? S::BYTES_RES : S::BYTES_STR;
   const int n_tiles = gfr_ceil_div(a.Cout, NT);
   int occ = (int)(225u * 1024u / (bytes + 1024u));
@@ -501,7 +561,7 @@ int launch_tc(const CUtensorMap& tm, const ConvTcArgs& a, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NT, KIND, HEAD>, tm, a);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NT, KIND, HEAD, TAPS>, tm, a);
   return e == cudaSuccess ? gfr_launch_status() : (int)e;
 }
 
@@ -636,13 +696,17 @@ extern "C" int gfr_conv_tc_pack_weights_f16(const float* w_host, int Cin, int Co
   return GFR_OK;
 }
 
-extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const float* bias, const float* res,
-                                  const float* post, float* out, int N, int Cin, int in_groups, int Cout, int H, int W,
-                                  int NT, int post_shift, int act, float out_scale, int precision, int weights_static, float x_scale,
-                                  float w_scale, void* stream) {
+// taps 9: 3x3 / pad 1 (Hin = H, Win = W, org 1).  taps 4: 2x2 taps, out[y][x] = sum_{ky,kx in {0,1}} w[ky][kx] in[y - org + ky][x - org + kx]:
+//   org 0 maps an (H+1) x (W+1) input to H x W (forward of PatchGAN's 4x4 / stride 2 layers over the space-to-depth of the padded
+//   input), org 1 maps Hin x Win to (Hin+1) x (Win+1) (its data gradient).  precision 1 TF32, 2 fp16 pair split, 3 3xTF32, 4 bf16.
+static int conv_tc_launch(const float* in, const float* w_packed, const float* bias, const float* res, const float* post, float* out,
+                          int N, int Cin, int in_groups, int Cout, int Hin, int Win, int H, int W, int NT, int taps, int org,
+                          int post_shift, int act, float out_scale, int precision, int weights_static, float x_scale, float w_scale,
+                          void* stream) {
   GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w_packed); GFR_RETURN_IF_NULL(bias); GFR_RETURN_IF_NULL(out);
-  if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
-  if (post_shift < 0 || post_shift > 1 || act < 0 || act > 2 || precision < 1 || precision > 3) return GFR_E_ARG;
+  if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0 || Hin <= 0 || Win <= 0) return GFR_E_SHAPE;
+  if (post_shift < 0 || post_shift > 1 || act < 0 || act > 2 || precision < 1 || precision > 4) return GFR_E_ARG;
+  if ((taps != 9 && taps != 4) || org < 0 || org > 1) return GFR_E_ARG;
   if (precision == 2 && !(x_scale > 0.f && w_scale > 0.f)) return GFR_E_ARG;
   if (post && post_shift && ((H | W) & 1)) return GFR_E_SHAPE;
   if (in_groups == 0) in_groups = (Cin + 3) / 4;
@@ -652,7 +716,7 @@ extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const 
     return GFR_E_ARG;
   ConvTcArgs a;
   a.wpk = w_packed; a.bias = bias; a.res = res; a.post = post; a.out = out;
-  a.N = N; a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W;
+  a.N = N; a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.Hin = Hin; a.Win = Win; a.org = org;
   a.ncb = gfr_ceil_div(Cin, CB);
   a.tiles_x = gfr_ceil_div(W, TILE_PX_W); a.tiles_y = gfr_ceil_div(H, TILE_PX_H);
   a.m_tiles = N * a.tiles_x * a.tiles_y;
@@ -662,15 +726,37 @@ extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const 
   a.static_w = weights_static ? 1 : 0;
   a.head = nullptr; a.head_out = nullptr; a.head_n = 0; a.head_act = 0; a.head_scale = 1.0f;
   CUtensorMap tm;
-  const int rc = make_c4_map(&tm, in, N, (Cin + 3) / 4, in_groups, H, W, HALO_W, HALO_H);
+  const int rc = make_c4_map(&tm, in, N, (Cin + 3) / 4, in_groups, Hin, Win, HALO_W, HALO_H);
   if (rc != GFR_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  switch (NT) {
-    case 16: return precision == 2 ? launch_tc<16, KIND_F16>(tm, a, s) : launch_tc<16, KIND_TF32>(tm, a, s);
-    case 32: return precision == 2 ? launch_tc<32, KIND_F16>(tm, a, s) : launch_tc<32, KIND_TF32>(tm, a, s);
-    case 64: return precision == 2 ? launch_tc<64, KIND_F16>(tm, a, s) : launch_tc<64, KIND_TF32>(tm, a, s);
-    default: return GFR_E_ARG;
-  }
+  const int kind = precision == 2 ? KIND_F16 : (precision == 4 ? KIND_BF16 : KIND_TF32);
+#define GFR_TC_CASE(nt, k, t) if (NT == nt && kind == k && taps == t) return launch_tc<nt, k, false, t>(tm, a, s)
+  GFR_TC_CASE(16, KIND_TF32, 9); GFR_TC_CASE(32, KIND_TF32, 9); GFR_TC_CASE(64, KIND_TF32, 9);
+  GFR_TC_CASE(16, KIND_F16, 9); GFR_TC_CASE(32, KIND_F16, 9); GFR_TC_CASE(64, KIND_F16, 9);
+  GFR_TC_CASE(16, KIND_BF16, 9); GFR_TC_CASE(32, KIND_BF16, 9); GFR_TC_CASE(64, KIND_BF16, 9); GFR_TC_CASE(128, KIND_BF16, 9);
+  GFR_TC_CASE(16, KIND_TF32, 4); GFR_TC_CASE(64, KIND_TF32, 4);
+  GFR_TC_CASE(16, KIND_BF16, 4); GFR_TC_CASE(64, KIND_BF16, 4); GFR_TC_CASE(128, KIND_BF16, 4);
+#undef GFR_TC_CASE
+  return GFR_E_ARG;
+}
+
+extern "C" int gfr_conv3x3_tc_fwd(const float* in, const float* w_packed, const float* bias, const float* res,
+                                  const float* post, float* out, int N, int Cin, int in_groups, int Cout, int H, int W,
+                                  int NT, int post_shift, int act, float out_scale, int precision, int weights_static, float x_scale,
+                                  float w_scale, void* stream) {
+  return conv_tc_launch(in, w_packed, bias, res, post, out, N, Cin, in_groups, Cout, H, W, H, W, NT, 9, 1, post_shift, act, out_scale,
+                        precision, weights_static, x_scale, w_scale, stream);
+}
+
+extern "C" int gfr_conv_tc_fwd_ex(const float* in, const float* w_packed, const float* bias, const float* res, const float* post,
+                                  float* out, int N, int Cin, int in_groups, int Cout, int Hin, int Win, int H, int W, int NT,
+                                  int taps, int org, int post_shift, int act, float out_scale, int precision, int weights_static,
+                                  void* stream) {
+  if (precision == 2) return GFR_E_ARG;          // the fp16 pair split is the eval path's (gfr_conv3x3_tc_fwd / gfr_conv3x3_p16_fwd)
+  if (taps == 9 && (Hin != H || Win != W)) return GFR_E_SHAPE;
+  if (taps == 4 && !((org == 0 && Hin == H + 1 && Win == W + 1) || (org == 1 && Hin + 1 == H && Win + 1 == W))) return GFR_E_SHAPE;
+  return conv_tc_launch(in, w_packed, bias, res, post, out, N, Cin, in_groups, Cout, Hin, Win, H, W, NT, taps, org, post_shift, act,
+                        out_scale, precision, weights_static, 1.0f, 1.0f, stream);
 }
 
 extern "C" int gfr_conv3x3_tc_head_fwd(const float* in, const float* w_packed, const float* bias, const float* head, float* out,
@@ -685,7 +771,7 @@ extern "C" int gfr_conv3x3_tc_head_fwd(const float* in, const float* w_packed, c
   if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(head)) & 15) return GFR_E_ARG;
   ConvTcArgs a;
   a.wpk = w_packed; a.bias = bias; a.res = nullptr; a.post = nullptr; a.out = nullptr;
-  a.N = N; a.Cin = Cin; a.Cout = 16; a.H = H; a.W = W;
+  a.N = N; a.Cin = Cin; a.Cout = 16; a.H = H; a.W = W; a.Hin = H; a.Win = W; a.org = 1;
   a.ncb = gfr_ceil_div(Cin, CB);
   a.tiles_x = gfr_ceil_div(W, TILE_PX_W); a.tiles_y = gfr_ceil_div(H, TILE_PX_H);
   a.m_tiles = N * a.tiles_x * a.tiles_y;

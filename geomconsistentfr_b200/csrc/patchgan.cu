@@ -56,6 +56,49 @@ __global__ void d2s_kernel(const float4* __restrict__ g, float* __restrict__ out
   }
 }
 
+// Space-to-depth of the 1-PADDED input: out[n][c][y'][x'][2dy+dx] = Xpad[2y'+dy][2x'+dx], Xpad[r][s] = X[r-1][s-1] (0 outside),
+// y' in [0, H/2], x' in [0, W/2].  A 4x4 / stride 2 / pad 1 convolution of X is then a 2x2-tap, stride-1 convolution of `out`
+// (blocks y, y+1 hold the rows 2y-1 .. 2y+2) whose weights W'[co][4c+2dy+dx][a][b] = w[co][c][2a+dy][2b+dx] have no zeros.
+__global__ void s2d_pad_kernel(const float* __restrict__ in, float4* __restrict__ out, int C, int H, int W, int planar, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [N][C][H/2+1][W/2+1]
+  if (i >= total) return;
+  const int Wo = (W >> 1) + 1, Ho = (H >> 1) + 1;
+  const int xo = (int)(i % Wo);
+  long long t = i / Wo;
+  const int yo = (int)(t % Ho); t /= Ho;
+  const int c = (int)(t % C);
+  const long long n = t / C;
+  float v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = 2 * yo + (k >> 1) - 1, q = 2 * xo + (k & 1) - 1;
+    float x = 0.f;
+    if (r >= 0 && r < H && q >= 0 && q < W) {
+      if (planar) x = __ldg(in + ((n * C + c) * H + r) * (long long)W + q);
+      else x = __ldg(in + (((n * ((C + 3) >> 2) + (c >> 2)) * H + r) * (long long)W + q) * 4 + (c & 3));
+    }
+    v[k] = x;
+  }
+  out[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// its backward: every input pixel belongs to exactly one (block, phase)
+__global__ void d2s_pad_kernel(const float4* __restrict__ g, float* __restrict__ out, int C, int H, int W, int planar, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [N][C][H][W]
+  if (i >= total) return;
+  const int q = (int)(i % W);
+  long long t = i / W;
+  const int r = (int)(t % H); t /= H;
+  const int c = (int)(t % C);
+  const long long n = t / C;
+  const int Wo = (W >> 1) + 1, Ho = (H >> 1) + 1;
+  const float4 v = __ldg(g + ((n * C + c) * Ho + ((r + 1) >> 1)) * (long long)Wo + ((q + 1) >> 1));
+  const int k = 2 * ((r + 1) & 1) + ((q + 1) & 1);
+  const float x = k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w;
+  if (planar) out[i] = x;
+  else out[(((n * ((C + 3) >> 2) + (c >> 2)) * H + r) * (long long)W + q) * 4 + (c & 3)] = x;
+}
+
 // g_pre = g_y * (y > 0 ? 1 : 0.2)   (y = LeakyReLU(pre): sign(y) = sign(pre))
 __global__ void lrelu_bwd_kernel(const float4* __restrict__ y, const float4* __restrict__ gy, float4* __restrict__ out, long long n4) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,5 +232,21 @@ extern "C" int gfr_conv4x4s1_to1_bwd(const float* in, const float* w, const floa
     if (!g_bias) return GFR_E_NULL;
     conv4x4s1_wgrad_kernel<<<(C * 16 + 1 + 3) / 4, 128, 0, s>>>(in, g_out, g_w, g_bias, N, C, H, W);
   }
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_space_to_depth_pad(const float* in, float* out, int N, int C, int H, int W, int in_is_nchw, void* stream) {
+  GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(out);
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || ((H | W) & 1)) return GFR_E_SHAPE;
+  const long long total = (long long)N * C * ((H >> 1) + 1) * ((W >> 1) + 1);
+  s2d_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<float4*>(out), C, H, W, in_is_nchw, total);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_depth_to_space_pad(const float* g, float* out, int N, int C, int H, int W, int out_is_nchw, void* stream) {
+  GFR_RETURN_IF_NULL(g); GFR_RETURN_IF_NULL(out);
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || ((H | W) & 1)) return GFR_E_SHAPE;
+  const long long total = (long long)N * C * H * W;
+  d2s_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(g), out, C, H, W, out_is_nchw, total);
   return gfr_launch_status();
 }

@@ -72,6 +72,8 @@ class RelightNet(nn.Module):
                                               # head kernel paid, so the two-launch tail stays the default
         self.tc_precision = 2                 # eval-mode convs: 2 = fp16 pair split (~22-bit products, half the operand bytes; needs
                                               # |activation| < 4094 — checked on the device, see range_check), 3 = 3xTF32, 1 = TF32
+        self.train_precision = 3              # train-mode conv operands: 3 = 3xTF32 (fp32-grade: the parity tests), 4 = bf16 with fp32
+                                              # accumulation (BASELINE configs[2] "bf16 CNN / fp32 ray-march"), 1 = TF32
         self.p16 = True                       # precision 2 on PRE-SPLIT fp16-pair activations (csrc/conv_p16.cu); False: the first-
                                               # generation kernel that splits fp32 C4 tiles in shared memory (kept for A/B runs)
         self.range_check = True               # precision 2: every conv output is range-checked on the device; an eager forward
@@ -417,7 +419,7 @@ class RelightNet(nn.Module):
         def unit(name, x, res=None, post=None, post_shift=0, act=1):
             mod, bn = getattr(self, name), getattr(self, _bn_name(name))
             meta = dict(cin=mod.in_channels, cout=mod.out_channels, deconv=isinstance(mod, nn.ConvTranspose2d), act=act,
-                        post_shift=post_shift, bn=bn)
+                        post_shift=post_shift, bn=bn, precision=self.train_precision)
             w, b = mod.weight, mod.bias
             if w.shape[-1] == 1:          # lighting-transfer 1x1 shortcut (TRAIN_LT:63-69,93-103,146-156): the centre tap of a 3x3
                 w = torch.nn.functional.pad(w, (1, 1, 1, 1))        # kernel, differentiably (its gradient is the centre of the 3x3 one)

@@ -19,26 +19,52 @@ def _chk(rc, what, n=1):
     ops._count(n)
 
 
-def _pack_dev(w, deconv, dgrad, Cin, Cout, NT):
+def _pack_dev(w, deconv, dgrad, Cin, Cout, NT, taps=9, precision=3):
+    """Device-side packing of the layer parameter for the tensor-core conv (forward or data-gradient operand)."""
     O, I = (Cin, Cout) if dgrad else (Cout, Cin)
-    n = _lib.load().gfr_conv_tc_pack_size(I, O, NT)
+    n = _lib.load().gfr_conv_tc_pack_size_ex(I, O, NT, taps, precision)
     packed = torch.empty(n, dtype=torch.float32, device=w.device)
-    _chk(_lib.load().gfr_conv_tc_pack_weights_dev(_ptr(w), int(deconv), int(dgrad), Cin, Cout, NT, _ptr(packed), _stream()),
-         "gfr_conv_tc_pack_weights_dev")
+    _chk(_lib.load().gfr_conv_tc_pack_weights_dev_ex(_ptr(w), int(deconv), int(dgrad), Cin, Cout, NT, taps, precision, _ptr(packed),
+                                                     _stream()), "gfr_conv_tc_pack_weights_dev_ex")
     return packed
 
 
-def _nt_for(cout):
+def _nt_for(cout, taps=9, precision=3):
+    """Output channels per CTA tile.  bf16 accumulates in TMEM and reads it in 16-column groups, so wide tiles (up to 128)
+    amortise the A-operand reads; the fp32-grade kinds keep per-step register accumulators (<= 64)."""
+    if precision == 4:
+        if taps == 4:
+            return 16 if cout <= 16 else (64 if cout <= 64 else 128)
+        return 16 if cout <= 16 else (32 if cout <= 32 else (64 if cout <= 64 else 128))
+    if taps == 4:
+        return 16 if cout <= 16 else 64
     return 16 if cout <= 16 else 32
 
 
-def _conv_raw(x_data, cin, packed, bias, Cout, NT):
-    """raw = conv3x3(x[:, :cin]) + bias on the tensor cores (3xTF32), C4 in / C4 out."""
-    N, G, H, W, _ = x_data.shape
+def _conv_raw(x_data, cin, packed, bias, Cout, NT, taps=9, org=1, precision=3, act=0):
+    """raw = conv(x[:, :cin]) + bias on the tensor cores, C4 in / C4 out.  taps 9: 3x3 / pad 1; taps 4: the 2x2-tap layers
+    (org 0: (H+1)x(W+1) -> HxW, org 1: HxW -> (H+1)x(W+1))."""
+    N, G, Hin, Win, _ = x_data.shape
+    H, W = (Hin, Win) if taps == 9 else ((Hin - 1, Win - 1) if org == 0 else (Hin + 1, Win + 1))
     out = torch.empty((N, (Cout + 3) // 4, H, W, 4), dtype=torch.float32, device=x_data.device)
-    _chk(_lib.load().gfr_conv3x3_tc_fwd(_ptr(x_data), _ptr(packed), _ptr(bias), None, None, _ptr(out), N, cin, G, Cout, H, W, NT,
-                                        0, 0, 1.0, 3, 0, 1.0, 1.0, _stream()), "gfr_conv3x3_tc_fwd")
+    _chk(_lib.load().gfr_conv_tc_fwd_ex(_ptr(x_data), _ptr(packed), _ptr(bias), None, None, _ptr(out), N, cin, G, Cout, Hin, Win, H, W,
+                                        NT, taps, org, 0, int(act), 1.0, int(precision), 0, _stream()), "gfr_conv_tc_fwd_ex")
     return out
+
+
+def _wgrad(x, g_raw, w, deconv, cin, Cout, taps=9):
+    """(g_w, g_b) of the conv layer from its input and dL/d(conv output) (fp32, CUDA cores)."""
+    N, G = x.shape[0], x.shape[1]
+    H, W = g_raw.shape[2], g_raw.shape[3]
+    g_w = torch.zeros_like(w)
+    g_b4 = torch.zeros(((Cout + 3) // 4) * 4, dtype=torch.float32, device=x.device)
+    if taps == 9:
+        _chk(_lib.load().gfr_conv3x3_wgrad(_ptr(x), _ptr(g_raw), _ptr(g_w), _ptr(g_b4), int(deconv), N, cin, G, Cout, H, W, _stream()),
+             "gfr_conv3x3_wgrad", 2)
+    else:
+        _chk(_lib.load().gfr_conv2x2_wgrad(_ptr(x), _ptr(g_raw), _ptr(g_w), _ptr(g_b4), N, cin, G, Cout, H, W, _stream()),
+             "gfr_conv2x2_wgrad", 2)
+    return g_w, g_b4[:Cout].contiguous()
 
 
 class _BN:
@@ -98,8 +124,9 @@ class ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, res, post, meta):
         cin, Cout, deconv, act, post_shift, bn = meta["cin"], meta["cout"], meta["deconv"], meta["act"], meta["post_shift"], meta["bn"]
-        NT = _nt_for(Cout)
-        raw = _conv_raw(x, cin, _pack_dev(w, deconv, False, cin, Cout, NT), b, Cout, NT)
+        taps, prec = meta.get("taps", 9), meta.get("precision", 3)
+        NT = _nt_for(Cout, taps, prec)
+        raw = _conv_raw(x, cin, _pack_dev(w, deconv, False, cin, Cout, NT, taps, prec), b, Cout, NT, taps, 0 if taps == 4 else 1, prec)
         mean, rstd, scale, shift = _BN.stats(raw, Cout, bn)
         y = _BN.apply(raw, Cout, scale, shift, res, post, post_shift, act)
         ctx.save_for_backward(x, w, raw, res, mean, rstd, scale, shift, gamma)
@@ -112,6 +139,7 @@ class ConvBNAct(torch.autograd.Function):
         x, w, raw, res, mean, rstd, scale, shift, gamma = ctx.saved_tensors
         m = ctx.meta
         cin, Cout, deconv, act, post_shift = m["cin"], m["cout"], m["deconv"], m["act"], m["post_shift"]
+        taps, prec = m.get("taps", 9), m.get("precision", 3)
         has_res, has_post = ctx.has
         g_y = g_y.contiguous()
         N, G, H, W, _ = x.shape
@@ -122,9 +150,9 @@ class ConvBNAct(torch.autograd.Function):
         # data gradient: the same tensor-core convolution, Cout -> cin, transposed + flipped kernel
         g_x = None
         if ctx.needs_input_grad[0]:
-            NTd = _nt_for(cin)
+            NTd = _nt_for(cin, taps, prec)
             zero_b = torch.zeros(cin, dtype=torch.float32, device=x.device)
-            g_in = _conv_raw(g_raw, Cout, _pack_dev(w, deconv, True, cin, Cout, NTd), zero_b, cin, NTd)
+            g_in = _conv_raw(g_raw, Cout, _pack_dev(w, deconv, True, cin, Cout, NTd, taps, prec), zero_b, cin, NTd, taps, 1, prec)
             if g_in.shape[1] == G:
                 g_x = g_in
             else:                                   # the layer read only the leading channels of a wider tensor (TRAIN:225)
@@ -132,11 +160,7 @@ class ConvBNAct(torch.autograd.Function):
                 g_x[:, :g_in.shape[1]] = g_in
         g_w = g_b = None
         if ctx.needs_input_grad[1]:          # frozen weights (the generator's pass through the discriminator) skip the wgrad
-            g_w = torch.zeros_like(w)
-            g_b4 = torch.zeros(((Cout + 3) // 4) * 4, dtype=torch.float32, device=x.device)
-            _chk(_lib.load().gfr_conv3x3_wgrad(_ptr(x), _ptr(g_raw), _ptr(g_w), _ptr(g_b4), int(deconv), N, cin, G, Cout, H, W,
-                                               _stream()), "gfr_conv3x3_wgrad", 2)
-            g_b = g_b4[:Cout].contiguous()
+            g_w, g_b = _wgrad(x, g_raw, w, deconv, cin, Cout, taps)
         return g_x, g_w, g_b, g_gamma, g_beta, g_res, g_post, None
 
 

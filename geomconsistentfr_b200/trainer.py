@@ -103,6 +103,7 @@ class TrainStep(GeneratorStep):
     def __init__(self, net, patchgan, intrinsic_matrix, lr=None, group=None):
         super().__init__(net, intrinsic_matrix, lr, group)
         self.D = patchgan.train()
+        self.D.train_precision = getattr(net, "train_precision", 3)          # one operand precision for both networks
         self.opt_d = FlatAdam(list(patchgan.parameters()), lr=net.lr if lr is None else lr)      # TRAIN:590
         self.GD_ratio = net.GD_ratio
 

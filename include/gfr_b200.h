@@ -174,6 +174,20 @@ int gfr_adam_step_segments(float* params, const float* grads, float* exp_avg, fl
 int gfr_conv_tc_pack_weights_dev(const float* w, int is_transposed_conv, int for_dgrad, int Cin, int Cout, int NT,
                                  float* packed, void* stream);
 
+/* The general forms (training path).  taps 9 = 3x3 / pad 1; taps 4 = 2x2 taps over k x k = 2 x 2 parameters [O][I][2][2]:
+ * PatchGAN's 4x4 / stride 2 / pad 1 layers (TRAIN:18-27) are 2x2-tap convolutions over the space-to-depth of the 1-padded
+ * input (gfr_space_to_depth_pad) with NO structurally-zero weights.  precision 1 TF32 | 3 3xTF32 | 4 bf16 (one bf16 operand
+ * per side, fp32 accumulation in TMEM — BASELINE configs[2] "bf16 CNN").  NT 16|32|64|128 (128: bf16 only; 2x2 taps: 16|64|128).
+ * gfr_conv_tc_pack_size_ex returns FLOATS.  gfr_conv_tc_fwd_ex: out[y][x] = sum_taps w . in[y - org + ky][x - org + kx];
+ * taps 9: Hin = H, Win = W, org 1; taps 4: org 0 with (Hin, Win) = (H+1, W+1), or org 1 with (H, W) = (Hin+1, Win+1) (the
+ * data gradient of the former).  Epilogue as gfr_conv3x3_tc_fwd. */
+long long gfr_conv_tc_pack_size_ex(int Cin, int Cout, int NT, int taps, int precision);
+int gfr_conv_tc_pack_weights_dev_ex(const float* w, int is_transposed_conv, int for_dgrad, int Cin, int Cout, int NT, int taps,
+                                    int precision, float* packed, void* stream);
+int gfr_conv_tc_fwd_ex(const float* in, const float* w_packed, const float* bias, const float* res, const float* post, float* out,
+                       int N, int Cin, int in_groups, int Cout, int Hin, int Win, int H, int W, int NT, int taps, int org,
+                       int post_shift, int act, float out_scale, int precision, int weights_static, void* stream);
+
 /* BatchNorm2d, training mode, part 1: batch statistics of x [N,C,H,W] (C4) -> mean, rstd = 1/sqrt(var_biased + eps),
  * scale = gamma*rstd, shift = beta - mean*scale (all [4*ceil(C/4)] floats, padded slots 0); running_mean/var (may be
  * NULL) are updated like torch (momentum, unbiased variance).  sums_scratch: 2*4*ceil(C/4) doubles. */
@@ -229,6 +243,17 @@ int gfr_stem_conv_wgrad(const float* img, const float* g_out, float* g_w, float*
  * gfr_depth_to_space is the inverse (= the backward). */
 int gfr_space_to_depth(const float* in, float* out, int N, int C, int H, int W, int in_is_nchw, void* stream);
 int gfr_depth_to_space(const float* g, float* out, int N, int C, int H, int W, int out_is_nchw, void* stream);
+
+/* The same over the 1-PADDED input: out [N,4C,H/2+1,W/2+1] with out[n][c][y'][x'][2dy+dx] = Xpad[2y'+dy][2x'+dx],
+ * Xpad[r][s] = X[r-1][s-1] (0 outside).  A 4x4 / stride 2 / pad 1 convolution of X (TRAIN:18-27) is a 2x2-tap / stride 1
+ * convolution of `out` (gfr_conv_tc_fwd_ex, taps 4) with weights W'[co][4c+2dy+dx][a][b] = w[co][c][2a+dy][2b+dx]: no
+ * structurally-zero weights (the 3x3 form above multiplies 5/9 zeros).  gfr_depth_to_space_pad is its backward
+ * (g [N,4C,H/2+1,W/2+1] -> [N,C,H,W]); gfr_conv2x2_wgrad the weight gradient of the 2x2-tap layer (in [N,Cin,H+1,W+1],
+ * g_out [N,Cout,H,W], g_w [Cout,Cin,2,2] +=). */
+int gfr_space_to_depth_pad(const float* in, float* out, int N, int C, int H, int W, int in_is_nchw, void* stream);
+int gfr_depth_to_space_pad(const float* g, float* out, int N, int C, int H, int W, int out_is_nchw, void* stream);
+int gfr_conv2x2_wgrad(const float* in, const float* g_out, float* g_w, float* g_bias, int N, int Cin, int in_groups, int Cout,
+                      int H, int W, void* stream);
 
 /* g_pre = g_y * (y > 0 ? 1 : 0.2): backward of y = LeakyReLU(pre, 0.2) from the forward OUTPUT (n_floats % 4 == 0). */
 int gfr_lrelu_bwd_c4(const float* y, const float* g_y, float* g_pre, long long n_floats, void* stream);

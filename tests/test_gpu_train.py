@@ -265,3 +265,56 @@ def test_full_train_iteration_losses_vs_oracle():
     moved = sum(float((p.detach().cpu() - d_sd[n]).abs().max()) > 0 for n, p in D.named_parameters())
     assert moved >= 10 and all(torch.isfinite(p).all() for p in D.parameters())
     assert torch.isfinite(total)
+
+
+def test_patchgan_bf16_mode_vs_oracle():
+    """BASELINE configs[2] "bf16 CNN": the same PatchGAN with bf16 conv operands (fp32 accumulation in TMEM, fp32 BatchNorm /
+    activations): logits and gradients agree with the fp32 oracle to bf16 accuracy (2^-8 per operand)."""
+    from geomconsistentfr_b200 import PatchGAN
+    from oracle import relight_oracle as O
+    torch.manual_seed(0)
+    ref = O.PatchGANOracle().cuda().train()
+    mine = PatchGAN().cuda().train()
+    mine.train_precision = 4
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    img = torch.rand(4, 3, 256, 256, device="cuda", generator=g)
+    Gl = torch.randn(4, 1, 15, 15, device="cuda", generator=g)
+    xr = img.clone().requires_grad_()
+    lr_ = ref(xr)
+    (lr_ * Gl).sum().backward()
+    xm = img.clone().requires_grad_()
+    lm = mine(xm)
+    assert _rel(lm.detach(), lr_.detach()) <= 3e-2
+    (lm * Gl).sum().backward()
+    l1 = lambda a, b: float((a - b).abs().sum() / b.abs().sum())
+    assert l1(xm.grad, xr.grad) <= 0.15                  # measured 0.086: four bf16 layers forward and backward (3xTF32: 2e-4)
+    for (n1, p1), (n2, p2) in zip(mine.named_parameters(), ref.named_parameters()):
+        if n1 in ("conv2.bias", "conv3.bias", "conv4.bias"):
+            continue
+        assert l1(p1.grad, p2.grad) <= 0.15, (n1, l1(p1.grad, p2.grad))
+
+
+@pytest.mark.parametrize("prec,tol", [(3, 2e-3), (4, 4e-2)])
+def test_conv_bn_act_unit_precisions_vs_torch_autograd(prec, tol):
+    """A RelightNet train unit (3x3) in 3xTF32 and in bf16 against torch fp64 autograd (L1-relative gradients)."""
+    from geomconsistentfr_b200 import ops, train_ops as T
+    g = torch.Generator(device="cuda").manual_seed(prec)
+    N, cin, cout, S = 3, 32, 64, 32
+    mod = torch.nn.Conv2d(cin, cout, 3, padding=1).cuda().double()
+    bn = torch.nn.BatchNorm2d(cout).cuda().double()
+    x = torch.randn(N, cin, S, S, device="cuda", generator=g)
+    Gy = torch.randn(N, cout, S, S, device="cuda", generator=g)
+    xr = x.double().requires_grad_()
+    y_ref = F.leaky_relu(bn(mod(xr)), 0.2)
+    (y_ref * Gy.double()).sum().backward()
+    bn2 = torch.nn.BatchNorm2d(cout).cuda()
+    w, b = mod.weight.detach().float().requires_grad_(), mod.bias.detach().float().requires_grad_()
+    xc = ops.nchw_to_c4(x).data.requires_grad_()
+    meta = dict(cin=cin, cout=cout, deconv=False, act=1, post_shift=0, bn=bn2, precision=prec)
+    y = T.ConvBNAct.apply(xc, w, b, bn2.weight, bn2.bias, None, None, meta)
+    l1 = lambda a, r: float((a.double() - r).abs().sum() / r.abs().sum())
+    assert l1(ops.c4_to_nchw(ops.C4(y.detach(), cout)), y_ref.detach()) <= tol
+    (y * ops.nchw_to_c4(Gy).data).sum().backward()
+    assert l1(w.grad, mod.weight.grad) <= tol and l1(ops.c4_to_nchw(ops.C4(xc.grad, cin)), xr.grad) <= tol
+    assert l1(bn2.weight.grad, bn.weight.grad) <= tol
