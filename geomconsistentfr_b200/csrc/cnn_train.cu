@@ -170,6 +170,7 @@ struct BnBwdArgs {
   float4* gx; float4* gres;    // apply phase outputs (gres may be null)
   int N, C4, HW, act, chunks;
   double count;
+  int C;                       // gamma_pad holds C floats when C > 0 (unpadded parameter), else C4*4
 };
 
 __device__ __forceinline__ void bn_gpre(const BnBwdArgs& a, size_t i, int g, float (&gp)[4], float (&xh)[4]) {
@@ -236,7 +237,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   for (int e = 0; e < 4; ++e) {
     const int c = g * 4 + e;
     const float sg = (float)(a.sums[c] / a.count), sgx = (float)(a.sums[a.C4 * 4 + c] / a.count);
-    out[e] = __ldg(a.gamma_pad + c) * __ldg(a.rstd + c) * (gp[e] - sg - xh[e] * sgx);
+    const float gam = (a.C > 0 && c >= a.C) ? 0.f : __ldg(a.gamma_pad + c);
+    out[e] = gam * __ldg(a.rstd + c) * (gp[e] - sg - xh[e] * sgx);
   }
   a.gx[i] = make_float4(out[0], out[1], out[2], out[3]);
 }
@@ -321,7 +323,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
 }
 
 // per-channel sum of a C4 tensor (bias gradient): sums[C4*4] += sum over (N,H,W)
-__global__ void __launch_bounds__(256) channel_sum_kernel(const float4* __restrict__ x, float* __restrict__ out, int C4, int HW, int chunks) {
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float4* __restrict__ x, float* __restrict__ out, int C4, int HW, int chunks,
+                                                          int C) {
   __shared__ float s_red[4][8];
   const int g = blockIdx.y, n = blockIdx.z;
   const int per = (HW + chunks - 1) / chunks;
@@ -341,8 +344,16 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const float4* __restri
   if (threadIdx.x < 4) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += s_red[threadIdx.x][w];
-    atomicAdd(out + g * 4 + threadIdx.x, t);
+    if (g * 4 + (int)threadIdx.x < C) atomicAdd(out + g * 4 + threadIdx.x, t);       // `out` may be exactly C floats long
   }
+}
+
+// gamma / beta gradients of a train-mode BatchNorm from the backward's fp64 sums: g_beta[c] += sums[0][c], g_gamma[c] += sums[1][c]
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, float* __restrict__ g_gamma, float* __restrict__ g_beta, int C, int Cpad) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (g_beta) g_beta[c] += (float)sums[c];
+  if (g_gamma) g_gamma[c] += (float)sums[Cpad + c];
 }
 
 // ------------------------------------------------------------------------------------------------- pools
@@ -748,10 +759,30 @@ extern "C" int gfr_bn_apply_bwd(const float* x, const float* res, const float* g
   if (e != cudaSuccess) return (int)e;
   BnBwdArgs a{reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(res), reinterpret_cast<const float4*>(g_y), scale,
               shift, mean, rstd, gamma_pad, sums_scratch, reinterpret_cast<float4*>(g_x), reinterpret_cast<float4*>(g_res), N, C4, HW, act,
-              chunks_for(N, C4, HW), (double)N * HW};
+              chunks_for(N, C4, HW), (double)N * HW, 0};
   bn_bwd_reduce_kernel<<<dim3(a.chunks, C4, N), 256, 0, s>>>(a);
   const long long total = (long long)N * C4 * HW;
   bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_bn_apply_bwd_ex(const float* x, const float* res, const float* g_y, const float* scale, const float* shift,
+                                   const float* mean, const float* rstd, const float* gamma, double* sums_scratch, float* g_x,
+                                   float* g_res, float* g_gamma, float* g_beta, int N, int C, int H, int W, int act, void* stream) {
+  GFR_RETURN_IF_NULL(x); GFR_RETURN_IF_NULL(g_y); GFR_RETURN_IF_NULL(scale); GFR_RETURN_IF_NULL(shift); GFR_RETURN_IF_NULL(mean);
+  GFR_RETURN_IF_NULL(rstd); GFR_RETURN_IF_NULL(gamma); GFR_RETURN_IF_NULL(sums_scratch); GFR_RETURN_IF_NULL(g_x);
+  if (N <= 0 || N > 65535 || C <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
+  const int C4 = (C + 3) / 4, HW = H * W;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums_scratch, 0, (size_t)2 * C4 * 4 * sizeof(double), s);
+  if (e != cudaSuccess) return (int)e;
+  BnBwdArgs a{reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(res), reinterpret_cast<const float4*>(g_y), scale,
+              shift, mean, rstd, gamma, sums_scratch, reinterpret_cast<float4*>(g_x), reinterpret_cast<float4*>(g_res), N, C4, HW, act,
+              chunks_for(N, C4, HW), (double)N * HW, C};
+  bn_bwd_reduce_kernel<<<dim3(a.chunks, C4, N), 256, 0, s>>>(a);
+  const long long total = (long long)N * C4 * HW;
+  bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
+  if (g_gamma || g_beta) bn_param_grads_kernel<<<gfr_ceil_div(C, 128), 128, 0, s>>>(sums_scratch, g_gamma, g_beta, C, C4 * 4);
   return gfr_launch_status();
 }
 
@@ -776,8 +807,16 @@ static int wgrad_launch(const float* in, const float* g_out, float* g_w, float* 
   else wgrad_kernel<2><<<dim3(gx, gy, gz), 256, 0, s>>>(a);
   if (g_bias) {
     const int C4 = (Cout + 3) / 4, chunks = chunks_for(N, C4, H * W);
-    channel_sum_kernel<<<dim3(chunks, C4, N), 256, 0, s>>>(reinterpret_cast<const float4*>(g_out), g_bias, C4, H * W, chunks);
+    channel_sum_kernel<<<dim3(chunks, C4, N), 256, 0, s>>>(reinterpret_cast<const float4*>(g_out), g_bias, C4, H * W, chunks, Cout);
   }
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_channel_sum_c4(const float* x, float* out, int N, int C, int H, int W, void* stream) {
+  GFR_RETURN_IF_NULL(x); GFR_RETURN_IF_NULL(out);
+  if (N <= 0 || N > 65535 || C <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
+  const int C4 = (C + 3) / 4, chunks = chunks_for(N, C4, H * W);
+  channel_sum_kernel<<<dim3(chunks, C4, N), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), out, C4, H * W, chunks, C);
   return gfr_launch_status();
 }
 

@@ -53,13 +53,13 @@ class _ConvLReLU(torch.autograd.Function):
         NT = train_ops._nt_for(cout, 4, prec)
         packed = train_ops._pack_dev(w, False, False, cin, cout, NT, 4, prec)
         y = train_ops._conv_raw(x, cin, packed, b, cout, NT, 4, 0, prec, act=1)
-        ctx.save_for_backward(x, w, y)
+        ctx.save_for_backward(x, w, y, b)
         ctx.cfg = (cin, cout, prec)
         return y
 
     @staticmethod
     def backward(ctx, g_y):
-        x, w, y = ctx.saved_tensors
+        x, w, y, b = ctx.saved_tensors
         cin, cout, prec = ctx.cfg
         g_raw = torch.empty_like(y)
         _chk(_lib.load().gfr_lrelu_bwd_c4(_ptr(y), _ptr(g_y.contiguous()), _ptr(g_raw), y.numel(), _stream()), "gfr_lrelu_bwd_c4")
@@ -70,7 +70,7 @@ class _ConvLReLU(torch.autograd.Function):
             g_x = train_ops._conv_raw(g_raw, cout, train_ops._pack_dev(w, False, True, cin, cout, NTd, 4, prec), zero_b, cin, NTd, 4, 1, prec)
         g_w = g_b = None
         if ctx.needs_input_grad[1]:
-            g_w, g_b = train_ops._wgrad(x, g_raw, w, False, cin, cout, 4)
+            g_w, g_b = train_ops._wgrad(x, g_raw, w, b, False, cin, cout, 4, prec)
         return g_x, g_w, g_b, None, None, None
 
 

@@ -52,19 +52,48 @@ def _conv_raw(x_data, cin, packed, bias, Cout, NT, taps=9, org=1, precision=3, a
     return out
 
 
-def _wgrad(x, g_raw, w, deconv, cin, Cout, taps=9):
-    """(g_w, g_b) of the conv layer from its input and dL/d(conv output) (fp32, CUDA cores)."""
+def _grad_target(p, like=None):
+    """Where a parameter gradient is accumulated.  A leaf parameter whose .grad already exists (FlatAdam keeps every .grad as a
+    view of ONE flat buffer, zeroed once per step) is accumulated IN PLACE by the kernels (they all `+=`), and the autograd
+    Function returns None for it: no zeros() temporary, no fill, no AccumulateGrad add per parameter — ~600 tiny launches per
+    training iteration.  Otherwise a fresh zero tensor that autograd accumulates as usual.  -> (tensor, direct)"""
+    if p is not None and p.is_leaf and p.requires_grad and p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32:
+        return p.grad, True
+    ref = p if like is None else like
+    return torch.zeros(ref.shape, dtype=torch.float32, device=ref.device), False
+
+
+_ZEROS = {}
+
+
+def _zeros(n, device):
+    """A cached all-zero vector (the bias operand of the data-gradient convolutions)."""
+    z = _ZEROS.get(device)
+    if z is None or z.numel() < n:
+        z = _ZEROS[device] = torch.zeros(max(n, 2048), dtype=torch.float32, device=device)
+    return z
+
+
+def _wgrad(x, g_raw, w, b, deconv, cin, Cout, taps=9, precision=3):
+    """Weight / bias gradient of the conv layer from its input and dL/d(conv output) -> (g_w, g_b) to return from the autograd
+    Function (None where the gradient went straight into the parameter's .grad).  precision 4: bf16 on the tensor cores
+    (csrc/wgrad_tc.cu); otherwise fp32 on CUDA cores."""
     N, G = x.shape[0], x.shape[1]
     H, W = g_raw.shape[2], g_raw.shape[3]
-    g_w = torch.zeros_like(w)
-    g_b4 = torch.zeros(((Cout + 3) // 4) * 4, dtype=torch.float32, device=x.device)
-    if taps == 9:
-        _chk(_lib.load().gfr_conv3x3_wgrad(_ptr(x), _ptr(g_raw), _ptr(g_w), _ptr(g_b4), int(deconv), N, cin, G, Cout, H, W, _stream()),
+    g_w, dw = _grad_target(w)
+    g_b, db = _grad_target(b) if b.requires_grad else (None, True)
+    if precision == 4:
+        _chk(_lib.load().gfr_conv_wgrad_tc_bf16(_ptr(x), _ptr(g_raw), _ptr(g_w), int(deconv), N, cin, G, Cout, x.shape[2], x.shape[3],
+                                                H, W, taps, _stream()), "gfr_conv_wgrad_tc_bf16")
+        if g_b is not None:
+            _chk(_lib.load().gfr_channel_sum_c4(_ptr(g_raw), _ptr(g_b), N, Cout, H, W, _stream()), "gfr_channel_sum_c4")
+    elif taps == 9:
+        _chk(_lib.load().gfr_conv3x3_wgrad(_ptr(x), _ptr(g_raw), _ptr(g_w), _ptr(g_b), int(deconv), N, cin, G, Cout, H, W, _stream()),
              "gfr_conv3x3_wgrad", 2)
     else:
-        _chk(_lib.load().gfr_conv2x2_wgrad(_ptr(x), _ptr(g_raw), _ptr(g_w), _ptr(g_b4), N, cin, G, Cout, H, W, _stream()),
+        _chk(_lib.load().gfr_conv2x2_wgrad(_ptr(x), _ptr(g_raw), _ptr(g_w), _ptr(g_b), N, cin, G, Cout, H, W, _stream()),
              "gfr_conv2x2_wgrad", 2)
-    return g_w, g_b4[:Cout].contiguous()
+    return (None if dw else g_w), (None if db else g_b)
 
 
 class _BN:
@@ -95,20 +124,19 @@ class _BN:
         return y
 
     @staticmethod
-    def backward(raw, C, res, g_y, mean, rstd, scale, shift, gamma, act, want_res):
-        """-> g_raw, g_res, g_gamma, g_beta"""
+    def backward(raw, C, res, g_y, mean, rstd, scale, shift, gamma, act, want_res, beta=None):
+        """-> g_raw, g_res, g_gamma, g_beta (the last two None when they were accumulated straight into gamma.grad / beta.grad)"""
         N, G, H, W, _ = raw.shape
         dev = raw.device
-        gamma_pad = torch.zeros(G * 4, dtype=torch.float32, device=dev)
-        gamma_pad[:C] = gamma
         sums = torch.empty(2 * G * 4, dtype=torch.float64, device=dev)
         g_raw = torch.empty_like(raw)
         g_res = torch.empty_like(raw) if want_res else None
-        _chk(_lib.load().gfr_bn_apply_bwd(_ptr(raw), _ptr(res), _ptr(g_y), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
-                                          _ptr(gamma_pad), _ptr(sums), _ptr(g_raw), _ptr(g_res), N, C, H, W, int(act), _stream()),
-             "gfr_bn_apply_bwd", 2)
-        s = sums.view(2, G * 4)[:, :C].to(torch.float32)
-        return g_raw, g_res, s[1].contiguous(), s[0].contiguous()
+        g_gamma, dg = _grad_target(gamma)
+        g_beta, db = _grad_target(beta, like=gamma)
+        _chk(_lib.load().gfr_bn_apply_bwd_ex(_ptr(raw), _ptr(res), _ptr(g_y), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
+                                             _ptr(gamma.detach().contiguous()), _ptr(sums), _ptr(g_raw), _ptr(g_res), _ptr(g_gamma),
+                                             _ptr(g_beta), N, C, H, W, int(act), _stream()), "gfr_bn_apply_bwd_ex", 3)
+        return g_raw, g_res, (None if dg else g_gamma), (None if db else g_beta)
 
 
 def _sumpool2(g):
@@ -129,14 +157,14 @@ class ConvBNAct(torch.autograd.Function):
         raw = _conv_raw(x, cin, _pack_dev(w, deconv, False, cin, Cout, NT, taps, prec), b, Cout, NT, taps, 0 if taps == 4 else 1, prec)
         mean, rstd, scale, shift = _BN.stats(raw, Cout, bn)
         y = _BN.apply(raw, Cout, scale, shift, res, post, post_shift, act)
-        ctx.save_for_backward(x, w, raw, res, mean, rstd, scale, shift, gamma)
+        ctx.save_for_backward(x, w, raw, res, mean, rstd, scale, shift, gamma, beta, b)
         ctx.meta = meta
         ctx.has = (res is not None, post is not None)
         return y
 
     @staticmethod
     def backward(ctx, g_y):
-        x, w, raw, res, mean, rstd, scale, shift, gamma = ctx.saved_tensors
+        x, w, raw, res, mean, rstd, scale, shift, gamma, beta, b = ctx.saved_tensors
         m = ctx.meta
         cin, Cout, deconv, act, post_shift = m["cin"], m["cout"], m["deconv"], m["act"], m["post_shift"]
         taps, prec = m.get("taps", 9), m.get("precision", 3)
@@ -146,13 +174,12 @@ class ConvBNAct(torch.autograd.Function):
         g_post = None
         if has_post:
             g_post = _sumpool2(g_y) if post_shift else g_y
-        g_raw, g_res, g_gamma, g_beta = _BN.backward(raw, Cout, res, g_y, mean, rstd, scale, shift, gamma, act, has_res)
+        g_raw, g_res, g_gamma, g_beta = _BN.backward(raw, Cout, res, g_y, mean, rstd, scale, shift, gamma, act, has_res, beta)
         # data gradient: the same tensor-core convolution, Cout -> cin, transposed + flipped kernel
         g_x = None
         if ctx.needs_input_grad[0]:
             NTd = _nt_for(cin, taps, prec)
-            zero_b = torch.zeros(cin, dtype=torch.float32, device=x.device)
-            g_in = _conv_raw(g_raw, Cout, _pack_dev(w, deconv, True, cin, Cout, NTd, taps, prec), zero_b, cin, NTd, taps, 1, prec)
+            g_in = _conv_raw(g_raw, Cout, _pack_dev(w, deconv, True, cin, Cout, NTd, taps, prec), _zeros(cin, x.device), cin, NTd, taps, 1, prec)
             if g_in.shape[1] == G:
                 g_x = g_in
             else:                                   # the layer read only the leading channels of a wider tensor (TRAIN:225)
@@ -160,7 +187,7 @@ class ConvBNAct(torch.autograd.Function):
                 g_x[:, :g_in.shape[1]] = g_in
         g_w = g_b = None
         if ctx.needs_input_grad[1]:          # frozen weights (the generator's pass through the discriminator) skip the wgrad
-            g_w, g_b = _wgrad(x, g_raw, w, deconv, cin, Cout, taps)
+            g_w, g_b = _wgrad(x, g_raw, w, b, deconv, cin, Cout, taps, prec)
         return g_x, g_w, g_b, g_gamma, g_beta, g_res, g_post, None
 
 
@@ -174,18 +201,17 @@ class StemBNAct(torch.autograd.Function):
         _chk(_lib.load().gfr_stem_conv_train_fwd(_ptr(img), _ptr(w), _ptr(b), _ptr(raw), N, H, W, _stream()), "gfr_stem_conv_train_fwd")
         mean, rstd, scale, shift = _BN.stats(raw, 16, bn)
         y = _BN.apply(raw, 16, scale, shift, None, None, 0, 1)
-        ctx.save_for_backward(img, raw, mean, rstd, scale, shift, gamma)
+        ctx.save_for_backward(img, raw, mean, rstd, scale, shift, gamma, beta, w, b)
         return y
 
     @staticmethod
     def backward(ctx, g_y):
-        img, raw, mean, rstd, scale, shift, gamma = ctx.saved_tensors
+        img, raw, mean, rstd, scale, shift, gamma, beta, w, b = ctx.saved_tensors
         N, H, W, _ = img.shape
-        g_raw, _, g_gamma, g_beta = _BN.backward(raw, 16, None, g_y.contiguous(), mean, rstd, scale, shift, gamma, 1, False)
-        g_w = torch.zeros((16, 3, 5, 5), dtype=torch.float32, device=img.device)
-        g_b = torch.zeros(16, dtype=torch.float32, device=img.device)
+        g_raw, _, g_gamma, g_beta = _BN.backward(raw, 16, None, g_y.contiguous(), mean, rstd, scale, shift, gamma, 1, False, beta)
+        (g_w, dw), (g_b, db) = _grad_target(w), _grad_target(b)
         _chk(_lib.load().gfr_stem_conv_wgrad(_ptr(img), _ptr(g_raw), _ptr(g_w), _ptr(g_b), N, H, W, _stream()), "gfr_stem_conv_wgrad")
-        return None, g_w, g_b, g_gamma, g_beta, None
+        return None, (None if dw else g_w), (None if db else g_b), g_gamma, g_beta, None
 
 
 class MaxPool2(torch.autograd.Function):
@@ -232,20 +258,20 @@ class PwConvBNAct(torch.autograd.Function):
         _chk(_lib.load().gfr_pw_conv16_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(raw), N, 16, H, W, 0, 0, 1.0, _stream()), "gfr_pw_conv16_fwd")
         mean, rstd, scale, shift = _BN.stats(raw, 16, bn)
         y = _BN.apply(raw, 16, scale, shift, None, None, 0, 1)
-        ctx.save_for_backward(x, w, raw, mean, rstd, scale, shift, gamma)
+        ctx.save_for_backward(x, w, raw, mean, rstd, scale, shift, gamma, beta, b)
         return y
 
     @staticmethod
     def backward(ctx, g_y):
-        x, w, raw, mean, rstd, scale, shift, gamma = ctx.saved_tensors
+        x, w, raw, mean, rstd, scale, shift, gamma, beta, b = ctx.saved_tensors
         N, G, H, W, _ = x.shape
-        g_raw, _, g_gamma, g_beta = _BN.backward(raw, 16, None, g_y.contiguous(), mean, rstd, scale, shift, gamma, 1, False)
+        g_raw, _, g_gamma, g_beta = _BN.backward(raw, 16, None, g_y.contiguous(), mean, rstd, scale, shift, gamma, 1, False, beta)
         g_x = torch.empty_like(x)
-        g_w = torch.zeros_like(w)
-        g_b = torch.zeros(16, dtype=torch.float32, device=x.device)
+        g_w = torch.zeros_like(w)                    # (w is a .view() of the parameter: not a leaf, autograd routes it)
+        (g_b, db) = _grad_target(b)
         _chk(_lib.load().gfr_pw_conv16_bwd(_ptr(x), _ptr(w), _ptr(g_raw), None, _ptr(g_x), _ptr(g_w), _ptr(g_b), N, 16, H, W, 0, 0,
                                            1.0, _stream()), "gfr_pw_conv16_bwd")
-        return g_x, g_w, g_b, g_gamma, g_beta, None
+        return g_x, g_w, (None if db else g_b), g_gamma, g_beta, None
 
 
 class PwHead(torch.autograd.Function):

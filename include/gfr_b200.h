@@ -208,11 +208,27 @@ int gfr_bn_apply_bwd(const float* x, const float* res, const float* g_y, const f
                      const float* mean, const float* rstd, const float* gamma_pad, double* sums_scratch, float* g_x,
                      float* g_res, int N, int C, int H, int W, int act, void* stream);
 
+/* gfr_bn_apply_bwd with the UNPADDED parameter gamma [C] and the parameter gradients accumulated in place:
+ * g_gamma[c] += sum g_pre*xhat, g_beta[c] += sum g_pre (either may be NULL) — the optimiser's flat gradient buffer can be
+ * passed directly (no temporaries, no separate add). */
+int gfr_bn_apply_bwd_ex(const float* x, const float* res, const float* g_y, const float* scale, const float* shift,
+                        const float* mean, const float* rstd, const float* gamma, double* sums_scratch, float* g_x,
+                        float* g_res, float* g_gamma, float* g_beta, int N, int C, int H, int W, int act, void* stream);
+
 /* Weight (and bias) gradient of a 3x3 stride-1 convolution: g_w (+=, parameter layout: Conv2d [Cout,Cin,3,3] or
- * ConvTranspose2d [Cin,Cout,3,3]) and g_bias [4*ceil(Cout/4)] (+=, may be NULL) from the layer input `in`
+ * ConvTranspose2d [Cin,Cout,3,3]) and g_bias [Cout] (+=, may be NULL) from the layer input `in`
  * (in_groups as in gfr_conv3x3_tc_fwd) and g_out = dL/d(conv output).  fp32 on CUDA cores. */
 int gfr_conv3x3_wgrad(const float* in, const float* g_out, float* g_w, float* g_bias, int is_transposed_conv, int N,
                       int Cin, int in_groups, int Cout, int H, int W, void* stream);
+
+/* The same weight gradient on the tensor cores with bf16 operands and fp32 accumulation in TMEM (train_precision 4,
+ * BASELINE configs[2] "bf16 CNN"): per filter tap a GEMM over PIXELS whose operands are the C4 tensors themselves as
+ * MN-major UMMA matrices (csrc/wgrad_tc.cu).  taps 9: 3x3 / pad 1 (Hin = H, Win = W); taps 4: the 2x2-tap layers
+ * (Hin = H+1, Win = W+1).  g_w (+=) in the parameter layout as gfr_conv3x3_wgrad; the bias gradient is
+ * gfr_channel_sum_c4(g_out): out[c] += sum over (N,H,W) of a C4 tensor, out exactly C floats. */
+int gfr_conv_wgrad_tc_bf16(const float* in, const float* g_out, float* g_w, int is_transposed_conv, int N, int Cin,
+                           int in_groups, int Cout, int Hin, int Win, int H, int W, int taps, void* stream);
+int gfr_channel_sum_c4(const float* x, float* out, int N, int C, int H, int W, void* stream);
 
 /* 2x2 max-pool backward (gradient to the first maximum, like torch), 2x2 sum (backward of the nearest x2 upsample),
  * global average pool of channels [c_first, c_first+n_ch) of a C4 map -> [N,n_ch] and its backward (+= into g_feat). */
