@@ -12,6 +12,7 @@ from .relightnet import RelightNet, intrinsic_matrix  # noqa: F401
 from .runner import RelightRunner  # noqa: F401
 from .patchgan import PatchGAN  # noqa: F401
 from .inference import lighting_transfer, relight, relight_single_image  # noqa: F401
+from .lpips_metric import LPIPSAlex, masked_lpips  # noqa: F401
 from .autograd import ShadowMarch, ShadeRender, SSIMPlanes, MaskedLosses, FlatAdam, dssim_loss  # noqa: F401
 
 __version__ = "0.1.0"

@@ -90,6 +90,11 @@ _PROTOS = {
     "gfr_export_planes_u8": [_c_void_p] * 6 + [_c_int] + [_c_void_p] * 6 + [_c_int, _c_int, _c_int, _c_void_p],
     "gfr_masked_mse_u8": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_masked_ssim_u8": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+    "gfr_lpips_layer_fwd": [_c_void_p] * 4 + [_c_int] * 3 + [_c_void_p],
+    "gfr_lpips_layer_bwd": [_c_void_p] * 6 + [_c_int] * 3 + [_c_void_p],
+    "gfr_bilinear_up_add": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
+    "gfr_bilinear_up_add_bwd": [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p],
+    "gfr_lpips_masked_sums": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_border_median_fix_u8": [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
 }
 _RESTYPES = {"gfr_error_string": ctypes.c_char_p, "gfr_conv_tc_pack_size": ctypes.c_longlong,

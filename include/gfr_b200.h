@@ -468,6 +468,20 @@ int gfr_masked_mse_u8(const uint8_t* recon, const uint8_t* gt, const uint8_t* ma
 int gfr_masked_ssim_u8(const uint8_t* recon, const uint8_t* gt, const uint8_t* mask, int mask_batch_stride, double* sums,
                        int B, int H, int W, int window_3d, void* stream);
 
+/* LPIPS (PerceptualSimilarity/lpips/lpips.py:112-144; test_network.py:41-48), the metric's own arithmetic, forward and backward.
+ * gfr_lpips_layer_fwd: out[n,p] = sum_c w[c] (f0[n,c,p]/(|f0[n,:,p]|+1e-10) - f1[n,c,p]/(|f1[n,:,p]|+1e-10))^2 for NCHW feature
+ * maps f0, f1 [N,C,HW] (normalize_tensor + squared difference + the learned 1x1 `lin` head).  gfr_lpips_layer_bwd: g_f0 / g_f1
+ * (either may be NULL) from g_out [N,HW].  gfr_bilinear_up_add: out[N,H,W] += nn.Upsample(size=(H,W), mode='bilinear',
+ * align_corners=False)(m[N,h,w]); _bwd: g_m (+=, zero it first) from g_out.  gfr_lpips_masked_sums: sums[n] = {sum(mask*map),
+ * count(mask*map > 0)} (mask float [H,W] with stride 0, or [N,H,W]); the metric of test_network.py:45 is sums[0]/sums[1]. */
+int gfr_lpips_layer_fwd(const float* f0, const float* f1, const float* w, float* out, int N, int C, int HW, void* stream);
+int gfr_lpips_layer_bwd(const float* f0, const float* f1, const float* w, const float* g_out, float* g_f0, float* g_f1, int N,
+                        int C, int HW, void* stream);
+int gfr_bilinear_up_add(const float* m, float* out, int N, int h, int w, int H, int W, void* stream);
+int gfr_bilinear_up_add_bwd(const float* g_out, float* g_m, int N, int h, int w, int H, int W, void* stream);
+int gfr_lpips_masked_sums(const float* map, const float* mask, int mask_batch_stride, double* sums, int N, int H, int W,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

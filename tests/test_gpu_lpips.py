@@ -1,0 +1,60 @@
+"""GPU: LPIPS-Alex spatial (lpips/lpips.py:112-144, test_network.py:39-45) on the library's kernels against the reference's
+VENDORED lpips module run unmodified (tests/golden/lpips.npz, oracle/make_golden_lpips.py): same seeded random AlexNet trunk
+(the ImageNet weights are not available offline), the SHIPPED linear heads; spatial map, masked metric and the gradient of the
+metric w.r.t. the predicted image ("LPIPS backward")."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _model():
+    from geomconsistentfr_b200.lpips_metric import LPIPSAlex
+    from oracle.make_golden_lpips import trunk_init
+    f = np.load(os.path.join(G, "lpips.npz"))
+    m = LPIPSAlex()
+    heads = {"lin%d.model.1.weight" % k: torch.from_numpy(f["lin%d" % k]).view(1, -1, 1, 1) for k in range(5)}
+    missing, unexpected = m.load_state_dict(heads, strict=False)          # what lpips.py:109 does with alex.pth
+    assert not unexpected and all(k.startswith(("net.", "scaling_layer.", "lins.")) for k in missing)
+    trunk_init(m.net)
+    return m.cuda(), f
+
+
+def test_spatial_map_metric_and_gradient_vs_vendored_lpips():
+    from geomconsistentfr_b200.lpips_metric import masked_lpips
+    from oracle.make_golden_lpips import case
+    m, f = _model()
+    ref, pred, mask = (t.cuda() for t in case())
+    pred = pred.clone().requires_grad_()
+    ex = m(ref, pred)
+    assert ex.shape == (2, 1, 256, 256)
+    want = f["map"]
+    assert np.abs(ex.detach().cpu().numpy() - want).max() <= 2e-5 * np.abs(want).max() + 1e-7
+    metric = masked_lpips(ex, mask)
+    assert np.abs(metric.cpu().numpy() - f["metric"]).max() <= 1e-5 * np.abs(f["metric"]).max()
+    # gradient of the metric (sum over the two images) w.r.t. the predicted image, through the kernels' backward
+    cnt = torch.stack([(mask * ex[i, 0] > 0).sum() for i in range(2)]).float()
+    (torch.stack([(mask * ex[i, 0]).sum() for i in range(2)]) / cnt).sum().backward()
+    g, gw = pred.grad.cpu().numpy()[:, :, ::2, ::2], f["grad_pred_s2"]
+    assert np.abs(g - gw).sum() / np.abs(gw).sum() <= 1e-3, np.abs(g - gw).sum() / np.abs(gw).sum()
+
+
+def test_lpips_properties():
+    m, _ = _model()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(1, 3, 128, 96, device="cuda", generator=g) * 2 - 1
+    y = torch.rand(1, 3, 128, 96, device="cuda", generator=g) * 2 - 1
+    assert float(m(x, x).abs().max()) == 0.0                                      # identical images: distance 0 everywhere
+    assert torch.allclose(m(x, y), m(y, x), atol=1e-7)                            # symmetric
+    assert float(m(x, y).min()) >= 0.0                                            # the shipped heads are non-negative
+    assert torch.allclose(m((x + 1) / 2, (y + 1) / 2, normalize=True), m(x, y), atol=1e-6)
