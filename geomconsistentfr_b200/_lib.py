@@ -38,7 +38,7 @@ _PROTOS = {
     "gfr_bn_train_stats": [_c_void_p] * 10 + [_c_int] * 4 + [_c_float, _c_float, _c_void_p],
     "gfr_bn_apply_fwd": [_c_void_p] * 6 + [_c_int] * 6 + [_c_void_p],
     "gfr_bn_apply_bwd": [_c_void_p] * 11 + [_c_int] * 5 + [_c_void_p],
-    "gfr_bn_apply_bwd_ex": [_c_void_p] * 13 + [_c_int] * 5 + [_c_void_p],
+    "gfr_bn_apply_bwd_ex": [_c_void_p] * 14 + [_c_int] * 5 + [_c_void_p],
     "gfr_conv_wgrad_tc_bf16": [_c_void_p] * 3 + [_c_int] * 10 + [_c_void_p],
     "gfr_channel_sum_c4": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_conv3x3_wgrad": [_c_void_p] * 4 + [_c_int] * 7 + [_c_void_p],

@@ -31,6 +31,7 @@ struct MarchArgs {
   int B, H, W, n;
   int lpf;                   // lights per face: (face, light) pair b reads depth / mask of face b / lpf
   float t0, inv_dt;          // uniform sample table t_k = t0 + k*dt (inv_dt = 0: not uniform, no sample-range culling)
+  int coarse;                // 1: the fast kernel builds the 8x8-block occupancy map and skips empty groups of 4 samples
   int fuse_shade;            // 1: normals + Lambert + blend + render of the pixel follow in the same thread (shade)
   gfr_shade::ShadeArgs shade;
   float bonus;
@@ -185,6 +186,40 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
     for (int i = threadIdx.y * TILE_W + threadIdx.x; i < words; i += TILE_W * TILE_H) s_mask[i] = __ldg(src + i);
   }
   __syncthreads();
+  // Coarse occupancy (a.coarse): one bit per 8x8-pixel block, set iff the block OR ANY OF ITS 8 NEIGHBOURS holds a mask pixel.
+  // A group of 4 consecutive samples stays within 3.2 pixels of its middle (1.5 dt x ray length <= 724 px at 512^2, + 0.5 for the
+  // nearest-pixel rounding), i.e. inside the 3x3 block neighbourhood of the middle's block: a clear bit proves that all 4
+  // nearest pixels are outside the face, so the warp skips the group (their distance is 1e6 anyway, TRAIN:510-512).
+  uint32_t* s_occ = s_mask + words;              // (H/8) x (W/8) bits, rows of W/256-rounded-up words... one word per 32 blocks
+  const int cbw = W >> 3, cbh = H >> 3, cwords = (cbw * cbh + 31) >> 5;
+  if (a.coarse) {
+    uint32_t* s_raw = s_occ + cwords;
+    const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    for (int i = tid; i < cwords; i += TILE_W * TILE_H) { s_occ[i] = 0u; s_raw[i] = 0u; }
+    __syncthreads();
+    for (int i = tid; i < cbw * cbh; i += TILE_W * TILE_H) {
+      const int by = i / cbw, bx = i % cbw;
+      uint32_t any = 0u;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int bit0 = (by * 8 + r) * W + bx * 8;             // W % 32 == 0: the 8 bits sit in one word
+        any |= (s_mask[bit0 >> 5] >> (bit0 & 31)) & 0xFFu;
+      }
+      if (any) atomicOr(&s_raw[i >> 5], 1u << (i & 31));
+    }
+    __syncthreads();
+    for (int i = tid; i < cbw * cbh; i += TILE_W * TILE_H) {
+      const int by = i / cbw, bx = i % cbw;
+      uint32_t any = 0u;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx2 = -1; dx2 <= 1; ++dx2) {
+          const int yy = by + dy, xx = bx + dx2;
+          if (yy >= 0 && yy < cbh && xx >= 0 && xx < cbw) { const int j = yy * cbw + xx; any |= (s_raw[j >> 5] >> (j & 31)) & 1u; }
+        }
+      if (any) atomicOr(&s_occ[i >> 5], 1u << (i & 31));
+    }
+    __syncthreads();
+  }
 
   const int col = blockIdx.x * TILE_W + threadIdx.x;
   const int row = blockIdx.y * TILE_H + threadIdx.y;
@@ -234,8 +269,22 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
 
   float qmin = __int_as_float(0x7f800000);   // +inf == "outside the face"
   int kmin = 255;
+  const float dxf32 = __fsub_rn(ex, x), dyf32 = __fsub_rn(ey, y);
+  const float dt32 = a.inv_dt != 0.f ? 1.0f / a.inv_dt : 0.f;
+  int k_skip_checked = k_begin - 1;          // the last group start that has been tested
 #pragma unroll 2
   for (int k = k_begin; k <= k_end; ++k) {
+    if (a.coarse && ((k - k_begin) & 3) == 0 && k + 3 <= k_end && k > k_skip_checked) {
+      // warp-uniform: k, k_begin, k_end are; every lane tests the block of ITS ray's group middle
+      const float tm = fmaf((float)k + 1.5f, dt32, a.t0);
+      const float pxm = fmaf(tm, dxf32, x), pym = fmaf(tm, dyf32, y);
+      int bxm = (int)floorf((pxm + halfW) * 0.125f), bym = (int)floorf((halfH - pym) * 0.125f);
+      bxm = min(max(bxm, 0), cbw - 1); bym = min(max(bym, 0), cbh - 1);
+      const int j = bym * cbw + bxm;
+      const bool occ = (s_occ[j >> 5] >> (j & 31)) & 1u;
+      k_skip_checked = k;
+      if (!__any_sync(0xffffffffu, occ)) { k += 3; continue; }                        // the four samples k .. k+3 are outside the face
+    }
     const double t = tab.t[k];
     const double px = __dadd_rn(xd, __dmul_rn(t, dx));                                // TRAIN:472,480
     const double py = __dadd_rn(yd, __dmul_rn(t, dy));
@@ -285,6 +334,105 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
   if (a.argmin) a.argmin[o] = (uint8_t)kmin;
   if (a.fuse_shade) gfr_shade::shade_pixel(a.shade, b, row, col, d);       // TRAIN:353-369, 517-522: d_min never leaves the SM
   else if (a.shadow) a.shadow[o] = shadow_weight(d);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Variant 2 (A/B only): the mapping the north star sketched — ONE WARP PER PIXEL-RAY, lanes = samples (k = lane, lane + 32, ...),
+// warp-shuffle arg-min over the 160 samples.  Same arithmetic as variant 0 (fp64 depth scratch, magic-add rounding), so the
+// results are bit-identical; a CTA owns the same 32 x 8 pixel tile, warp w walks the 32 pixels of tile row w one after the
+// other.  The depth map cannot be staged in shared memory (a ray crosses the whole image: 256 KB fp32 / 512 KB fp64 per face
+// against 227 KB), so the gathers go through L1 like in variant 0.  Measured slower (profiles/r02_summary.md): the per-ray
+// setup (two fp32 divisions, the 9-way end-point select) is replicated in 32 lanes, the lanes of one ray walk ALONG the ray
+// (up to 32 cache lines per gather), in-mask / out-of-mask samples of one ray diverge, and every pixel pays a 10-shuffle
+// reduction.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_W * TILE_H)
+shadow_march_fwd_warp_ray(const MarchArgs a, const double* __restrict__ depth64, const __grid_constant__ SampleTable tab) {
+  extern __shared__ uint32_t s_mask[];
+  const int b = blockIdx.z, f = b / a.lpf;
+  const int H = a.H, W = a.W;
+  const int words = (H * W) >> 5;
+  {
+    const uint32_t* src = a.mask_bits + (size_t)f * a.mask_stride;
+    for (int i = threadIdx.y * TILE_W + threadIdx.x; i < words; i += TILE_W * TILE_H) s_mask[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x;                   // blockDim = (32, 8): warp = threadIdx.y
+  const int row = blockIdx.y * TILE_H + threadIdx.y;
+  const double* D = depth64 + (size_t)f * H * W;
+  const float halfW = 0.5f * W, halfH = 0.5f * H;
+  const float xmin = -halfW, xmax = W - halfW - 1.0f, ymin = 1.0f - halfH, ymax = halfH;
+  const float Lx = __ldg(a.light + 3 * b), Ly = __ldg(a.light + 3 * b + 1), Lz = __ldg(a.light + 3 * b + 2);
+  const double hW = a.hWd, hH = a.hHd, neg_eps = a.neg_eps;
+  const int cW = W >> 1, cH = H >> 1;
+  for (int pc = 0; pc < TILE_W; ++pc) {
+    const int col = blockIdx.x * TILE_W + pc;
+    const float x = (float)col - halfW, y = halfH - (float)row;
+    const float z = __ldg(a.depth + (size_t)f * H * W + row * W + col);
+    float ex, ey;
+    ray_end(x, y, Lx, Ly, xmin, xmax, ymin, ymax, ex, ey);
+    const double dx = (double)__fsub_rn(ex, x), dy = (double)__fsub_rn(ey, y);
+    const double xd = (double)x, yd = (double)y;
+    const float bcx = __fsub_rn(Lx, x), bcy = __fsub_rn(Ly, y), bcz = __fsub_rn(Lz, z);
+    float qmin = __int_as_float(0x7f800000);
+    int kmin = 255;
+    for (int k = lane; k < a.n; k += 32) {
+      const double t = tab.t[k];
+      const double px = __dadd_rn(xd, __dmul_rn(t, dx));
+      const double py = __dadd_rn(yd, __dmul_rn(t, dy));
+      const int ci = __double2loint(__dadd_rn(px, kMagic)) + cW;
+      const int ri = cH - __double2loint(__dadd_rn(py, kMagic));
+      const int mi = ri * W + ci;
+      if (!((s_mask[mi >> 5] >> (mi & 31)) & 1u)) continue;
+      const double u = __dadd_rn(__dadd_rn(px, hW), neg_eps);
+      const double v = __dadd_rn(__dsub_rn(hH, py), neg_eps);
+      const double sfu = __dadd_rd(u, kMagic), scu = __dadd_ru(u, kMagic);
+      const double sfv = __dadd_rd(v, kMagic), scv = __dadd_ru(v, kMagic);
+      const int uf = __double2loint(sfu), uc = __double2loint(scu);
+      const int vf = __double2loint(sfv), vc = __double2loint(scv);
+      const double ufd = __dsub_rn(sfu, kMagic), ucd = __dsub_rn(scu, kMagic);
+      const double vfd = __dsub_rn(sfv, kMagic), vcd = __dsub_rn(scv, kMagic);
+      const unsigned ufi = uf < 0 ? uf + W : uf, vfi = vf < 0 ? vf + H : vf;
+      const double wu0 = __dsub_rn(ucd, u), wu1 = __dsub_rn(u, ufd);
+      const double wv0 = __dsub_rn(vcd, v), wv1 = __dsub_rn(v, vfd);
+      const double* p00 = D + (vfi * (unsigned)W + ufi);
+      const int du = uc - (int)ufi, dv = (vc - (int)vfi) * W;
+      const double* p10 = p00 + dv;
+      const double ul = __ldg(p00), ur = __ldg(p00 + du);
+      const double ll = __ldg(p10), lr = __ldg(p10 + du);
+      const double up = __dadd_rn(__dmul_rn(ul, wu0), __dmul_rn(ur, wu1));
+      const double lo = __dadd_rn(__dmul_rn(ll, wu0), __dmul_rn(lr, wu1));
+      const double zi = __dadd_rn(__dmul_rn(up, wv0), __dmul_rn(lo, wv1));
+      const float ax = (float)__dsub_rn(u, hW), ay = (float)__dsub_rn(hH, v), az = (float)zi;
+      const float bax = __fsub_rn(ax, x), bay = __fsub_rn(ay, y), baz = __fsub_rn(az, z);
+      const float c0 = __fsub_rn(__fmul_rn(bay, bcz), __fmul_rn(baz, bcy));
+      const float c1 = __fsub_rn(__fmul_rn(baz, bcx), __fmul_rn(bax, bcz));
+      const float c2 = __fsub_rn(__fmul_rn(bax, bcy), __fmul_rn(bay, bcx));
+      const float q = __fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fmul_rn(c2, c2));
+      if (q < qmin) { qmin = q; kmin = k; }          // k ascends within a lane: the first minimum is kept
+    }
+    // warp arg-min; among equal q the smallest k wins (what the sequential loop keeps)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float q2 = __shfl_xor_sync(0xffffffffu, qmin, o);
+      const int k2 = __shfl_xor_sync(0xffffffffu, kmin, o);
+      if (q2 < qmin || (q2 == qmin && k2 < kmin)) { qmin = q2; kmin = k2; }
+    }
+    if (lane == 0) {
+      float d;
+      if (kmin == 255) {
+        d = 1000000.0f;
+      } else {
+        const float den = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bcx, bcx), __fmul_rn(bcy, bcy)), __fmul_rn(bcz, bcz)), 1e-4f));
+        d = __fdiv_rn(sqrtf(__fadd_rn(qmin, 1e-4f)), den);
+      }
+      if (a.bonus != 0.0f && Lx >= a.bx0 && Lx <= a.bx1 && Ly >= a.by0 && Ly <= a.by1) d = __fadd_rn(d, a.bonus);
+      const size_t o = (size_t)b * H * W + row * W + col;
+      if (a.dmin) a.dmin[o] = d;
+      if (a.argmin) a.argmin[o] = (uint8_t)kmin;
+      if (a.shadow) a.shadow[o] = shadow_weight(d);
+    }
+  }
 }
 
 __global__ void widen_depth_kernel(const float4* __restrict__ in, double* __restrict__ out, size_t n4) {
@@ -353,7 +501,8 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
   if (B <= 0 || H <= 0 || W <= 0 || (W % TILE_W) || (H % TILE_H) || H > 512 || W > 512 || B > 65535) return GFR_E_SHAPE;
   if (n <= 0 || n > 255) return GFR_E_ARG;     // 255 is the "no sample inside the face" argmin code
   if (mask_batch_stride != 0 && mask_batch_stride != (H * W) / 32 + GFR_MASK_EXTRA_WORDS) return GFR_E_ARG;
-  if (variant < 0 || variant > 1) return GFR_E_ARG;
+  if (variant < 0 || variant > 2) return GFR_E_ARG;
+  if (variant == 2 && depth64_scratch == nullptr) return GFR_E_NULL;
   if (lights_per_face < 1 || B % lights_per_face) return GFR_E_ARG;
   const int faces = B / lights_per_face;
   SampleTable tab;
@@ -364,7 +513,8 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
     const double dt = (t_host[n - 1] - t_host[0]) / (n - 1);
     bool uniform = dt > 0.0;
     for (int k = 0; k < n && uniform; ++k) uniform = fabs(t_host[k] - (t_host[0] + k * dt)) <= 1e-9;
-    if (uniform && getenv("GFR_MARCH_NO_CULL") == nullptr) inv_dt = (float)(1.0 / dt);
+    static const bool no_cull = getenv("GFR_MARCH_NO_CULL") != nullptr;          // read once, not per launch
+    if (uniform && !no_cull) inv_dt = (float)(1.0 / dt);
   }
   MarchArgs a = {};
   a.depth = depth; a.mask_bits = mask_bits; a.light = light_pt; a.dmin = d_min; a.argmin = argmin; a.shadow = shadow;
@@ -378,11 +528,21 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
   }
   if (fuse != nullptr) { a.fuse_shade = 1; a.shade = *fuse; }
   dim3 grid(W / TILE_W, H / TILE_H, B), block(TILE_W, TILE_H);
-  const size_t smem = (size_t)(H * W / 32) * sizeof(uint32_t);
+  // A/B result (tools/time_march.py, B = 8, 256^2): 231.5 us with the coarse group skip vs 189.6 us without — the per-group test
+  // (~15 instructions per 4 samples, two more registers) costs more than the skipped samples save on face-like masks, where the
+  // bounding-box culling has already removed most out-of-mask samples.  Kept as an opt-in (GFR_MARCH_COARSE=1) for sparse masks.
+  static const bool want_coarse = getenv("GFR_MARCH_COARSE") != nullptr;
+  a.coarse = (inv_dt != 0.f && want_coarse && (W % 32) == 0 && (H % 8) == 0) ? 1 : 0;
+  const size_t smem = (size_t)(H * W / 32 + 2 * (((H / 8) * (W / 8) + 31) / 32 + 1)) * sizeof(uint32_t);
   static const int fast_th = [] { const char* e = getenv("GFR_MARCH_TILE_H"); return (e && atoi(e) == 8) ? 8 : 4; }();
   const bool fast_ok = ((size_t)faces * H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
   if (fuse != nullptr && !fast_ok) return GFR_E_SHAPE;
-  if (variant == 0 && depth64_scratch != nullptr && fast_ok) {
+  if (variant == 2) {
+    if (!fast_ok) return GFR_E_SHAPE;
+    const size_t n4 = (size_t)faces * H * W / 4;
+    widen_depth_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch, n4);
+    shadow_march_fwd_warp_ray<<<grid, block, smem, (cudaStream_t)stream>>>(a, depth64_scratch, tab);
+  } else if (variant == 0 && depth64_scratch != nullptr && fast_ok) {
     const size_t n4 = (size_t)faces * H * W / 4;
     widen_depth_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch, n4);
     if (fast_th == 4 && H % 4 == 0) {

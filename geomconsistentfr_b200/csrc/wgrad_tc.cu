@@ -34,7 +34,8 @@ constexpr int TW = 8, TH = 16;                     // pixel tile (128 pixels = 8
 constexpr int HW_ = TW + 2, HH = TH + 2;           // halo tile of the layer input
 constexpr int N_PROD = 256, N_THREADS = N_PROD + 32;
 constexpr uint32_t G_CHUNK = TH * TW * 16;         // 2048: one 8-channel chunk of the g tile
-constexpr uint32_t G_BYTES = 16 * G_CHUNK;         // M = 128 rows = 16 chunks, always addressed by the MMA
+constexpr uint32_t G_BYTES = 16 * G_CHUNK;         // M = 128 rows = 16 chunks (M = 64: the first 8), always addressed by the MMA
+constexpr int N_GROUPS = 2, GROUP_THREADS = N_PROD / N_GROUPS;   // producer groups take alternate tiles (two tiles' loads in flight)
 constexpr uint32_t X_CHUNK = HH * HW_ * 16;        // 2880
 constexpr int MAX_STAGES = 4;
 
@@ -45,6 +46,7 @@ struct WgradTcArgs {
   long long so, si; int flip;
   int tiles_x, tiles_y, n_tiles;
   int NB, stages, org;
+  int M;                               // UMMA M: 128, or 64 when Cout <= 64 (half the A-operand reads; D rows 16 q + i live in TMEM lanes 32 q + i)
 };
 
 __host__ __device__ constexpr uint32_t idesc_bf16_mnmajor(int M, int N) {
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
   for (uint32_t i = tid; i < (uint32_t)STAGES * stage_bytes / 16; i += N_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, N_PROD);
+      mbar_init(bar_full + 8 * s, GROUP_THREADS);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_done, 1);
@@ -98,9 +100,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
   tc_fence_after_sync();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_bars + TMEM_SLOT);
 
-  const int cob = blockIdx.y * 128, cib = blockIdx.z * NB;
+  const int cob = blockIdx.y * a.M, cib = blockIdx.z * NB;
   const int C4out = (a.Cout + 3) >> 2;
-  const int co_chunks = min(16, (a.Cout - cob + 7) >> 3);
+  const int co_chunks = min(a.M >> 3, (a.Cout - cob + 7) >> 3);
   const size_t gplane = (size_t)a.H * a.W, iplane = (size_t)a.Hin * a.Win;
   const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -108,15 +110,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
     // =============================== producers ===============================
     const float4* gsrc = reinterpret_cast<const float4*>(a.g);
     const float4* isrc = reinterpret_cast<const float4*>(a.in);
+    const int grp_id = tid / GROUP_THREADS, gtid = tid % GROUP_THREADS;
     int s = 0, ph = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const bool mine = (it % N_GROUPS) == grp_id;
+      if (!mine) { if (++s == STAGES) { s = 0; ph ^= 1; } continue; }
       const int tx = tile % a.tiles_x, t2 = tile / a.tiles_x;
       const int ty = t2 % a.tiles_y, n = t2 / a.tiles_y;
       const int x0 = tx * TW, y0 = ty * TH;
       if (it >= STAGES) mbar_wait(bar_empty + 8 * s, ph ^ 1);
       uint8_t* st = smem + (size_t)s * stage_bytes;
       // g tile: chunk c8 holds channels cob + 8 c8 .. + 7 = C4 groups 2 c8', 2 c8' + 1
-      for (int i = tid; i < co_chunks * (TH * TW); i += N_PROD) {
+      for (int i = gtid; i < co_chunks * (TH * TW); i += GROUP_THREADS) {
         const int c8 = i / (TH * TW), pix = i % (TH * TW);
         const int gy = y0 + (pix >> 3), gx = x0 + (pix & 7);
         const int grp = ((cob >> 3) + c8) * 2;
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
       }
       // halo tile of the layer input: chunk c8 holds input channels cib + 8 c8 .. + 7
       uint8_t* xt = st + G_BYTES;
-      for (int i = tid; i < (NB >> 3) * (HH * HW_); i += N_PROD) {
+      for (int i = gtid; i < (NB >> 3) * (HH * HW_); i += GROUP_THREADS) {
         const int c8 = i / (HH * HW_), pix = i % (HH * HW_);
         const int gy = y0 + pix / HW_ - a.org, gx = x0 + pix % HW_ - a.org;
         const int grp = ((cib >> 3) + c8) * 2;
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
     }
   } else {
     // =============================== MMA issuer ===============================
-    const uint32_t idesc = idesc_bf16_mnmajor(128, NB);
+    const uint32_t idesc = idesc_bf16_mnmajor(a.M, NB);
     int s = 0, ph = 0;
     for (int it = 0; it < n_my; ++it) {
       mbar_wait(bar_full + 8 * s, ph);
@@ -176,7 +181,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
   if (warp < 4 && n_my > 0) {
     mbar_wait(bar_done, 0);
     tc_fence_after_sync();
-    const int co = cob + warp * 32 + lane;
+    // M = 128: D row r is TMEM lane r.  M = 64: rows 16 q .. 16 q + 15 are lanes 32 q .. 32 q + 15 (the other lanes are unused)
+    const int co = a.M == 128 ? cob + warp * 32 + lane : (lane < 16 ? cob + warp * 16 + lane : a.Cout);
     for (int tap = 0; tap < TAPS; ++tap) {
       const int t_out = a.flip ? TAPS - 1 - tap : tap;
       for (int c0 = 0; c0 < NB; c0 += 16) {
@@ -212,12 +218,13 @@ int launch_wgrad_tc(WgradTcArgs a, cudaStream_t s) {
   const int cin16 = (a.Cin + 15) & ~15;
   if (NB > cin16) NB = cin16;
   a.NB = NB;
+  a.M = a.Cout <= 64 ? 64 : 128;
   const uint32_t stage = G_BYTES + (uint32_t)(NB >> 3) * X_CHUNK;
   int stages = (int)((220u * 1024u) / stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return GFR_E_UNSUPPORTED;
   a.stages = stages;
-  const int gy = gfr_ceil_div(a.Cout, 128), gz = gfr_ceil_div(a.Cin, NB);
+  const int gy = gfr_ceil_div(a.Cout, a.M), gz = gfr_ceil_div(a.Cin, NB);
   int gx = 148 / (gy * gz);                // one CTA per SM (all 512 TMEM columns); pixel splits: every split adds one round of atomics on the whole (co, ci, tap) block
   if (gx < 1) gx = 1;
   if (gx > a.n_tiles) gx = a.n_tiles;
@@ -244,6 +251,6 @@ extern "C" int gfr_conv_wgrad_tc_bf16(const float* in, const float* g_out, float
   else { a.so = taps; a.si = (long long)Cout * taps; a.flip = 1; }                         // dW_param[ci][co][taps - 1 - tap]
   a.tiles_x = gfr_ceil_div(W, TW); a.tiles_y = gfr_ceil_div(H, TH); a.n_tiles = N * a.tiles_x * a.tiles_y;
   a.org = taps == 9 ? 1 : 0;
-  a.NB = 0; a.stages = 0;
+  a.NB = 0; a.stages = 0; a.M = 128;
   return taps == 9 ? launch_wgrad_tc<9>(a, (cudaStream_t)stream) : launch_wgrad_tc<4>(a, (cudaStream_t)stream);
 }

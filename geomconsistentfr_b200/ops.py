@@ -106,12 +106,12 @@ def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0,
     arg = torch.empty((B, H, W), dtype=torch.uint8, device=depth.device) if want_argmin else None
     shadow = torch.empty((B, H, W), dtype=torch.float32, device=depth.device) if want_shadow else None
     stride = 0 if mask_bits.shape[0] == 1 else H * W // 32 + MASK_EXTRA_WORDS
-    scratch = torch.empty((F, H, W), dtype=torch.float64, device=depth.device) if variant == 0 else None
+    scratch = torch.empty((F, H, W), dtype=torch.float64, device=depth.device) if variant in (0, 2) else None
     _keep, rect = _bonus_rect(bonus_rect)
     rc = _lib.load().gfr_shadow_march_fwd(
         _ptr(depth), _ptr(mask_bits), stride, _ptr(light_pt), t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]),
         float(inside_bonus), rect, _ptr(dmin), _ptr(arg), _ptr(shadow), _ptr(scratch), B, H, W, B // F, int(variant), _stream())
-    _lib.check(rc, "gfr_shadow_march_fwd"); _count(2 if variant == 0 else 1)
+    _lib.check(rc, "gfr_shadow_march_fwd"); _count(2 if variant in (0, 2) else 1)
     return dmin, arg, shadow
 
 

@@ -102,6 +102,7 @@ class RelightNet(nn.Module):
             self._add("conv_%s_c2_2" % p, nn.Conv2d, 16, 16, 1)
             self._add("conv_%s_c2_3" % p, nn.Conv2d, 16, 16, 1)
             setattr(self, "conv_%s_c2_o" % p, nn.Conv2d(16, 3 if p == "albedo" else 1, 1))
+        self.parallel_decoders_train = os.environ.get("GFR_TRAIN_PARALLEL_DECODERS", "1") != "0"   # train mode: depth decoder on a side stream
         self.track_gated_skip_stats = True    # train mode: run the encoder-skip blocks whose epoch gate is still closed (no gradient)
                                               # so that their BN running statistics follow the reference's (TRAIN:240-246)
         self._folded = None
@@ -452,8 +453,7 @@ class RelightNet(nn.Module):
         pooled = T.AvgPoolChannels.apply(h4, 155, 128, 27)                                        # TRAIN:226-230
         sl = self.linear_SL2(torch.nn.functional.leaky_relu(self.linear_SL1(pooled), 0.2))         # [B,4], 3.5 kMAC of glue
         skips = {"s1": h3_og, "s2": h2_og, "s3": h1_og, "s4": c1_og}
-        outs = []
-        for p in ("albedo", "depth"):
+        def decoder(p):
             h = h4                                                       # the first two convs read channels 0..127 in place
             for blk, sc, _, cout, skip in _UP_BLOCKS:
                 a = unit("deconv_%s_%s_1" % (p, blk), h)
@@ -469,10 +469,22 @@ class RelightNet(nn.Module):
                 h = T.PwConvBNAct.apply(h, mod.weight.view(16, 16), mod.bias, bn.weight, bn.bias, bn)
             mod = getattr(self, "conv_%s_c2_o" % p)
             if p == "albedo":
-                outs.append(T.PwHead.apply(h, mod.weight.view(3, 16), mod.bias, 2, 1.0))           # TRAIN:289-290
-            else:
-                outs.append(T.PwHead.apply(h, mod.weight.view(1, 16), mod.bias, 0, 100.0))         # TRAIN:349-350
-        return outs[0], outs[1], sl
+                return T.PwHead.apply(h, mod.weight.view(3, 16), mod.bias, 2, 1.0)                 # TRAIN:289-290
+            return T.PwHead.apply(h, mod.weight.view(1, 16), mod.bias, 0, 100.0)                   # TRAIN:349-350
+
+        if not self.parallel_decoders_train:
+            return decoder("albedo"), decoder("depth"), sl
+        # the two decoders are independent (TRAIN:235-290 / 293-350): the depth decoder runs on a side stream, forward AND backward
+        # (autograd replays every backward node on the stream of its forward) — two parallel branches of the captured step graph
+        cur = torch.cuda.current_stream()
+        side = self._side_stream("_train_side")
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            depth = decoder("depth")
+        albedo = decoder("albedo")
+        cur.wait_stream(side)
+        depth.record_stream(cur)
+        return albedo, depth, sl
 
     def _forward_train(self, img, epoch, intrinsic_matrix, masks):
         """TRAIN:196-524, differentiable: CNN (train mode) -> ShadowMarch / ShadeRender autograd Functions."""

@@ -81,7 +81,7 @@ def _wgrad(x, g_raw, w, b, deconv, cin, Cout, taps=9, precision=3):
     N, G = x.shape[0], x.shape[1]
     H, W = g_raw.shape[2], g_raw.shape[3]
     g_w, dw = _grad_target(w)
-    g_b, db = _grad_target(b) if b.requires_grad else (None, True)
+    g_b, db = _grad_target(b) if (b is not None and b.requires_grad) else (None, True)
     if precision == 4:
         _chk(_lib.load().gfr_conv_wgrad_tc_bf16(_ptr(x), _ptr(g_raw), _ptr(g_w), int(deconv), N, cin, G, Cout, x.shape[2], x.shape[3],
                                                 H, W, taps, _stream()), "gfr_conv_wgrad_tc_bf16")
@@ -103,13 +103,13 @@ class _BN:
     def stats(raw, C, bn):
         N, G, H, W, _ = raw.shape
         dev = raw.device
-        sums = torch.empty(2 * G * 4, dtype=torch.float64, device=dev)
+        sums = torch.empty(2 * G * 4 + 1, dtype=torch.float64, device=dev)          # + the ticket counter of the fused finalise
         mean, rstd, scale, shift = (torch.empty(G * 4, dtype=torch.float32, device=dev) for _ in range(4))
         track = bn.training and bn.track_running_stats
         _chk(_lib.load().gfr_bn_train_stats(_ptr(raw), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean) if track else None,
                                             _ptr(bn.running_var) if track else None, _ptr(sums), _ptr(mean), _ptr(rstd),
                                             _ptr(scale), _ptr(shift), N, C, H, W, float(bn.eps), float(bn.momentum), _stream()),
-             "gfr_bn_train_stats", 2)
+             "gfr_bn_train_stats", 1)
         if track:
             bn.num_batches_tracked += 1
             ops.bump_param_generation()
@@ -124,8 +124,9 @@ class _BN:
         return y
 
     @staticmethod
-    def backward(raw, C, res, g_y, mean, rstd, scale, shift, gamma, act, want_res, beta=None):
-        """-> g_raw, g_res, g_gamma, g_beta (the last two None when they were accumulated straight into gamma.grad / beta.grad)"""
+    def backward(raw, C, res, g_y, mean, rstd, scale, shift, gamma, act, want_res, beta=None, conv_bias=None):
+        """-> g_raw, g_res, g_gamma, g_beta, g_conv_bias (None where a gradient was accumulated straight into the parameter's
+        .grad; g_conv_bias = sum of g_raw per channel, from the same pass, when `conv_bias` is given)"""
         N, G, H, W, _ = raw.shape
         dev = raw.device
         sums = torch.empty(2 * G * 4, dtype=torch.float64, device=dev)
@@ -133,10 +134,11 @@ class _BN:
         g_res = torch.empty_like(raw) if want_res else None
         g_gamma, dg = _grad_target(gamma)
         g_beta, db = _grad_target(beta, like=gamma)
+        g_cb, dcb = (_grad_target(conv_bias) if conv_bias is not None and conv_bias.requires_grad else (None, True))
         _chk(_lib.load().gfr_bn_apply_bwd_ex(_ptr(raw), _ptr(res), _ptr(g_y), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
                                              _ptr(gamma.detach().contiguous()), _ptr(sums), _ptr(g_raw), _ptr(g_res), _ptr(g_gamma),
-                                             _ptr(g_beta), N, C, H, W, int(act), _stream()), "gfr_bn_apply_bwd_ex", 3)
-        return g_raw, g_res, (None if dg else g_gamma), (None if db else g_beta)
+                                             _ptr(g_beta), _ptr(g_cb), N, C, H, W, int(act), _stream()), "gfr_bn_apply_bwd_ex", 2)
+        return g_raw, g_res, (None if dg else g_gamma), (None if db else g_beta), (None if dcb else g_cb)
 
 
 def _sumpool2(g):
@@ -174,7 +176,7 @@ class ConvBNAct(torch.autograd.Function):
         g_post = None
         if has_post:
             g_post = _sumpool2(g_y) if post_shift else g_y
-        g_raw, g_res, g_gamma, g_beta = _BN.backward(raw, Cout, res, g_y, mean, rstd, scale, shift, gamma, act, has_res, beta)
+        g_raw, g_res, g_gamma, g_beta, g_b = _BN.backward(raw, Cout, res, g_y, mean, rstd, scale, shift, gamma, act, has_res, beta, b)
         # data gradient: the same tensor-core convolution, Cout -> cin, transposed + flipped kernel
         g_x = None
         if ctx.needs_input_grad[0]:
@@ -185,9 +187,11 @@ class ConvBNAct(torch.autograd.Function):
             else:                                   # the layer read only the leading channels of a wider tensor (TRAIN:225)
                 g_x = torch.zeros_like(x)
                 g_x[:, :g_in.shape[1]] = g_in
-        g_w = g_b = None
+        g_w = None
         if ctx.needs_input_grad[1]:          # frozen weights (the generator's pass through the discriminator) skip the wgrad
-            g_w, g_b = _wgrad(x, g_raw, w, b, deconv, cin, Cout, taps, prec)
+            g_w, _ = _wgrad(x, g_raw, w, None, deconv, cin, Cout, taps, prec)        # (the bias gradient came out of the BN backward)
+        else:
+            g_b = None
         return g_x, g_w, g_b, g_gamma, g_beta, g_res, g_post, None
 
 
@@ -208,7 +212,7 @@ class StemBNAct(torch.autograd.Function):
     def backward(ctx, g_y):
         img, raw, mean, rstd, scale, shift, gamma, beta, w, b = ctx.saved_tensors
         N, H, W, _ = img.shape
-        g_raw, _, g_gamma, g_beta = _BN.backward(raw, 16, None, g_y.contiguous(), mean, rstd, scale, shift, gamma, 1, False, beta)
+        g_raw, _, g_gamma, g_beta, _ = _BN.backward(raw, 16, None, g_y.contiguous(), mean, rstd, scale, shift, gamma, 1, False, beta)
         (g_w, dw), (g_b, db) = _grad_target(w), _grad_target(b)
         _chk(_lib.load().gfr_stem_conv_wgrad(_ptr(img), _ptr(g_raw), _ptr(g_w), _ptr(g_b), N, H, W, _stream()), "gfr_stem_conv_wgrad")
         return None, (None if dw else g_w), (None if db else g_b), g_gamma, g_beta, None
@@ -265,7 +269,7 @@ class PwConvBNAct(torch.autograd.Function):
     def backward(ctx, g_y):
         x, w, raw, mean, rstd, scale, shift, gamma, beta, b = ctx.saved_tensors
         N, G, H, W, _ = x.shape
-        g_raw, _, g_gamma, g_beta = _BN.backward(raw, 16, None, g_y.contiguous(), mean, rstd, scale, shift, gamma, 1, False, beta)
+        g_raw, _, g_gamma, g_beta, _ = _BN.backward(raw, 16, None, g_y.contiguous(), mean, rstd, scale, shift, gamma, 1, False, beta)
         g_x = torch.empty_like(x)
         g_w = torch.zeros_like(w)                    # (w is a .view() of the parameter: not a leaf, autograd routes it)
         (g_b, db) = _grad_target(b)

@@ -190,7 +190,8 @@ int gfr_conv_tc_fwd_ex(const float* in, const float* w_packed, const float* bias
 
 /* BatchNorm2d, training mode, part 1: batch statistics of x [N,C,H,W] (C4) -> mean, rstd = 1/sqrt(var_biased + eps),
  * scale = gamma*rstd, shift = beta - mean*scale (all [4*ceil(C/4)] floats, padded slots 0); running_mean/var (may be
- * NULL) are updated like torch (momentum, unbiased variance).  sums_scratch: 2*4*ceil(C/4) doubles. */
+ * NULL) are updated like torch (momentum, unbiased variance).  sums_scratch: 2*4*ceil(C/4) + 1 doubles (the last one is the
+ * ticket counter with which the last CTA of the statistics pass finalises: one launch). */
 int gfr_bn_train_stats(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                        double* sums_scratch, float* mean, float* rstd, float* scale, float* shift, int N, int C, int H,
                        int W, float eps, float momentum, void* stream);
@@ -210,10 +211,12 @@ int gfr_bn_apply_bwd(const float* x, const float* res, const float* g_y, const f
 
 /* gfr_bn_apply_bwd with the UNPADDED parameter gamma [C] and the parameter gradients accumulated in place:
  * g_gamma[c] += sum g_pre*xhat, g_beta[c] += sum g_pre (either may be NULL) — the optimiser's flat gradient buffer can be
- * passed directly (no temporaries, no separate add). */
+ * passed directly (no temporaries, no separate add).  g_bias (may be NULL): g_bias[c] += sum over (N,H,W) of g_x[:,c] — the
+ * gradient of the bias of the convolution in front of the BatchNorm, from the same pass. */
 int gfr_bn_apply_bwd_ex(const float* x, const float* res, const float* g_y, const float* scale, const float* shift,
                         const float* mean, const float* rstd, const float* gamma, double* sums_scratch, float* g_x,
-                        float* g_res, float* g_gamma, float* g_beta, int N, int C, int H, int W, int act, void* stream);
+                        float* g_res, float* g_gamma, float* g_beta, float* g_bias, int N, int C, int H, int W, int act,
+                        void* stream);
 
 /* Weight (and bias) gradient of a 3x3 stride-1 convolution: g_w (+=, parameter layout: Conv2d [Cout,Cin,3,3] or
  * ConvTranspose2d [Cin,Cout,3,3]) and g_bias [Cout] (+=, may be NULL) from the layer input `in`

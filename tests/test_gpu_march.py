@@ -33,7 +33,7 @@ def _light_pt(L):
     return O.light_point(torch.as_tensor(L, dtype=torch.float32).view(-1, 3))[1]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("tag", TAGS)
 def test_march_vs_reference_golden(ops, march, tag, variant):
     depth = torch.from_numpy(march["depth"]).view(1, 1, 256, 256).cuda()
@@ -44,7 +44,7 @@ def test_march_vs_reference_golden(ops, march, tag, variant):
     assert diff.max() <= SHADOW_TOL, (tag, diff.max(), int((diff > SHADOW_TOL).sum()))
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("H,W,B", [(64, 64, 3), (96, 128, 2), (256, 256, 2)])
 def test_march_vs_oracle_seeded(ops, H, W, B, variant):
     """Per-image masks (TRAIN:510), argmin, d_min, odd sizes; lights from all quadrants incl. inside."""
@@ -113,6 +113,32 @@ def test_march_culling_is_exact_on_offcentre_masks(ops):
     d1, a1, _ = ops.shadow_march_fwd(depth, bits, P_L, inside_bonus=5.0, want_argmin=True, variant=1)
     assert torch.equal(d0, d1) and torch.equal(a0, a1)
     assert float(d0[3].min()) >= 1e6                                                         # empty mask: every ray misses
+    # variant 2 = the warp-per-ray mapping of the north-star sketch (A/B only): the same bits, arg-min ties included
+    d2, a2, _ = ops.shadow_march_fwd(depth, bits, P_L, inside_bonus=5.0, want_argmin=True, variant=2)
+    assert torch.equal(d0, d2) and torch.equal(a0, a2)
+
+
+def test_coarse_group_skip_is_exact_on_masks_with_holes(ops):
+    """The 8x8-block occupancy map lets a warp skip groups of 4 samples whose nearest pixels are provably outside the face
+    (variant 0); variant 1 tests every sample.  Masks with holes, thin bridges, isolated pixels and a frame around the image
+    border, 256x256 like the bench: bit-identical."""
+    H = W = 256
+    g = torch.Generator().manual_seed(5)
+    depth = (torch.rand(4, 1, H, W, generator=g) * 60.0).cuda()
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    masks = torch.zeros(4, H, W, dtype=torch.uint8)
+    masks[0] = ((((xx - 128) / 80.0) ** 2 + ((yy - 128) / 100.0) ** 2) < 1.0).to(torch.uint8)
+    masks[0, 90:150, 100:160] = 0                                        # a big hole
+    masks[0, 118:122, 100:160] = 1                                       # a thin bridge through it
+    masks[1] = (torch.rand(H, W, generator=g) > 0.9995).to(torch.uint8)  # isolated pixels
+    masks[2, :3, :] = 1; masks[2, -3:, :] = 1; masks[2, :, :3] = 1; masks[2, :, -3:] = 1      # a frame on the border
+    masks[3, 40:200:16, 40:200] = 1                                      # stripes one pixel thick, 16 apart
+    bits = ops.mask_pack(masks.cuda())
+    for L in ((0.7518, 0.0, 0.6594), (-0.5151, 0.4722, 0.7154), (0.01, 0.02, 0.9997), (0.8138, -0.3420, 0.4698)):
+        P_L = (4013.0 * torch.nn.functional.normalize(torch.tensor([L] * 4), dim=1)).cuda()
+        d0, a0, _ = ops.shadow_march_fwd(depth, bits, P_L, inside_bonus=5.0, want_argmin=True, variant=0)
+        d1, a1, _ = ops.shadow_march_fwd(depth, bits, P_L, inside_bonus=5.0, want_argmin=True, variant=1)
+        assert torch.equal(d0, d1) and torch.equal(a0, a1), L
 
 
 def test_shade_render_vs_oracle(ops, march):

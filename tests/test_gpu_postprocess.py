@@ -160,7 +160,7 @@ def test_masked_dssim_metric_vs_numpy_restatement(window_3d):
     for (B, H, W, shared) in ((3, 256, 256, True), (2, 70, 45, False)):
         a = rs.randint(0, 256, (B, H, W, 3)).astype(np.uint8)
         b = np.clip(a.astype(np.int32) + rs.randint(-40, 41, a.shape), 0, 255).astype(np.uint8)
-        m = (rs.uniform(size=(1 if shared else B, H, W)) < 0.6).astype(np.uint8) * rs.choice([64, 128, 255])
+        m = ((rs.uniform(size=(1 if shared else B, H, W)) < 0.6) * int(rs.choice([64, 128, 255]))).astype(np.uint8)
         got = ops.masked_dssim_u8(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(m[0] if shared else m).cuda(),
                                   window_3d=window_3d).cpu().numpy()
         want = np.array([M.dssim_mp_rgb(a[i], b[i], m[0] if shared else m[i], window_3d) for i in range(B)])

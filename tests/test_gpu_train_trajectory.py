@@ -44,7 +44,8 @@ def test_patchgan_vs_reference_class_outputs():
             continue                                   # bias before a train-mode BN: zero gradient up to rounding
         g = p.grad.reshape(-1)
         got = g[:: max(1, g.numel() // 4096)].cpu().numpy()
-        assert _rel(got, f["gsample_" + n]) <= 1e-2, (n, _rel(got, f["gsample_" + n]))
+        assert _rel_l1(got, f["gsample_" + n]) <= 2e-3, (n, _rel_l1(got, f["gsample_" + n]))
+        assert _rel(got, f["gsample_" + n]) <= 3e-2, (n, _rel(got, f["gsample_" + n]))       # isolated LeakyReLU / BN ties
     for n, b in D.named_buffers():
         if "num_batches" not in n:
             assert np.abs(b.cpu().numpy() - f["buf_" + n]).max() <= 1e-4, n

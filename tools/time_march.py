@@ -1,29 +1,25 @@
-"""Dev tool: CUDA-event timing of the march / shade kernels at B=8 256x256 (not the bench)."""
-import sys, os, numpy as np, torch
+"""Times the three ray-march variants on the bench shapes (B = 8, 256x256, synthetic ellipse mask + FFHQ-like depth)."""
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
 from geomconsistentfr_b200 import ops
-from geomconsistentfr_b200 import synthetic as O
-
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-depth = torch.zeros(B, 1, 256, 256); masks = torch.zeros(B, 256, 256, dtype=torch.uint8)
-for b in range(B):
-    d, m = O.synthetic_face(seed=b); depth[b, 0] = d; masks[b] = m
-lights = torch.tensor([O.LIGHTS_18[i % 18] for i in range(B)], dtype=torch.float32)
-P_L = O.light_point(lights)[1].cuda(); depth = depth.cuda(); bits = ops.mask_pack(masks.cuda())
-albedo = torch.rand(B, 3, 256, 256, device="cuda"); amb = torch.full((B,), 0.3, device="cuda")
-for variant in (1, 0):
-    for _ in range(3): ops.shadow_march_fwd(depth, bits, P_L, variant=variant)
+from geomconsistentfr_b200.synthetic import LIGHTS_18, synthetic_face
+B = 8
+faces = [synthetic_face(seed=i, noise=2.0) for i in range(B)]
+depth = torch.stack([d for d, _ in faces]).view(B, 1, 256, 256).cuda()
+bits = ops.mask_pack((faces[0][1] * 255).view(1, 256, 256).cuda())
+light = (4013.0 * torch.nn.functional.normalize(torch.tensor(LIGHTS_18[:B]), dim=1)).cuda()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for variant in (0, 1, 2):
+    fn = lambda: ops.shadow_march_fwd(depth, bits, light, inside_bonus=5.0, variant=variant)
+    for _ in range(3):
+        fn()
+    torch.cuda._sleep(20_000_000)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        fn()
+    b.record()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20): dmin, _, _ = ops.shadow_march_fwd(depth, bits, P_L, variant=variant)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
-    print("march variant %d: %.3f ms for B=%d  -> %.1f us/img, %.2f Gsamples/s, alg %.1f GB/s" % (
-        variant, ms, B, 1e3 * ms / B, B * 160 * 65536 / ms / 1e6, B * 786432 / ms / 1e6))
-for _ in range(3): ops.shade_render_fwd(albedo, depth, dmin, P_L, amb)
-torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(20): ops.shade_render_fwd(albedo, depth, dmin, P_L, amb)
-e1.record(); torch.cuda.synchronize()
-print("shade_render: %.3f ms for B=%d" % (e0.elapsed_time(e1) / 20, B))
+    print("variant %d (%s): %.1f us per launch (20 back-to-back launches incl. the depth widening pass)" % (
+        variant, ("thread-per-ray, culled + coarse skip", "thread-per-ray, literal", "warp-per-ray")[variant], 1e3 * a.elapsed_time(b) / 20))
