@@ -78,6 +78,11 @@ _PROTOS = {
     "gfr_conv_p16_pack_weights": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
     "gfr_conv3x3_p16_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p]
                            + [_c_int] * 12 + [_c_float, _c_float, _c_int, _c_void_p],
+    "gfr_conv_p16_fwd_ex": [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_void_p]
+                           + [_c_int] * 13 + [_c_float, _c_float, _c_int, _c_void_p],
+    "gfr_conv_p16_pack_size_taps": [_c_int] * 5,
+    "gfr_conv_p16_pack_weights_taps": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p],
+    "gfr_stem_unroll_p16": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_nchw_to_p16": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_p16_to_nchw": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_maxpool2_p16_fwd": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
@@ -99,7 +104,7 @@ _PROTOS = {
 }
 _RESTYPES = {"gfr_error_string": ctypes.c_char_p, "gfr_conv_tc_pack_size": ctypes.c_longlong,
              "gfr_conv_tc_pack_size_f16": ctypes.c_longlong, "gfr_conv_p16_pack_size": ctypes.c_longlong,
-             "gfr_conv_tc_pack_size_ex": ctypes.c_longlong}
+             "gfr_conv_tc_pack_size_ex": ctypes.c_longlong, "gfr_conv_p16_pack_size_taps": ctypes.c_longlong}
 
 _lib = None
 

@@ -38,8 +38,11 @@ using namespace gfr_tc;
 
 namespace {
 
-constexpr int TILE_H = 16, HALO_H = TILE_H + 2;
+constexpr int TILE_H = 16;
 constexpr int MAX_STAGES = 8;
+// filter geometry: GEO 0 = 3x3 / pad 1 (halo 1 px all round, 9 taps); GEO 1 = 5x1 VERTICAL / pad (2, 0) (halo 2 rows above and
+// below, none sideways, 5 taps) — the stem's 5x5 convolution after its five horizontal taps have been unrolled into channels
+// (gfr_stem_unroll_p16): conv5x5(img)[co] = sum_ky sum_{c' = kx*3 + c} W[co][c][ky][kx] * U[c'][y + ky - 2][x]
 
 struct ConvP16Args {
   const __half* wpk;     // packed weights, see gfr_conv_p16_pack_weights
@@ -56,18 +59,23 @@ struct ConvP16Args {
   int static_w;          // 1: the weights were not written by the preceding kernel (fetch them before griddepcontrol.wait)
   float inv_scale;       // 1 / (X_SCALE * w_scale)
   float out_scale;
+  __half* pool;          // P16 [N][out_groups][2][H/2][W/2][8] or null: the 2x2 / stride 2 max pool of `out`, from the same epilogue
 };
 
-template <int NT, int MH, int KS>
+template <int NT, int MH, int KS, int GEO = 0>
 struct Cfg {
-  static constexpr int TILE_W = 8 * MH, HALO_W = TILE_W + 2;
+  static constexpr int TAPS = GEO == 0 ? 9 : 5;
+  static constexpr int PAD_X = GEO == 0 ? 1 : 0, PAD_Y = GEO == 0 ? 1 : 2;
+  static constexpr int TILE_W = 8 * MH, HALO_W = TILE_W + 2 * PAD_X, HALO_H = TILE_H + 2 * PAD_Y;
   static constexpr uint32_t PART = HALO_H * HALO_W * 16;        // one part (hi or lo) of one 8-channel chunk of the halo tile
   static constexpr uint32_t A_LBO = 2 * PART;                   // K direction: the next 8-channel chunk
   static constexpr uint32_t A_SBO = HALO_W * 16;                // M direction: the next tile row (8 pixels further in M)
   static constexpr uint32_t A_BYTES = KS * A_LBO;
   static constexpr uint32_t B_LBO = 2 * NT * 16;                // [W1 rows | W2 rows] of one 8-channel chunk
   static constexpr uint32_t B_TAP = KS * B_LBO;
-  static constexpr uint32_t W_STEP = 9 * B_TAP;
+  static constexpr uint32_t W_STEP = TAPS * B_TAP;
+  // halo-tile offset (in pixels) of filter tap t
+  __host__ __device__ static constexpr uint32_t tap_px(int t) { return GEO == 0 ? (uint32_t)((t / 3) * HALO_W + (t % 3)) : (uint32_t)(t * HALO_W); }
   static constexpr int EPI_WARPS = 4 * MH, THREADS = 64 + 32 * EPI_WARPS;
   static constexpr uint32_t ACC_COLS = MH * 2 * NT;             // one accumulator buffer: per M-half [main NT | correction NT]
   static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
@@ -75,10 +83,10 @@ struct Cfg {
   static_assert(A_BYTES % 128 == 0 && W_STEP % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
 
-template <int NT, int MH, int KS>
-__global__ void __launch_bounds__(Cfg<NT, MH, KS>::THREADS, (NT * MH <= 32) ? 2 : 1)
+template <int NT, int MH, int KS, int GEO = 0>
+__global__ void __launch_bounds__(Cfg<NT, MH, KS, GEO>::THREADS, (NT * MH <= 32) ? 2 : 1)
 conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args a) {
-  using C = Cfg<NT, MH, KS>;
+  using C = Cfg<NT, MH, KS, GEO>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool resident = a.nsteps == 1;
@@ -140,7 +148,7 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
             mbar_wait(bar_empty + 8 * s, ph ^ 1);
             mbar_expect_tx(bar_full + 8 * s, C::A_BYTES + (load_w ? C::W_STEP : 0u));
           }
-          tma_load_5d(slot, &tm_in, bar_full + 8 * s, (tx * C::TILE_W - 1) * 8, ty * TILE_H - 1, 0, st * KS, n);
+          tma_load_5d(slot, &tm_in, bar_full + 8 * s, (tx * C::TILE_W - C::PAD_X) * 8, ty * TILE_H - C::PAD_Y, 0, st * KS, n);
           if (load_w && (g >= n_pre || !a.static_w))
             bulk_load(resident ? smem0 : slot + C::A_BYTES, wsrc + (size_t)st * (C::W_STEP / 2), C::W_STEP, bar_full + 8 * s);
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -167,10 +175,10 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
         for (int h = 0; h < MH; ++h) {
           const uint32_t d_main = tmem + (uint32_t)(p * C::ACC_COLS + h * 2 * NT), d_corr = d_main + NT;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < C::TAPS; ++tap) {
 #pragma unroll
             for (int j = 0; j < KS / 2; ++j) {          // one K = 16 MMA covers two 8-channel chunks
-              const uint32_t ao = ((uint32_t)((tap / 3) * C::HALO_W + (tap % 3)) * 16u + (uint32_t)h * 128u + (uint32_t)j * 2u * C::A_LBO) >> 4;
+              const uint32_t ao = (C::tap_px(tap) * 16u + (uint32_t)h * 128u + (uint32_t)j * 2u * C::A_LBO) >> 4;
               const uint32_t bo = ((uint32_t)tap * C::B_TAP + (uint32_t)j * 2u * C::B_LBO) >> 4;
               const uint32_t acc = (tap == 0 && j == 0) ? 0u : 1u;
               umma_f16(d_main, dA_hi + ao, dB0 + bo, IDESC_2N, acc);     // main += hi*W1 ; corr += hi*W2
@@ -248,48 +256,68 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
         tc_fence_before_sync();
         mbar_arrive(bar_accempty + 8 * p);
       }
-      if (ok) {
+      // every lane walks the chunks (warp-uniform control flow: the fused pool shuffles); loads / stores are predicated by `ok`
+      const size_t qplane = (size_t)(a.H >> 1) * (a.W >> 1) * 8;
+      __half* pool_p = a.pool ? a.pool + gfr_p16::unit_offset(n, a.out_groups, n0 >> 3, a.H >> 1, a.W >> 1, y >> 1, x >> 1) : nullptr;
+      const bool pool_writer = ok && !(lane & 1) && !(lane & 8);
 #pragma unroll
-        for (int c = 0; c < NT / 8; ++c) {
-          if (c >= n_chunks) break;
-          float v[8];
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias16 + 8 * c), b1 = *reinterpret_cast<const float4*>(s_bias16 + 8 * c + 4);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      for (int c = 0; c < NT / 8; ++c) {
+        if (c >= n_chunks) break;
+        float v[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bias16 + 8 * c), b1 = *reinterpret_cast<const float4*>(s_bias16 + 8 * c + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = fmaf(sum[8 * c + k], inv16, bb[k]);
-          if (res_p) {
-            float rv[8];
-            gfr_p16::join8_x16(__ldg(reinterpret_cast<const uint4*>(res_p + 2 * c * plane)),
-                               __ldg(reinterpret_cast<const uint4*>(res_p + (2 * c + 1) * plane)), rv);
+        for (int k = 0; k < 8; ++k) v[k] = fmaf(sum[8 * c + k], inv16, bb[k]);
+        if (res_p && ok) {
+          float rv[8];
+          gfr_p16::join8_x16(__ldg(reinterpret_cast<const uint4*>(res_p + 2 * c * plane)),
+                             __ldg(reinterpret_cast<const uint4*>(res_p + (2 * c + 1) * plane)), rv);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] += rv[k];
-          }
-          const bool do_act = n0 + 8 * c < a.act_channels;       // act_channels is a multiple of 8 (checked by the host)
-          if (a.act == 1 && do_act) {
+          for (int k = 0; k < 8; ++k) v[k] += rv[k];
+        }
+        const bool do_act = n0 + 8 * c < a.act_channels;       // act_channels is a multiple of 8 (checked by the host)
+        if (a.act == 1 && do_act) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.2f * v[k]);
-          } else if (a.act == 2 && do_act) {
+          for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.2f * v[k]);
+        } else if (a.act == 2 && do_act) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              v[k] = n0 + 8 * c + k < a.Cout ? gfr_p16::X_SCALE / (1.0f + expf(-v[k] * gfr_p16::X_INV)) : 0.f;
-          }
-          if (post_p) {
-            float pv[8];
-            gfr_p16::join8_x16(__ldg(reinterpret_cast<const uint4*>(post_p + 2 * c * pplane)),
-                               __ldg(reinterpret_cast<const uint4*>(post_p + (2 * c + 1) * pplane)), pv);
+          for (int k = 0; k < 8; ++k)
+            v[k] = n0 + 8 * c + k < a.Cout ? gfr_p16::X_SCALE / (1.0f + expf(-v[k] * gfr_p16::X_INV)) : 0.f;
+        }
+        if (post_p && ok) {
+          float pv[8];
+          gfr_p16::join8_x16(__ldg(reinterpret_cast<const uint4*>(post_p + 2 * c * pplane)),
+                             __ldg(reinterpret_cast<const uint4*>(post_p + (2 * c + 1) * pplane)), pv);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] += pv[k];
-          }
-          if (a.out_scale != 1.0f) {
+          for (int k = 0; k < 8; ++k) v[k] += pv[k];
+        }
+        if (a.out_scale != 1.0f) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] *= a.out_scale;
-          }
+          for (int k = 0; k < 8; ++k) v[k] *= a.out_scale;
+        }
+        if (ok) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) overflow = overflow || !(fabsf(v[k]) < lim16);     // also catches NaN
           uint4 hi, lo;
           gfr_p16::split8_x16(v, hi, lo);
           *reinterpret_cast<uint4*>(out_p + 2 * c * plane) = hi;
           *reinterpret_cast<uint4*>(out_p + (2 * c + 1) * plane) = lo;
+        }
+        if (pool_p != nullptr) {
+          // 2x2 / stride 2 max pool of the finished values: lane = (tile row & 3) * 8 + px, so the quad partners of a pixel are
+          // lanes ^1 (x) and ^8 (y) of its own warp; the even/even lane writes.  H, W even (host-checked) and tile origins even,
+          // so a quad never straddles tiles or the image edge.
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            v[k] = fmaxf(v[k], __shfl_xor_sync(0xffffffffu, v[k], 1));
+            v[k] = fmaxf(v[k], __shfl_xor_sync(0xffffffffu, v[k], 8));
+          }
+          if (pool_writer) {
+            uint4 hi, lo;
+            gfr_p16::split8_x16(v, hi, lo);
+            *reinterpret_cast<uint4*>(pool_p + 2 * c * qplane) = hi;
+            *reinterpret_cast<uint4*>(pool_p + (2 * c + 1) * qplane) = lo;
+          }
         }
       }
     }
@@ -330,13 +358,13 @@ int sm_count() {
 
 // tensor [N][groups][2][H][W][8] fp16 described as 5-D {W*8, H, 2, C8, N} (pixel and channel slot merged: one contiguous
 // 16*bw-byte run per box row); box {8*bw, 18, 2, KS, 1}
-int make_p16_map(CUtensorMap* tm, const void* base, int N, int C8, int groups, int H, int W, int bw, int ks) {
+int make_p16_map(CUtensorMap* tm, const void* base, int N, int C8, int groups, int H, int W, int bw, int bh, int ks) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return GFR_E_UNSUPPORTED;
   const cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, 2, (cuuint64_t)C8, (cuuint64_t)N};
   const cuuint64_t hw16 = (cuuint64_t)H * W * 16;
   const cuuint64_t strides[4] = {(cuuint64_t)W * 16, hw16, 2 * hw16, (cuuint64_t)groups * 2 * hw16};
-  const cuuint32_t box[5] = {(cuuint32_t)bw * 8, HALO_H, 2, (cuuint32_t)ks, 1};
+  const cuuint32_t box[5] = {(cuuint32_t)bw * 8, (cuuint32_t)bh, 2, (cuuint32_t)ks, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -344,13 +372,13 @@ int make_p16_map(CUtensorMap* tm, const void* base, int N, int C8, int groups, i
   return r == CUDA_SUCCESS ? GFR_OK : GFR_E_ARG;
 }
 
-template <int NT, int MH, int KS>
+template <int NT, int MH, int KS, int GEO = 0>
 int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s) {
-  using C = Cfg<NT, MH, KS>;
+  using C = Cfg<NT, MH, KS, GEO>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv3x3_p16_kernel<NT, MH, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv3x3_p16_kernel<NT, MH, KS, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
   const bool resident = a.nsteps == 1;
@@ -385,7 +413,7 @@ int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_p16_kernel<NT, MH, KS>, tm, a);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_p16_kernel<NT, MH, KS, GEO>, tm, a);
   return e == cudaSuccess ? gfr_launch_status() : (int)e;
 }
 
@@ -455,22 +483,73 @@ __global__ void maxpool2_p16_kernel(const __half* __restrict__ in, __half* __res
   *reinterpret_cast<uint4*>(o + oplane) = lo;
 }
 
-}  // namespace
-
-extern "C" long long gfr_conv_p16_pack_size(int Cin, int Cout, int NT, int KS) {
-  if (Cin <= 0 || Cout <= 0 || (NT != 16 && NT != 32) || (KS != 2 && KS != 4)) return GFR_E_ARG;
-  return (long long)gfr_ceil_div(Cout, NT) * gfr_ceil_div(Cin, 8 * KS) * 9 * KS * 2 * NT * 8;     // in halfs
+// U[n][y][x][kx*3 + c] = img[n][y][x + kx - 2][c] (zero outside), channel 15 = 0: the five horizontal taps of the stem's 5x5
+// convolution unrolled into 15 (+1) channels of a P16 tensor, so the 5x5 layer becomes a 5x1 vertical-tap layer on the tensor cores
+__global__ void __launch_bounds__(256) stem_unroll_p16_kernel(const float* __restrict__ img, __half* __restrict__ out, int H, int W, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [N][H][W]
+  if (i >= total) return;
+  const int x = (int)(i % W);
+  const long long t = i / W;
+  const int y = (int)(t % H);
+  const long long n = t / H;
+  const float* row = img + (n * H + y) * (long long)W * 3;
+  float v[16];
+#pragma unroll
+  for (int kx = 0; kx < 5; ++kx) {
+    const int xx = x + kx - 2;
+    const bool in = xx >= 0 && xx < W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[kx * 3 + c] = in ? __ldg(row + (size_t)xx * 3 + c) : 0.f;
+  }
+  v[15] = 0.f;
+  const size_t plane = (size_t)H * W * 8;
+  __half* o = out + ((size_t)n * 2 * 2 * H + y) * (size_t)W * 8 + (size_t)x * 8;      // [n][chunk][part][y][x][8]
+#pragma unroll
+  for (int c8 = 0; c8 < 2; ++c8) {
+    float w8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w8[k] = v[c8 * 8 + k];
+    uint4 hi, lo;
+    gfr_p16::split8(w8, hi, lo);
+    *reinterpret_cast<uint4*>(o + (size_t)(2 * c8) * plane) = hi;
+    *reinterpret_cast<uint4*>(o + (size_t)(2 * c8 + 1) * plane) = lo;
+  }
 }
 
+}  // namespace
+
+extern "C" int gfr_stem_unroll_p16(const float* img, void* out, int N, int H, int W, void* stream) {
+  GFR_RETURN_IF_NULL(img); GFR_RETURN_IF_NULL(out);
+  if (N <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
+  const long long total = (long long)N * H * W;
+  stem_unroll_p16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, reinterpret_cast<__half*>(out), H, W, total);
+  return gfr_launch_status();
+}
+
+static long long p16_pack_size(int Cin, int Cout, int NT, int KS, int taps) {
+  if (Cin <= 0 || Cout <= 0 || (NT != 16 && NT != 32) || (KS != 2 && KS != 4) || (taps != 9 && taps != 5)) return GFR_E_ARG;
+  return (long long)gfr_ceil_div(Cout, NT) * gfr_ceil_div(Cin, 8 * KS) * taps * KS * 2 * NT * 8;     // in halfs
+}
+
+extern "C" long long gfr_conv_p16_pack_size(int Cin, int Cout, int NT, int KS) { return p16_pack_size(Cin, Cout, NT, KS, 9); }
+extern "C" long long gfr_conv_p16_pack_size_taps(int Cin, int Cout, int NT, int KS, int taps) { return p16_pack_size(Cin, Cout, NT, KS, taps); }
+
+extern "C" int gfr_conv_p16_pack_weights_taps(const float* w_host, int Cin, int Cout, int NT, int KS, int taps, float w_scale, void* packed_host);
+
 extern "C" int gfr_conv_p16_pack_weights(const float* w_host, int Cin, int Cout, int NT, int KS, float w_scale, void* packed_host) {
+  return gfr_conv_p16_pack_weights_taps(w_host, Cin, Cout, NT, KS, 9, w_scale, packed_host);
+}
+
+// w_host [Cout][Cin][taps]
+extern "C" int gfr_conv_p16_pack_weights_taps(const float* w_host, int Cin, int Cout, int NT, int KS, int taps, float w_scale, void* packed_host) {
   GFR_RETURN_IF_NULL(w_host); GFR_RETURN_IF_NULL(packed_host);
-  if (Cin <= 0 || Cout <= 0 || (NT != 16 && NT != 32) || (KS != 2 && KS != 4) || !(w_scale > 0.f)) return GFR_E_ARG;
+  if (Cin <= 0 || Cout <= 0 || (NT != 16 && NT != 32) || (KS != 2 && KS != 4) || (taps != 9 && taps != 5) || !(w_scale > 0.f)) return GFR_E_ARG;
   const int n_tiles = gfr_ceil_div(Cout, NT), nsteps = gfr_ceil_div(Cin, 8 * KS);
   __half* out = reinterpret_cast<__half*>(packed_host);
   size_t o = 0;
   for (int nt = 0; nt < n_tiles; ++nt)
     for (int st = 0; st < nsteps; ++st)
-      for (int tap = 0; tap < 9; ++tap)
+      for (int tap = 0; tap < taps; ++tap)
         for (int kc = 0; kc < KS; ++kc)
           for (int part = 0; part < 2; ++part)
             for (int n = 0; n < NT; ++n)
@@ -478,7 +557,7 @@ extern "C" int gfr_conv_p16_pack_weights(const float* w_host, int Cin, int Cout,
                 const int co = nt * NT + n, ci = (st * KS + kc) * 8 + e;
                 float v = 0.f;
                 if (co < Cout && ci < Cin) {
-                  const float w = w_host[((size_t)co * Cin + ci) * 9 + tap] * w_scale;
+                  const float w = w_host[((size_t)co * Cin + ci) * taps + tap] * w_scale;
                   if (!(fabsf(w) < 65000.f)) return GFR_E_ARG;            // w_scale too large for fp16
                   const float w1 = __half2float(__float2half_rn(w));
                   v = part == 0 ? w1 : w - w1;
@@ -488,11 +567,35 @@ extern "C" int gfr_conv_p16_pack_weights(const float* w_host, int Cin, int Cout,
   return GFR_OK;
 }
 
+static int conv_p16_launch(const void* in, const void* w_packed, const float* bias, const void* res, int res_c8,
+                           int res_groups, const void* post, int post_groups, void* out, int out_groups, void* pool, int* flags,
+                           int N, int Cin, int in_groups, int Cout, int H, int W, int NT, int MH, int KS, int geo, int post_shift,
+                           int act, int act_channels, float out_scale, float w_scale, int weights_static, void* stream);
+
 extern "C" int gfr_conv3x3_p16_fwd(const void* in, const void* w_packed, const float* bias, const void* res, int res_c8,
                                    int res_groups, const void* post, int post_groups, void* out, int out_groups, int* flags,
                                    int N, int Cin, int in_groups, int Cout, int H, int W, int NT, int MH, int KS, int post_shift,
                                    int act, int act_channels, float out_scale, float w_scale, int weights_static, void* stream) {
+  return conv_p16_launch(in, w_packed, bias, res, res_c8, res_groups, post, post_groups, out, out_groups, nullptr, flags, N, Cin, in_groups,
+                         Cout, H, W, NT, MH, KS, 0, post_shift, act, act_channels, out_scale, w_scale, weights_static, stream);
+}
+
+extern "C" int gfr_conv_p16_fwd_ex(const void* in, const void* w_packed, const float* bias, const void* res, int res_c8,
+                                   int res_groups, const void* post, int post_groups, void* out, int out_groups, void* pool_out, int* flags,
+                                   int N, int Cin, int in_groups, int Cout, int H, int W, int NT, int MH, int KS, int geometry,
+                                   int post_shift, int act, int act_channels, float out_scale, float w_scale, int weights_static,
+                                   void* stream) {
+  return conv_p16_launch(in, w_packed, bias, res, res_c8, res_groups, post, post_groups, out, out_groups, pool_out, flags, N, Cin, in_groups,
+                         Cout, H, W, NT, MH, KS, geometry, post_shift, act, act_channels, out_scale, w_scale, weights_static, stream);
+}
+
+static int conv_p16_launch(const void* in, const void* w_packed, const float* bias, const void* res, int res_c8,
+                           int res_groups, const void* post, int post_groups, void* out, int out_groups, void* pool, int* flags,
+                           int N, int Cin, int in_groups, int Cout, int H, int W, int NT, int MH, int KS, int geo, int post_shift,
+                           int act, int act_channels, float out_scale, float w_scale, int weights_static, void* stream) {
   GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w_packed); GFR_RETURN_IF_NULL(bias); GFR_RETURN_IF_NULL(out);
+  if (geo < 0 || geo > 1) return GFR_E_ARG;
+  if (pool != nullptr && ((H | W) & 1)) return GFR_E_SHAPE;
   if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
   if (post_shift < 0 || post_shift > 1 || act < 0 || act > 2 || !(w_scale > 0.f)) return GFR_E_ARG;
   if (post && post_shift && ((H | W) & 1)) return GFR_E_SHAPE;
@@ -518,10 +621,16 @@ extern "C" int gfr_conv3x3_p16_fwd(const void* in, const void* w_packed, const f
   a.act = act; a.act_channels = act_channels <= 0 ? 8 * out_groups : act_channels;
   a.static_w = weights_static ? 1 : 0;
   a.inv_scale = 1.0f / (gfr_p16::X_SCALE * w_scale); a.out_scale = out_scale;
+  a.pool = reinterpret_cast<__half*>(pool);
   CUtensorMap tm;
-  const int rc = make_p16_map(&tm, in, N, C8in, in_groups, H, W, 8 * MH + 2, KS);
+  const int rc = geo == 0 ? make_p16_map(&tm, in, N, C8in, in_groups, H, W, 8 * MH + 2, TILE_H + 2, KS)
+                          : make_p16_map(&tm, in, N, C8in, in_groups, H, W, 8 * MH, TILE_H + 4, KS);
   if (rc != GFR_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  if (geo == 1) {
+    if (NT == 16 && MH == 2 && KS == 2) return launch_p16<16, 2, 2, 1>(tm, a, s);
+    return GFR_E_ARG;
+  }
 #define GFR_P16_CASE(nt, mh, ks) if (NT == nt && MH == mh && KS == ks) return launch_p16<nt, mh, ks>(tm, a, s)
   GFR_P16_CASE(16, 1, 2); GFR_P16_CASE(16, 2, 2); GFR_P16_CASE(16, 1, 4); GFR_P16_CASE(16, 2, 4);
   GFR_P16_CASE(32, 1, 2); GFR_P16_CASE(32, 2, 2); GFR_P16_CASE(32, 1, 4); GFR_P16_CASE(32, 2, 4);

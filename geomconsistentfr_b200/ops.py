@@ -498,8 +498,33 @@ def conv_p16_pack_weights(w, NT, KS):
     return packed.to(w.device), w_scale
 
 
+def conv_p16_pack_weights_taps(w, NT, KS):
+    """w [Cout,Cin,taps] (taps = 5: the vertical taps of the unrolled stem) -> (packed fp16 tensor, w_scale)."""
+    wc = w.detach().to("cpu", torch.float32).contiguous()
+    Cout, Cin, taps = wc.shape
+    mx = float(wc.abs().max())
+    w_scale = 2.0 ** min(12, int(np.floor(np.log2(16384.0 / max(mx, 1e-30)))))
+    n = _lib.load().gfr_conv_p16_pack_size_taps(Cin, Cout, NT, KS, taps)
+    if n < 0:
+        raise RuntimeError("gfr_conv_p16_pack_size_taps: bad arguments")
+    packed = torch.empty(n, dtype=torch.float16)
+    rc = _lib.load().gfr_conv_p16_pack_weights_taps(ctypes.c_void_p(wc.data_ptr()), Cin, Cout, NT, KS, taps, ctypes.c_float(w_scale),
+                                                    ctypes.c_void_p(packed.data_ptr()))
+    _lib.check(rc, "gfr_conv_p16_pack_weights_taps")
+    return packed.to(w.device), w_scale
+
+
+def stem_unroll_p16(img):
+    """img [N,H,W,3] fp32 CUDA -> P16 [N,16,H,W]: channel kx*3 + c = img[..., x + kx - 2, c] (the stem's horizontal taps as channels)."""
+    img = _need(img, torch.float32, "img")
+    N, H, W, _ = img.shape
+    out = _p16_empty(N, 16, H, W, img.device)
+    _lib.check(_lib.load().gfr_stem_unroll_p16(_ptr(img), _ptr(out), N, H, W, _stream()), "gfr_stem_unroll_p16"); _count()
+    return P16(out, 16)
+
+
 def conv3x3_p16_fwd(x, w_packed, bias, Cout, cfg, w_scale, res=None, res_c=0, post=None, post_shift=0, act="lrelu",
-                    act_channels=0, out_scale=1.0, cin=None, flags=None):
+                    act_channels=0, out_scale=1.0, cin=None, flags=None, pool=False, geometry=0):
     """x: P16; w_packed / w_scale from conv_p16_pack_weights(w, NT, KS); cfg = (NT, MH, KS).
     out = out_scale * (act(conv(x[:, :cin]) + bias + res[:, res_c:res_c+Cout]) + up(post)) as P16 (the activation only on
     output channels < act_channels when given).  `flags`: int32[1] CUDA tensor that collects range overflows."""
@@ -517,12 +542,15 @@ def conv3x3_p16_fwd(x, w_packed, bias, Cout, cfg, w_scale, res=None, res_c=0, po
         assert res.shape[0] == N and res.shape[2:] == (H, W) and res_c % 8 == 0 and res_c + Cout <= res.groups * 8
     if post is not None:
         assert post.shape == (N, Cout, H >> post_shift, W >> post_shift)
-    rc = _lib.load().gfr_conv3x3_p16_fwd(
+    pooled = _p16_empty(N, Cout, H // 2, W // 2, x.data.device) if pool else None
+    rc = _lib.load().gfr_conv_p16_fwd_ex(
         _ptr(x.data), _ptr(w_packed), _ptr(bias), _ptr(res.data if res is not None else None), res_c // 8,
         res.groups if res is not None else 0, _ptr(post.data if post is not None else None), post.groups if post is not None else 0,
-        _ptr(out), 0, _ptr(flags), N, Cin, x.groups, Cout, H, W, NT, MH, KS, int(post_shift), _ACT[act], int(act_channels),
-        float(out_scale), float(w_scale), 1, _stream())
-    _lib.check(rc, "gfr_conv3x3_p16_fwd"); _count()
+        _ptr(out), 0, _ptr(pooled), _ptr(flags), N, Cin, x.groups, Cout, H, W, NT, MH, KS, int(geometry), int(post_shift), _ACT[act],
+        int(act_channels), float(out_scale), float(w_scale), 1, _stream())
+    _lib.check(rc, "gfr_conv_p16_fwd_ex"); _count()
+    if pool:
+        return P16(out, Cout), P16(pooled, Cout)
     return P16(out, Cout)
 
 

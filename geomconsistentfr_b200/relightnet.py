@@ -74,6 +74,8 @@ class RelightNet(nn.Module):
                                               # |activation| < 4094 — checked on the device, see range_check), 3 = 3xTF32, 1 = TF32
         self.train_precision = 3              # train-mode conv operands: 3 = 3xTF32 (fp32-grade: the parity tests), 4 = bf16 with fp32
                                               # accumulation (BASELINE configs[2] "bf16 CNN / fp32 ray-march"), 1 = TF32
+        self.stem_tc = os.environ.get("GFR_STEM_TC", "1") != "0"      # P16 path: the 5x5 stem as unroll + 5 vertical taps on tcgen05, and the
+                                              # encoder's max pools fused into the producing epilogues (0: CUDA-core stem + pool kernels)
         self.p16 = True                       # precision 2 on PRE-SPLIT fp16-pair activations (csrc/conv_p16.cu); False: the first-
                                               # generation kernel that splits fp32 C4 tiles in shared memory (kept for A/B runs)
         self.range_check = True               # precision 2: every conv output is range-checked on the device; an eager forward
@@ -244,6 +246,13 @@ class RelightNet(nn.Module):
             Cpad = (Cout + 7) // 8 * 8
             wz, bz = w1.new_zeros((Cpad - Cout,) + tuple(w1.shape[1:])), b1.new_zeros(Cpad - Cout)
             t["cat:" + n1] = pack(torch.cat([w1, wz, wsc]), torch.cat([b1, bz, bsc])) + (Cpad, Cout)
+        # the stem on the tensor cores: its five horizontal taps are unrolled into channels (ops.stem_unroll_p16), the layer is
+        # then a 5x1 vertical-tap convolution 16 -> 16 with W5[co][kx*3 + c][ky] = w[co][c][ky][kx]
+        w, b = f["conv_c1_og"]
+        w5 = w.new_zeros((16, 16, 5))
+        w5[:, :15, :] = w.permute(0, 3, 1, 2).reshape(16, 15, 5)            # [co][kx][c][ky] -> [co][kx*3 + c][ky]
+        packed, w_scale = ops.conv_p16_pack_weights_taps(w5, 16, 2)
+        t["stem5"] = (packed, b.contiguous(), 16, (16, 2), w_scale)
         self._p16w, self._p16w_key = t, key
         return t
 
@@ -262,11 +271,11 @@ class RelightNet(nn.Module):
             MH = 2 if N * ((h + 15) // 16) * ((w + 15) // 16) * ((Cout + NT - 1) // NT) >= 296 else 1
             return ops.conv3x3_p16_fwd(x, wp, b, Cout, (NT, MH, KS), w_scale, flags=flags, **kw)
 
-        def res_block(n1, n2, x, cin=None):
+        def res_block(n1, n2, x, cin=None, pool=False):
             """lrelu(bn(conv_sc(x)) + bn(conv2(lrelu(bn(conv1(x)))))) — TRAIN:203-223, 235-239: conv1 and conv_sc in one launch."""
             Cpad, Cout = t["cat:" + n1][5:7]
             both = conv("cat:" + n1, x, cin=cin, act_channels=Cpad)
-            return conv(n2, both, cin=Cout, res=both, res_c=Cpad)
+            return conv(n2, both, cin=Cout, res=both, res_c=Cpad, pool=pool)
 
         def up_and_skip(p, skip, tt, enc):
             if epoch > _EPOCH_GATES[skip]:
@@ -274,13 +283,22 @@ class RelightNet(nn.Module):
                 return conv("conv_%s_skip_%s_2" % (p, skip), s1, res=enc, post=tt, post_shift=1)
             return ops.upsample2_p16_fwd(tt)
 
-        c1_og, c1 = ops.stem_conv_p16_fwd(img, *t["conv_c1_og"])            # TRAIN:197-201 (conv + BN + LReLU + pool)
-        h1_og = conv("conv_h1_2", conv("conv_h1_1", c1), res=c1)
-        h1 = ops.maxpool2_p16_fwd(h1_og)
-        h2_og = res_block("conv_h2_1", "conv_h2_2", h1)
-        h2 = ops.maxpool2_p16_fwd(h2_og)
-        h3_og = res_block("conv_h3_1", "conv_h3_2", h2)
-        h3 = ops.maxpool2_p16_fwd(h3_og)
+        # TRAIN:197-201 (conv + BN + LReLU + pool).  stem_tc: on the tensor cores (unroll + 5 vertical taps), the max pools of
+        # the encoder (TRAIN:201,206,212,218) come out of the producing layer's epilogue
+        if self.stem_tc and H % 2 == 0 and W % 2 == 0:
+            wp, b, _, _, w_scale = t["stem5"]
+            c1_og, c1 = ops.conv3x3_p16_fwd(ops.stem_unroll_p16(img), wp, b, 16, (16, 2, 2), w_scale, flags=flags, pool=True, geometry=1)
+            h1_og, h1 = conv("conv_h1_2", conv("conv_h1_1", c1), res=c1, pool=True)
+            h2_og, h2 = res_block("conv_h2_1", "conv_h2_2", h1, pool=True)
+            h3_og, h3 = res_block("conv_h3_1", "conv_h3_2", h2, pool=True)
+        else:
+            c1_og, c1 = ops.stem_conv_p16_fwd(img, *t["conv_c1_og"])
+            h1_og = conv("conv_h1_2", conv("conv_h1_1", c1), res=c1)
+            h1 = ops.maxpool2_p16_fwd(h1_og)
+            h2_og = res_block("conv_h2_1", "conv_h2_2", h1)
+            h2 = ops.maxpool2_p16_fwd(h2_og)
+            h3_og = res_block("conv_h3_1", "conv_h3_2", h2)
+            h3 = ops.maxpool2_p16_fwd(h3_og)
         h4 = res_block("conv_h4_1", "conv_h4_2", h3)
         cur = torch.cuda.current_stream()
         side, aux = self._side_stream(), self._side_stream("_aux")

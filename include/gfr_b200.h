@@ -377,6 +377,21 @@ int gfr_conv3x3_p16_fwd(const void* in, const void* w_packed, const float* bias,
                         int in_groups, int Cout, int H, int W, int NT, int MH, int KS, int post_shift, int act,
                         int act_channels, float out_scale, float w_scale, int weights_static, void* stream);
 
+/* The general form.  geometry 0: 3x3 / pad 1 (gfr_conv3x3_p16_fwd).  geometry 1: 5x1 VERTICAL taps / pad (2, 0), weights
+ * [Cout][Cin][5] packed with gfr_conv_p16_pack_weights_taps(taps = 5) — the stem's 5x5 / pad 2 convolution (conv_c1_og,
+ * TRAIN:197-200) after gfr_stem_unroll_p16 has unrolled its five horizontal taps into channels:
+ *     U[n][kx*3 + c][y][x] = img[n][y][x + kx - 2][c]  (P16, 16 channels, channel 15 = 0; img NHWC fp32)
+ *     conv5x5(img)[co][y][x] = sum_ky sum_c' W5[co][c'][ky] U[c'][y + ky - 2][x],  W5[co][kx*3 + c][ky] = w[co][c][ky][kx]
+ * (NT 16, MH 2, KS 2 only).  pool_out (may be NULL): P16 [N][out_groups][2][H/2][W/2][8], the 2x2 / stride 2 max pool of the
+ * layer's output (TRAIN:201,206,212,218) written by the same epilogue (warp shuffles across the 2x2 quad; H, W even). */
+int gfr_conv_p16_fwd_ex(const void* in, const void* w_packed, const float* bias, const void* res, int res_c8, int res_groups,
+                        const void* post, int post_groups, void* out, int out_groups, void* pool_out, int* flags, int N, int Cin,
+                        int in_groups, int Cout, int H, int W, int NT, int MH, int KS, int geometry, int post_shift, int act,
+                        int act_channels, float out_scale, float w_scale, int weights_static, void* stream);
+long long gfr_conv_p16_pack_size_taps(int Cin, int Cout, int NT, int KS, int taps);
+int gfr_conv_p16_pack_weights_taps(const float* w_host, int Cin, int Cout, int NT, int KS, int taps, float w_scale, void* packed_host);
+int gfr_stem_unroll_p16(const float* img, void* out, int N, int H, int W, void* stream);
+
 /* NCHW fp32 <-> P16, 2x2 max pool on P16 (compares the joined fp32 values), and the P16 forms of the stem (out / pooled
  * P16 [N,16,H,W] / [N,16,H/2,W/2]), the fused 1x1 decoder tail (in P16 [N,16,H,W]) and the light head (feat P16 with
  * `groups` chunks). */

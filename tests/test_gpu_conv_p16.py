@@ -144,3 +144,39 @@ def test_stem_head_light_p16_equal_their_c4_forms():
     l4 = ops.light_head_c4_fwd(ops.nchw_to_c4(fq), 128, w1, b1, wl, bl)
     l16 = ops.light_head_p16_fwd(ops.nchw_to_p16(fq), 128, w1, b1, wl, bl)
     assert float((l4 - l16).abs().max()) <= 1e-6
+
+
+def test_stem_on_tensor_cores_and_fused_pool():
+    """The 5x5 stem as horizontal-tap unroll + 5 vertical taps on tcgen05 (geometry 1) against torch fp64, and the 2x2 max pool
+    that the epilogue writes alongside (stem: no residual; a 3x3 layer with a residual operand and LeakyReLU)."""
+    from geomconsistentfr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    img = torch.rand(2, 64, 96, 3, device="cuda", generator=g)
+    w = torch.randn(16, 3, 5, 5, device="cuda", generator=g) * 0.1
+    b = torch.randn(16, device="cuda", generator=g) * 0.1
+    w5 = w.new_zeros((16, 16, 5))
+    w5[:, :15, :] = w.permute(0, 3, 1, 2).reshape(16, 15, 5)
+    wp, ws = ops.conv_p16_pack_weights_taps(w5, 16, 2)
+    u = ops.stem_unroll_p16(img)
+    un = ops.p16_to_nchw(u)
+    x = img.permute(0, 3, 1, 2)
+    for kx in range(5):                                        # the unroll itself: channel kx*3 + c = img shifted by kx - 2
+        sh = F.pad(x, (2, 2, 0, 0))[:, :, :, kx:kx + 96]
+        assert float((un[:, kx * 3:kx * 3 + 3] - sh).abs().max()) <= 2.0 ** -21
+    assert float(un[:, 15].abs().max()) == 0.0
+    full, pooled = ops.conv3x3_p16_fwd(u, wp, b, 16, (16, 2, 2), ws, pool=True, geometry=1)
+    ref = F.leaky_relu(F.conv2d(x.double(), w.double(), b.double(), padding=2), 0.2)
+    got = ops.p16_to_nchw(full)
+    assert float((got.double() - ref).abs().max()) <= 3e-6 * float(ref.abs().max())
+    assert torch.equal(ops.p16_to_nchw(pooled), F.max_pool2d(got, 2))
+    # fused pool behind residual + activation, all three tile shapes
+    for (N, C, S, cfg) in ((2, 16, 64, (16, 2, 2)), (2, 32, 32, (32, 1, 4)), (1, 16, 32, (16, 1, 2))):
+        xx = _acts((N, C, S, S), g, 4.0)
+        ww = torch.randn(C, C, 3, 3, device="cuda", generator=g) / (3.0 * C ** 0.5)
+        bb = torch.randn(C, device="cuda", generator=g)
+        rr = _acts((N, C, S, S), g, 4.0)
+        wq, sq = ops.conv_p16_pack_weights(ww, cfg[0], cfg[2])
+        y, yp = ops.conv3x3_p16_fwd(ops.nchw_to_p16(xx), wq, bb, C, cfg, sq, res=ops.nchw_to_p16(rr), pool=True)
+        y0 = ops.conv3x3_p16_fwd(ops.nchw_to_p16(xx), wq, bb, C, cfg, sq, res=ops.nchw_to_p16(rr))
+        assert torch.equal(ops.p16_to_nchw(y), ops.p16_to_nchw(y0))
+        assert torch.equal(ops.p16_to_nchw(yp), F.max_pool2d(ops.p16_to_nchw(y), 2))
