@@ -590,7 +590,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=3, help="runner lanes the e2e (host-buffer) path rotates over")
     ap.add_argument("--e2e-f32", action="store_true", help="e2e reads back fp32 rendered_images (6.3 MB) instead of the 8-bit BGR composite")
     ap.add_argument("--no-gan", action="store_true", help="train workload without the PatchGAN terms")
-    ap.add_argument("--train-precision", type=int, default=0, help="train-mode conv operand precision (3 = 3xTF32, 1 = TF32, 4 = bf16)")
+    ap.add_argument("--train-precision", type=int, default=4, help="train-mode conv operand precision: 4 = bf16 operands / fp32 accumulation "
+                                                                   "(BASELINE configs[2]: 'bf16 CNN / fp32 ray-march', the default), 3 = 3xTF32 "
+                                                                   "(fp32-grade: what the parity tests run), 1 = TF32")
     ap.add_argument("--no-pin", action="store_true", help="do not pin each rank to its own host cores")
     ap.add_argument("--workload", default="all", choices=["all", "forward", "train", "sweep"],
                     help="all (default) = the configs[1] forward line with `train` (configs[2]/[3]) and `sweep` (configs[4]) "

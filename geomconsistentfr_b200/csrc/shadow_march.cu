@@ -40,6 +40,9 @@ struct MarchArgs {
 };
 
 constexpr int TILE_W = 32, TILE_H = 8;
+#ifndef GFR_MARCH_DEFAULT_ILP
+#define GFR_MARCH_DEFAULT_ILP 1
+#endif
 
 // End point of the 2-D ray (pixel -> projected light) on the image rectangle, fp32, reference op order.
 // TRAIN:378-465.  Rectangle: x in [-W/2, W/2-1], y in [1-H/2, H/2].
@@ -169,14 +172,65 @@ __device__ __forceinline__ void round_parts(double v, int& r, double& rd) {
   rd = __dsub_rn(s, kMagic);
 }
 
+// The in-mask part of one sample (TRAIN:481-509): bilinear depth at the sample in fp64, then the fp32 squared distance of the
+// surface point from the pixel -> light line (times |BC|^2).  Every address is inside the image for every walked sample (the
+// ray is clipped to the image rectangle), so callers may evaluate it speculatively for out-of-mask samples and discard q.
+struct RayConst {
+  double hW, hH, neg_eps;
+  float x, y, z, bcx, bcy, bcz;
+  int W, H;
+};
+
+__device__ __forceinline__ float sample_q(const double* D, const RayConst& r, double px, double py) {
+  const double u = __dadd_rn(__dadd_rn(px, r.hW), r.neg_eps);                         // TRAIN:481,483
+  const double v = __dadd_rn(__dsub_rn(r.hH, py), r.neg_eps);                         // TRAIN:482,483
+  // floor / ceil: the magic add in round-down / round-up mode (TRAIN:486-487)
+  const double sfu = __dadd_rd(u, kMagic), scu = __dadd_ru(u, kMagic);
+  const double sfv = __dadd_rd(v, kMagic), scv = __dadd_ru(v, kMagic);
+  const int uf = __double2loint(sfu), uc = __double2loint(scu);
+  const int vf = __double2loint(sfv), vc = __double2loint(scv);
+  const double ufd = __dsub_rn(sfu, kMagic), ucd = __dsub_rn(scu, kMagic);
+  const double vfd = __dsub_rn(sfv, kMagic), vcd = __dsub_rn(scv, kMagic);
+  const unsigned ufi = uf < 0 ? uf + r.W : uf, vfi = vf < 0 ? vf + r.H : vf;          // python negative index
+  const double wu0 = __dsub_rn(ucd, u), wu1 = __dsub_rn(u, ufd);
+  const double wv0 = __dsub_rn(vcd, v), wv1 = __dsub_rn(v, vfd);
+  // four corners from ONE 64-bit address: the other three are 32-bit element offsets (one IMAD.WIDE each)
+  const double* p00 = D + (vfi * (unsigned)r.W + ufi);
+  const int du = uc - (int)ufi, dv = (vc - (int)vfi) * r.W;                           // +1 / 0, or -(W-1) / -(H-1)*W on a wrap
+  const double* p10 = p00 + dv;
+  const double ul = __ldg(p00), ur = __ldg(p00 + du);
+  const double ll = __ldg(p10), lr = __ldg(p10 + du);
+  const double up = __dadd_rn(__dmul_rn(ul, wu0), __dmul_rn(ur, wu1));                // TRAIN:492
+  const double lo = __dadd_rn(__dmul_rn(ll, wu0), __dmul_rn(lr, wu1));                // TRAIN:493
+  const double zi = __dadd_rn(__dmul_rn(up, wv0), __dmul_rn(lo, wv1));                // TRAIN:494
+  const float ax = (float)__dsub_rn(u, r.hW), ay = (float)__dsub_rn(r.hH, v), az = (float)zi;   // TRAIN:498-502
+  const float bax = __fsub_rn(ax, r.x), bay = __fsub_rn(ay, r.y), baz = __fsub_rn(az, r.z);
+  const float c0 = __fsub_rn(__fmul_rn(bay, r.bcz), __fmul_rn(baz, r.bcy));           // TRAIN:508
+  const float c1 = __fsub_rn(__fmul_rn(baz, r.bcx), __fmul_rn(bax, r.bcz));
+  const float c2 = __fsub_rn(__fmul_rn(bax, r.bcy), __fmul_rn(bay, r.bcx));
+  return __fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fmul_rn(c2, c2));
+}
+
 // TH = rows of the CTA tile (32 x TH pixels, TH warps).  TH = 8: 256-thread CTAs, 4 per SM.  TH = 4: 128-thread CTAs (8 per
 // SM) that also fit beside two resident tcgen05 conv CTAs (2 x 320 threads x 84 registers + 175 KB shared memory leave
 // room for 128 x 62 registers + 8 KB), so the issue-bound march of one runner lane can share SMs with the shared-memory /
 // tensor-bound convolutions of another.
-template <int TH>
-__global__ void __launch_bounds__(TILE_W * TH, 1024 / (TILE_W * TH))
+//
+// WS = warp shape.  0: a warp is 32 x 1 pixels of the tile (round 1).  1: a warp is 8 x 4 pixels (warp w of the CTA owns columns
+// 8w .. 8w+7 of the 32 x 4 tile; TH = 4 only): the 32 rays of a warp start closer together, so their sample-range union is
+// shorter and they cross the face-mask boundary at more nearly the same k (tools/sim_march_warp_shape.py on the bench masks:
+// 85.8 -> 79.1 walked and 68.6 -> 62.3 in-mask warp-iterations per warp, -9 % instructions), and a gather touches 4 x 64 B
+// instead of 1 x 256 B of each of its two rows.
+// ILP = 2 walks the samples in pairs: both positions / mask tests first, then both in-mask bodies back to back in one basic
+// block (the second is speculative where only one of the pair is inside the face; every address is valid), so the scheduler has
+// two independent fp64 dependency chains per warp to hide the fixed-latency stalls that dominated round 1's stall sampling
+// (`wait` 2.9 and `not selected` 2.2 warps per issue at 6.6 resident warps per scheduler).  Same arithmetic per sample, same
+// first-minimum rule: bit-identical results (tests/test_gpu_march_edges.py compares every variant with the literal kernel).
+template <int TH, int WS, int ILP>
+__global__ void __launch_bounds__(TILE_W * TH, ILP == 2 ? 6 : 1024 / (TILE_W * TH))
 shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, const __grid_constant__ SampleTable tab) {
   constexpr int TILE_H = TH;
+  static_assert(WS == 0 || TH == 4, "the 8 x 4 warp shape is laid out for 32 x 4 CTA tiles");
   extern __shared__ uint32_t s_mask[];
   const int b = blockIdx.z, f = b / a.lpf;
   const int H = a.H, W = a.W;
@@ -221,8 +275,8 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
     __syncthreads();
   }
 
-  const int col = blockIdx.x * TILE_W + threadIdx.x;
-  const int row = blockIdx.y * TILE_H + threadIdx.y;
+  const int col = WS == 0 ? blockIdx.x * TILE_W + threadIdx.x : blockIdx.x * TILE_W + threadIdx.y * 8 + (threadIdx.x & 7);
+  const int row = WS == 0 ? blockIdx.y * TILE_H + threadIdx.y : blockIdx.y * TILE_H + (threadIdx.x >> 3);
   const double* D = depth64 + (size_t)f * H * W;
   asm volatile("" : "+l"(D));               // one 64-bit base register pair: every gather address is then a single IMAD.WIDE
   const float halfW = 0.5f * W, halfH = 0.5f * H;
@@ -269,6 +323,25 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
 
   float qmin = __int_as_float(0x7f800000);   // +inf == "outside the face"
   int kmin = 255;
+  RayConst rc;
+  rc.hW = hW; rc.hH = hH; rc.neg_eps = neg_eps; rc.x = x; rc.y = y; rc.z = z; rc.bcx = bcx; rc.bcy = bcy; rc.bcz = bcz; rc.W = W; rc.H = H;
+  if (ILP == 2) {
+    for (int k = k_begin; k <= k_end; k += 2) {
+      const int k1 = min(k + 1, k_end);                                               // odd tail: the pair's second sample repeats k
+      const double t0 = tab.t[k], t1 = tab.t[k1];
+      const double px0 = __dadd_rn(xd, __dmul_rn(t0, dx)), px1 = __dadd_rn(xd, __dmul_rn(t1, dx));    // TRAIN:472,480
+      const double py0 = __dadd_rn(yd, __dmul_rn(t0, dy)), py1 = __dadd_rn(yd, __dmul_rn(t1, dy));
+      const int mi0 = (cH - __double2loint(__dadd_rn(py0, kMagic))) * W + __double2loint(__dadd_rn(px0, kMagic)) + cW;
+      const int mi1 = (cH - __double2loint(__dadd_rn(py1, kMagic))) * W + __double2loint(__dadd_rn(px1, kMagic)) + cW;
+      const bool in0 = (s_mask[mi0 >> 5] >> (mi0 & 31)) & 1u;                         // TRAIN:510-512
+      const bool in1 = ((s_mask[mi1 >> 5] >> (mi1 & 31)) & 1u) && k1 != k;
+      if (!(in0 || in1)) continue;
+      const float q0 = sample_q(D, rc, px0, py0);
+      const float q1 = sample_q(D, rc, px1, py1);
+      if (in0 && q0 < qmin) { qmin = q0; kmin = k; }
+      if (in1 && q1 < qmin) { qmin = q1; kmin = k1; }
+    }
+  } else {
   const float dxf32 = __fsub_rn(ex, x), dyf32 = __fsub_rn(ey, y);
   const float dt32 = a.inv_dt != 0.f ? 1.0f / a.inv_dt : 0.f;
   int k_skip_checked = k_begin - 1;          // the last group start that has been tested
@@ -292,34 +365,9 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
     const int ri = cH - __double2loint(__dadd_rn(py, kMagic));
     const int mi = ri * W + ci;
     if (!((s_mask[mi >> 5] >> (mi & 31)) & 1u)) continue;                             // TRAIN:510-512
-    const double u = __dadd_rn(__dadd_rn(px, hW), neg_eps);                           // TRAIN:481,483
-    const double v = __dadd_rn(__dsub_rn(hH, py), neg_eps);                           // TRAIN:482,483
-    // floor / ceil: the same magic add in round-down / round-up mode (TRAIN:486-487)
-    const double sfu = __dadd_rd(u, kMagic), scu = __dadd_ru(u, kMagic);
-    const double sfv = __dadd_rd(v, kMagic), scv = __dadd_ru(v, kMagic);
-    const int uf = __double2loint(sfu), uc = __double2loint(scu);
-    const int vf = __double2loint(sfv), vc = __double2loint(scv);
-    const double ufd = __dsub_rn(sfu, kMagic), ucd = __dsub_rn(scu, kMagic);
-    const double vfd = __dsub_rn(sfv, kMagic), vcd = __dsub_rn(scv, kMagic);
-    const unsigned ufi = uf < 0 ? uf + W : uf, vfi = vf < 0 ? vf + H : vf;            // python negative index
-    const double wu0 = __dsub_rn(ucd, u), wu1 = __dsub_rn(u, ufd);
-    const double wv0 = __dsub_rn(vcd, v), wv1 = __dsub_rn(v, vfd);
-    // four corners from ONE 64-bit address: the other three are 32-bit element offsets (one IMAD.WIDE each)
-    const double* p00 = D + (vfi * (unsigned)W + ufi);
-    const int du = uc - (int)ufi, dv = (vc - (int)vfi) * W;                           // +1 / 0, or -(W-1) / -(H-1)*W on a wrap
-    const double* p10 = p00 + dv;
-    const double ul = __ldg(p00), ur = __ldg(p00 + du);
-    const double ll = __ldg(p10), lr = __ldg(p10 + du);
-    const double up = __dadd_rn(__dmul_rn(ul, wu0), __dmul_rn(ur, wu1));              // TRAIN:492
-    const double lo = __dadd_rn(__dmul_rn(ll, wu0), __dmul_rn(lr, wu1));              // TRAIN:493
-    const double zi = __dadd_rn(__dmul_rn(up, wv0), __dmul_rn(lo, wv1));              // TRAIN:494
-    const float ax = (float)__dsub_rn(u, hW), ay = (float)__dsub_rn(hH, v), az = (float)zi;   // TRAIN:498-502
-    const float bax = __fsub_rn(ax, x), bay = __fsub_rn(ay, y), baz = __fsub_rn(az, z);
-    const float c0 = __fsub_rn(__fmul_rn(bay, bcz), __fmul_rn(baz, bcy));             // TRAIN:508
-    const float c1 = __fsub_rn(__fmul_rn(baz, bcx), __fmul_rn(bax, bcz));
-    const float c2 = __fsub_rn(__fmul_rn(bax, bcy), __fmul_rn(bay, bcx));
-    const float q = __fadd_rn(__fadd_rn(__fmul_rn(c0, c0), __fmul_rn(c1, c1)), __fmul_rn(c2, c2));
+    const float q = sample_q(D, rc, px, py);
     if (q < qmin) { qmin = q; kmin = k; }
+  }
   }
   float d;
   if (kmin == 255) {
@@ -490,6 +538,15 @@ extern "C" int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int 
   return gfr_launch_status();
 }
 
+// A/B configuration of the fast march kernel: -1 / 0 = the default (environment, else the built-in choice)
+static int g_march_warp_shape = -1, g_march_ilp = 0;
+
+extern "C" int gfr_march_config(int warp_shape, int ilp) {
+  if (warp_shape < -1 || warp_shape > 1 || ilp < 0 || ilp > 2) return GFR_E_ARG;
+  g_march_warp_shape = warp_shape; g_march_ilp = ilp;
+  return GFR_OK;
+}
+
 static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_batch_stride, const float* light_pt,
                       const double* t_host, int n, float inside_bonus, const float* bonus_rect_host, float* d_min, uint8_t* argmin, float* shadow,
                       double* depth64_scratch, int B, int H, int W, int lights_per_face, int variant,
@@ -545,11 +602,23 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
   } else if (variant == 0 && depth64_scratch != nullptr && fast_ok) {
     const size_t n4 = (size_t)faces * H * W / 4;
     widen_depth_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch, n4);
+    // A/B switches (read once): GFR_MARCH_WARP = 0 -> 32 x 1 warps (round 1), GFR_MARCH_ILP = 1 / 2 -> samples one by one / in pairs
+    static const int env_warp_shape = [] { const char* e = getenv("GFR_MARCH_WARP"); return (e && atoi(e) == 0) ? 0 : 1; }();
+    static const int env_ilp = [] { const char* e = getenv("GFR_MARCH_ILP"); return e ? (atoi(e) == 2 ? 2 : 1) : GFR_MARCH_DEFAULT_ILP; }();
+    const int warp_shape = g_march_warp_shape >= 0 ? g_march_warp_shape : env_warp_shape;
+    const int ilp = g_march_ilp > 0 ? g_march_ilp : env_ilp;
+    cudaStream_t st = (cudaStream_t)stream;
     if (fast_th == 4 && H % 4 == 0) {
       grid.y = H / 4; block.y = 4;
-      shadow_march_fwd_fast<4><<<grid, block, smem, (cudaStream_t)stream>>>(a, depth64_scratch, tab);
+      if (warp_shape == 1 && !a.coarse) {
+        if (ilp == 2) shadow_march_fwd_fast<4, 1, 2><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
+        else shadow_march_fwd_fast<4, 1, 1><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
+      } else {
+        if (ilp == 2 && !a.coarse) shadow_march_fwd_fast<4, 0, 2><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
+        else shadow_march_fwd_fast<4, 0, 1><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
+      }
     } else {
-      shadow_march_fwd_fast<8><<<grid, block, smem, (cudaStream_t)stream>>>(a, depth64_scratch, tab);
+      shadow_march_fwd_fast<8, 0, 1><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
     }
   } else {
     shadow_march_fwd_l1<<<grid, block, smem, (cudaStream_t)stream>>>(a, tab);

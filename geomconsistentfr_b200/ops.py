@@ -115,6 +115,12 @@ def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0,
     return dmin, arg, shadow
 
 
+def march_config(warp_shape=-1, ilp=0):
+    """A/B switches of the default march kernel (process-wide): warp_shape 0 = 32x1, 1 = 8x4 pixels per warp; ilp 1 / 2 =
+    samples one by one / in pairs; -1 / 0 = defaults.  Bit-identical results in every setting."""
+    _lib.check(_lib.load().gfr_march_config(int(warp_shape), int(ilp)), "gfr_march_config")
+
+
 def shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx=1570.0, fy=1570.0, cx=None, cy=None,
                      depth_offset=1610.0, intensity=0.5, want=("shadow", "full", "final", "rendered", "normals")):
     """TRAIN:353-369, 517-522.  albedo/depth/ambient hold F faces, d_min/light_pt B = F * L (face, light) pairs.

@@ -78,6 +78,12 @@ int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask
                          const float* bonus_rect_host, float* d_min, uint8_t* argmin, float* shadow, double* depth64_scratch, int B, int H, int W,
                          int lights_per_face, int variant, void* stream);
 
+/* A/B configuration of variant 0's kernel (process-wide; results are bit-identical in every setting):
+ *   warp_shape  -1 default (environment GFR_MARCH_WARP, else 1), 0 = a warp marches 32 x 1 pixels, 1 = 8 x 4 pixels
+ *   ilp          0 default (environment GFR_MARCH_ILP, else the built-in choice), 1 = samples one by one, 2 = in pairs
+ * Same loop as TRAIN:467-515 either way; no reference counterpart (a tuning knob for tests / tools). */
+int gfr_march_config(int warp_shape, int ilp);
+
 /* Normals + Lambertian shading + shadow blend + albedo render.  Replaces TRAIN:353-369 and 517-522
  * (kornia depth_to_normals(depth + depth_offset, K), y flip, double normalise, l = normalize(P_L - P),
  * dir = intensity * max(n.l, 0), full = ambient + dir, s = shadow(d_min),

@@ -141,6 +141,42 @@ def test_coarse_group_skip_is_exact_on_masks_with_holes(ops):
         assert torch.equal(d0, d1) and torch.equal(a0, a1), L
 
 
+def test_warp_shape_and_sample_pairs_are_bit_identical(ops):
+    """Round 2: the default kernel's A/B configurations — 32x1 vs 8x4 pixels per warp, samples one by one vs in pairs (the
+    second sample of a pair is evaluated speculatively) — against the literal kernel: bit-identical d_min / arg-min / fused
+    shading on ragged masks, an odd sample count (the pair loop's tail) and lights on every side."""
+    H = W = 128
+    g = torch.Generator().manual_seed(33)
+    depth = (torch.rand(4, 1, H, W, generator=g) * 50.0).cuda()
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    masks = torch.zeros(4, H, W, dtype=torch.uint8)
+    masks[0] = ((((xx - 64) / 40.0) ** 2 + ((yy - 64) / 50.0) ** 2) < 1.0).to(torch.uint8)
+    masks[1, 5:60, 70:128] = 1
+    masks[2] = (torch.rand(H, W, generator=g) > 0.9).to(torch.uint8)
+    masks[3, 64:65, :] = 1
+    bits = ops.mask_pack(masks.cuda())
+    albedo = torch.rand(4, 3, H, W, generator=g).cuda()
+    amb = torch.full((4,), 0.3, device="cuda")
+    L = torch.tensor([(0.7, 0.1, 0.7), (-0.6, -0.5, 0.62), (0.004, 0.003, 1.0), (0.0, 0.7071, 0.7071)])
+    P_L = (4013.0 * torch.nn.functional.normalize(L, dim=1)).cuda()
+    try:
+        for t in (None, np.arange(0.025, 0.825, 0.005)[:157]):
+            d1, a1, _ = ops.shadow_march_fwd(depth, bits, P_L, samples=t, inside_bonus=5.0, want_argmin=True, variant=1)
+            ref = None
+            for ws in (0, 1):
+                for ilp in (1, 2):
+                    ops.march_config(ws, ilp)
+                    d0, a0, _ = ops.shadow_march_fwd(depth, bits, P_L, samples=t, inside_bonus=5.0, want_argmin=True, variant=0)
+                    assert torch.equal(d0, d1) and torch.equal(a0, a1), (ws, ilp)
+                    o = ops.march_shade_fwd(albedo, depth, bits, P_L, amb, inside_bonus=5.0, samples=t, want=("rendered", "normals", "d_min"))
+                    assert torch.equal(o["d_min"], d1), (ws, ilp)
+                    if ref is None:
+                        ref = o
+                    assert torch.equal(o["rendered"], ref["rendered"]) and torch.equal(o["normals"], ref["normals"]), (ws, ilp)
+    finally:
+        ops.march_config(-1, 0)
+
+
 def test_shade_render_vs_oracle(ops, march):
     """TRAIN:353-369, 517-522 on the golden depth: normals, full/final shading, rendered.
     Tolerance 2e-5 absolute (all outputs are O(1); fp32 with a different summation order)."""

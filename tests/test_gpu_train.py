@@ -170,16 +170,27 @@ def test_generator_step_losses_and_all_gradients_vs_oracle():
         a, b = float(terms[k]), float(terms_ref[k])
         assert abs(a - b) <= 2e-3 * max(abs(b), 1e-3), (k, a, b)
     total.backward()
-    worst = {}
+    worst, l1 = {}, {}
     for (n1, p1), (n2, p2) in zip(net.named_parameters(), ref.named_parameters()):
         assert n1 == n2
         if n1.endswith(".bias") and ("conv" in n1 or "deconv" in n1) and not n1.endswith("c2_o.bias"):
             continue                                  # conv bias before a train-mode BN: gradient is 0 up to rounding on both sides
         g1, g2 = p1.grad.cpu(), p2.grad
         worst[n1] = float((g1 - g2).abs().max() / (g2.abs().max() + 1e-12))
+        l1[n1] = float((g1 - g2).abs().sum() / (g2.abs().sum() + 1e-12))
+    # Two metrics per parameter tensor.  L1-relative (the bulk): what 3xTF32 convs + fp64 BN sums + atomics deliver.  Max-norm
+    # (the worst element): carries the isolated discontinuities of the path — a LeakyReLU / BN unit whose pre-activation is
+    # within rounding of 0 flips its slope (1 vs 0.2), a ray-march arg-min tie moves the gradient to another depth pixel, a
+    # max-pool tie to another input — each moves one contribution by O(1) of its size in the oracle's own fp32 run as well.
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:6]
+    print("worst max-norm gradient errors:", ["%s %.1e (L1 %.1e)" % (k, v, l1[k]) for k, v in top])
+    print("worst L1 gradient errors:", ["%s %.1e" % kv for kv in sorted(l1.items(), key=lambda kv: -kv[1])[:6]],
+          "median max-norm %.1e, median L1 %.1e" % (np.median(list(worst.values())), np.median(list(l1.values()))))
     bad = {k: v for k, v in worst.items() if v > 3e-2}
     assert not bad, bad
     assert np.median(list(worst.values())) <= 5e-3
+    assert max(l1.values()) <= 1e-2, max(l1.values())
+    assert np.median(list(l1.values())) <= 2e-3
 
 
 def test_patchgan_forward_backward_vs_oracle():

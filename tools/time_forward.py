@@ -3,7 +3,7 @@ import sys, os, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from geomconsistentfr_b200 import RelightNet, intrinsic_matrix
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-PREC = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+PREC = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 G = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 f = np.load(os.path.join(G, "ffhq.npz"))
 net = RelightNet(); net.load_state_dict(torch.load(os.path.join(G, "model_epoch99.pth"), map_location="cpu")); net = net.cuda().eval(); net.tc_precision = PREC

@@ -1,4 +1,6 @@
-"""Times the three ray-march variants on the bench shapes (B = 8, 256x256, synthetic ellipse mask + FFHQ-like depth)."""
+"""Times the ray-march variants on the bench shapes (B = 8, 256x256, synthetic ellipse mask + FFHQ-like depth): the default
+kernel in its four A/B configurations (warp shape x sample pairing, ops.march_config), the literal kernel and the warp-per-ray
+mapping; stand-alone march (incl. the depth widening pass) and the fused march + shade launch the forward uses."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,17 +11,31 @@ faces = [synthetic_face(seed=i, noise=2.0) for i in range(B)]
 depth = torch.stack([d for d, _ in faces]).view(B, 1, 256, 256).cuda()
 bits = ops.mask_pack((faces[0][1] * 255).view(1, 256, 256).cuda())
 light = (4013.0 * torch.nn.functional.normalize(torch.tensor(LIGHTS_18[:B]), dim=1)).cuda()
-flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for variant in (0, 1, 2):
-    fn = lambda: ops.shadow_march_fwd(depth, bits, light, inside_bonus=5.0, variant=variant)
+albedo = torch.rand(B, 3, 256, 256, device="cuda")
+amb = torch.full((B,), 0.4, device="cuda")
+
+
+def timed(fn, n=20):
     for _ in range(3):
         fn()
     torch.cuda._sleep(20_000_000)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(20):
+    for _ in range(n):
         fn()
     b.record()
     torch.cuda.synchronize()
-    print("variant %d (%s): %.1f us per launch (20 back-to-back launches incl. the depth widening pass)" % (
-        variant, ("thread-per-ray, culled + coarse skip", "thread-per-ray, literal", "warp-per-ray")[variant], 1e3 * a.elapsed_time(b) / 20))
+    return 1e3 * a.elapsed_time(b) / n
+
+
+for ws in (0, 1):
+    for ilp in (1, 2):
+        ops.march_config(ws, ilp)
+        t_m = timed(lambda: ops.shadow_march_fwd(depth, bits, light, inside_bonus=5.0, variant=0))
+        t_f = timed(lambda: ops.march_shade_fwd(albedo, depth, bits, light, amb, inside_bonus=5.0))
+        print("variant 0, warp %s, samples %s: march %.1f us, fused march+shade %.1f us (20 back-to-back launches incl. the depth widening pass)"
+              % (("32x1", "8x4")[ws], ("one by one", "in pairs")[ilp - 1], t_m, t_f))
+ops.march_config(-1, 0)
+for variant in (1, 2):
+    t = timed(lambda: ops.shadow_march_fwd(depth, bits, light, inside_bonus=5.0, variant=variant))
+    print("variant %d (%s): %.1f us per launch" % (variant, ("", "thread-per-ray, literal", "warp-per-ray")[variant], t))
