@@ -31,6 +31,7 @@ struct MarchArgs {
   int B, H, W, n;
   int lpf;                   // lights per face: (face, light) pair b reads depth / mask of face b / lpf
   float t0, inv_dt;          // uniform sample table t_k = t0 + k*dt (inv_dt = 0: not uniform, no sample-range culling)
+  int order;                 // fast kernel: block order, 0 = tile-major (round 1), 1 = pairs interleaved, far-from-light tiles first
   int coarse;                // 1: the fast kernel builds the 8x8-block occupancy map and skips empty groups of 4 samples
   int fuse_shade;            // 1: normals + Lambert + blend + render of the pixel follow in the same thread (shade)
   gfr_shade::ShadeArgs shade;
@@ -41,7 +42,10 @@ struct MarchArgs {
 
 constexpr int TILE_W = 32, TILE_H = 8;
 #ifndef GFR_MARCH_DEFAULT_ILP
-#define GFR_MARCH_DEFAULT_ILP 1
+#define GFR_MARCH_DEFAULT_ILP 2
+#endif
+#ifndef GFR_MARCH_ILP2_BLOCKS
+#define GFR_MARCH_ILP2_BLOCKS 6      // resident 128-thread CTAs per SM the paired-sample kernel is compiled for (80 registers)
 #endif
 
 // End point of the 2-D ray (pixel -> projected light) on the image rectangle, fp32, reference op order.
@@ -227,13 +231,38 @@ __device__ __forceinline__ float sample_q(const double* D, const RayConst& r, do
 // (`wait` 2.9 and `not selected` 2.2 warps per issue at 6.6 resident warps per scheduler).  Same arithmetic per sample, same
 // first-minimum rule: bit-identical results (tests/test_gpu_march_edges.py compares every variant with the literal kernel).
 template <int TH, int WS, int ILP>
-__global__ void __launch_bounds__(TILE_W * TH, ILP == 2 ? 6 : 1024 / (TILE_W * TH))
+__global__ void __launch_bounds__(TILE_W * TH, ILP == 2 ? GFR_MARCH_ILP2_BLOCKS : (ILP == 3 ? 5 : (ILP == 4 ? 4 : 1024 / (TILE_W * TH))))
 shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, const __grid_constant__ SampleTable tab) {
   constexpr int TILE_H = TH;
   static_assert(WS == 0 || TH == 4, "the 8 x 4 warp shape is laid out for 32 x 4 CTA tiles");
   extern __shared__ uint32_t s_mask[];
-  const int b = blockIdx.z, f = b / a.lpf;
   const int H = a.H, W = a.W;
+  // Block order (1-D grid).  a.order = 0: tile column fastest, then tile row, then the (face, light) pair — round 1's 3-D grid.
+  // a.order = 1: the pair index runs fastest and every pair walks ITS tiles starting on the side of the image that is far from
+  // its light, along the axis the light direction is closer to.  A ray marches towards the light: the far side's rays cross
+  // the whole face (160 in-mask samples), the near side's leave the image after a few, so a CTA's cost varies 1 : 700 across
+  // the image and round 1's order ended with one face's 512 tiles, the expensive ones included, on a half-empty GPU
+  // (tools/sim_march_order.py: makespan 1.23x the ideal; far-side-first with the pairs interleaved: 1.06x).
+  int b, bx, by;
+  {
+    const int tiles_x = W / TILE_W, tiles_y = H / TILE_H;
+    const int id = blockIdx.x;
+    if (a.order == 0) {
+      bx = id % tiles_x; by = (id / tiles_x) % tiles_y; b = id / (tiles_x * tiles_y);
+    } else {
+      b = id % a.B;
+      const int i = id / a.B;
+      const float lx = __ldg(a.light + 3 * b), ly = __ldg(a.light + 3 * b + 1);
+      if (fabsf(lx) >= fabsf(ly)) {                 // light to the left / right: tile columns slowest, far column first
+        bx = i / tiles_y; by = i % tiles_y;
+        if (!(lx > 0.f)) bx = tiles_x - 1 - bx;
+      } else {                                      // light above / below (+y is up = small rows): far row first
+        by = i / tiles_x; bx = i % tiles_x;
+        if (ly > 0.f) by = tiles_y - 1 - by;
+      }
+    }
+  }
+  const int f = b / a.lpf;
   const int words = (H * W) >> 5;
   {
     const uint32_t* src = a.mask_bits + (size_t)f * a.mask_stride;
@@ -275,8 +304,8 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
     __syncthreads();
   }
 
-  const int col = WS == 0 ? blockIdx.x * TILE_W + threadIdx.x : blockIdx.x * TILE_W + threadIdx.y * 8 + (threadIdx.x & 7);
-  const int row = WS == 0 ? blockIdx.y * TILE_H + threadIdx.y : blockIdx.y * TILE_H + (threadIdx.x >> 3);
+  const int col = WS == 0 ? bx * TILE_W + threadIdx.x : bx * TILE_W + threadIdx.y * 8 + (threadIdx.x & 7);
+  const int row = WS == 0 ? by * TILE_H + threadIdx.y : by * TILE_H + (threadIdx.x >> 3);
   const double* D = depth64 + (size_t)f * H * W;
   asm volatile("" : "+l"(D));               // one 64-bit base register pair: every gather address is then a single IMAD.WIDE
   const float halfW = 0.5f * W, halfH = 0.5f * H;
@@ -325,21 +354,27 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
   int kmin = 255;
   RayConst rc;
   rc.hW = hW; rc.hH = hH; rc.neg_eps = neg_eps; rc.x = x; rc.y = y; rc.z = z; rc.bcx = bcx; rc.bcy = bcy; rc.bcz = bcz; rc.W = W; rc.H = H;
-  if (ILP == 2) {
-    for (int k = k_begin; k <= k_end; k += 2) {
-      const int k1 = min(k + 1, k_end);                                               // odd tail: the pair's second sample repeats k
-      const double t0 = tab.t[k], t1 = tab.t[k1];
-      const double px0 = __dadd_rn(xd, __dmul_rn(t0, dx)), px1 = __dadd_rn(xd, __dmul_rn(t1, dx));    // TRAIN:472,480
-      const double py0 = __dadd_rn(yd, __dmul_rn(t0, dy)), py1 = __dadd_rn(yd, __dmul_rn(t1, dy));
-      const int mi0 = (cH - __double2loint(__dadd_rn(py0, kMagic))) * W + __double2loint(__dadd_rn(px0, kMagic)) + cW;
-      const int mi1 = (cH - __double2loint(__dadd_rn(py1, kMagic))) * W + __double2loint(__dadd_rn(px1, kMagic)) + cW;
-      const bool in0 = (s_mask[mi0 >> 5] >> (mi0 & 31)) & 1u;                         // TRAIN:510-512
-      const bool in1 = ((s_mask[mi1 >> 5] >> (mi1 & 31)) & 1u) && k1 != k;
-      if (!(in0 || in1)) continue;
-      const float q0 = sample_q(D, rc, px0, py0);
-      const float q1 = sample_q(D, rc, px1, py1);
-      if (in0 && q0 < qmin) { qmin = q0; kmin = k; }
-      if (in1 && q1 < qmin) { qmin = q1; kmin = k1; }
+  if (ILP >= 2) {
+    for (int k = k_begin; k <= k_end; k += ILP) {
+      double px[ILP], py[ILP];
+      bool in[ILP], any = false;
+#pragma unroll
+      for (int j = 0; j < ILP; ++j) {
+        const int kj = min(k + j, k_end);                                             // tail: the group's last samples repeat k_end
+        const double t = tab.t[kj];
+        px[j] = __dadd_rn(xd, __dmul_rn(t, dx));                                      // TRAIN:472,480
+        py[j] = __dadd_rn(yd, __dmul_rn(t, dy));
+        const int mi = (cH - __double2loint(__dadd_rn(py[j], kMagic))) * W + __double2loint(__dadd_rn(px[j], kMagic)) + cW;
+        in[j] = ((s_mask[mi >> 5] >> (mi & 31)) & 1u) && (j == 0 || k + j <= k_end);  // TRAIN:510-512
+        any = any || in[j];
+      }
+      if (!any) continue;
+      float q[ILP];
+#pragma unroll
+      for (int j = 0; j < ILP; ++j) q[j] = sample_q(D, rc, px[j], py[j]);
+#pragma unroll
+      for (int j = 0; j < ILP; ++j)
+        if (in[j] && q[j] < qmin) { qmin = q[j]; kmin = k + j; }
     }
   } else {
   const float dxf32 = __fsub_rn(ex, x), dyf32 = __fsub_rn(ey, y);
@@ -539,11 +574,11 @@ extern "C" int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int 
 }
 
 // A/B configuration of the fast march kernel: -1 / 0 = the default (environment, else the built-in choice)
-static int g_march_warp_shape = -1, g_march_ilp = 0;
+static int g_march_warp_shape = -1, g_march_ilp = 0, g_march_order = -1;
 
-extern "C" int gfr_march_config(int warp_shape, int ilp) {
-  if (warp_shape < -1 || warp_shape > 1 || ilp < 0 || ilp > 2) return GFR_E_ARG;
-  g_march_warp_shape = warp_shape; g_march_ilp = ilp;
+extern "C" int gfr_march_config(int warp_shape, int ilp, int block_order) {
+  if (warp_shape < -1 || warp_shape > 1 || ilp < 0 || ilp > 4 || block_order < -1 || block_order > 1) return GFR_E_ARG;
+  g_march_warp_shape = warp_shape; g_march_ilp = ilp; g_march_order = block_order;
   return GFR_OK;
 }
 
@@ -555,7 +590,7 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
   GFR_RETURN_IF_NULL(t_host);
   if (fuse == nullptr) GFR_RETURN_IF_NULL(d_min);
   if (fuse != nullptr && (variant != 0 || depth64_scratch == nullptr)) return GFR_E_ARG;
-  if (B <= 0 || H <= 0 || W <= 0 || (W % TILE_W) || (H % TILE_H) || H > 512 || W > 512 || B > 65535) return GFR_E_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || (W % TILE_W) || (H % TILE_H) || H > 512 || W > 512 || B > 65535) return GFR_E_SHAPE;   // (B: the 3-D grids of variants 1, 2)
   if (n <= 0 || n > 255) return GFR_E_ARG;     // 255 is the "no sample inside the face" argmin code
   if (mask_batch_stride != 0 && mask_batch_stride != (H * W) / 32 + GFR_MASK_EXTRA_WORDS) return GFR_E_ARG;
   if (variant < 0 || variant > 2) return GFR_E_ARG;
@@ -604,20 +639,25 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
     widen_depth_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch, n4);
     // A/B switches (read once): GFR_MARCH_WARP = 0 -> 32 x 1 warps (round 1), GFR_MARCH_ILP = 1 / 2 -> samples one by one / in pairs
     static const int env_warp_shape = [] { const char* e = getenv("GFR_MARCH_WARP"); return (e && atoi(e) == 0) ? 0 : 1; }();
-    static const int env_ilp = [] { const char* e = getenv("GFR_MARCH_ILP"); return e ? (atoi(e) == 2 ? 2 : 1) : GFR_MARCH_DEFAULT_ILP; }();
+    static const int env_ilp = [] { const char* e = getenv("GFR_MARCH_ILP"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 4 ? v : GFR_MARCH_DEFAULT_ILP; }();
     const int warp_shape = g_march_warp_shape >= 0 ? g_march_warp_shape : env_warp_shape;
     const int ilp = g_march_ilp > 0 ? g_march_ilp : env_ilp;
+    static const int env_order = [] { const char* e = getenv("GFR_MARCH_ORDER"); return (e && atoi(e) == 0) ? 0 : 1; }();
+    a.order = g_march_order >= 0 ? g_march_order : env_order;
     cudaStream_t st = (cudaStream_t)stream;
     if (fast_th == 4 && H % 4 == 0) {
-      grid.y = H / 4; block.y = 4;
+      grid = dim3((unsigned)((W / TILE_W) * (H / 4)) * (unsigned)B, 1, 1); block.y = 4;
       if (warp_shape == 1 && !a.coarse) {
-        if (ilp == 2) shadow_march_fwd_fast<4, 1, 2><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
+        if (ilp == 4) shadow_march_fwd_fast<4, 1, 4><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
+        else if (ilp == 3) shadow_march_fwd_fast<4, 1, 3><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
+        else if (ilp == 2) shadow_march_fwd_fast<4, 1, 2><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
         else shadow_march_fwd_fast<4, 1, 1><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
       } else {
-        if (ilp == 2 && !a.coarse) shadow_march_fwd_fast<4, 0, 2><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
+        if (ilp >= 2 && !a.coarse) shadow_march_fwd_fast<4, 0, 2><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
         else shadow_march_fwd_fast<4, 0, 1><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
       }
     } else {
+      grid = dim3((unsigned)((W / TILE_W) * (H / TILE_H)) * (unsigned)B, 1, 1);
       shadow_march_fwd_fast<8, 0, 1><<<grid, block, smem, st>>>(a, depth64_scratch, tab);
     }
   } else {

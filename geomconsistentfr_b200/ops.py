@@ -115,10 +115,11 @@ def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0,
     return dmin, arg, shadow
 
 
-def march_config(warp_shape=-1, ilp=0):
-    """A/B switches of the default march kernel (process-wide): warp_shape 0 = 32x1, 1 = 8x4 pixels per warp; ilp 1 / 2 =
-    samples one by one / in pairs; -1 / 0 = defaults.  Bit-identical results in every setting."""
-    _lib.check(_lib.load().gfr_march_config(int(warp_shape), int(ilp)), "gfr_march_config")
+def march_config(warp_shape=-1, ilp=0, block_order=-1):
+    """A/B switches of the default march kernel (process-wide): warp_shape 0 = 32x1, 1 = 8x4 pixels per warp; ilp 1..4 =
+    samples one by one / in groups; block_order 0 = tile-major, 1 = pairs interleaved + far-from-light tiles first;
+    -1 / 0 = defaults.  Bit-identical results in every setting."""
+    _lib.check(_lib.load().gfr_march_config(int(warp_shape), int(ilp), int(block_order)), "gfr_march_config")
 
 
 def shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx=1570.0, fy=1570.0, cx=None, cy=None,

@@ -80,9 +80,11 @@ int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask
 
 /* A/B configuration of variant 0's kernel (process-wide; results are bit-identical in every setting):
  *   warp_shape  -1 default (environment GFR_MARCH_WARP, else 1), 0 = a warp marches 32 x 1 pixels, 1 = 8 x 4 pixels
- *   ilp          0 default (environment GFR_MARCH_ILP, else the built-in choice), 1 = samples one by one, 2 = in pairs
+ *   ilp          0 default (environment GFR_MARCH_ILP, else 2), 1 = samples one by one, 2..4 = in groups of 2..4
+ *   block_order -1 default (environment GFR_MARCH_ORDER, else 1), 0 = tile-major CTA order, 1 = (face, light) pairs interleaved,
+ *               each pair's tiles far-from-its-light first (load balance: a CTA's cost varies 1 : 700 across the image)
  * Same loop as TRAIN:467-515 either way; no reference counterpart (a tuning knob for tests / tools). */
-int gfr_march_config(int warp_shape, int ilp);
+int gfr_march_config(int warp_shape, int ilp, int block_order);
 
 /* Normals + Lambertian shading + shadow blend + albedo render.  Replaces TRAIN:353-369 and 517-522
  * (kornia depth_to_normals(depth + depth_offset, K), y flip, double normalise, l = normalize(P_L - P),

@@ -142,8 +142,8 @@ def test_coarse_group_skip_is_exact_on_masks_with_holes(ops):
 
 
 def test_warp_shape_and_sample_pairs_are_bit_identical(ops):
-    """Round 2: the default kernel's A/B configurations — 32x1 vs 8x4 pixels per warp, samples one by one vs in pairs (the
-    second sample of a pair is evaluated speculatively) — against the literal kernel: bit-identical d_min / arg-min / fused
+    """Round 2: the default kernel's A/B configurations — 32x1 vs 8x4 pixels per warp, samples one by one vs in groups of 2 / 3 / 4 (the
+    group's other samples are evaluated speculatively), tile-major vs light-aware CTA order — against the literal kernel: bit-identical d_min / arg-min / fused
     shading on ragged masks, an odd sample count (the pair loop's tail) and lights on every side."""
     H = W = 128
     g = torch.Generator().manual_seed(33)
@@ -163,18 +163,18 @@ def test_warp_shape_and_sample_pairs_are_bit_identical(ops):
         for t in (None, np.arange(0.025, 0.825, 0.005)[:157]):
             d1, a1, _ = ops.shadow_march_fwd(depth, bits, P_L, samples=t, inside_bonus=5.0, want_argmin=True, variant=1)
             ref = None
-            for ws in (0, 1):
-                for ilp in (1, 2):
-                    ops.march_config(ws, ilp)
+            for ws, ilp, order in ((0, 1, 0), (0, 2, 1), (1, 1, 1), (1, 2, 0), (1, 2, 1), (1, 3, 1), (1, 4, 0)):
+                if True:
+                    ops.march_config(ws, ilp, order)
                     d0, a0, _ = ops.shadow_march_fwd(depth, bits, P_L, samples=t, inside_bonus=5.0, want_argmin=True, variant=0)
-                    assert torch.equal(d0, d1) and torch.equal(a0, a1), (ws, ilp)
+                    assert torch.equal(d0, d1) and torch.equal(a0, a1), (ws, ilp, order)
                     o = ops.march_shade_fwd(albedo, depth, bits, P_L, amb, inside_bonus=5.0, samples=t, want=("rendered", "normals", "d_min"))
                     assert torch.equal(o["d_min"], d1), (ws, ilp)
                     if ref is None:
                         ref = o
                     assert torch.equal(o["rendered"], ref["rendered"]) and torch.equal(o["normals"], ref["normals"]), (ws, ilp)
     finally:
-        ops.march_config(-1, 0)
+        ops.march_config(-1, 0, -1)
 
 
 def test_shade_render_vs_oracle(ops, march):

@@ -1,7 +1,7 @@
 """CPU estimate of the ray march instruction volume per warp for different warp shapes on the bench masks: warp-iterations walked
 (sample-range union over the 32 rays) and warp-iterations with at least one in-mask lane, x 17 / 67 instructions (DESIGN K1)."""
-import numpy as np, sys
-sys.path.insert(0,'/root/repo')
+import numpy as np, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from geomconsistentfr_b200.synthetic import synthetic_face, LIGHTS_18
 H=W=256
 t=np.arange(0.025,0.825,0.005)
