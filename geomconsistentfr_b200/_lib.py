@@ -89,6 +89,7 @@ _PROTOS = {
     "gfr_maxpool2_p16_fwd": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_stem_conv_p16_fwd": [_c_void_p] * 5 + [_c_int] * 3 + [_c_void_p],
     "gfr_head_1x1_p16_fwd": [_c_void_p] * 8 + [_c_int] * 5 + [_c_float, _c_void_p],
+    "gfr_conv3x3_p16_head_fwd": [_c_void_p] * 3 + [_c_int] * 6 + [_c_float, _c_int] + [_c_void_p] * 7 + [_c_int, _c_int, _c_float, _c_void_p],
     "gfr_light_head_p16_fwd": [_c_void_p, _c_int, _c_int, _c_int] + [_c_void_p] * 5 + [_c_int, _c_void_p],
     # output stage of the inference drivers
     "gfr_composite_bgr_u8": [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p],

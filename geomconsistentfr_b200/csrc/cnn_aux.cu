@@ -8,6 +8,7 @@
 //   * light  — global average pool of the 27 lighting channels + the 2-layer MLP (TRAIN:225-232) on a C4 feature map.
 #include "gfr_common.cuh"
 #include "p16.cuh"
+#include "head_device.cuh"
 
 #include <stdlib.h>
 
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemArgs a, const 
 }
 
 // ------------------------------------------------------------------------------------------------- head
-struct HeadWeights { float w2[16][16]; float b2[16]; float w3[16][16]; float b3[16]; float wo[3][16]; float bo[3]; };   // [co][ci]
+using gfr_head::HeadWeights;
 
 struct HeadArgs {
   const float* in;    // C4 [N,4,H,W,4]
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256) head_1x1_kernel(const HeadArgs a, const _
   if (i >= a.total) return;
   const long long n = i / a.hw, p = i % a.hw;
   const float4* src = reinterpret_cast<const float4*>(a.in) + n * 4 * a.hw + p;
-  float x[16], h[16];
+  float x[16];
   if (a.p16) {
     const __half* hp = reinterpret_cast<const __half*>(a.in) + ((size_t)n * 4 * a.hw + p) * 8;      // [n][c8][part][hw][8]
 #pragma unroll
@@ -217,29 +218,11 @@ __global__ void __launch_bounds__(256) head_1x1_kernel(const HeadArgs a, const _
       x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
     }
   }
+  float o3[3];
+  gfr_head::apply(wt, x, a.n_out, a.act, a.scale, o3);
 #pragma unroll
-  for (int o = 0; o < 16; ++o) {
-    float s = wt.b2[o];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) s = fmaf(wt.w2[o][c], x[c], s);
-    h[o] = s > 0.f ? s : 0.2f * s;
-  }
-#pragma unroll
-  for (int o = 0; o < 16; ++o) {
-    float s = wt.b3[o];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) s = fmaf(wt.w3[o][c], h[c], s);
-    x[o] = s > 0.f ? s : 0.2f * s;
-  }
-#pragma unroll
-  for (int o = 0; o < 3; ++o) {
-    if (o >= a.n_out) break;
-    float s = wt.bo[o];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) s = fmaf(wt.wo[o][c], x[c], s);
-    if (a.act == 2) s = 1.0f / (1.0f + expf(-s));
-    a.out[(n * a.n_out + o) * a.hw + p] = s * a.scale;
-  }
+  for (int o = 0; o < 3; ++o)
+    if (o < a.n_out) a.out[(n * a.n_out + o) * a.hw + p] = o3[o];
 }
 
 // ------------------------------------------------------------------------------------------------- light head (C4)
@@ -320,14 +303,7 @@ static int head_launch(const float* in, const float* w2_host, const float* b2_ho
   if (N <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
   if (n_out < 1 || n_out > 3 || (act != 0 && act != 2)) return GFR_E_ARG;
   HeadWeights wt;
-  for (int o = 0; o < 16; ++o) {
-    wt.b2[o] = b2_host[o]; wt.b3[o] = b3_host[o];
-    for (int c = 0; c < 16; ++c) { wt.w2[o][c] = w2_host[o * 16 + c]; wt.w3[o][c] = w3_host[o * 16 + c]; }
-  }
-  for (int o = 0; o < 3; ++o) {
-    wt.bo[o] = o < n_out ? bo_host[o] : 0.f;
-    for (int c = 0; c < 16; ++c) wt.wo[o][c] = o < n_out ? wo_host[o * 16 + c] : 0.f;
-  }
+  gfr_head::fill(wt, w2_host, b2_host, w3_host, b3_host, wo_host, bo_host, n_out);
   HeadArgs a{in, out, (long long)H * W, (long long)N * H * W, n_out, act, out_scale, p16};
   head_1x1_kernel<<<(unsigned)((a.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, wt);
   return gfr_launch_status();

@@ -26,6 +26,7 @@
 // epilogue warps: the tensor core's accumulate truncates); warp 0 = TMA producer, warp 1 = MMA issuer, 4*MH epilogue warps.
 #include "gfr_common.cuh"
 #include "p16.cuh"
+#include "head_device.cuh"
 #include "tc_common.cuh"
 
 #include <cuda_fp16.h>
@@ -33,6 +34,7 @@
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 using namespace gfr_tc;
 
@@ -83,10 +85,23 @@ struct Cfg {
   static_assert(A_BYTES % 128 == 0 && W_STEP % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
 
-template <int NT, int MH, int KS, int GEO = 0>
+// HEAD = true: the layer is a decoder's last 3x3 convolution (conv_*_c2_1 + BN + LeakyReLU, 16 channels) and its epilogue runs
+// the decoder's 1x1 tail (head_device.cuh: two 16 -> 16 layers + the output layer) on the pixel it holds, then stores the
+// n_out fp32 planes: the 16-channel activation (4 B x 16 per pixel written, then read again by a second kernel) never exists.
+struct HeadParams {
+  gfr_head::HeadWeights wt;
+  float* out;            // [N][n_out][H][W] fp32
+  int n_out, act;        // act: 0 none, 2 sigmoid
+  float scale;
+};
+struct NoHead { int unused; };
+
+template <int NT, int MH, int KS, int GEO = 0, bool HEAD = false>
 __global__ void __launch_bounds__(Cfg<NT, MH, KS, GEO>::THREADS, (NT * MH <= 32) ? 2 : 1)
-conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args a) {
+conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args a,
+                   const __grid_constant__ typename std::conditional<HEAD, HeadParams, NoHead>::type hp) {
   using C = Cfg<NT, MH, KS, GEO>;
+  static_assert(!HEAD || NT == 16, "the fused 1x1 tail works on 16 channels");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool resident = a.nsteps == 1;
@@ -256,6 +271,24 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
         tc_fence_before_sync();
         mbar_arrive(bar_accempty + 8 * p);
       }
+      if constexpr (HEAD) {
+        // conv + bias + LeakyReLU of the 16 channels (no residual / skip operand on this layer: host-checked), back from the
+        // x16 domain, then the 1x1 tail; a warp stores 4 rows x 8 pixels = four full 32-byte sectors per output plane
+        float xv[16], o3[3];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float v = fmaf(sum[k], inv16, s_bias16[k]);
+          xv[k] = fmaxf(v, 0.2f * v) * gfr_p16::X_INV;
+        }
+        gfr_head::apply(hp.wt, xv, hp.n_out, hp.act, hp.scale, o3);
+        if (ok) {
+          float* o = hp.out + ((size_t)n * hp.n_out * a.H + y) * a.W + x;
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (k < hp.n_out) o[(size_t)k * a.H * a.W] = o3[k];
+        }
+        continue;
+      }
       // every lane walks the chunks (warp-uniform control flow: the fused pool shuffles); loads / stores are predicated by `ok`
       const size_t qplane = (size_t)(a.H >> 1) * (a.W >> 1) * 8;
       __half* pool_p = a.pool ? a.pool + gfr_p16::unit_offset(n, a.out_groups, n0 >> 3, a.H >> 1, a.W >> 1, y >> 1, x >> 1) : nullptr;
@@ -372,13 +405,13 @@ int make_p16_map(CUtensorMap* tm, const void* base, int N, int C8, int groups, i
   return r == CUDA_SUCCESS ? GFR_OK : GFR_E_ARG;
 }
 
-template <int NT, int MH, int KS, int GEO = 0>
-int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s) {
+template <int NT, int MH, int KS, int GEO = 0, bool HEAD = false>
+int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s, const HeadParams* head = nullptr) {
   using C = Cfg<NT, MH, KS, GEO>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv3x3_p16_kernel<NT, MH, KS, GEO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv3x3_p16_kernel<NT, MH, KS, GEO, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
   const bool resident = a.nsteps == 1;
@@ -413,7 +446,9 @@ int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_p16_kernel<NT, MH, KS, GEO>, tm, a);
+  cudaError_t e;
+  if constexpr (HEAD) e = cudaLaunchKernelEx(&cfg, conv3x3_p16_kernel<NT, MH, KS, GEO, true>, tm, a, *head);
+  else e = cudaLaunchKernelEx(&cfg, conv3x3_p16_kernel<NT, MH, KS, GEO, false>, tm, a, NoHead{0});
   return e == cudaSuccess ? gfr_launch_status() : (int)e;
 }
 
@@ -570,7 +605,8 @@ extern "C" int gfr_conv_p16_pack_weights_taps(const float* w_host, int Cin, int 
 static int conv_p16_launch(const void* in, const void* w_packed, const float* bias, const void* res, int res_c8,
                            int res_groups, const void* post, int post_groups, void* out, int out_groups, void* pool, int* flags,
                            int N, int Cin, int in_groups, int Cout, int H, int W, int NT, int MH, int KS, int geo, int post_shift,
-                           int act, int act_channels, float out_scale, float w_scale, int weights_static, void* stream);
+                           int act, int act_channels, float out_scale, float w_scale, int weights_static, void* stream,
+                           const HeadParams* head = nullptr);
 
 extern "C" int gfr_conv3x3_p16_fwd(const void* in, const void* w_packed, const float* bias, const void* res, int res_c8,
                                    int res_groups, const void* post, int post_groups, void* out, int out_groups, int* flags,
@@ -592,8 +628,12 @@ extern "C" int gfr_conv_p16_fwd_ex(const void* in, const void* w_packed, const f
 static int conv_p16_launch(const void* in, const void* w_packed, const float* bias, const void* res, int res_c8,
                            int res_groups, const void* post, int post_groups, void* out, int out_groups, void* pool, int* flags,
                            int N, int Cin, int in_groups, int Cout, int H, int W, int NT, int MH, int KS, int geo, int post_shift,
-                           int act, int act_channels, float out_scale, float w_scale, int weights_static, void* stream) {
-  GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w_packed); GFR_RETURN_IF_NULL(bias); GFR_RETURN_IF_NULL(out);
+                           int act, int act_channels, float out_scale, float w_scale, int weights_static, void* stream,
+                           const HeadParams* head) {
+  GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(w_packed); GFR_RETURN_IF_NULL(bias);
+  if (head == nullptr) GFR_RETURN_IF_NULL(out);
+  if (head != nullptr && (Cout != 16 || NT != 16 || KS != 2 || geo != 0 || res || post || pool || act != 1 || out_scale != 1.0f || head->out == nullptr))
+    return GFR_E_ARG;
   if (geo < 0 || geo > 1) return GFR_E_ARG;
   if (pool != nullptr && ((H | W) & 1)) return GFR_E_SHAPE;
   if (N <= 0 || Cin <= 0 || Cout <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
@@ -631,11 +671,31 @@ static int conv_p16_launch(const void* in, const void* w_packed, const float* bi
     if (NT == 16 && MH == 2 && KS == 2) return launch_p16<16, 2, 2, 1>(tm, a, s);
     return GFR_E_ARG;
   }
+  if (head != nullptr) {
+    if (MH == 2) return launch_p16<16, 2, 2, 0, true>(tm, a, s, head);
+    if (MH == 1) return launch_p16<16, 1, 2, 0, true>(tm, a, s, head);
+    return GFR_E_ARG;
+  }
 #define GFR_P16_CASE(nt, mh, ks) if (NT == nt && MH == mh && KS == ks) return launch_p16<nt, mh, ks>(tm, a, s)
   GFR_P16_CASE(16, 1, 2); GFR_P16_CASE(16, 2, 2); GFR_P16_CASE(16, 1, 4); GFR_P16_CASE(16, 2, 4);
   GFR_P16_CASE(32, 1, 2); GFR_P16_CASE(32, 2, 2); GFR_P16_CASE(32, 1, 4); GFR_P16_CASE(32, 2, 4);
 #undef GFR_P16_CASE
   return GFR_E_ARG;
+}
+
+// conv_*_c2_1 (3x3, Cin -> 16, + BN + LeakyReLU) with the decoder's 1x1 tail in its epilogue -> out [N][n_out][H][W] fp32
+extern "C" int gfr_conv3x3_p16_head_fwd(const void* in, const void* w_packed, const float* bias, int N, int Cin, int in_groups, int H, int W,
+                                        int MH, float w_scale, int weights_static, const float* w2_host, const float* b2_host,
+                                        const float* w3_host, const float* b3_host, const float* wo_host, const float* bo_host,
+                                        float* out, int n_out, int act, float out_scale, void* stream) {
+  GFR_RETURN_IF_NULL(w2_host); GFR_RETURN_IF_NULL(b2_host); GFR_RETURN_IF_NULL(w3_host); GFR_RETURN_IF_NULL(b3_host);
+  GFR_RETURN_IF_NULL(wo_host); GFR_RETURN_IF_NULL(bo_host); GFR_RETURN_IF_NULL(out);
+  if (n_out < 1 || n_out > 3 || (act != 0 && act != 2)) return GFR_E_ARG;
+  HeadParams hp;
+  gfr_head::fill(hp.wt, w2_host, b2_host, w3_host, b3_host, wo_host, bo_host, n_out);
+  hp.out = out; hp.n_out = n_out; hp.act = act; hp.scale = out_scale;
+  return conv_p16_launch(in, w_packed, bias, nullptr, 0, 0, nullptr, 0, nullptr, 2, nullptr, nullptr, N, Cin, in_groups, 16, H, W, 16, MH, 2, 0, 0,
+                         1, 0, 1.0f, w_scale, weights_static, stream, &hp);
 }
 
 extern "C" int gfr_nchw_to_p16(const float* in, void* out, int N, int C, int H, int W, void* stream) {

@@ -603,6 +603,27 @@ def head_1x1_p16_fwd(x, w2, b2, w3, b3, wo, bo, act=None, out_scale=1.0):
     return out
 
 
+def conv3x3_p16_head_fwd(x, w_packed, bias, MH, w_scale, w2, b2, w3, b3, wo, bo, act=None, out_scale=1.0, cin=None):
+    """conv3x3_p16_fwd (Cin -> 16, LeakyReLU, cfg (16, MH, 2)) + head_1x1_p16_fwd in ONE launch (the 1x1 tail runs in the conv's
+    epilogue) -> NCHW [N,n_out,H,W]."""
+    N, Cin, H, W = x.shape
+    if cin is not None:
+        assert cin <= Cin
+        Cin = cin
+    if not x.data.is_cuda:
+        raise RuntimeError("conv3x3_p16_head_fwd: x must be on CUDA")
+    w_packed = _need(w_packed, torch.float16, "w_packed")
+    bias = _need(bias, torch.float32, "bias")
+    n_out = wo.shape[0]
+    out = torch.empty((N, n_out, H, W), dtype=torch.float32, device=x.data.device)
+    hp = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = _lib.load().gfr_conv3x3_p16_head_fwd(_ptr(x.data), _ptr(w_packed), _ptr(bias), N, Cin, x.groups, H, W, int(MH), float(w_scale), 1,
+                                              hp(w2), hp(b2), hp(w3), hp(b3), hp(wo), hp(bo), _ptr(out), n_out, _ACT[act],
+                                              float(out_scale), _stream())
+    _lib.check(rc, "gfr_conv3x3_p16_head_fwd"); _count()
+    return out
+
+
 def light_head_p16_fwd(feat, c_first, w1, b1, w2, b2):
     """feat P16 [N,C,h,w]; channels [c_first, c_first+27) -> [N,4] (TRAIN:225-232)."""
     N, C, h, w = feat.shape

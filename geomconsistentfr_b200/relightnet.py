@@ -76,6 +76,7 @@ class RelightNet(nn.Module):
                                               # accumulation (BASELINE configs[2] "bf16 CNN / fp32 ray-march"), 1 = TF32
         self.stem_tc = os.environ.get("GFR_STEM_TC", "1") != "0"      # P16 path: the 5x5 stem as unroll + 5 vertical taps on tcgen05, and the
                                               # encoder's max pools fused into the producing epilogues (0: CUDA-core stem + pool kernels)
+        self.fuse_head_p16 = True             # P16 path: the decoders' 1x1 tails run in the epilogue of their last 3x3 layer (A/B switch)
         self.p16 = True                       # precision 2 on PRE-SPLIT fp16-pair activations (csrc/conv_p16.cu); False: the first-
                                               # generation kernel that splits fp32 C4 tiles in shared memory (kept for A/B runs)
         self.range_check = True               # precision 2: every conv output is range-checked on the device; an eager forward
@@ -317,13 +318,16 @@ class RelightNet(nn.Module):
             a = conv("deconv_%s_h8_1" % p, h)
             tt = conv("deconv_%s_h8_2" % p, a, res=h)
             h = up_and_skip(p, "s4", tt, skips["s4"])
-            h = conv("conv_%s_c2_1" % p, h)
             w2, b2 = t["conv_%s_c2_2" % p]
             w3, b3 = t["conv_%s_c2_3" % p]
             wo, bo = t["conv_%s_c2_o" % p]
-            if p == "albedo":
-                return ops.head_1x1_p16_fwd(h, w2, b2, w3, b3, wo, bo, act="sigmoid")              # TRAIN:285-290
-            return ops.head_1x1_p16_fwd(h, w2, b2, w3, b3, wo, bo, act=None, out_scale=100.0)      # TRAIN:345-350
+            act, scale = ("sigmoid", 1.0) if p == "albedo" else (None, 100.0)                      # TRAIN:285-290 / 345-350
+            if self.fuse_head_p16:   # the 1x1 tail in the epilogue of conv_*_c2_1: one launch, no 16-channel round trip
+                wp, b, _, _, w_scale = t["conv_%s_c2_1" % p][:5]
+                MH = 2 if N * ((H + 15) // 16) * ((W + 15) // 16) >= 296 else 1
+                return ops.conv3x3_p16_head_fwd(h, wp, b, MH, w_scale, w2, b2, w3, b3, wo, bo, act=act, out_scale=scale)
+            h = conv("conv_%s_c2_1" % p, h)
+            return ops.head_1x1_p16_fwd(h, w2, b2, w3, b3, wo, bo, act=act, out_scale=scale)
 
         side.wait_stream(cur)
         with torch.cuda.stream(side):

@@ -414,6 +414,16 @@ int gfr_head_1x1_p16_fwd(const void* in, const float* w2_host, const float* b2_h
 int gfr_light_head_p16_fwd(const void* feat, int groups, int c_first, int HW, const float* w1, const float* b1,
                            const float* w2, const float* b2, float* out, int N, void* stream);
 
+/* A decoder's last 3x3 layer with its 1x1 tail in the epilogue (round 2): conv_*_c2_1 + BN(folded) + LeakyReLU (Cin -> 16,
+ * TRAIN:284 / 344) followed, on the pixel each epilogue thread holds, by conv_*_c2_2 / c2_3 (+ BN + LeakyReLU) and
+ * conv_*_c2_o (+ sigmoid for the albedo, TRAIN:285-290; x out_scale = 100 for the depth, TRAIN:345-350) — the arguments of
+ * gfr_conv3x3_p16_fwd (NT = 16, KS = 2) and of gfr_head_1x1_p16_fwd in one launch; the 16-channel activation between them is
+ * never stored.  out [N,n_out,H,W] fp32. */
+int gfr_conv3x3_p16_head_fwd(const void* in, const void* w_packed, const float* bias, int N, int Cin, int in_groups, int H, int W,
+                             int MH, float w_scale, int weights_static, const float* w2_host, const float* b2_host,
+                             const float* w3_host, const float* b3_host, const float* wo_host, const float* bo_host,
+                             float* out, int n_out, int act, float out_scale, void* stream);
+
 /* Stem: conv_c1_og (5x5, 3 -> 16, padding 2) + BatchNorm(eval, folded) + LeakyReLU(0.2) on the NHWC image, with the
  * first 2x2 max pool fused (TRAIN:197-201).  img [N,H,W,3]; w_host [16,3,5,5] and bias_host [16] are HOST pointers
  * (they travel as kernel parameters); out C4 [N,16,H,W]; pooled C4 [N,16,H/2,W/2] or NULL. */

@@ -146,6 +146,38 @@ def test_stem_head_light_p16_equal_their_c4_forms():
     assert float((l4 - l16).abs().max()) <= 1e-6
 
 
+@pytest.mark.parametrize("N,H,W,MH,n_out,act,scale", [(2, 64, 96, 2, 3, "sigmoid", 1.0), (1, 256, 256, 2, 1, None, 100.0),
+                                                       (3, 40, 24, 1, 1, None, 100.0), (8, 128, 128, 1, 3, "sigmoid", 1.0)])
+def test_conv_with_fused_1x1_tail_equals_the_two_launches(N, H, W, MH, n_out, act, scale):
+    """gfr_conv3x3_p16_head_fwd (the decoder's 1x1 tail in the epilogue of its last 3x3 layer) against conv3x3_p16_fwd +
+    head_1x1_p16_fwd: the same arithmetic except that the 16-channel activation is not rounded to the fp16 pair (22 bits) in
+    between — tolerance 2e-6 of the output range — and against torch fp64."""
+    from geomconsistentfr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(N + H + n_out)
+    x = _acts((N, 16, H, W), g, 4.0)
+    w = torch.randn(16, 16, 3, 3, device="cuda", generator=g) / 12.0
+    b = torch.randn(16, device="cuda", generator=g) * 0.1
+    w2, w3 = (torch.randn(16, 16, device="cuda", generator=g) * 0.3 for _ in range(2))
+    b2, b3 = (torch.randn(16, device="cuda", generator=g) * 0.1 for _ in range(2))
+    wo, bo = torch.randn(n_out, 16, device="cuda", generator=g) * 0.3, torch.randn(n_out, device="cuda", generator=g) * 0.1
+    c = lambda t: t.cpu().contiguous()
+    xp = ops.nchw_to_p16(x)
+    wp, s = ops.conv_p16_pack_weights(w, 16, 2)
+    two = ops.head_1x1_p16_fwd(ops.conv3x3_p16_fwd(xp, wp, b, 16, (16, MH, 2), s), c(w2), c(b2), c(w3), c(b3), c(wo), c(bo), act=act, out_scale=scale)
+    one = ops.conv3x3_p16_head_fwd(xp, wp, b, MH, s, c(w2), c(b2), c(w3), c(b3), c(wo), c(bo), act=act, out_scale=scale)
+    assert one.shape == two.shape == (N, n_out, H, W)
+    tol = 2e-6 * max(1.0, float(two.abs().max()))
+    assert float((one - two).abs().max()) <= tol, float((one - two).abs().max())
+    xq = ops.p16_to_nchw(xp).double()
+    lr = lambda v: F.leaky_relu(v, 0.2)
+    h = lr(F.conv2d(xq, w.double(), b.double(), padding=1))
+    h = lr(F.conv2d(h, w2.double()[:, :, None, None], b2.double()))
+    h = lr(F.conv2d(h, w3.double()[:, :, None, None], b3.double()))
+    ref = F.conv2d(h, wo.double()[:, :, None, None], bo.double())
+    ref = (torch.sigmoid(ref) if act == "sigmoid" else ref) * scale
+    assert float((one.double() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+
+
 def test_stem_on_tensor_cores_and_fused_pool():
     """The 5x5 stem as horizontal-tap unroll + 5 vertical taps on tcgen05 (geometry 1) against torch fp64, and the 2x2 max pool
     that the epilogue writes alongside (stem: no residual; a 3x3 layer with a residual operand and LeakyReLU)."""

@@ -138,12 +138,30 @@ def test_relight_sweep_equals_per_light_forward(net, ffhq):
         assert torch.equal(sw["shadow"][:, j], o[2])
 
 
+def test_p16_fused_decoder_tail_equals_the_two_launch_tail(net, ffhq):
+    """The P16 path's default (gfr_conv3x3_p16_head_fwd: c2_1 with the 1x1 tail in its epilogue) against its two-launch form on the
+    shipped weights: the only difference is that the 16-channel activation between them is not rounded to the fp16 pair
+    (22 bits), so albedo agrees to 1e-6 and depth (100 x a value of order 1) to 2e-4."""
+    x = _inputs(ffhq, [1, 4, 7]).cuda()
+    assert net.tc_precision == 2 and net.p16 and net.fuse_head_p16
+    try:
+        with torch.no_grad():
+            a1, d1, sl1 = net._cnn_eval(x, 200)
+            net.fuse_head_p16 = False
+            a0, d0, sl0 = net._cnn_eval(x, 200)
+    finally:
+        net.fuse_head_p16 = True
+    assert float((a1 - a0).abs().max()) <= 1e-6, float((a1 - a0).abs().max())
+    assert float((d1 - d0).abs().max()) <= 2e-4, float((d1 - d0).abs().max())
+    assert torch.equal(sl1, sl0)
+
+
 @pytest.mark.parametrize("precision", [2, 3])
 def test_fused_decoder_tail_equals_the_two_launch_tail(net, ffhq, precision):
     """gfr_conv3x3_tc_head_fwd (c2_1 with c2_2 -> c2_3 -> c2_o in its epilogue) against gfr_conv3x3_tc_fwd followed by
     gfr_head_1x1_fwd: same accumulation order, so albedo and depth agree to the last bit or two."""
     x = _inputs(ffhq, [1, 4, 7]).cuda()
-    net.tc_precision = precision
+    net.tc_precision, net.p16 = precision, False         # the first-generation kernel (conv_tc.cu) in both precisions
     try:
         with torch.no_grad():
             net.fuse_head = True
@@ -151,7 +169,7 @@ def test_fused_decoder_tail_equals_the_two_launch_tail(net, ffhq, precision):
             net.fuse_head = False
             a0, d0, sl0 = net._cnn_eval(x, 200)
     finally:
-        net.fuse_head, net.tc_precision = False, 2
+        net.fuse_head, net.tc_precision, net.p16 = False, 2, True
     assert a1.shape == a0.shape == (3, 3, 256, 256) and d1.shape == d0.shape == (3, 1, 256, 256)
     assert float((a1 - a0).abs().max()) <= 2e-7
     assert float((d1 - d0).abs().max()) <= 2e-5          # 100 x a value of order 1
