@@ -417,9 +417,12 @@ int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s, const HeadP
   const bool resident = a.nsteps == 1;
   const uint32_t fixed = (resident ? C::W_STEP : 0u) + C::BAR_BYTES;
   const uint32_t per_stage = C::A_BYTES + (resident ? 0u : C::W_STEP);
-  // ring depth: as deep as a two-CTAs-per-SM budget allows (the epilogue of one CTA overlaps the MMAs of the other); layers
-  // whose stage is too large for that run one CTA per SM with the whole shared memory
-  static const int max_stages = [] { const char* e = getenv("GFR_P16_STAGES"); const int v = e ? atoi(e) : 0; return v >= 2 && v <= MAX_STAGES ? v : 6; }();
+  // ring depth: two CTAs per SM where the stage size allows (the epilogue of one CTA overlaps the MMAs of the other); layers
+  // whose stage is too large for that run one CTA per SM.  The ring itself is kept at TWO stages (GFR_P16_STAGES raises the
+  // cap, up to what shared memory holds): measured on the forward (profiles/r02_summary.md), deeper rings change neither
+  // the latency of one forward nor any layer's duration, but the shared memory they pin keeps the CTAs of another runner
+  // lane's layer off the SM — 2 stages: 15.6k faces/s, 6 stages: 15.2k.
+  static const int max_stages = [] { const char* e = getenv("GFR_P16_STAGES"); const int v = e ? atoi(e) : 0; return v >= 2 && v <= MAX_STAGES ? v : 2; }();
   const bool two_ok = (NT * MH <= 32);
   int stages = two_ok ? (int)((110u * 1024u - fixed) / per_stage) : 0;
   int occ = 2;
