@@ -120,32 +120,49 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
       const int x0 = tx * TW, y0 = ty * TH;
       if (it >= STAGES) mbar_wait(bar_empty + 8 * s, ph ^ 1);
       uint8_t* st = smem + (size_t)s * stage_bytes;
-      // g tile: chunk c8 holds channels cob + 8 c8 .. + 7 = C4 groups 2 c8', 2 c8' + 1
-      for (int i = gtid; i < co_chunks * (TH * TW); i += GROUP_THREADS) {
-        const int c8 = i / (TH * TW), pix = i % (TH * TW);
-        const int gy = y0 + (pix >> 3), gx = x0 + (pix & 7);
-        const int grp = ((cob >> 3) + c8) * 2;
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (gy < a.H && gx < a.W) {
-          const size_t o = (size_t)gy * a.W + gx;
-          if (grp < C4out) v0 = __ldg(gsrc + ((size_t)n * C4out + grp) * gplane + o);
-          if (grp + 1 < C4out) v1 = __ldg(gsrc + ((size_t)n * C4out + grp + 1) * gplane + o);
-        }
-        *reinterpret_cast<uint4*>(st + (size_t)c8 * G_CHUNK + (size_t)pix * 16) = pack_bf16x8(v0, v1);
-      }
-      // halo tile of the layer input: chunk c8 holds input channels cib + 8 c8 .. + 7
+      // One task = one 16-byte operand unit (8 bf16 channels of one pixel) = two float4 loads.  Tasks [0, n_g) fill the g tile
+      // (chunk c8 holds channels cob + 8 c8 .. + 7 = C4 groups 2 c8', 2 c8' + 1), tasks [n_g, n_g + n_x) the halo tile of the
+      // layer input (chunk c8 holds input channels cib + 8 c8 .. + 7).  A thread takes LD_BATCH tasks at a time and issues all
+      // of their loads before the first conversion: the loop used to run one task per iteration (two loads in flight per
+      // thread), which made every tile cost five L2 / DRAM latencies per producer group — the 16-channel layers at 256^2 ran
+      // at 2.2 us per tile against 0.7 us of MMA time.
+      constexpr int LD_BATCH = 5;
+      const int n_g = co_chunks * (TH * TW), n_tasks = n_g + (NB >> 3) * (HH * HW_);
       uint8_t* xt = st + G_BYTES;
-      for (int i = gtid; i < (NB >> 3) * (HH * HW_); i += GROUP_THREADS) {
-        const int c8 = i / (HH * HW_), pix = i % (HH * HW_);
-        const int gy = y0 + pix / HW_ - a.org, gx = x0 + pix % HW_ - a.org;
-        const int grp = ((cib >> 3) + c8) * 2;
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win) {
-          const size_t o = (size_t)gy * a.Win + gx;
-          if (grp * 4 < a.Cin) v0 = __ldg(isrc + ((size_t)n * a.in_groups + grp) * iplane + o);
-          if ((grp + 1) * 4 < a.Cin) v1 = __ldg(isrc + ((size_t)n * a.in_groups + grp + 1) * iplane + o);
+      for (int base = gtid; base < n_tasks; base += GROUP_THREADS * LD_BATCH) {
+        float4 v0[LD_BATCH], v1[LD_BATCH];
+        uint8_t* dst[LD_BATCH];
+#pragma unroll
+        for (int u = 0; u < LD_BATCH; ++u) {
+          const int i = base + u * GROUP_THREADS;
+          v0[u] = make_float4(0.f, 0.f, 0.f, 0.f); v1[u] = v0[u];
+          dst[u] = nullptr;
+          if (i < n_g) {
+            const int c8 = i / (TH * TW), pix = i % (TH * TW);
+            const int gy = y0 + (pix >> 3), gx = x0 + (pix & 7);
+            const int grp = ((cob >> 3) + c8) * 2;
+            dst[u] = st + (size_t)c8 * G_CHUNK + (size_t)pix * 16;
+            if (gy < a.H && gx < a.W) {
+              const size_t o = (size_t)gy * a.W + gx;
+              if (grp < C4out) v0[u] = __ldg(gsrc + ((size_t)n * C4out + grp) * gplane + o);
+              if (grp + 1 < C4out) v1[u] = __ldg(gsrc + ((size_t)n * C4out + grp + 1) * gplane + o);
+            }
+          } else if (i < n_tasks) {
+            const int j = i - n_g;
+            const int c8 = j / (HH * HW_), pix = j % (HH * HW_);
+            const int gy = y0 + pix / HW_ - a.org, gx = x0 + pix % HW_ - a.org;
+            const int grp = ((cib >> 3) + c8) * 2;
+            dst[u] = xt + (size_t)c8 * X_CHUNK + (size_t)pix * 16;
+            if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win) {
+              const size_t o = (size_t)gy * a.Win + gx;
+              if (grp * 4 < a.Cin) v0[u] = __ldg(isrc + ((size_t)n * a.in_groups + grp) * iplane + o);
+              if ((grp + 1) * 4 < a.Cin) v1[u] = __ldg(isrc + ((size_t)n * a.in_groups + grp + 1) * iplane + o);
+            }
+          }
         }
-        *reinterpret_cast<uint4*>(xt + (size_t)c8 * X_CHUNK + (size_t)pix * 16) = pack_bf16x8(v0, v1);
+#pragma unroll
+        for (int u = 0; u < LD_BATCH; ++u)
+          if (dst[u] != nullptr) *reinterpret_cast<uint4*>(dst[u]) = pack_bf16x8(v0[u], v1[u]);
       }
       fence_proxy_async_smem();
       mbar_arrive(bar_full + 8 * s);
