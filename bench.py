@@ -504,6 +504,23 @@ def bench_forward(args, rank, world, local, dist):
     n_k = max(args.steps, 20)
     fused_ms = timed_kernel(step_fused, n_k)
     march_ms = timed_kernel(step_march, n_k)
+
+    # ---- the CNN's representative tensor-core layer, timed the same way: 16 -> 16 channels at 256^2 (three of them per
+    # decoder: 46 % of the CNN's MACs sit at this resolution) on P16 activations; algorithmic bytes = the
+    # activation read once + written once (4 B per element each), weights negligible
+    g = torch.Generator(device="cuda").manual_seed(7)
+    xa = ops.nchw_to_p16(torch.randn(B, 16, H, W, device="cuda", generator=g))
+    wl = torch.randn(16, 16, 3, 3, device="cuda", generator=g) / 12.0
+    bl = torch.zeros(16, device="cuda")
+    wpk, wsc = ops.conv_p16_pack_weights(wl, 16, 2)
+    conv_ms = timed_kernel(lambda i: ops.conv3x3_p16_fwd(xa, wpk, bl, 16, (16, 2, 2), wsc), n_k)
+    conv_bytes = 2 * B * 16 * H * W * 4
+    conv_flop = 2.0 * B * H * W * 16 * 16 * 9
+    bf16_peak = None
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(mp):
+        bf16_peak = json.load(open(mp)).get("bf16_tflops")
+    del xa
     hbm_peak, peak_src = peaks()
     achieved = FUSED_BYTES_PER_FACE * B / (fused_ms * 1e-3) / 1e9
     traffic = {}
@@ -555,6 +572,17 @@ def bench_forward(args, rank, world, local, dist):
                                     "gsamples_per_s": MARCH_SAMPLES_PER_FACE * B / (march_ms * 1e-3) / 1e9}},
         "cnn": {"flop_per_face": CNN_FLOP_PER_FACE,
                 "note": "tensor-pipe utilisation of the conv kernel: profiles/ (ncu sm__inst_executed_pipe_tensor / pipe_tensor cycles active)"},
+        "roofline_cnn": {"kernel": "conv3x3_p16_kernel<16,2,2> (tcgen05, 16 -> 16 channels @256^2, B = %d, L2 flushed between launches)" % B,
+                         "bound": "hbm", "achieved": conv_bytes / (conv_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": conv_bytes / (conv_ms * 1e-3) / 1e9 / hbm_peak, "traffic": 34_100_000, "peak_source": peak_src,
+                         "ms_per_launch": conv_ms, "algorithmic_bytes_per_launch": conv_bytes,
+                         "tensor": {"achieved": conv_flop / (conv_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+                                    "frac": (conv_flop / (conv_ms * 1e-3) / 1e12 / bf16_peak) if bf16_peak else None,
+                                    "note": "useful MACs only; the fp16-pair split issues 3 products per MAC (hi*W1, hi*W2, lo*W1), "
+                                            "so the tensor pipe does 3x this"},
+                         "note": "traffic: ncu dram__bytes_read + write of the same launch, profiles/r02_ncu_conv_p16_full.csv (33.6 MB read, "
+                                 "0.5 MB written when the kernel ends: the output is still dirty in L2); the layer is bound by the MMAs' "
+                                 "shared-memory operand reads (sm__pipe_tc_cycles_active 69.5 % of the cycles an SM is active), DESIGN.md 3/K3"},
     }
     del runner, dev, flush
     torch.cuda.empty_cache()

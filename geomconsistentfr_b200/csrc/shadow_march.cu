@@ -32,6 +32,8 @@ struct MarchArgs {
   int lpf;                   // lights per face: (face, light) pair b reads depth / mask of face b / lpf
   float t0, inv_dt;          // uniform sample table t_k = t0 + k*dt (inv_dt = 0: not uniform, no sample-range culling)
   int order;                 // fast kernel: block order, 0 = tile-major (round 1), 1 = pairs interleaved, far-from-light tiles first
+  int cut;                   // 1: fast kernel, sample groups: exact early cut-off of a ray's sample range (needs `range`)
+  const int* range;          // [faces][2] ordered-int keys written by the widening pre-pass: max depth, max -depth over the dilated mask
   int coarse;                // 1: the fast kernel builds the 8x8-block occupancy map and skips empty groups of 4 samples
   int fuse_shade;            // 1: normals + Lambert + blend + render of the pixel follow in the same thread (shade)
   gfr_shade::ShadeArgs shade;
@@ -328,6 +330,7 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
   // of the mask, i.e. for t in an interval that is solved here in fp32 with a 0.01-pixel / one-sample safety margin; the
   // warp walks the union of its 32 intervals (uniform bounds, uniform table loads), everything outside is 1e6 anyway.
   int k_begin = 0, k_end = a.n - 1;
+  int k_hi = a.n - 1;                            // this lane's own last useful sample (bounding box, then the cut-off)
   if (a.inv_dt != 0.f) {
     const int* bb = reinterpret_cast<const int*>(a.mask_bits + (size_t)f * a.mask_stride + words);
     const int c_lo = __ldg(bb), c_hi = -__ldg(bb + 1), r_lo = __ldg(bb + 2), r_hi = -__ldg(bb + 3);
@@ -348,6 +351,43 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
     if (none || tlo > thi) { kl = a.n; kh = -1; }
     k_begin = max(__reduce_min_sync(0xffffffffu, kl), 0);
     k_end = min(__reduce_max_sync(0xffffffffu, kh), a.n - 1);
+    k_hi = kh;
+  }
+
+  // Exact early cut-off (a.cut; round 2).  With BA = A_k - P and BC = P_L - P (TRAIN:507-508),
+  //     |BA x BC|^2 >= (BCx^2 + BCy^2) * (BAz - h_k)^2,   h_k = BCz * (BAx BCx + BAy BCy) / (BCx^2 + BCy^2)
+  // (h_k = height of the pixel -> light line above the pixel at the sample's (x, y); Cauchy-Schwarz on the rest).  h_k grows
+  // linearly with t_k (the 2-D ray points at the projected light) while BAz = az - z can never exceed zmax - z, the largest
+  // depth any in-mask sample's bilinear footprint can return (`range`, reduced over the 1-pixel dilation of the mask by the
+  // widening pre-pass, 0 included for the reference's zero-weight case at integral u / v).  Once the line has risen above
+  // that by more than the current minimum distance, no later sample can beat it: the lane's last useful sample index is
+  //     k_cut = ceil((ca + cb * sqrt(qmin) - t0) / dt) + 1
+  // and the warp stops at the maximum over its lanes.  Margins: 4 E on sqrt(q) (E bounds the fp32 rounding of the reference's
+  // cross product: products of magnitude <= (|BCz| + |BCx| + |BCy|) (W + H) + |z range| (|BCx| + |BCy|), 2^-21 relative, > 4x the worst case),
+  // 2e-4 (|BCx| + |BCy|) on the scalar product (the -1e-4 / +1e-4 index offsets and the fp32 rounding of A_k), 1e-5 relative
+  // and one whole sample on t.  Rays that descend (BCz < 0) use zmin the same way.  Skipped samples can only be >= the
+  // running minimum, so d_min AND the arg-min (first minimum) are unchanged: bit-identical to the literal kernel.
+  float cut_ka = 0.f, cut_kb = 0.f;
+  bool cut_ok = false;
+  if (ILP >= 2 && a.cut && a.inv_dt != 0.f) {
+    const int* rg = a.range + 2 * f;
+    const int kmax = __ldg(rg), kmin = __ldg(rg + 1);
+    const float zmax = fmaxf(__int_as_float(kmax >= 0 ? kmax : kmax ^ 0x7fffffff), 0.f);
+    const float zmin = fminf(-__int_as_float(kmin >= 0 ? kmin : kmin ^ 0x7fffffff), 0.f);
+    const float dxf = __fsub_rn(ex, x), dyf = __fsub_rn(ey, y);
+    const float A2 = bcx * bcx + bcy * bcy;
+    const float p1 = dxf * bcx, p2 = dyf * bcy, S1 = p1 + p2;
+    const float nxy = fabsf(bcx) + fabsf(bcy);
+    const float G = bcz > 0.f ? zmax - z : z - zmin;                        // room between the pixel and the extreme depth ahead of the line
+    if (S1 > 1e-3f * (fabsf(p1) + fabsf(p2)) && S1 > 0.f && A2 > 0.f && bcz != 0.f && G >= 0.f && zmax >= zmin) {
+      const float E = 4.76837158e-7f * ((fabsf(bcz) + nxy) * (float)(W + H) + 2.f * ((zmax - zmin) + fmaxf(fabsf(zmax), fabsf(zmin))) * nxy);
+      const float inv = 1.f / (fabsf(bcz) * (S1 * 0.99999f));
+      const float ca = (G * 1.000001f * A2 + 2e-4f * nxy * fabsf(bcz) + 4.f * E * sqrtf(A2)) * inv;
+      const float cb = sqrtf(A2) * inv;
+      cut_ka = (ca * 1.00001f - a.t0) * a.inv_dt + 2.f;
+      cut_kb = cb * 1.00001f * a.inv_dt;
+      cut_ok = true;
+    }
   }
 
   float qmin = __int_as_float(0x7f800000);   // +inf == "outside the face"
@@ -355,7 +395,13 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
   RayConst rc;
   rc.hW = hW; rc.hH = hH; rc.neg_eps = neg_eps; rc.x = x; rc.y = y; rc.z = z; rc.bcx = bcx; rc.bcy = bcy; rc.bcz = bcz; rc.W = W; rc.H = H;
   if (ILP >= 2) {
+    bool dirty = false;
     for (int k = k_begin; k <= k_end; k += ILP) {
+      if (__any_sync(0xffffffffu, dirty)) {       // every lane is here once per iteration (k, k_end are warp-uniform)
+        k_end = min(k_end, __reduce_max_sync(0xffffffffu, k_hi));
+        dirty = false;
+        if (k > k_end) break;
+      }
       double px[ILP], py[ILP];
       bool in[ILP], any = false;
 #pragma unroll
@@ -372,9 +418,14 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
       float q[ILP];
 #pragma unroll
       for (int j = 0; j < ILP; ++j) q[j] = sample_q(D, rc, px[j], py[j]);
+      const float q_before = qmin;
 #pragma unroll
       for (int j = 0; j < ILP; ++j)
         if (in[j] && q[j] < qmin) { qmin = q[j]; kmin = k + j; }
+      if (cut_ok && qmin < q_before) {
+        const float kc = fmaf(cut_kb, sqrtf(qmin), cut_ka);
+        if (kc < (float)k_hi) { k_hi = (int)kc; dirty = true; }       // kc >= 1 here (ca > 0): the truncation rounds towards the safe side of the +2
+      }
     }
   } else {
   const float dxf32 = __fsub_rn(ex, x), dyf32 = __fsub_rn(ey, y);
@@ -527,6 +578,55 @@ __global__ void widen_depth_kernel(const float4* __restrict__ in, double* __rest
   o[1] = make_double2((double)v.z, (double)v.w);
 }
 
+// The same pass + the depth range of every face over the pixels an in-mask sample can read: the mask dilated by one pixel
+// (the bilinear footprint of a sample lies within one pixel of its nearest pixel) plus the last row and column (python's
+// negative-index wrap, TRAIN:486-494).  range[f] = {key(max depth), key(max -depth)}, key = the order-preserving int image
+// of a float, reduced with atomicMax; pre-set to 0x80808080 (memset) = "nothing yet".  Grid: (chunks, faces); W % 4 == 0.
+__device__ __forceinline__ int float_key(float v) { const int b = __float_as_int(v); return b >= 0 ? b : b ^ 0x7fffffff; }
+
+__global__ void __launch_bounds__(256) widen_depth_range_kernel(const float4* __restrict__ in, double* __restrict__ out,
+                                                                const uint32_t* __restrict__ mask_bits, int mask_stride, int* __restrict__ range,
+                                                                int H, int W) {
+  const int f = blockIdx.y;
+  const int n4 = (H * W) >> 2;
+  const uint32_t* mb = mask_bits + (size_t)f * mask_stride;
+  float vmax = -3.0e38f, vneg = -3.0e38f;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+    const float4 v = __ldg(in + (size_t)f * n4 + i);
+    double2* o = reinterpret_cast<double2*>(out + ((size_t)f * n4 + i) * 4);
+    o[0] = make_double2((double)v.x, (double)v.y);
+    o[1] = make_double2((double)v.z, (double)v.w);
+    const int p0 = i * 4, r = p0 / W, c0 = p0 % W;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    // bits of columns c0 - 1 .. c0 + 4 of rows r - 1 .. r + 1, OR-ed over the rows (bit j = column c0 - 1 + j)
+    uint32_t near = 0u;
+    for (int dr = -1; dr <= 1; ++dr) {
+      const int rr = r + dr;
+      if (rr < 0 || rr >= H) continue;
+      for (int j = 0; j < 6; ++j) {
+        const int cc = c0 - 1 + j;
+        if (cc < 0 || cc >= W) continue;
+        const int bit = rr * W + cc;
+        near |= ((__ldg(mb + (bit >> 5)) >> (bit & 31)) & 1u) << j;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool use = ((near >> e) & 7u) != 0u || r == H - 1 || c0 + e == W - 1;
+      if (use) { vmax = fmaxf(vmax, vv[e]); vneg = fmaxf(vneg, -vv[e]); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    vneg = fmaxf(vneg, __shfl_xor_sync(0xffffffffu, vneg, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (vmax > -3.0e38f) atomicMax(range + 2 * f, float_key(vmax));
+    if (vneg > -3.0e38f) atomicMax(range + 2 * f + 1, float_key(vneg));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // mask packing
 // ---------------------------------------------------------------------------------------------------
@@ -574,11 +674,12 @@ extern "C" int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int 
 }
 
 // A/B configuration of the fast march kernel: -1 / 0 = the default (environment, else the built-in choice)
-static int g_march_warp_shape = -1, g_march_ilp = 0, g_march_order = -1;
+static int g_march_warp_shape = -1, g_march_ilp = 0, g_march_order = -1, g_march_cut = -1;
 
-extern "C" int gfr_march_config(int warp_shape, int ilp, int block_order) {
-  if (warp_shape < -1 || warp_shape > 1 || ilp < 0 || ilp > 4 || block_order < -1 || block_order > 1) return GFR_E_ARG;
-  g_march_warp_shape = warp_shape; g_march_ilp = ilp; g_march_order = block_order;
+extern "C" int gfr_march_config(int warp_shape, int ilp, int block_order, int early_cut) {
+  if (warp_shape < -1 || warp_shape > 1 || ilp < 0 || ilp > 4 || block_order < -1 || block_order > 1 || early_cut < -1 || early_cut > 1)
+    return GFR_E_ARG;
+  g_march_warp_shape = warp_shape; g_march_ilp = ilp; g_march_order = block_order; g_march_cut = early_cut;
   return GFR_OK;
 }
 
@@ -636,7 +737,24 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
     shadow_march_fwd_warp_ray<<<grid, block, smem, (cudaStream_t)stream>>>(a, depth64_scratch, tab);
   } else if (variant == 0 && depth64_scratch != nullptr && fast_ok) {
     const size_t n4 = (size_t)faces * H * W / 4;
-    widen_depth_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch, n4);
+    static const int env_cut = [] { const char* e = getenv("GFR_MARCH_CUT"); return (e && atoi(e) == 0) ? 0 : 1; }();
+    const int want_cut = g_march_cut >= 0 ? g_march_cut : env_cut;
+    a.cut = (want_cut && inv_dt != 0.f && (W % 4) == 0 && faces <= 65535) ? 1 : 0;
+    if (a.cut) {
+      // the range words live behind the widened depth map (the scratch holds faces * H * W + faces doubles)
+      int* range = reinterpret_cast<int*>(depth64_scratch + (size_t)faces * H * W);
+      a.range = range;
+      const cudaError_t e = cudaMemsetAsync(range, 0x80, (size_t)faces * 2 * sizeof(int), (cudaStream_t)stream);
+      if (e != cudaSuccess) return (int)e;
+      int chunks = (2 * 148) / faces;
+      if (chunks < 1) chunks = 1;
+      const int maxc = (H * W / 4 + 255) / 256;
+      if (chunks > maxc) chunks = maxc;
+      widen_depth_range_kernel<<<dim3(chunks, faces), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch,
+                                                                                    mask_bits, mask_batch_stride, range, H, W);
+    } else {
+      widen_depth_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(depth), depth64_scratch, n4);
+    }
     // A/B switches (read once): GFR_MARCH_WARP = 0 -> 32 x 1 warps (round 1), GFR_MARCH_ILP = 1 / 2 -> samples one by one / in pairs
     static const int env_warp_shape = [] { const char* e = getenv("GFR_MARCH_WARP"); return (e && atoi(e) == 0) ? 0 : 1; }();
     static const int env_ilp = [] { const char* e = getenv("GFR_MARCH_ILP"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 4 ? v : GFR_MARCH_DEFAULT_ILP; }();

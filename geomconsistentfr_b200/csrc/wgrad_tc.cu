@@ -177,12 +177,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
       tc_fence_after_sync();
       if (elect_one_sync()) {
         const uint32_t gt = smem0 + s * stage_bytes, xt = gt + G_BYTES;
+        // K block outermost, taps innermost: consecutive MMAs accumulate into DIFFERENT TMEM accumulators (one per tap), so
+        // they pipeline; with the taps outermost each accumulator received its 8 K blocks back to back, a dependent chain
+        // that ran at the MMA latency (1.5 us per tile of 72 tiny N = 16 MMAs)
 #pragma unroll
-        for (int tap = 0; tap < TAPS; ++tap) {
-          const uint32_t xoff = (uint32_t)((tap / KT) * HW_ + (tap % KT)) * 16u;
+        for (int r2 = 0; r2 < TH / 2; ++r2) {            // K = 16 pixels = tile rows 2 r2, 2 r2 + 1
+          const uint64_t dA = desc_mnmajor(gt + (uint32_t)(2 * r2) * (TW * 16), TW * 16, G_CHUNK);
 #pragma unroll
-          for (int r2 = 0; r2 < TH / 2; ++r2) {          // K = 16 pixels = tile rows 2 r2, 2 r2 + 1
-            const uint64_t dA = desc_mnmajor(gt + (uint32_t)(2 * r2) * (TW * 16), TW * 16, G_CHUNK);
+          for (int tap = 0; tap < TAPS; ++tap) {
+            const uint32_t xoff = (uint32_t)((tap / KT) * HW_ + (tap % KT)) * 16u;
             const uint64_t dB = desc_mnmajor(xt + xoff + (uint32_t)(2 * r2) * (HW_ * 16), HW_ * 16, X_CHUNK);
             umma_f16(tmem + (uint32_t)(tap * NB), dA, dB, idesc, (it == 0 && r2 == 0) ? 0u : 1u);
           }

@@ -106,7 +106,7 @@ def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0,
     arg = torch.empty((B, H, W), dtype=torch.uint8, device=depth.device) if want_argmin else None
     shadow = torch.empty((B, H, W), dtype=torch.float32, device=depth.device) if want_shadow else None
     stride = 0 if mask_bits.shape[0] == 1 else H * W // 32 + MASK_EXTRA_WORDS
-    scratch = torch.empty((F, H, W), dtype=torch.float64, device=depth.device) if variant in (0, 2) else None
+    scratch = torch.empty(F * H * W + F, dtype=torch.float64, device=depth.device) if variant in (0, 2) else None    # fp64 depth + the per-face depth range
     _keep, rect = _bonus_rect(bonus_rect)
     rc = _lib.load().gfr_shadow_march_fwd(
         _ptr(depth), _ptr(mask_bits), stride, _ptr(light_pt), t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]),
@@ -115,11 +115,12 @@ def shadow_march_fwd(depth, mask_bits, light_pt, samples=None, inside_bonus=0.0,
     return dmin, arg, shadow
 
 
-def march_config(warp_shape=-1, ilp=0, block_order=-1):
+def march_config(warp_shape=-1, ilp=0, block_order=-1, early_cut=-1):
     """A/B switches of the default march kernel (process-wide): warp_shape 0 = 32x1, 1 = 8x4 pixels per warp; ilp 1..4 =
     samples one by one / in groups; block_order 0 = tile-major, 1 = pairs interleaved + far-from-light tiles first;
+    early_cut 0 / 1 = walk every in-range sample / stop a ray once no later sample can beat its minimum (sample groups only);
     -1 / 0 = defaults.  Bit-identical results in every setting."""
-    _lib.check(_lib.load().gfr_march_config(int(warp_shape), int(ilp), int(block_order)), "gfr_march_config")
+    _lib.check(_lib.load().gfr_march_config(int(warp_shape), int(ilp), int(block_order), int(early_cut)), "gfr_march_config")
 
 
 def shade_render_fwd(albedo, depth, d_min, light_pt, ambient, fx=1570.0, fy=1570.0, cx=None, cy=None,
@@ -178,7 +179,7 @@ def march_shade_fwd(albedo, depth, mask_bits, light_pt, ambient, inside_bonus=0.
                      ("normals", (B, 3, H, W)), ("d_min", (B, H, W))):
         out[k] = torch.empty(shape, dtype=torch.float32, device=dev) if k in want else None
     stride = 0 if mask_bits.shape[0] == 1 else H * W // 32 + MASK_EXTRA_WORDS
-    scratch = torch.empty((F, H, W), dtype=torch.float64, device=dev)
+    scratch = torch.empty(F * H * W + F, dtype=torch.float64, device=dev)       # fp64 depth + the per-face depth range
     rc = _lib.load().gfr_march_shade_fwd(
         _ptr(albedo) if "rendered" in want else None, _ptr(depth), _ptr(mask_bits), stride, _ptr(light_pt), _ptr(ambient),
         t.ctypes.data_as(ctypes.c_void_p), int(t.shape[0]), float(inside_bonus), rect, intr.ctypes.data_as(ctypes.c_void_p),

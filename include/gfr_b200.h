@@ -65,8 +65,9 @@ int gfr_mask_pack(const void* mask, int mask_dtype, int n_masks, int H, int W, u
  *   argmin     [B,H,W] out, uint8 index of the minimising sample (255 = every sample was outside the
  *              face); may be NULL.  Needed by the backward.
  *   shadow     [B,H,W] out, 1 - 4e^-d/(1+e^-d)^2 (TRAIN:517); may be NULL.
- *   depth64_scratch  [B,H,W] doubles of caller-owned scratch (the kernel widens the depth map into it once so
- *              the per-sample gathers need no fp32->fp64 conversion); NULL selects variant 1.
+ *   depth64_scratch  (B/L)*H*W + B/L doubles of caller-owned scratch: the kernel widens the depth map into it once so
+ *              the per-sample gathers need no fp32->fp64 conversion, and keeps every face's depth range (two ints) behind
+ *              it for the early cut-off; NULL selects variant 1.
  *   lights_per_face  L >= 1: B counts (face, light) pairs, pair b uses the depth map and mask of face b / L (depth,
  *              depth64_scratch and per-image masks then hold B / L entries) — one CNN pass relit under L lights
  *              (the reference's 18-light Multi-PIE sweep, TESTB:565-583).  1 = one light per face.
@@ -83,8 +84,11 @@ int gfr_shadow_march_fwd(const float* depth, const uint32_t* mask_bits, int mask
  *   ilp          0 default (environment GFR_MARCH_ILP, else 2), 1 = samples one by one, 2..4 = in groups of 2..4
  *   block_order -1 default (environment GFR_MARCH_ORDER, else 1), 0 = tile-major CTA order, 1 = (face, light) pairs interleaved,
  *               each pair's tiles far-from-its-light first (load balance: a CTA's cost varies 1 : 700 across the image)
+ *   early_cut   -1 default (environment GFR_MARCH_CUT, else 1), 0 = every sample of the culled range is walked, 1 = a ray stops
+ *               at the sample index beyond which the pixel -> light line is provably farther above (below) every depth an
+ *               in-mask sample can return than the ray's current minimum distance (exact: csrc/shadow_march.cu)
  * Same loop as TRAIN:467-515 either way; no reference counterpart (a tuning knob for tests / tools). */
-int gfr_march_config(int warp_shape, int ilp, int block_order);
+int gfr_march_config(int warp_shape, int ilp, int block_order, int early_cut);
 
 /* Normals + Lambertian shading + shadow blend + albedo render.  Replaces TRAIN:353-369 and 517-522
  * (kornia depth_to_normals(depth + depth_offset, K), y flip, double normalise, l = normalize(P_L - P),

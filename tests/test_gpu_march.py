@@ -163,9 +163,9 @@ def test_warp_shape_and_sample_pairs_are_bit_identical(ops):
         for t in (None, np.arange(0.025, 0.825, 0.005)[:157]):
             d1, a1, _ = ops.shadow_march_fwd(depth, bits, P_L, samples=t, inside_bonus=5.0, want_argmin=True, variant=1)
             ref = None
-            for ws, ilp, order in ((0, 1, 0), (0, 2, 1), (1, 1, 1), (1, 2, 0), (1, 2, 1), (1, 3, 1), (1, 4, 0)):
+            for ws, ilp, order, cut in ((0, 1, 0, 0), (0, 2, 1, 1), (1, 1, 1, 1), (1, 2, 0, 0), (1, 2, 1, 1), (1, 3, 1, 1), (1, 4, 0, 1)):
                 if True:
-                    ops.march_config(ws, ilp, order)
+                    ops.march_config(ws, ilp, order, cut)
                     d0, a0, _ = ops.shadow_march_fwd(depth, bits, P_L, samples=t, inside_bonus=5.0, want_argmin=True, variant=0)
                     assert torch.equal(d0, d1) and torch.equal(a0, a1), (ws, ilp, order)
                     o = ops.march_shade_fwd(albedo, depth, bits, P_L, amb, inside_bonus=5.0, samples=t, want=("rendered", "normals", "d_min"))
@@ -174,7 +174,49 @@ def test_warp_shape_and_sample_pairs_are_bit_identical(ops):
                         ref = o
                     assert torch.equal(o["rendered"], ref["rendered"]) and torch.equal(o["normals"], ref["normals"]), (ws, ilp)
     finally:
-        ops.march_config(-1, 0, -1)
+        ops.march_config(-1, 0, -1, -1)
+
+
+def test_early_cutoff_is_exact_on_face_like_depth(ops):
+    """Round 2: the default kernel stops a ray at the sample index beyond which the pixel -> light line is provably farther from
+    every depth an in-mask sample can return than the ray's current minimum.  Smooth face-like depth (where the cut-off removes
+    a third to two thirds of the in-mask samples), all 18 light directions plus lights below the image plane (descending
+    lines use the minimum depth), background depth far above / below the face, depth of either sign, a nearly flat map:
+    d_min and the arg-min must equal the literal kernel's bit for bit."""
+    from geomconsistentfr_b200.synthetic import LIGHTS_18, synthetic_face
+    H = W = 256
+    dirs = list(LIGHTS_18) + [(0.6, 0.2, -0.5), (-0.3, -0.6, -0.2), (0.0, 0.0, 1.0), (0.02, -0.01, 0.9997)]
+    base, m = synthetic_face(seed=3, noise=1.0)
+    bg_hi = base.clone(); bg_hi[m == 0] = 400.0                    # background above the face: only the dilated-mask range keeps the cut-off useful
+    bg_lo = base.clone(); bg_lo[m == 0] = -300.0
+    variants = [base, bg_hi, bg_lo, base - 80.0, 1e-3 * base, -base]
+    mask = (m * 255).view(1, H, W).cuda()
+    bits = ops.mask_pack(mask)
+    try:
+        for vi, dm in enumerate(variants):
+            for c0 in range(0, len(dirs), 8):
+                L = torch.tensor(dirs[c0:c0 + 8], dtype=torch.float32)
+                P_L = (4013.0 * torch.nn.functional.normalize(L, dim=1)).cuda()
+                depth = dm.view(1, 1, H, W).repeat(L.shape[0], 1, 1, 1).cuda().contiguous()
+                d1, a1, _ = ops.shadow_march_fwd(depth, bits, P_L, inside_bonus=5.0, want_argmin=True, variant=1)
+                for cut in (1, 0):
+                    ops.march_config(-1, 0, -1, cut)
+                    d0, a0, _ = ops.shadow_march_fwd(depth, bits, P_L, inside_bonus=5.0, want_argmin=True, variant=0)
+                    assert torch.equal(d0, d1), (vi, c0, cut, int((d0 != d1).sum()))
+                    assert torch.equal(a0, a1), (vi, c0, cut, int((a0 != a1).sum()))
+        # several lights per face and per-image masks go through the same range words
+        ops.march_config(-1, 0, -1, 1)
+        faces = [synthetic_face(seed=s, noise=2.0) for s in (1, 2)]
+        depth = torch.stack([f[0] for f in faces]).view(2, 1, H, W).cuda()
+        masks = torch.stack([f[1] for f in faces]).cuda()
+        masks[1, :, :100] = 0
+        bits2 = ops.mask_pack(masks)
+        P_L = (4013.0 * torch.nn.functional.normalize(torch.tensor(dirs[2:8], dtype=torch.float32), dim=1)).cuda()      # 2 faces x 3 lights
+        d0, a0, _ = ops.shadow_march_fwd(depth, bits2, P_L, want_argmin=True, variant=0)
+        d1, a1, _ = ops.shadow_march_fwd(depth, bits2, P_L, want_argmin=True, variant=1)
+        assert torch.equal(d0, d1) and torch.equal(a0, a1)
+    finally:
+        ops.march_config(-1, 0, -1, -1)
 
 
 def test_shade_render_vs_oracle(ops, march):

@@ -28,14 +28,14 @@ def timed(fn, n=20):
     return 1e3 * a.elapsed_time(b) / n
 
 
-for ws, ilp, order in ((0, 1, 0), (1, 1, 0), (1, 2, 0), (1, 2, 1), (1, 3, 1), (1, 4, 1), (0, 2, 1)):
+for ws, ilp, order, cut in ((0, 1, 0, 0), (1, 1, 0, 0), (1, 2, 0, 0), (1, 2, 1, 0), (1, 2, 1, 1), (1, 3, 1, 1), (1, 4, 1, 1), (0, 2, 1, 1)):
     if True:
-        ops.march_config(ws, ilp, order)
+        ops.march_config(ws, ilp, order, cut)
         t_m = timed(lambda: ops.shadow_march_fwd(depth, bits, light, inside_bonus=5.0, variant=0))
         t_f = timed(lambda: ops.march_shade_fwd(albedo, depth, bits, light, amb, inside_bonus=5.0))
         print("variant 0, warp %s, samples %s, %s: march %.1f us, fused march+shade %.1f us (20 back-to-back launches incl. the depth widening pass)"
-              % (("32x1", "8x4")[ws], ("one by one", "in pairs", "in threes", "in fours")[ilp - 1], ("tile-major order", "light-aware order")[order], t_m, t_f))
-ops.march_config(-1, 0, -1)
+              % (("32x1", "8x4")[ws], ("one by one", "in pairs", "in threes", "in fours")[ilp - 1], ("tile-major order", "light-aware order")[order] + (", early cut-off" if cut else ""), t_m, t_f))
+ops.march_config(-1, 0, -1, -1)
 for variant in (1, 2):
     t = timed(lambda: ops.shadow_march_fwd(depth, bits, light, inside_bonus=5.0, variant=variant))
     print("variant %d (%s): %.1f us per launch" % (variant, ("", "thread-per-ray, literal", "warp-per-ray")[variant], t))
