@@ -235,8 +235,26 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
       const __half* res_p = a.res ? a.res + gfr_p16::unit_offset(n, a.res_groups, a.res_c8 + (n0 >> 3), a.H, a.W, y, x) : nullptr;
       const __half* post_p = a.post ? a.post + gfr_p16::unit_offset(n, a.post_groups, n0 >> 3, pH, pW, y >> a.post_shift, x >> a.post_shift) : nullptr;
       __half* out_p = a.out + gfr_p16::unit_offset(n, a.out_groups, n0 >> 3, a.H, a.W, y, x);
-      // residual / skip operands: an L2 prefetch now, the loads after the MMAs
-      if (ok && (res_p || post_p)) {
+      // residual / skip operands.  NT = 16 (the 128^2 / 256^2 layers, where these reads were 12 of 33 us): the loads are issued
+      // NOW, before the wait for the accumulators, so their L2 / DRAM latency overlaps the MMAs of this tile; wider layers
+      // (32 accumulator registers more per thread) keep the L2 prefetch and load after the MMAs.
+      constexpr bool EARLY = (NT == 16) && !HEAD;
+      uint4 e_res[EARLY ? 4 : 1], e_post[EARLY ? 4 : 1];
+      if (EARLY) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const bool lc = ok && c < n_chunks;
+          e_res[2 * c] = e_res[2 * c + 1] = e_post[2 * c] = e_post[2 * c + 1] = make_uint4(0u, 0u, 0u, 0u);
+          if (res_p && lc) {
+            e_res[2 * c] = __ldg(reinterpret_cast<const uint4*>(res_p + 2 * c * plane));
+            e_res[2 * c + 1] = __ldg(reinterpret_cast<const uint4*>(res_p + (2 * c + 1) * plane));
+          }
+          if (post_p && lc) {
+            e_post[2 * c] = __ldg(reinterpret_cast<const uint4*>(post_p + 2 * c * pplane));
+            e_post[2 * c + 1] = __ldg(reinterpret_cast<const uint4*>(post_p + (2 * c + 1) * pplane));
+          }
+        }
+      } else if (ok && (res_p || post_p)) {
         for (int c = 0; c < n_chunks; ++c) {
           if (res_p) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(res_p + 2 * c * plane));
@@ -303,8 +321,9 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
         for (int k = 0; k < 8; ++k) v[k] = fmaf(sum[8 * c + k], inv16, bb[k]);
         if (res_p && ok) {
           float rv[8];
-          gfr_p16::join8_x16(__ldg(reinterpret_cast<const uint4*>(res_p + 2 * c * plane)),
-                             __ldg(reinterpret_cast<const uint4*>(res_p + (2 * c + 1) * plane)), rv);
+          if (EARLY) gfr_p16::join8_x16(e_res[(2 * c) & 3], e_res[(2 * c + 1) & 3], rv);
+          else gfr_p16::join8_x16(__ldg(reinterpret_cast<const uint4*>(res_p + 2 * c * plane)),
+                                  __ldg(reinterpret_cast<const uint4*>(res_p + (2 * c + 1) * plane)), rv);
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] += rv[k];
         }
@@ -319,8 +338,9 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
         }
         if (post_p && ok) {
           float pv[8];
-          gfr_p16::join8_x16(__ldg(reinterpret_cast<const uint4*>(post_p + 2 * c * pplane)),
-                             __ldg(reinterpret_cast<const uint4*>(post_p + (2 * c + 1) * pplane)), pv);
+          if (EARLY) gfr_p16::join8_x16(e_post[(2 * c) & 3], e_post[(2 * c + 1) & 3], pv);
+          else gfr_p16::join8_x16(__ldg(reinterpret_cast<const uint4*>(post_p + 2 * c * pplane)),
+                                  __ldg(reinterpret_cast<const uint4*>(post_p + (2 * c + 1) * pplane)), pv);
 #pragma unroll
           for (int k = 0; k < 8; ++k) v[k] += pv[k];
         }
@@ -435,7 +455,15 @@ int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s, const HeadP
   a.stages = stages;
   const uint32_t bytes = fixed + (uint32_t)stages * per_stage;
   const int n_tiles = gfr_ceil_div(a.Cout, NT);
-  int gx = (sm_count() * occ) / n_tiles;
+  // Persistent grid: ONE CTA per SM even where two fit.  The second slot then goes to whatever else is running — the other
+  // decoder's layer, another runner lane's layer or its ray march — so the ramp (first TMA box, ~2 us with an idle tensor
+  // pipe) and the tail of one kernel overlap another kernel's MMAs; two CTAs of the SAME kernel per SM ramp and drain
+  // together.  Measured on the forward (3 lanes): 18.7k vs 17.7k faces/s, e2e 19.2k vs 18.6k; the latency of ONE forward is
+  // 3 % worse (0.510 vs 0.493 ms) — GFR_P16_GRID_OCC=2 restores the latency-optimal grid; GFR_P16_GRID_CTAS caps the grid.
+  static const int grid_occ = [] { const char* e = getenv("GFR_P16_GRID_OCC"); const int v = e ? atoi(e) : 0; return v == 2 ? 2 : 1; }();
+  static const int grid_cap = [] { const char* e = getenv("GFR_P16_GRID_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }();
+  int gx = (sm_count() * (occ < grid_occ ? occ : grid_occ)) / n_tiles;
+  if (grid_cap > 0 && gx * n_tiles > grid_cap) gx = grid_cap / n_tiles > 0 ? grid_cap / n_tiles : 1;
   if (gx < 1) gx = 1;
   if (gx > a.m_tiles) gx = a.m_tiles;
   static const bool no_pdl = [] { const char* e = getenv("GFR_PDL"); return e != nullptr && e[0] == '0'; }();
