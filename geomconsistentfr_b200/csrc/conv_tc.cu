@@ -544,7 +544,9 @@ int launch_tc(const CUtensorMap& tm, const ConvTcArgs& a, cudaStream_t s) {
   const int occ_max = NT <= 32 ? (NT <= 16 ? GFR_CONV_OCC : 2) : 1;
   if (occ > occ_max) occ = occ_max;
   if (occ < 1) occ = 1;
-  int gx = (sm_count() * occ) / n_tiles;
+  // GFR_TC_GRID_OCC=1: one persistent CTA per SM even where two fit (see conv_p16.cu: the free slot overlaps another kernel)
+  static const int grid_occ = [] { const char* e = getenv("GFR_TC_GRID_OCC"); const int v = e ? atoi(e) : 0; return v == 1 ? 1 : 2; }();
+  int gx = (sm_count() * (occ < grid_occ ? occ : grid_occ)) / n_tiles;
   if (gx < 1) gx = 1;
   if (gx > a.m_tiles) gx = a.m_tiles;
   // Programmatic dependent launch between consecutive conv layers (the next layer's prologue - barriers, TMEM, static weight
