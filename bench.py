@@ -514,6 +514,9 @@ def bench_forward(args, rank, world, local, dist):
     bl = torch.zeros(16, device="cuda")
     wpk, wsc = ops.conv_p16_pack_weights(wl, 16, 2)
     conv_ms = timed_kernel(lambda i: ops.conv3x3_p16_fwd(xa, wpk, bl, 16, (16, 2, 2), wsc), n_k)
+    ops.conv_p16_config(2)           # the same launch with two CTAs per SM: fastest alone, slower in the overlapped step
+    conv_ms_2 = timed_kernel(lambda i: ops.conv3x3_p16_fwd(xa, wpk, bl, 16, (16, 2, 2), wsc), n_k)
+    ops.conv_p16_config(0)
     conv_bytes = 2 * B * 16 * H * W * 4
     conv_flop = 2.0 * B * H * W * 16 * 16 * 9
     bf16_peak = None
@@ -576,6 +579,9 @@ def bench_forward(args, rank, world, local, dist):
                          "bound": "hbm", "achieved": conv_bytes / (conv_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": conv_bytes / (conv_ms * 1e-3) / 1e9 / hbm_peak, "traffic": 34_100_000, "peak_source": peak_src,
                          "ms_per_launch": conv_ms, "algorithmic_bytes_per_launch": conv_bytes,
+                         "grid": "one persistent CTA per SM (the step's default: the free slot overlaps another lane's kernel)",
+                         "two_ctas_per_sm": {"ms_per_launch": conv_ms_2, "achieved": conv_bytes / (conv_ms_2 * 1e-3) / 1e9,
+                                             "frac": conv_bytes / (conv_ms_2 * 1e-3) / 1e9 / hbm_peak},
                          "tensor": {"achieved": conv_flop / (conv_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
                                     "frac": (conv_flop / (conv_ms * 1e-3) / 1e12 / bf16_peak) if bf16_peak else None,
                                     "note": "useful MACs only; the fp16-pair split issues 3 products per MAC (hi*W1, hi*W2, lo*W1), "

@@ -425,6 +425,8 @@ int make_p16_map(CUtensorMap* tm, const void* base, int N, int C8, int groups, i
   return r == CUDA_SUCCESS ? GFR_OK : GFR_E_ARG;
 }
 
+int g_p16_grid_occ = 0;      // 0 = default (environment, else 1), 1 | 2 = persistent CTAs per SM (gfr_conv_p16_config)
+
 template <int NT, int MH, int KS, int GEO = 0, bool HEAD = false>
 int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s, const HeadParams* head = nullptr) {
   using C = Cfg<NT, MH, KS, GEO>;
@@ -460,7 +462,8 @@ int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s, const HeadP
   // pipe) and the tail of one kernel overlap another kernel's MMAs; two CTAs of the SAME kernel per SM ramp and drain
   // together.  Measured on the forward (3 lanes): 18.7k vs 17.7k faces/s, e2e 19.2k vs 18.6k; the latency of ONE forward is
   // 3 % worse (0.510 vs 0.493 ms) — GFR_P16_GRID_OCC=2 restores the latency-optimal grid; GFR_P16_GRID_CTAS caps the grid.
-  static const int grid_occ = [] { const char* e = getenv("GFR_P16_GRID_OCC"); const int v = e ? atoi(e) : 0; return v == 2 ? 2 : 1; }();
+  static const int env_grid_occ = [] { const char* e = getenv("GFR_P16_GRID_OCC"); const int v = e ? atoi(e) : 0; return v == 2 ? 2 : 1; }();
+  const int grid_occ = g_p16_grid_occ > 0 ? g_p16_grid_occ : env_grid_occ;
   static const int grid_cap = [] { const char* e = getenv("GFR_P16_GRID_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }();
   int gx = (sm_count() * (occ < grid_occ ? occ : grid_occ)) / n_tiles;
   if (grid_cap > 0 && gx * n_tiles > grid_cap) gx = grid_cap / n_tiles > 0 ? grid_cap / n_tiles : 1;
@@ -583,6 +586,12 @@ __global__ void __launch_bounds__(256) stem_unroll_p16_kernel(const float* __res
 }
 
 }  // namespace
+
+extern "C" int gfr_conv_p16_config(int grid_ctas_per_sm) {
+  if (grid_ctas_per_sm < 0 || grid_ctas_per_sm > 2) return GFR_E_ARG;
+  g_p16_grid_occ = grid_ctas_per_sm;
+  return GFR_OK;
+}
 
 extern "C" int gfr_stem_unroll_p16(const float* img, void* out, int N, int H, int W, void* stream) {
   GFR_RETURN_IF_NULL(img); GFR_RETURN_IF_NULL(out);

@@ -604,6 +604,11 @@ def head_1x1_p16_fwd(x, w2, b2, w3, b3, wo, bo, act=None, out_scale=1.0):
     return out
 
 
+def conv_p16_config(grid_ctas_per_sm=0):
+    """Persistent grid of the P16 convolutions: 0 default, 1 = one CTA per SM (throughput), 2 = two where they fit (latency)."""
+    _lib.check(_lib.load().gfr_conv_p16_config(int(grid_ctas_per_sm)), "gfr_conv_p16_config")
+
+
 def conv3x3_p16_head_fwd(x, w_packed, bias, MH, w_scale, w2, b2, w3, b3, wo, bo, act=None, out_scale=1.0, cin=None):
     """conv3x3_p16_fwd (Cin -> 16, LeakyReLU, cfg (16, MH, 2)) + head_1x1_p16_fwd in ONE launch (the 1x1 tail runs in the conv's
     epilogue) -> NCHW [N,n_out,H,W]."""

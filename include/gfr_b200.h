@@ -403,6 +403,10 @@ int gfr_conv_p16_fwd_ex(const void* in, const void* w_packed, const float* bias,
 long long gfr_conv_p16_pack_size_taps(int Cin, int Cout, int NT, int KS, int taps);
 int gfr_conv_p16_pack_weights_taps(const float* w_host, int Cin, int Cout, int NT, int KS, int taps, float w_scale, void* packed_host);
 int gfr_stem_unroll_p16(const float* img, void* out, int N, int H, int W, void* stream);
+/* Persistent grid of the P16 convolutions (process-wide A/B knob, results identical): 0 = default (environment
+ * GFR_P16_GRID_OCC, else 1), 1 = one CTA per SM (throughput: the free slot overlaps another kernel), 2 = two where they fit
+ * (lowest latency of a single launch). */
+int gfr_conv_p16_config(int grid_ctas_per_sm);
 
 /* NCHW fp32 <-> P16, 2x2 max pool on P16 (compares the joined fp32 values), and the P16 forms of the stem (out / pooled
  * P16 [N,16,H,W] / [N,16,H/2,W/2]), the fused 1x1 decoder tail (in P16 [N,16,H,W]) and the light head (feat P16 with
