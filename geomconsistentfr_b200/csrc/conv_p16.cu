@@ -42,6 +42,12 @@ namespace {
 
 constexpr int TILE_H = 16;
 constexpr int MAX_STAGES = 8;
+#ifndef GFR_P16_MINBLOCKS
+#define GFR_P16_MINBLOCKS 2     // CTAs per SM the 16-channel kernels are compiled for (register cap 65536 / (320 * n))
+#endif
+#ifndef GFR_P16_EARLY_LOADS
+#define GFR_P16_EARLY_LOADS 1   // residual / skip operands loaded before the accumulator wait (32 registers more)
+#endif
 // filter geometry: GEO 0 = 3x3 / pad 1 (halo 1 px all round, 9 taps); GEO 1 = 5x1 VERTICAL / pad (2, 0) (halo 2 rows above and
 // below, none sideways, 5 taps) — the stem's 5x5 convolution after its five horizontal taps have been unrolled into channels
 // (gfr_stem_unroll_p16): conv5x5(img)[co] = sum_ky sum_{c' = kx*3 + c} W[co][c][ky][kx] * U[c'][y + ky - 2][x]
@@ -97,7 +103,7 @@ struct HeadParams {
 struct NoHead { int unused; };
 
 template <int NT, int MH, int KS, int GEO = 0, bool HEAD = false>
-__global__ void __launch_bounds__(Cfg<NT, MH, KS, GEO>::THREADS, (NT * MH <= 32) ? 2 : 1)
+__global__ void __launch_bounds__(Cfg<NT, MH, KS, GEO>::THREADS, (NT * MH <= 32) ? GFR_P16_MINBLOCKS : 1)
 conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args a,
                    const __grid_constant__ typename std::conditional<HEAD, HeadParams, NoHead>::type hp) {
   using C = Cfg<NT, MH, KS, GEO>;
@@ -238,7 +244,7 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
       // residual / skip operands.  NT = 16 (the 128^2 / 256^2 layers, where these reads were 12 of 33 us): the loads are issued
       // NOW, before the wait for the accumulators, so their L2 / DRAM latency overlaps the MMAs of this tile; wider layers
       // (32 accumulator registers more per thread) keep the L2 prefetch and load after the MMAs.
-      constexpr bool EARLY = (NT == 16) && !HEAD;
+      constexpr bool EARLY = (NT == 16) && !HEAD && GFR_P16_EARLY_LOADS;
       uint4 e_res[EARLY ? 4 : 1], e_post[EARLY ? 4 : 1];
       if (EARLY) {
 #pragma unroll
