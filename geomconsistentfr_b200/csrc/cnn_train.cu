@@ -73,6 +73,7 @@ struct BnFinalizeArgs {
   const float* gamma; const float* beta; float* running_mean; float* running_var;
   float* mean_out; float* rstd_out; float* scale; float* shift;
   int C, Cpad; double count; float eps, momentum;
+  long long* num_batches_tracked;     // BatchNorm2d.num_batches_tracked (+= 1 by the finalising CTA) or null
 };
 
 __device__ __forceinline__ void bn_finalize_channel(const double* __restrict__ sums, const BnFinalizeArgs& f, int c) {
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float4* __restrict_
   if (s_last) {
     __threadfence();
     for (int c = threadIdx.x; c < fin.Cpad; c += 256) bn_finalize_channel(sums, fin, c);
+    if (threadIdx.x == 0 && fin.num_batches_tracked != nullptr) *fin.num_batches_tracked += 1;     // torch.nn.BatchNorm2d does this per forward
   }
 }
 
@@ -802,9 +804,20 @@ extern "C" int gfr_conv_tc_pack_weights_dev_ex(const float* w, int is_transposed
   return gfr_launch_status();
 }
 
+extern "C" int gfr_bn_train_stats_ex(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     long long* num_batches_tracked, double* sums_scratch, float* mean, float* rstd, float* scale,
+                                     float* shift, int N, int C, int H, int W, float eps, float momentum, void* stream);
+
 extern "C" int gfr_bn_train_stats(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                                   double* sums_scratch, float* mean, float* rstd, float* scale, float* shift, int N, int C, int H,
                                   int W, float eps, float momentum, void* stream) {
+  return gfr_bn_train_stats_ex(x, gamma, beta, running_mean, running_var, nullptr, sums_scratch, mean, rstd, scale, shift, N, C, H, W, eps,
+                               momentum, stream);
+}
+
+extern "C" int gfr_bn_train_stats_ex(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     long long* num_batches_tracked, double* sums_scratch, float* mean, float* rstd, float* scale,
+                                     float* shift, int N, int C, int H, int W, float eps, float momentum, void* stream) {
   GFR_RETURN_IF_NULL(x); GFR_RETURN_IF_NULL(gamma); GFR_RETURN_IF_NULL(beta); GFR_RETURN_IF_NULL(sums_scratch);
   GFR_RETURN_IF_NULL(mean); GFR_RETURN_IF_NULL(rstd); GFR_RETURN_IF_NULL(scale); GFR_RETURN_IF_NULL(shift);
   if (N <= 0 || N > 65535 || C <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
@@ -813,7 +826,8 @@ extern "C" int gfr_bn_train_stats(const float* x, const float* gamma, const floa
   cudaError_t e = cudaMemsetAsync(sums_scratch, 0, ((size_t)2 * C4 * 4 + 1) * sizeof(double), s);      // + the ticket counter
   if (e != cudaSuccess) return (int)e;
   const int chunks = chunks_for(N, C4, HW);
-  const BnFinalizeArgs fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, C, C4 * 4, (double)N * HW, eps, momentum};
+  const BnFinalizeArgs fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, C, C4 * 4, (double)N * HW, eps, momentum,
+                           num_batches_tracked};
   bn_stats_kernel<<<dim3(chunks, C4, N), 256, 0, s>>>(reinterpret_cast<const float4*>(x), sums_scratch, N, C4, HW, chunks, fin);
   return gfr_launch_status();
 }

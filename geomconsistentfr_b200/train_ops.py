@@ -106,12 +106,15 @@ class _BN:
         sums = torch.empty(2 * G * 4 + 1, dtype=torch.float64, device=dev)          # + the ticket counter of the fused finalise
         mean, rstd, scale, shift = (torch.empty(G * 4, dtype=torch.float32, device=dev) for _ in range(4))
         track = bn.training and bn.track_running_stats
-        _chk(_lib.load().gfr_bn_train_stats(_ptr(raw), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean) if track else None,
-                                            _ptr(bn.running_var) if track else None, _ptr(sums), _ptr(mean), _ptr(rstd),
-                                            _ptr(scale), _ptr(shift), N, C, H, W, float(bn.eps), float(bn.momentum), _stream()),
-             "gfr_bn_train_stats", 1)
+        nbt = bn.num_batches_tracked if (track and bn.num_batches_tracked is not None and bn.num_batches_tracked.is_cuda
+                                         and bn.num_batches_tracked.dtype == torch.int64) else None
+        _chk(_lib.load().gfr_bn_train_stats_ex(_ptr(raw), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean) if track else None,
+                                               _ptr(bn.running_var) if track else None, _ptr(nbt), _ptr(sums), _ptr(mean), _ptr(rstd),
+                                               _ptr(scale), _ptr(shift), N, C, H, W, float(bn.eps), float(bn.momentum), _stream()),
+             "gfr_bn_train_stats_ex", 1)
         if track:
-            bn.num_batches_tracked += 1
+            if nbt is None and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1          # (a counter that is not a CUDA int64 tensor: torch's own increment)
             ops.bump_param_generation()
         return mean, rstd, scale, shift
 

@@ -207,6 +207,11 @@ int gfr_conv_tc_fwd_ex(const float* in, const float* w_packed, const float* bias
 int gfr_bn_train_stats(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                        double* sums_scratch, float* mean, float* rstd, float* scale, float* shift, int N, int C, int H,
                        int W, float eps, float momentum, void* stream);
+/* the same + BatchNorm2d's `num_batches_tracked += 1` (device int64, may be NULL) from the finalising CTA: the 65 BatchNorms of
+ * a generator forward otherwise cost 65 one-element launches per iteration (TRAIN:197-350 in train mode) */
+int gfr_bn_train_stats_ex(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                          long long* num_batches_tracked, double* sums_scratch, float* mean, float* rstd, float* scale,
+                          float* shift, int N, int C, int H, int W, float eps, float momentum, void* stream);
 
 /* part 2: y = act(scale*x + shift + res) + up(post)  — BatchNorm + residual add + LeakyReLU(0.2) (act 1) + skip /
  * nearest-x2-upsample add, the epilogue of gfr_conv3x3_tc_fwd as its own pass.  res/post may be NULL. */

@@ -28,7 +28,7 @@ def timed(fn, n=20):
     return 1e3 * a.elapsed_time(b) / n
 
 
-for ws, ilp, order, cut in ((0, 1, 0, 0), (1, 1, 0, 0), (1, 2, 0, 0), (1, 2, 1, 0), (1, 2, 1, 1), (1, 3, 1, 1), (1, 4, 1, 1), (0, 2, 1, 1)):
+for ws, ilp, order, cut in ((0, 1, 0, 0), (1, 1, 0, 0), (1, 2, 0, 0), (1, 2, 1, 0), (1, 2, 0, 1), (1, 2, 1, 1), (1, 3, 1, 1), (1, 4, 1, 1), (0, 2, 1, 1)):
     if True:
         ops.march_config(ws, ilp, order, cut)
         t_m = timed(lambda: ops.shadow_march_fwd(depth, bits, light, inside_bonus=5.0, variant=0))
