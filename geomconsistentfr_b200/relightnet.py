@@ -31,6 +31,9 @@ ENCODER_LAYERS = [  # (name, cin, cout, k)   TRAIN:58-70
 # decoder stages: (block, cin, cout) for the h5..h7 up-blocks and the matching encoder-skip blocks  TRAIN:91-114
 _UP_BLOCKS = [("h5", "shortcut_all_features", 128, 64, "s1"), ("h6", "shortcut_h5_out", 64, 32, "s2"),
               ("h7", "shortcut_h6_out", 32, 16, "s3")]
+# P16 convs: 16x16-pixel tiles (two M = 128 MMAs per box) once a layer has at least this many of them, 8x16 tiles below
+_P16_MH2_TILES = int(os.environ.get("GFR_P16_MH2_TILES", "296"))
+
 _EPOCH_GATES = {"s1": 8, "s2": 10, "s3": 12, "s4": 14}     # TRAIN:245,258,271,283
 
 
@@ -269,7 +272,7 @@ class RelightNet(nn.Module):
         def conv(name, x, **kw):
             wp, b, Cout, (NT, KS), w_scale = t[name][:5]
             _, _, h, w = x.shape
-            MH = 2 if N * ((h + 15) // 16) * ((w + 15) // 16) * ((Cout + NT - 1) // NT) >= 296 else 1
+            MH = 2 if N * ((h + 15) // 16) * ((w + 15) // 16) * ((Cout + NT - 1) // NT) >= _P16_MH2_TILES else 1
             return ops.conv3x3_p16_fwd(x, wp, b, Cout, (NT, MH, KS), w_scale, flags=flags, **kw)
 
         def res_block(n1, n2, x, cin=None, pool=False):
@@ -324,7 +327,7 @@ class RelightNet(nn.Module):
             act, scale = ("sigmoid", 1.0) if p == "albedo" else (None, 100.0)                      # TRAIN:285-290 / 345-350
             if self.fuse_head_p16:   # the 1x1 tail in the epilogue of conv_*_c2_1: one launch, no 16-channel round trip
                 wp, b, _, _, w_scale = t["conv_%s_c2_1" % p][:5]
-                MH = 2 if N * ((H + 15) // 16) * ((W + 15) // 16) >= 296 else 1
+                MH = 2 if N * ((H + 15) // 16) * ((W + 15) // 16) >= _P16_MH2_TILES else 1
                 return ops.conv3x3_p16_head_fwd(h, wp, b, MH, w_scale, w2, b2, w3, b3, wo, bo, act=act, out_scale=scale)
             h = conv("conv_%s_c2_1" % p, h)
             return ops.head_1x1_p16_fwd(h, w2, b2, w3, b3, wo, bo, act=act, out_scale=scale)
