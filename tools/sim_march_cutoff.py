@@ -2,7 +2,7 @@
 that survive, and a check that no skipped sample ever beats the running minimum."""
 import numpy as np, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-exec(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'sim_march_warp_shape.py')).read().split("def run(shape):")[0])
+exec(open(os.path.join(os.path.dirname(os.path.abspath(__file__)) if '__file__' in dir() else HERE, 'sim_march_warp_shape.py')).read().split("def run(shape):")[0])
 from geomconsistentfr_b200.synthetic import synthetic_face
 depth,_=synthetic_face(seed=0,noise=2.0); D=depth.numpy().astype(np.float64)
 # dilated-mask depth range
