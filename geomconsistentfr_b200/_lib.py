@@ -17,6 +17,7 @@ _PROTOS = {
                              _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_march_config": [_c_int, _c_int, _c_int, _c_int],
     "gfr_conv_p16_config": [_c_int],
+    "gfr_wgrad_tc_config": [_c_int],
     "gfr_shade_render_fwd": [_c_void_p] * 11 + [_c_int, _c_int, _c_int, _c_int, _c_void_p],
     "gfr_march_shade_fwd": [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_float] + [_c_void_p] * 10
                            + [_c_int] * 4 + [_c_void_p],

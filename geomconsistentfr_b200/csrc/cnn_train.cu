@@ -562,9 +562,15 @@ struct PwBwdArgs {
   int Cout, planar, act; float scale;
 };
 
+// Round 2: every shared-memory access is a 16-byte one.  The data gradient reads the weight rows as float4 broadcasts (64 LDS.128
+// per pixel instead of 256 LDS.32); for the weight gradient thread t owns the 4x4 block (o4, c4) = (t & 15) >> 2, t & 3 and the
+// pixels p = 16 j + (t >> 4) of the CTA's 256: two LDS.128 feed 16 multiply-adds (the first version: two LDS.32 per multiply-add),
+// the 16 pixel groups are then summed through shared memory, one global atomicAdd per (o, c) and CTA as before.
+constexpr int PW_PITCH = 20;      // floats per pixel row in shared memory: 16-byte aligned, rows 16 apart land on different banks
+
 __global__ void __launch_bounds__(256) pw_conv16_bwd_kernel(const PwBwdArgs a) {
-  __shared__ float s_w[16][16];
-  __shared__ float s_x[256][17], s_g[256][17];     // this CTA's 256 pixels: forward input and output gradient
+  __shared__ __align__(16) float s_w[16][16];
+  __shared__ __align__(16) float s_x[256 * PW_PITCH], s_g[256 * PW_PITCH];     // this CTA's 256 pixels: forward input and output gradient
   for (int i = threadIdx.x; i < 16 * 16; i += 256) s_w[i >> 4][i & 15] = (i >> 4) < a.Cout ? __ldg(a.w + i) : 0.f;
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -589,32 +595,70 @@ __global__ void __launch_bounds__(256) pw_conv16_bwd_kernel(const PwBwdArgs a) {
     }
     float gi[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float s = 0.f;
+    for (int c = 0; c < 16; ++c) gi[c] = 0.f;
 #pragma unroll
-      for (int o = 0; o < 16; ++o) s = fmaf(s_w[o][c], g[o], s);
-      gi[c] = s;
+    for (int o = 0; o < 16; ++o) {
+      const float go = g[o];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&s_w[o][4 * q]);
+        gi[4 * q] = fmaf(w4.x, go, gi[4 * q]); gi[4 * q + 1] = fmaf(w4.y, go, gi[4 * q + 1]);
+        gi[4 * q + 2] = fmaf(w4.z, go, gi[4 * q + 2]); gi[4 * q + 3] = fmaf(w4.w, go, gi[4 * q + 3]);
+      }
     }
     float4* dst = reinterpret_cast<float4*>(a.gin) + n * 4 * a.hw + p;
 #pragma unroll
     for (int q = 0; q < 4; ++q) dst[q * a.hw] = make_float4(gi[4 * q], gi[4 * q + 1], gi[4 * q + 2], gi[4 * q + 3]);
   }
-  // weight / bias gradients: the CTA's [256 px x 16] tiles of x and g go through shared memory, thread (o, c) reduces
-  // its product over the 256 pixels, one global atomicAdd per (o, c) and CTA
+  // weight / bias gradients
 #pragma unroll
-  for (int c = 0; c < 16; ++c) { s_x[threadIdx.x][c] = x[c]; s_g[threadIdx.x][c] = g[c]; }
+  for (int q = 0; q < 4; ++q) {
+    *reinterpret_cast<float4*>(&s_x[threadIdx.x * PW_PITCH + 4 * q]) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+    *reinterpret_cast<float4*>(&s_g[threadIdx.x * PW_PITCH + 4 * q]) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
+  }
   __syncthreads();
-  const int o = threadIdx.x >> 4, c = threadIdx.x & 15;
-  if (o < a.Cout) {
-    float acc = 0.f, accb = 0.f;
-#pragma unroll 8
-    for (int px = 0; px < 256; ++px) {
-      const float gv = s_g[px][o];
-      acc = fmaf(gv, s_x[px][c], acc);
-      accb += gv;
+  const int blk = threadIdx.x & 15, o4 = blk >> 2, c4 = blk & 3, pg = threadIdx.x >> 4;
+  float acc[4][4];
+  float4 accb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < 16; ++j) {
+    const int px = 16 * j + pg;
+    const float4 gv = *reinterpret_cast<const float4*>(&s_g[px * PW_PITCH + 4 * o4]);
+    const float4 xv = *reinterpret_cast<const float4*>(&s_x[px * PW_PITCH + 4 * c4]);
+    const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(gg[r], xx[c], acc[r][c]);
+    accb.x += gv.x; accb.y += gv.y; accb.z += gv.z; accb.w += gv.w;
+  }
+  __syncthreads();                                 // s_x / s_g are free: reuse them for the cross-group sums
+  float* s_part = s_x;                             // [16 groups][16 blocks][16] = 4096 floats (s_x holds 5120)
+  float* s_pb = s_g;                               // [16 groups][4 o4][4]
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    *reinterpret_cast<float4*>(&s_part[(pg * 16 + blk) * 16 + 4 * r]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  if (c4 == 0) *reinterpret_cast<float4*>(&s_pb[(pg * 4 + o4) * 4]) = accb;
+  __syncthreads();
+  {
+    const int o = threadIdx.x >> 4, c = threadIdx.x & 15;                          // one (o, c) per thread
+    if (o < a.Cout) {
+      const int b2 = (o >> 2) * 4 + (c >> 2), e = (o & 3) * 4 + (c & 3);
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += s_part[(k * 16 + b2) * 16 + e];
+      if (t != 0.f) atomicAdd(a.gw + o * 16 + c, t);
+      if (c == 0) {
+        float tb = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) tb += s_pb[(k * 4 + (o >> 2)) * 4 + (o & 3)];
+        if (tb != 0.f) atomicAdd(a.gb + o, tb);
+      }
     }
-    if (acc != 0.f) atomicAdd(a.gw + o * 16 + c, acc);
-    if (c == 0 && accb != 0.f) atomicAdd(a.gb + o, accb);
   }
 }
 

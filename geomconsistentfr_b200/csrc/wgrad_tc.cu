@@ -25,6 +25,7 @@
 
 #include <cuda_bf16.h>
 #include <mutex>
+#include <stdlib.h>
 
 using namespace gfr_tc;
 
@@ -38,6 +39,9 @@ constexpr uint32_t G_BYTES = 16 * G_CHUNK;         // M = 128 rows = 16 chunks (
 constexpr int N_GROUPS = 2, GROUP_THREADS = N_PROD / N_GROUPS;   // producer groups take alternate tiles (two tiles' loads in flight)
 constexpr uint32_t X_CHUNK = HH * HW_ * 16;        // 2880
 constexpr int MAX_STAGES = 4;
+#ifndef GFR_WGRAD_XSHIFT_DEFAULT
+#define GFR_WGRAD_XSHIFT_DEFAULT 0
+#endif
 
 struct WgradTcArgs {
   const float* in; const float* g;     // C4 [N][in_groups][Hin][Win][4], C4 [N][ceil(Cout/4)][H][W][4]
@@ -47,6 +51,8 @@ struct WgradTcArgs {
   int tiles_x, tiles_y, n_tiles;
   int NB, stages, org;
   int M;                               // UMMA M: 128, or 64 when Cout <= 64 (half the A-operand reads; D rows 16 q + i live in TMEM lanes 32 q + i)
+  int xshift;                          // 1 (3x3, Cin <= 16): the INPUT is the M operand and its row blocks are pixel shifts — see the MMA issuer
+  int Ng;                              // xshift: N = output channels of the CTA's slice, rounded up to 16
 };
 
 __host__ __device__ constexpr uint32_t idesc_bf16_mnmajor(int M, int N) {
@@ -177,6 +183,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
       tc_fence_after_sync();
       if (elect_one_sync()) {
         const uint32_t gt = smem0 + s * stage_bytes, xt = gt + G_BYTES;
+        if (a.xshift) {
+          // 16-input-channel layers (the 128^2 / 256^2 ones): A = the input halo tile with SBO = 16 bytes, i.e. M row block j is
+          // the SAME 8-channel chunk one pixel further along the row — the three horizontal taps of a filter row come out of
+          // one MMA as D rows (j, c) = dW[co][c][ky][kx = j] (rows j >= 3 are never read), B = g (N = output channels).  Six
+          // MMAs per K block (3 filter rows x 2 input chunks) instead of nine with 7/8 of the M operand zero padding.
+          const uint32_t idx = idesc_bf16_mnmajor(64, a.Ng);
+#pragma unroll
+          for (int r2 = 0; r2 < TH / 2; ++r2) {
+            const uint64_t dG = desc_mnmajor(gt + (uint32_t)(2 * r2) * (TW * 16), TW * 16, G_CHUNK);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+              for (int ch = 0; ch < 2; ++ch) {
+                const uint64_t dX = desc_mnmajor(xt + (uint32_t)ch * X_CHUNK + (uint32_t)(ky * HW_) * 16u + (uint32_t)(2 * r2) * (HW_ * 16), HW_ * 16, 16u);
+                umma_f16(tmem + (uint32_t)((ky * 2 + ch) * a.Ng), dX, dG, idx, (it == 0 && r2 == 0) ? 0u : 1u);
+              }
+            }
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (it == n_my - 1) umma_commit(bar_done);
+        } else {
         // K block outermost, taps innermost: consecutive MMAs accumulate into DIFFERENT TMEM accumulators (one per tap), so
         // they pipeline; with the taps outermost each accumulator received its 8 K blocks back to back, a dependent chain
         // that ran at the MMA latency (1.5 us per tile of 72 tiny N = 16 MMAs)
@@ -192,11 +219,39 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
         }
         umma_commit(bar_empty + 8 * s);
         if (it == n_my - 1) umma_commit(bar_done);
+        }
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   }
+  // =============================== epilogue (xshift): D row 8 j + c of accumulator (ky, chunk) = dW[.][ci = 8 chunk + c][ky][kx = j] ===============
+  if (a.xshift) {
+    if (warp < 2 && n_my > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after_sync();
+      // M = 64: rows 0..15 are TMEM lanes 0..15 (warp 0), rows 16..23 lanes 32..39 (warp 1)
+      const int row = warp * 16 + lane, j = row >> 3, c = row & 7;
+      const bool useful = lane < 16 && row < 24;
+      for (int acc = 0; acc < 6; ++acc) {
+        const int ky = acc >> 1, ch = acc & 1;
+        const int ci = cib + ch * 8 + c;
+        const int tap = ky * 3 + j, t_out = a.flip ? 8 - tap : tap;
+        for (int c0 = 0; c0 < a.Ng; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * a.Ng + c0), r);
+          tmem_ld_wait();
+          if (useful && ci < a.Cin) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int co = cob + c0 + k;
+              if (co < a.Cout) atomicAdd(a.dw + co * a.so + ci * a.si + t_out, __uint_as_float(r[k]));
+            }
+          }
+        }
+      }
+    }
+  } else
   // =============================== epilogue: warps 0-3, lane = co ===============================
   if (warp < 4 && n_my > 0) {
     mbar_wait(bar_done, 0);
@@ -224,6 +279,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+int g_wgrad_xshift = -1;      // -1 default (environment GFR_WGRAD_XSHIFT, else the built-in choice), 0 / 1 (gfr_wgrad_tc_config)
+
 template <int TAPS>
 int launch_wgrad_tc(WgradTcArgs a, cudaStream_t s) {
   static std::once_flag once;
@@ -239,6 +296,11 @@ int launch_wgrad_tc(WgradTcArgs a, cudaStream_t s) {
   if (NB > cin16) NB = cin16;
   a.NB = NB;
   a.M = a.Cout <= 64 ? 64 : 128;
+  // the pixel-shift form for the 16-input-channel 3x3 layers (one CTA covers every output channel: Cout <= 64)
+  static const bool env_xshift = [] { const char* e = getenv("GFR_WGRAD_XSHIFT"); return e ? atoi(e) != 0 : GFR_WGRAD_XSHIFT_DEFAULT != 0; }();
+  const bool want_xshift = g_wgrad_xshift >= 0 ? g_wgrad_xshift != 0 : env_xshift;
+  a.xshift = (want_xshift && TAPS == 9 && a.Cin <= 16 && a.Cout <= 64) ? 1 : 0;
+  a.Ng = (a.Cout + 15) & ~15;
   const uint32_t stage = G_BYTES + (uint32_t)(NB >> 3) * X_CHUNK;
   int stages = (int)((220u * 1024u) / stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -253,6 +315,12 @@ int launch_wgrad_tc(WgradTcArgs a, cudaStream_t s) {
 }
 
 }  // namespace
+
+extern "C" int gfr_wgrad_tc_config(int pixel_shift_form) {
+  if (pixel_shift_form < -1 || pixel_shift_form > 1) return GFR_E_ARG;
+  g_wgrad_xshift = pixel_shift_form;
+  return GFR_OK;
+}
 
 extern "C" int gfr_conv_wgrad_tc_bf16(const float* in, const float* g_out, float* g_w, int is_transposed_conv, int N, int Cin,
                                       int in_groups, int Cout, int Hin, int Win, int H, int W, int taps, void* stream) {

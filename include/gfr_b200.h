@@ -248,6 +248,10 @@ int gfr_conv3x3_wgrad(const float* in, const float* g_out, float* g_w, float* g_
  * gfr_channel_sum_c4(g_out): out[c] += sum over (N,H,W) of a C4 tensor, out exactly C floats. */
 int gfr_conv_wgrad_tc_bf16(const float* in, const float* g_out, float* g_w, int is_transposed_conv, int N, int Cin,
                            int in_groups, int Cout, int Hin, int Win, int H, int W, int taps, void* stream);
+/* A/B switch of gfr_conv_wgrad_tc_bf16 for 3x3 layers with <= 16 input channels (process-wide; same sums in a different MMA
+ * arrangement): -1 default, 0 = one MMA per filter tap, 1 = the input as the M operand with pixel-shifted row blocks (the three
+ * taps of a filter row per MMA: 6 instead of 9 MMAs per K block). */
+int gfr_wgrad_tc_config(int pixel_shift_form);
 int gfr_channel_sum_c4(const float* x, float* out, int N, int C, int H, int W, void* stream);
 
 /* 2x2 max-pool backward (gradient to the first maximum, like torch), 2x2 sum (backward of the nearest x2 upsample),

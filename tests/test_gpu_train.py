@@ -329,3 +329,32 @@ def test_conv_bn_act_unit_precisions_vs_torch_autograd(prec, tol):
     (y * ops.nchw_to_c4(Gy).data).sum().backward()
     assert l1(w.grad, mod.weight.grad) <= tol and l1(ops.c4_to_nchw(ops.C4(xc.grad, cin)), xr.grad) <= tol
     assert l1(bn2.weight.grad, bn.weight.grad) <= tol
+
+
+@pytest.mark.parametrize("cin,cout,deconv,S", [(16, 16, False, 64), (16, 32, False, 32), (16, 16, True, 48), (13, 16, False, 40), (32, 16, False, 32)])
+def test_wgrad_tc_bf16_both_mma_arrangements_vs_torch(cin, cout, deconv, S):
+    """gfr_conv_wgrad_tc_bf16 (weight gradient on tcgen05, bf16 operands) against torch's conv weight gradient in fp64 on the
+    bf16-rounded operands, in both MMA arrangements (one MMA per tap / the pixel-shift form for <= 16 input channels): fp32
+    accumulation order is the only difference -> 2e-5 of the largest gradient."""
+    from geomconsistentfr_b200 import _lib, ops, train_ops as T
+    g = torch.Generator(device="cuda").manual_seed(cin * 100 + cout + S)
+    N = 3
+    x = torch.randn(N, cin, S, S, device="cuda", generator=g).bfloat16().float()
+    gy = torch.randn(N, cout, S, S, device="cuda", generator=g).bfloat16().float()
+    if deconv:       # ConvTranspose2d(k=3, s=1, p=1): weight [cin, cout, 3, 3]
+        w = torch.zeros(cin, cout, 3, 3, device="cuda", dtype=torch.float64, requires_grad=True)
+        F.conv_transpose2d(x.double(), w, padding=1).mul(gy.double()).sum().backward()
+    else:
+        w = torch.zeros(cout, cin, 3, 3, device="cuda", dtype=torch.float64, requires_grad=True)
+        F.conv2d(x.double(), w, padding=1).mul(gy.double()).sum().backward()
+    xc, gc = ops.nchw_to_c4(x).data, ops.nchw_to_c4(gy).data
+    try:
+        for form in (0, 1):
+            _lib.check(_lib.load().gfr_wgrad_tc_config(form), "gfr_wgrad_tc_config")
+            wp = torch.zeros(w.shape, device="cuda", dtype=torch.float32, requires_grad=True)
+            wp.grad = torch.zeros_like(wp)
+            T._wgrad(xc, gc, wp, None, deconv, cin, cout, taps=9, precision=4)
+            err = float((wp.grad.double() - w.grad).abs().max() / w.grad.abs().max())
+            assert err <= 2e-5, (form, err)
+    finally:
+        _lib.load().gfr_wgrad_tc_config(-1)
