@@ -363,7 +363,7 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
   // that by more than the current minimum distance, no later sample can beat it: the lane's last useful sample index is
   //     k_cut = ceil((ca + cb * sqrt(qmin) - t0) / dt) + 1
   // and the warp stops at the maximum over its lanes.  Margins: 4 E on sqrt(q) (E bounds the fp32 rounding of the reference's
-  // cross product: products of magnitude <= (|BCz| + |BCx| + |BCy|) (W + H) + |z range| (|BCx| + |BCy|), 2^-21 relative, > 4x the worst case),
+  // cross product: products of magnitude <= (|BCz| + |BCx| + |BCy|) (W + H) + (|z range| + |z|) (|BCx| + |BCy|), 2^-21 relative, > 4x the worst case),
   // 2e-4 (|BCx| + |BCy|) on the scalar product (the -1e-4 / +1e-4 index offsets and the fp32 rounding of A_k), 1e-5 relative
   // and one whole sample on t.  Rays that descend (BCz < 0) use zmin the same way.  Skipped samples can only be >= the
   // running minimum, so d_min AND the arg-min (first minimum) are unchanged: bit-identical to the literal kernel.
@@ -380,7 +380,7 @@ shadow_march_fwd_fast(const MarchArgs a, const double* __restrict__ depth64, con
     const float nxy = fabsf(bcx) + fabsf(bcy);
     const float G = bcz > 0.f ? zmax - z : z - zmin;                        // room between the pixel and the extreme depth ahead of the line
     if (S1 > 1e-3f * (fabsf(p1) + fabsf(p2)) && S1 > 0.f && A2 > 0.f && bcz != 0.f && G >= 0.f && zmax >= zmin) {
-      const float E = 4.76837158e-7f * ((fabsf(bcz) + nxy) * (float)(W + H) + 2.f * ((zmax - zmin) + fmaxf(fabsf(zmax), fabsf(zmin))) * nxy);
+      const float E = 4.76837158e-7f * ((fabsf(bcz) + nxy) * (float)(W + H) + 2.f * ((zmax - zmin) + fmaxf(fmaxf(fabsf(zmax), fabsf(zmin)), fabsf(z))) * nxy);
       const float inv = 1.f / (fabsf(bcz) * (S1 * 0.99999f));
       const float ca = (G * 1.000001f * A2 + 2e-4f * nxy * fabsf(bcz) + 4.f * E * sqrtf(A2)) * inv;
       const float cb = sqrtf(A2) * inv;

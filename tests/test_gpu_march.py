@@ -189,7 +189,9 @@ def test_early_cutoff_is_exact_on_face_like_depth(ops):
     base, m = synthetic_face(seed=3, noise=1.0)
     bg_hi = base.clone(); bg_hi[m == 0] = 400.0                    # background above the face: only the dilated-mask range keeps the cut-off useful
     bg_lo = base.clone(); bg_lo[m == 0] = -300.0
-    variants = [base, bg_hi, bg_lo, base - 80.0, 1e-3 * base, -base]
+    bg_far = base.clone(); bg_far[m == 0] = 1.0e5                  # a pixel depth far outside the face's range (rounding-error bound of its rays)
+    bg_neg = base.clone(); bg_neg[m == 0] = -1.0e5
+    variants = [base, bg_hi, bg_lo, base - 80.0, 1e-3 * base, -base, bg_far, bg_neg]
     mask = (m * 255).view(1, H, W).cuda()
     bits = ops.mask_pack(mask)
     try:
