@@ -726,7 +726,10 @@ static int march_impl(const float* depth, const uint32_t* mask_bits, int mask_ba
   // bounding-box culling has already removed most out-of-mask samples.  Kept as an opt-in (GFR_MARCH_COARSE=1) for sparse masks.
   static const bool want_coarse = getenv("GFR_MARCH_COARSE") != nullptr;
   a.coarse = (inv_dt != 0.f && want_coarse && (W % 32) == 0 && (H % 8) == 0) ? 1 : 0;
-  const size_t smem = (size_t)(H * W / 32 + 2 * (((H / 8) * (W / 8) + 31) / 32 + 1)) * sizeof(uint32_t);
+  size_t smem = (size_t)(H * W / 32 + 2 * (((H / 8) * (W / 8) + 31) / 32 + 1)) * sizeof(uint32_t);
+#ifdef GFR_MARCH_SMEM_PAD_KB        // A/B builds only: pad the dynamic shared memory so that fewer march CTAs share an SM
+  if (smem < (size_t)GFR_MARCH_SMEM_PAD_KB * 1024) smem = (size_t)GFR_MARCH_SMEM_PAD_KB * 1024;
+#endif
   static const int fast_th = [] { const char* e = getenv("GFR_MARCH_TILE_H"); return (e && atoi(e) == 8) ? 8 : 4; }();
   const bool fast_ok = ((size_t)faces * H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
   if (fuse != nullptr && !fast_ok) return GFR_E_SHAPE;
