@@ -79,6 +79,7 @@ class RelightNet(nn.Module):
                                               # accumulation (BASELINE configs[2] "bf16 CNN / fp32 ray-march"), 1 = TF32
         self.stem_tc = os.environ.get("GFR_STEM_TC", "1") != "0"      # P16 path: the 5x5 stem as unroll + 5 vertical taps on tcgen05, and the
                                               # encoder's max pools fused into the producing epilogues (0: CUDA-core stem + pool kernels)
+        self.hoist_skip_convs = False         # P16 path A/B: first conv of each encoder-skip block issued right after the encoder on its own stream (measured slower: 17.8k vs 18.7k faces/s, latency 0.565 vs 0.512 ms - the big layers delay the decoders' latency-bound low-resolution stages)
         self.fuse_head_p16 = True             # P16 path: the decoders' 1x1 tails run in the epilogue of their last 3x3 layer (A/B switch)
         self.p16 = True                       # precision 2 on PRE-SPLIT fp16-pair activations (csrc/conv_p16.cu); False: the first-
                                               # generation kernel that splits fp32 C4 tiles in shared memory (kept for A/B runs)
@@ -281,9 +282,16 @@ class RelightNet(nn.Module):
             both = conv("cat:" + n1, x, cin=cin, act_channels=Cpad)
             return conv(n2, both, cin=Cout, res=both, res_c=Cpad, pool=pool)
 
+        early = {}                        # (decoder, skip) -> (first conv of the skip block, event on the stream that ran it)
+
         def up_and_skip(p, skip, tt, enc):
             if epoch > _EPOCH_GATES[skip]:
-                s1 = conv("conv_%s_skip_%s_1" % (p, skip), enc)
+                if (p, skip) in early:
+                    s1, ev = early[(p, skip)]
+                    torch.cuda.current_stream().wait_event(ev)
+                    s1.data.record_stream(torch.cuda.current_stream())
+                else:
+                    s1 = conv("conv_%s_skip_%s_1" % (p, skip), enc)
                 return conv("conv_%s_skip_%s_2" % (p, skip), s1, res=enc, post=tt, post_shift=1)
             return ops.upsample2_p16_fwd(tt)
 
@@ -312,6 +320,20 @@ class RelightNet(nn.Module):
                                         self.linear_SL2.weight, self.linear_SL2.bias)    # [B,4]  TRAIN:225-232
             prep = after_encoder(sl) if after_encoder is not None else None
         skips = {"s1": h3_og, "s2": h2_og, "s3": h1_og, "s4": c1_og}
+        if self.hoist_skip_convs:
+            # The first conv of every encoder-skip block (TRAIN:240-241 etc.) reads encoder outputs only: it is issued NOW, on
+            # its own stream, so the four big 16- / 32- / 64-channel layers of each decoder overlap the decoders' low-resolution
+            # stages (a handful of CTAs each) instead of sitting on their critical path.
+            pre = self._side_stream("_pre")
+            pre.wait_stream(cur)
+            with torch.cuda.stream(pre):
+                for skip in ("s1", "s2", "s3", "s4"):
+                    if epoch > _EPOCH_GATES[skip]:
+                        for p in ("albedo", "depth"):
+                            s1 = conv("conv_%s_skip_%s_1" % (p, skip), skips[skip])
+                            ev = torch.cuda.Event()
+                            ev.record(pre)
+                            early[(p, skip)] = (s1, ev)
 
         def decoder(p):
             h, cin = h4, 128                                                # TRAIN:225: the first 128 channels, in place
@@ -338,6 +360,8 @@ class RelightNet(nn.Module):
         albedo = decoder("albedo")
         cur.wait_stream(side)
         cur.wait_stream(aux)
+        if early:
+            cur.wait_stream(self._side_stream("_pre"))
         depth.record_stream(cur)
         for tns in [sl] + [v for v in (prep or {}).values() if torch.is_tensor(v)]:
             tns.record_stream(cur)
