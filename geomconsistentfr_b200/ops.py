@@ -532,17 +532,21 @@ def stem_unroll_p16(img):
 
 
 def conv3x3_p16_fwd(x, w_packed, bias, Cout, cfg, w_scale, res=None, res_c=0, post=None, post_shift=0, act="lrelu",
-                    act_channels=0, out_scale=1.0, cin=None, flags=None, pool=False, geometry=0):
+                    act_channels=0, out_scale=1.0, cin=None, flags=None, pool=False, geometry=0, cin_first=0):
     """x: P16; w_packed / w_scale from conv_p16_pack_weights(w, NT, KS); cfg = (NT, MH, KS).
     out = out_scale * (act(conv(x[:, :cin]) + bias + res[:, res_c:res_c+Cout]) + up(post)) as P16 (the activation only on
     output channels < act_channels when given).  `flags`: int32[1] CUDA tensor that collects range overflows."""
     N, Cin, H, W = x.shape
     if cin is not None:
-        assert cin <= Cin
+        assert cin_first + cin <= x.groups * 8
         Cin = cin
+    assert cin_first % 8 == 0 and (cin_first == 0 or cin is not None)
     NT, MH, KS = cfg
     if not x.data.is_cuda:
         raise RuntimeError("conv3x3_p16_fwd: x must be on CUDA")
+    # the input channels [cin_first, cin_first + Cin) of a wider tensor: the chunk offset goes into the base pointer, the
+    # stride between images stays that of the whole tensor (in_groups)
+    x_ptr = ctypes.c_void_p(x.data.data_ptr() + (cin_first // 8) * 2 * H * W * 8 * 2)
     w_packed = _need(w_packed, torch.float16, "w_packed")
     bias = _need(bias, torch.float32, "bias")
     out = _p16_empty(N, Cout, H, W, x.data.device)
@@ -552,7 +556,7 @@ def conv3x3_p16_fwd(x, w_packed, bias, Cout, cfg, w_scale, res=None, res_c=0, po
         assert post.shape == (N, Cout, H >> post_shift, W >> post_shift)
     pooled = _p16_empty(N, Cout, H // 2, W // 2, x.data.device) if pool else None
     rc = _lib.load().gfr_conv_p16_fwd_ex(
-        _ptr(x.data), _ptr(w_packed), _ptr(bias), _ptr(res.data if res is not None else None), res_c // 8,
+        x_ptr, _ptr(w_packed), _ptr(bias), _ptr(res.data if res is not None else None), res_c // 8,
         res.groups if res is not None else 0, _ptr(post.data if post is not None else None), post.groups if post is not None else 0,
         _ptr(out), 0, _ptr(pooled), _ptr(flags), N, Cin, x.groups, Cout, H, W, NT, MH, KS, int(geometry), int(post_shift), _ACT[act],
         int(act_channels), float(out_scale), float(w_scale), 1, _stream())

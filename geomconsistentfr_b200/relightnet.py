@@ -79,6 +79,7 @@ class RelightNet(nn.Module):
                                               # accumulation (BASELINE configs[2] "bf16 CNN / fp32 ray-march"), 1 = TF32
         self.stem_tc = os.environ.get("GFR_STEM_TC", "1") != "0"      # P16 path: the 5x5 stem as unroll + 5 vertical taps on tcgen05, and the
                                               # encoder's max pools fused into the producing epilogues (0: CUDA-core stem + pool kernels)
+        self.merge_skip_convs = os.environ.get("GFR_MERGE_SKIP", "0") != "0"   # P16 path A/B: the two decoders' first skip-block convs of the 16-channel levels as ONE 32-channel launch (measured slower: 18.1k vs 18.7k faces/s, latency 0.521 vs 0.510 ms - the shared launch couples the two decoder streams)
         self.hoist_skip_convs = False         # P16 path A/B: first conv of each encoder-skip block issued right after the encoder on its own stream (measured slower: 17.8k vs 18.7k faces/s, latency 0.565 vs 0.512 ms - the big layers delay the decoders' latency-bound low-resolution stages)
         self.fuse_head_p16 = True             # P16 path: the decoders' 1x1 tails run in the epilogue of their last 3x3 layer (A/B switch)
         self.p16 = True                       # precision 2 on PRE-SPLIT fp16-pair activations (csrc/conv_p16.cu); False: the first-
@@ -251,6 +252,12 @@ class RelightNet(nn.Module):
             Cpad = (Cout + 7) // 8 * 8
             wz, bz = w1.new_zeros((Cpad - Cout,) + tuple(w1.shape[1:])), b1.new_zeros(Cpad - Cout)
             t["cat:" + n1] = pack(torch.cat([w1, wz, wsc]), torch.cat([b1, bz, bsc])) + (Cpad, Cout)
+        # the two decoders' first skip-block convs of a level read the SAME encoder tensor: for the 16-channel levels (128^2, 256^2,
+        # where the pixel-operand reads bound the layer) they are packed as ONE layer with 32 output channels
+        for skip in ("s3", "s4"):
+            (wa, ba), (wd, bd) = f["conv_albedo_skip_%s_1" % skip], f["conv_depth_skip_%s_1" % skip]
+            if wa.shape[0] == 16 and wd.shape[0] == 16 and wa.shape[1] == 16:
+                t["xdec:skip_%s_1" % skip] = pack(torch.cat([wa, wd]), torch.cat([ba, bd]))
         # the stem on the tensor cores: its five horizontal taps are unrolled into channels (ops.stem_unroll_p16), the layer is
         # then a 5x1 vertical-tap convolution 16 -> 16 with W5[co][kx*3 + c][ky] = w[co][c][ky][kx]
         w, b = f["conv_c1_og"]
@@ -283,9 +290,23 @@ class RelightNet(nn.Module):
             return conv(n2, both, cin=Cout, res=both, res_c=Cpad, pool=pool)
 
         early = {}                        # (decoder, skip) -> (first conv of the skip block, event on the stream that ran it)
+        merged = {}                       # skip -> (32-channel output of both decoders' first skip conv, event): issued by whichever decoder gets there first
 
         def up_and_skip(p, skip, tt, enc):
             if epoch > _EPOCH_GATES[skip]:
+                if self.merge_skip_convs and ("xdec:skip_%s_1" % skip) in t:
+                    here = torch.cuda.current_stream()
+                    if skip not in merged:
+                        both = conv("xdec:skip_%s_1" % skip, enc)
+                        ev = torch.cuda.Event()
+                        ev.record(here)
+                        merged[skip] = (both, ev)
+                    else:
+                        both, ev = merged[skip]
+                        here.wait_event(ev)
+                        both.data.record_stream(here)
+                    return conv("conv_%s_skip_%s_2" % (p, skip), both, cin=16, cin_first=(0 if p == "albedo" else 16),
+                                res=enc, post=tt, post_shift=1)
                 if (p, skip) in early:
                     s1, ev = early[(p, skip)]
                     torch.cuda.current_stream().wait_event(ev)
