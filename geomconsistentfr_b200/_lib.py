@@ -37,9 +37,13 @@ _PROTOS = {
     "gfr_conv_tc_pack_weights_dev": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p],
     "gfr_conv_tc_pack_size_ex": [_c_int] * 5,
     "gfr_conv_tc_pack_weights_dev_ex": [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p],
+    "gfr_conv_tc_pack_job_size": [],
+    "gfr_conv_tc_pack_job_fill": [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, ctypes.c_longlong],
+    "gfr_conv_tc_pack_weights_batch": [_c_void_p, _c_int, ctypes.c_longlong, _c_void_p],
     "gfr_conv_tc_fwd_ex": [_c_void_p] * 6 + [_c_int] * 13 + [_c_float, _c_int, _c_int, _c_void_p],
     "gfr_bn_train_stats": [_c_void_p] * 10 + [_c_int] * 4 + [_c_float, _c_float, _c_void_p],
     "gfr_bn_train_stats_ex": [_c_void_p] * 11 + [_c_int] * 4 + [_c_float, _c_float, _c_void_p],
+    "gfr_bn_running_update": [_c_void_p] * 4 + [_c_int] * 4 + [_c_float, _c_void_p],
     "gfr_bn_apply_fwd": [_c_void_p] * 6 + [_c_int] * 6 + [_c_void_p],
     "gfr_bn_apply_bwd": [_c_void_p] * 11 + [_c_int] * 5 + [_c_void_p],
     "gfr_bn_apply_bwd_ex": [_c_void_p] * 14 + [_c_int] * 5 + [_c_void_p],
@@ -109,7 +113,7 @@ _PROTOS = {
 }
 _RESTYPES = {"gfr_error_string": ctypes.c_char_p, "gfr_conv_tc_pack_size": ctypes.c_longlong,
              "gfr_conv_tc_pack_size_f16": ctypes.c_longlong, "gfr_conv_p16_pack_size": ctypes.c_longlong,
-             "gfr_conv_tc_pack_size_ex": ctypes.c_longlong, "gfr_conv_p16_pack_size_taps": ctypes.c_longlong}
+             "gfr_conv_tc_pack_size_ex": ctypes.c_longlong, "gfr_conv_tc_pack_job_fill": ctypes.c_longlong, "gfr_conv_p16_pack_size_taps": ctypes.c_longlong}
 
 _lib = None
 

@@ -15,6 +15,7 @@
 #include "gfr_common.cuh"
 
 #include <cuda_bf16.h>
+#include <string.h>
 
 namespace {
 
@@ -68,6 +69,58 @@ __global__ void pack_weights_bf16_kernel(const float* __restrict__ w, __nv_bfloa
   packed[idx] = __float2bfloat16_rn(v);
 }
 
+// All packed operands of a training step in ONE launch (gfr_conv_tc_pack_weights_batch): a job = one layer's forward or
+// data-gradient operand; a 256-thread block belongs to exactly one job (the jobs' block ranges are prefix sums).
+struct PackJob {
+  const float* w; void* packed;
+  long long first_block, total, so, si;
+  int O, I, NT, taps, flip, bf16;
+};
+
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
+  __shared__ PackJob job;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_jobs - 1;                     // last job whose first_block <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].first_block <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    job = jobs[lo];
+  }
+  __syncthreads();
+  const long long idx = ((long long)blockIdx.x - job.first_block) * 256 + threadIdx.x;
+  if (idx >= job.total) return;
+  const int taps = job.taps, NT = job.NT, ncb = (job.I + 15) / 16;
+  if (job.bf16) {
+    const int e = (int)(idx & 7);
+    long long t = idx >> 3;
+    const int n = (int)(t % NT); t /= NT;
+    const int ch = (int)(t & 1); t >>= 1;
+    const int tap = (int)(t % taps); t /= taps;
+    const int cb = (int)(t % ncb), nt = (int)(t / ncb);
+    const int o = nt * NT + n, i = cb * 16 + ch * 8 + e;
+    float v = 0.f;
+    if (o < job.O && i < job.I) v = __ldg(job.w + o * job.so + i * job.si + (job.flip ? taps - 1 - tap : tap));
+    reinterpret_cast<__nv_bfloat16*>(job.packed)[idx] = __float2bfloat16_rn(v);
+  } else {
+    const int e = (int)(idx & 3);
+    long long t = idx >> 2;
+    const int n = (int)(t % NT); t /= NT;
+    const int part = (int)(t & 1); t >>= 1;
+    const int kc = (int)(t & 3); t >>= 2;
+    const int tap = (int)(t % taps); t /= taps;
+    const int cb = (int)(t % ncb), nt = (int)(t / ncb);
+    const int o = nt * NT + n, i = cb * 16 + kc * 4 + e;
+    float v = 0.f;
+    if (o < job.O && i < job.I) {
+      const float x = __ldg(job.w + o * job.so + i * job.si + (job.flip ? taps - 1 - tap : tap));
+      const float hi = tf32_rna_dev(x);
+      v = part == 0 ? hi : tf32_rna_dev(x - hi);
+    }
+    reinterpret_cast<float*>(job.packed)[idx] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- BN statistics
 struct BnFinalizeArgs {
   const float* gamma; const float* beta; float* running_mean; float* running_var;
@@ -75,6 +128,13 @@ struct BnFinalizeArgs {
   int C, Cpad; double count; float eps, momentum;
   long long* num_batches_tracked;     // BatchNorm2d.num_batches_tracked (+= 1 by the finalising CTA) or null
 };
+
+// running = (1 - momentum) * running + momentum * batch  (nn.BatchNorm2d, TRAIN:59 ff.; unbiased batch variance), with the rounding
+// steps spelled out so that every kernel that applies it produces the same bits
+__device__ __forceinline__ void bn_running_update(float* running_mean, float* running_var, int c, float mean, float var_unbiased, float momentum) {
+  running_mean[c] = __fmaf_rn(momentum, mean, __fmul_rn(1.f - momentum, running_mean[c]));
+  running_var[c] = __fmaf_rn(momentum, var_unbiased, __fmul_rn(1.f - momentum, running_var[c]));
+}
 
 __device__ __forceinline__ void bn_finalize_channel(const double* __restrict__ sums, const BnFinalizeArgs& f, int c) {
   if (c >= f.C) { f.scale[c] = 0.f; f.shift[c] = 0.f; f.mean_out[c] = 0.f; f.rstd_out[c] = 0.f; return; }   // padded channel slots stay 0
@@ -86,10 +146,20 @@ __device__ __forceinline__ void bn_finalize_channel(const double* __restrict__ s
   f.mean_out[c] = (float)m; f.rstd_out[c] = rstd;
   f.scale[c] = g * rstd;
   f.shift[c] = f.beta[c] - (float)m * g * rstd;
-  if (f.running_mean) {
-    f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * (float)m;
-    f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)(var * f.count / (f.count - 1.0));
-  }
+  if (f.running_mean) bn_running_update(f.running_mean, f.running_var, c, (float)m, (float)(var * f.count / (f.count - 1.0)), f.momentum);
+}
+
+// One more momentum update of the running statistics from the SAME batch sums (gfr_bn_running_update): what a second forward pass
+// over the same input with the same weights would do to the buffers, without the pass.
+__global__ void bn_running_replay_kernel(const double* __restrict__ sums, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                         long long* __restrict__ num_batches_tracked, int C, int Cpad, double count, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+  if (c >= C) return;
+  const double m = sums[c] / count;
+  double var = sums[Cpad + c] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  bn_running_update(running_mean, running_var, c, (float)m, (float)(var * count / (count - 1.0)), momentum);
 }
 
 // The LAST CTA to finish (a ticket counter behind the sums) turns the sums into mean / rstd / scale / shift and updates the running
@@ -164,10 +234,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
   mean_out[c] = (float)m; rstd_out[c] = rstd;
   scale[c] = g * rstd;
   shift[c] = beta[c] - (float)m * g * rstd;
-  if (running_mean) {
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * count / (count - 1.0));
-  }
+  if (running_mean) bn_running_update(running_mean, running_var, c, (float)m, (float)(var * count / (count - 1.0)), momentum);
 }
 
 struct BnApplyArgs {
@@ -823,20 +890,54 @@ extern "C" long long gfr_conv_tc_pack_size_ex(int Cin, int Cout, int NT, int tap
   return precision == 4 ? steps * 2 * NT * 4 : steps * 4 * 2 * NT * 4;      // in floats (8 bf16 = 4 floats)
 }
 
+namespace {
+// Cin / Cout are those of the LAYER (forward direction).  The packed operand computes O outputs from I inputs.
+int pack_geometry(int is_transposed_conv, int for_dgrad, int Cin, int Cout, int NT, int taps, int precision, int* O, int* I, long long* so,
+                  long long* si, int* flip, long long* steps) {
+  if (Cin <= 0 || Cout <= 0 || (NT != 16 && NT != 32 && NT != 64 && NT != 128) || (taps != 9 && taps != 4)) return GFR_E_ARG;
+  if (precision != 1 && precision != 3 && precision != 4) return GFR_E_ARG;
+  *O = for_dgrad ? Cin : Cout; *I = for_dgrad ? Cout : Cin;
+  if (!is_transposed_conv) {        // Conv2d parameter [Cout][Cin][k][k]
+    if (!for_dgrad) { *so = (long long)Cin * taps; *si = taps; *flip = 0; } else { *so = taps; *si = (long long)Cin * taps; *flip = 1; }
+  } else {                          // ConvTranspose2d parameter [Cin][Cout][k][k]; forward = conv with w.transpose(0,1).flip(2,3)
+    if (!for_dgrad) { *so = taps; *si = (long long)Cout * taps; *flip = 1; } else { *so = (long long)Cout * taps; *si = taps; *flip = 0; }
+  }
+  *steps = (long long)gfr_ceil_div(*O, NT) * gfr_ceil_div(*I, 16) * taps;
+  return GFR_OK;
+}
+}  // namespace
+
+extern "C" int gfr_conv_tc_pack_job_size(void) { return (int)sizeof(PackJob); }
+
+// Fills one record of the job table of gfr_conv_tc_pack_weights_batch (host memory, gfr_conv_tc_pack_job_size() bytes) and returns
+// the number of 256-thread blocks the job takes (< 0: error).  first_block = the sum of the earlier jobs' block counts.
+extern "C" long long gfr_conv_tc_pack_job_fill(void* job_host, const float* w, int is_transposed_conv, int for_dgrad, int Cin, int Cout,
+                                               int NT, int taps, int precision, float* packed, long long first_block) {
+  if (job_host == nullptr || w == nullptr || packed == nullptr || first_block < 0) return GFR_E_NULL;
+  PackJob j;
+  long long steps;
+  const int rc = pack_geometry(is_transposed_conv, for_dgrad, Cin, Cout, NT, taps, precision, &j.O, &j.I, &j.so, &j.si, &j.flip, &steps);
+  if (rc != GFR_OK) return rc;
+  j.w = w; j.packed = packed; j.first_block = first_block; j.NT = NT; j.taps = taps; j.bf16 = precision == 4 ? 1 : 0;
+  j.total = precision == 4 ? steps * 2 * NT * 8 : steps * 4 * 2 * NT * 4;
+  memcpy(job_host, &j, sizeof(j));
+  return (j.total + 255) / 256;
+}
+
+// jobs_dev: n_jobs records (device copy of the table), n_blocks = the sum of the jobs' block counts
+extern "C" int gfr_conv_tc_pack_weights_batch(const void* jobs_dev, int n_jobs, long long n_blocks, void* stream) {
+  GFR_RETURN_IF_NULL(jobs_dev);
+  if (n_jobs <= 0 || n_blocks <= 0 || n_blocks > 0x7fffffffLL) return GFR_E_ARG;
+  pack_weights_batch_kernel<<<(unsigned)n_blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackJob*>(jobs_dev), n_jobs);
+  return gfr_launch_status();
+}
+
 extern "C" int gfr_conv_tc_pack_weights_dev_ex(const float* w, int is_transposed_conv, int for_dgrad, int Cin, int Cout, int NT,
                                                int taps, int precision, float* packed, void* stream) {
   GFR_RETURN_IF_NULL(w); GFR_RETURN_IF_NULL(packed);
-  if (Cin <= 0 || Cout <= 0 || (NT != 16 && NT != 32 && NT != 64 && NT != 128) || (taps != 9 && taps != 4)) return GFR_E_ARG;
-  if (precision != 1 && precision != 3 && precision != 4) return GFR_E_ARG;
-  // Cin / Cout are those of the LAYER (forward direction).  The packed operand computes O outputs from I inputs:
-  const int O = for_dgrad ? Cin : Cout, I = for_dgrad ? Cout : Cin;
-  long long so, si; int flip;
-  if (!is_transposed_conv) {        // Conv2d parameter [Cout][Cin][k][k]
-    if (!for_dgrad) { so = (long long)Cin * taps; si = taps; flip = 0; } else { so = taps; si = (long long)Cin * taps; flip = 1; }
-  } else {                          // ConvTranspose2d parameter [Cin][Cout][k][k]; forward = conv with w.transpose(0,1).flip(2,3)
-    if (!for_dgrad) { so = taps; si = (long long)Cout * taps; flip = 1; } else { so = (long long)Cout * taps; si = taps; flip = 0; }
-  }
-  const long long steps = (long long)gfr_ceil_div(O, NT) * gfr_ceil_div(I, 16) * taps;
+  int O, I, flip; long long so, si, steps;
+  const int rc = pack_geometry(is_transposed_conv, for_dgrad, Cin, Cout, NT, taps, precision, &O, &I, &so, &si, &flip, &steps);
+  if (rc != GFR_OK) return rc;
   if (precision == 4) {
     const long long total = steps * 2 * NT * 8;
     pack_weights_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), total,
@@ -873,6 +974,16 @@ extern "C" int gfr_bn_train_stats_ex(const float* x, const float* gamma, const f
   const BnFinalizeArgs fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, C, C4 * 4, (double)N * HW, eps, momentum,
                            num_batches_tracked};
   bn_stats_kernel<<<dim3(chunks, C4, N), 256, 0, s>>>(reinterpret_cast<const float4*>(x), sums_scratch, N, C4, HW, chunks, fin);
+  return gfr_launch_status();
+}
+
+extern "C" int gfr_bn_running_update(const double* sums, float* running_mean, float* running_var, long long* num_batches_tracked,
+                                     int N, int C, int H, int W, float momentum, void* stream) {
+  GFR_RETURN_IF_NULL(sums); GFR_RETURN_IF_NULL(running_mean); GFR_RETURN_IF_NULL(running_var);
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return GFR_E_SHAPE;
+  const int Cpad = (C + 3) / 4 * 4;
+  bn_running_replay_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, running_mean, running_var, num_batches_tracked, C, Cpad,
+                                                                             (double)N * H * W, momentum);
   return gfr_launch_status();
 }
 

@@ -90,13 +90,21 @@ struct Smem {
 #ifndef GFR_CONV_STAGES_STR
 #define GFR_CONV_STAGES_STR 2
 #endif
-  static constexpr int STAGES_RES = NT <= 32 ? GFR_CONV_STAGES_RES : 2, STAGES_STR = NT <= 32 ? GFR_CONV_STAGES_STR : 2;
-  static constexpr int MAX_STAGES = STAGES_RES > STAGES_STR ? STAGES_RES : STAGES_STR;
+#ifndef GFR_CONV_STAGES_WIDE
+#define GFR_CONV_STAGES_WIDE 2
+#endif
+  // NT >= 64 (one CTA per SM: PatchGAN's layers and the 64 / 128 / 155-channel generator layers in bf16 training): ring depth
+  // GFR_CONV_STAGES_WIDE (a step streams 11.5 KB of pixels + up to 16 KB of weights out of L2)
   // TF32: [tap][4-ch group (4)][hi|lo][n][4 floats];  F16: [tap][8-ch chunk (2)][w1|w2][n][8 halfs]  — of one 16-channel step
   //   BF16: [tap][8-ch chunk (2)][n][8 bf16].  TAPS = 9 (3x3) or 4 (2x2: PatchGAN's 4x4 / stride 2 layers over a space-to-depth)
   static constexpr uint32_t W_STEP = TAPS * (KIND == KIND_TF32 ? CB / 4 : CB / 8) * (KIND == KIND_BF16 ? 1 : 2) * NT * 16;
   // resident-weights mode (Cin <= 16): [W][slot: A_hi, A_lo] ; streaming mode: [slot: A_hi, A_lo, W]
   static constexpr uint32_t SLOT_RES = 2 * A_BYTES, SLOT_STR = 2 * A_BYTES + W_STEP;
+  static constexpr int FIT_RES = (int)((226u * 1024u - 256u - W_STEP) / SLOT_RES), FIT_STR = (int)((226u * 1024u - 256u) / SLOT_STR);   // what shared memory holds
+  static constexpr int WIDE_RES = GFR_CONV_STAGES_WIDE < FIT_RES ? GFR_CONV_STAGES_WIDE : FIT_RES, WIDE_STR = GFR_CONV_STAGES_WIDE < FIT_STR ? GFR_CONV_STAGES_WIDE : FIT_STR;
+  static constexpr int STAGES_RES = NT <= 32 ? GFR_CONV_STAGES_RES : WIDE_RES, STAGES_STR = NT <= 32 ? GFR_CONV_STAGES_STR : WIDE_STR;
+  static constexpr int MAX_STAGES = STAGES_RES > STAGES_STR ? STAGES_RES : STAGES_STR;
+  static_assert(STAGES_RES >= 2 && STAGES_STR >= 2, "the ring needs two slots");
   static constexpr uint32_t BYTES_RES = W_STEP + STAGES_RES * SLOT_RES + 256;
   static constexpr uint32_t BYTES_STR = STAGES_STR * SLOT_STR + 256;
   static constexpr uint32_t ACC = (KIND == KIND_BF16 ? 1 : 2) * NT;          // columns of one accumulator buffer

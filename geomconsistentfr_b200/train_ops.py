@@ -19,8 +19,89 @@ def _chk(rc, what, n=1):
     ops._count(n)
 
 
+class PackPlan:
+    """The packed conv operands of a training step as ONE launch (gfr_conv_tc_pack_weights_batch).
+
+    A step re-packs every layer's forward and data-gradient operand after the optimiser moved the parameters (TRAIN:656):
+    ~120 launches of 2-4 us, each in front of the layer that needs it.  While a plan is active (`with plan:`) `_pack_dev`
+    registers every (parameter storage, direction, tile) it is asked for — parameters only: a temporary (PatchGAN's permuted
+    weight view) has no stable address — and hands out a persistent buffer; `plan.run()` at the start of the next step fills
+    all registered buffers in one launch, and `_pack_dev` then returns them without launching.  `plan.invalidate()` after
+    an optimiser step.  The job table is rebuilt (one small host->device copy) when new jobs appeared — never during a
+    stream capture: the eager warm-up steps in front of a capture register them."""
+
+    active = None
+
+    def __init__(self, params=()):
+        self.param_ptrs = {p.data_ptr() for p in params}     # storages with a stable address (call after FlatAdam re-seated them)
+        self.jobs = {}                 # key -> [w, deconv, dgrad, Cin, Cout, NT, taps, precision, packed, in the device table?]
+        self.fresh = False
+        self._table = None
+        self._n_table = 0
+        self._blocks = 0
+
+    def __enter__(self):
+        self._outer, PackPlan.active = PackPlan.active, self
+        return self
+
+    def __exit__(self, *exc):
+        PackPlan.active = self._outer
+        return False
+
+    def invalidate(self):
+        self.fresh = False
+
+    def run(self):
+        """Pack every registered operand from the current parameter values (one launch)."""
+        if not self.jobs:
+            return
+        if self._n_table != len(self.jobs):
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("PackPlan: new conv layers appeared during a stream capture (run an eager step first)")
+            lib = _lib.load()
+            rec = lib.gfr_conv_tc_pack_job_size()
+            buf = ctypes.create_string_buffer(rec * len(self.jobs))
+            first = 0
+            for i, (w, deconv, dgrad, Cin, Cout, NT, taps, prec, packed, _) in enumerate(self.jobs.values()):
+                n = lib.gfr_conv_tc_pack_job_fill(ctypes.c_void_p(ctypes.addressof(buf) + i * rec), _ptr(w), int(deconv), int(dgrad), Cin, Cout,
+                                                  NT, taps, prec, _ptr(packed), first)
+                if n < 0:
+                    _lib.check(int(n), "gfr_conv_tc_pack_job_fill")
+                first += n
+            dev = next(iter(self.jobs.values()))[0].device
+            self._table = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+            self._n_table, self._blocks = len(self.jobs), first
+            for job in self.jobs.values():
+                job[9] = True                                  # in the table: filled by every run() from now on
+        _chk(_lib.load().gfr_conv_tc_pack_weights_batch(_ptr(self._table), self._n_table, self._blocks, _stream()),
+             "gfr_conv_tc_pack_weights_batch")
+        self.fresh = True
+
+    def get(self, w, deconv, dgrad, Cin, Cout, NT, taps, precision):
+        """-> (packed buffer, already filled by run()?) for a parameter; None for a tensor that is not one."""
+        if w.data_ptr() not in self.param_ptrs:
+            return None
+        key = (w.data_ptr(), int(deconv), int(dgrad), Cin, Cout, NT, taps, precision)
+        job = self.jobs.get(key)
+        if job is None:
+            O, I = (Cin, Cout) if dgrad else (Cout, Cin)
+            n = _lib.load().gfr_conv_tc_pack_size_ex(I, O, NT, taps, precision)
+            job = self.jobs[key] = [w, int(deconv), int(dgrad), Cin, Cout, NT, taps, precision,
+                                    torch.empty(n, dtype=torch.float32, device=w.device), False]
+        return job[8], self.fresh and job[9]
+
+
 def _pack_dev(w, deconv, dgrad, Cin, Cout, NT, taps=9, precision=3):
     """Device-side packing of the layer parameter for the tensor-core conv (forward or data-gradient operand)."""
+    plan = PackPlan.active
+    if plan is not None:
+        got = plan.get(w, deconv, dgrad, Cin, Cout, NT, taps, precision)
+        if got is not None:
+            packed, filled = got
+            if not filled:
+                _chk(_lib.load().gfr_conv_tc_pack_weights_dev_ex(_ptr(w), int(deconv), int(dgrad), Cin, Cout, NT, taps, precision, _ptr(packed),
+                                                                 _stream()), "gfr_conv_tc_pack_weights_dev_ex")
+            return packed
     O, I = (Cin, Cout) if dgrad else (Cout, Cin)
     n = _lib.load().gfr_conv_tc_pack_size_ex(I, O, NT, taps, precision)
     packed = torch.empty(n, dtype=torch.float32, device=w.device)
@@ -116,7 +197,25 @@ class _BN:
             if nbt is None and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked += 1          # (a counter that is not a CUDA int64 tensor: torch's own increment)
             ops.bump_param_generation()
+            if _BN.recording is not None:
+                _BN.recording.append((bn, sums, N, C, H, W))
         return mean, rstd, scale, shift
+
+    recording = None          # a list while `record_running_updates()` is active: (bn, batch sums, N, C, H, W) of every tracked BatchNorm pass
+
+    @staticmethod
+    def replay_running_updates(records):
+        """Apply the running-statistics update of the recorded passes once more (gfr_bn_running_update) — what a repeated forward
+        over the same input with the same weights does to the BatchNorm buffers."""
+        for bn, sums, N, C, H, W in records:
+            nbt = bn.num_batches_tracked if (bn.num_batches_tracked is not None and bn.num_batches_tracked.is_cuda
+                                             and bn.num_batches_tracked.dtype == torch.int64) else None
+            _chk(_lib.load().gfr_bn_running_update(_ptr(sums), _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(nbt), N, C, H, W,
+                                                   float(bn.momentum), _stream()), "gfr_bn_running_update")
+            if nbt is None and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        if records:
+            ops.bump_param_generation()
 
     @staticmethod
     def apply(raw, C, scale, shift, res, post, post_shift, act):
@@ -142,6 +241,20 @@ class _BN:
                                              _ptr(gamma.detach().contiguous()), _ptr(sums), _ptr(g_raw), _ptr(g_res), _ptr(g_gamma),
                                              _ptr(g_beta), _ptr(g_cb), N, C, H, W, int(act), _stream()), "gfr_bn_apply_bwd_ex", 2)
         return g_raw, g_res, (None if dg else g_gamma), (None if db else g_beta), (None if dcb else g_cb)
+
+
+class record_running_updates:
+    """Context manager: collects the batch statistics of every tracked BatchNorm forward inside it -> `.records` for
+    `_BN.replay_running_updates`."""
+
+    def __enter__(self):
+        self.records, self._outer = [], _BN.recording
+        _BN.recording = self.records
+        return self
+
+    def __exit__(self, *exc):
+        _BN.recording = self._outer
+        return False
 
 
 def _sumpool2(g):

@@ -7,10 +7,12 @@
 (TRAIN:617-656): discriminator loss on (composite, real) with an Adam step every GD_ratio-th iteration, then the
 generator loss with the 0.01*BCE(D(composite), 1) term (TRAIN:641-642) and its Adam step.
 TRAIN = train_raytracing_relighting_CelebAHQ_DSSIM_8x.py."""
+import os
+
 import torch
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, train_ops
 from .autograd import FlatAdam, MaskedLosses, dssim_loss
 
 LOSS_TERMS = ("recon", "depth", "ambient", "lighting", "albedo", "DSSIM")     # TRAIN:672-682 names, minus the GAN terms
@@ -23,6 +25,8 @@ class GeneratorStep:
         self.opt = FlatAdam(list(net.parameters()), lr=net.lr if lr is None else lr)      # TRAIN:589: Adam(lr=0.0001)
         self.group = group
         self._active_sig = None
+        self.batch_packs = os.environ.get("GFR_TRAIN_PACK_PLAN", "1") != "0"      # A/B switch: 0 = every layer packs its own operand
+        self.pack_plan = train_ops.PackPlan(list(net.parameters()))      # the generator's packed conv operands: one launch per step
 
     def _declare_active(self, epoch):
         """Parameters of encoder-skip blocks whose gate is closed get no gradient: tell the optimiser (torch.optim.Adam skips
@@ -79,8 +83,17 @@ class GeneratorStep:
         ops.bump_param_generation()                 # the replay wrote parameters and BN buffers behind torch's back
         return self._static_out
 
-    def step(self, img, epoch, masks_fill, masks, depth_gt, albedo_gt, lighting_gt):
+    def step(self, img, epoch, masks_fill, masks, depth_gt, albedo_gt, lighting_gt, **kw):
         """One optimiser step.  Returns (total, terms) as device tensors (no host sync)."""
+        with self.pack_plan:
+            if self.batch_packs:
+                self.pack_plan.run()                       # every conv operand of the generator from the current parameters, one launch
+            try:
+                return self._step(img, epoch, masks_fill, masks, depth_gt, albedo_gt, lighting_gt, **kw)
+            finally:
+                self.pack_plan.invalidate()            # the optimiser moved the parameters (TRAIN:656)
+
+    def _step(self, img, epoch, masks_fill, masks, depth_gt, albedo_gt, lighting_gt):
         self._declare_active(epoch)
         self.opt.zero_grad()                                                              # TRAIN:631
         B, H, W, _ = img.shape
@@ -106,9 +119,25 @@ class TrainStep(GeneratorStep):
         self.D.train_precision = getattr(net, "train_precision", 3)          # one operand precision for both networks
         self.opt_d = FlatAdam(list(patchgan.parameters()), lr=net.lr if lr is None else lr)      # TRAIN:590
         self.GD_ratio = net.GD_ratio
+        self.dedup_d = os.environ.get("GFR_TRAIN_DEDUP_D", "1") != "0"      # one discriminator pass over the composite instead of two on iterations without a D update (A/B switch)
 
-    def step(self, img, epoch, masks_fill, masks, depth_gt, albedo_gt, lighting_gt, j=0):
-        """Iteration j of an epoch.  Returns (total, terms) with the reference's loss names (TRAIN:672-682)."""
+    def _d_frozen(self, composite, record=False):
+        """D(composite) with the discriminator's weights frozen (its input gradient still flows)."""
+        for p in self.D.parameters():
+            p.requires_grad_(False)
+        try:
+            if record:
+                with train_ops.record_running_updates() as rec:
+                    out = self.D(composite)
+                self._fake_records = rec.records
+                return out
+            return self.D(composite)
+        finally:
+            for p in self.D.parameters():
+                p.requires_grad_(True)
+
+    def _step(self, img, epoch, masks_fill, masks, depth_gt, albedo_gt, lighting_gt, j=0):
+        """Iteration j of an epoch (`step(..., j=j)`).  Returns (total, terms) with the reference's loss names (TRAIN:672-682)."""
         B, H, W, _ = img.shape
         update_d = (j % self.GD_ratio) == 0                                               # TRAIN:624
         self._declare_active(epoch)
@@ -118,8 +147,23 @@ class TrainStep(GeneratorStep):
         target = img.permute(0, 3, 1, 2).contiguous()
         m3 = masks_fill.float()[:, None]
         composite = rendered * m3 + (1.0 - m3) * target
-        logits_fake = self.D(composite.detach())                                          # TRAIN:619
-        logits_real = self.D(target)                                                      # TRAIN:620
+        fake_records = None
+        if update_d or not self.dedup_d:
+            logits_fake = self.D(composite.detach())                                      # TRAIN:619
+        else:
+            # No discriminator update this iteration (TRAIN:624): D(composite) of TRAIN:641 is the same function of the same
+            # input as D(composite) of TRAIN:619, so ONE pass serves both — run here (the reference's BatchNorm update order is
+            # fake, real, fake) with frozen weights and the input gradient the generator loss needs; the running-statistics
+            # update of the pass that is not run is replayed from this pass's batch sums after D(real).
+            logits_fake2 = self._d_frozen(composite, record=True)
+            fake_records, logits_fake = self._fake_records, logits_fake2.detach()
+        if update_d:
+            logits_real = self.D(target)                                                  # TRAIN:620
+        else:
+            with torch.no_grad():                                                         # (d_loss is only reported on these iterations)
+                logits_real = self.D(target)
+        if fake_records is not None:
+            train_ops._BN.replay_running_updates(fake_records)                            # the buffers' third update (TRAIN:641)
         d_fake = 0.01 * F.binary_cross_entropy_with_logits(logits_fake, torch.zeros_like(logits_fake))   # TRAIN:621
         d_real = 0.01 * F.binary_cross_entropy_with_logits(logits_real, torch.ones_like(logits_real))    # TRAIN:622
         d_loss = d_fake + d_real
@@ -128,13 +172,8 @@ class TrainStep(GeneratorStep):
             self.opt_d.step(grad_scale=self.opt_d.all_reduce_grads(self.group))           # TRAIN:626
         self.opt.zero_grad()                                                              # TRAIN:631
         total, terms = self.losses(out, img, masks_fill, masks, depth_gt, albedo_gt, lighting_gt)
-        for p in self.D.parameters():
-            p.requires_grad_(False)
-        try:
-            logits_fake2 = self.D(composite)                                              # TRAIN:641 (after the D update)
-        finally:
-            for p in self.D.parameters():
-                p.requires_grad_(True)
+        if fake_records is None:
+            logits_fake2 = self._d_frozen(composite)                                      # TRAIN:641 (after the D update)
         g_loss = 0.01 * F.binary_cross_entropy_with_logits(logits_fake2, torch.ones_like(logits_fake2))  # TRAIN:642
         total = total + g_loss
         total.backward()                                                                  # TRAIN:655

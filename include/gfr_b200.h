@@ -196,6 +196,16 @@ int gfr_conv_tc_pack_weights_dev(const float* w, int is_transposed_conv, int for
 long long gfr_conv_tc_pack_size_ex(int Cin, int Cout, int NT, int taps, int precision);
 int gfr_conv_tc_pack_weights_dev_ex(const float* w, int is_transposed_conv, int for_dgrad, int Cin, int Cout, int NT, int taps,
                                     int precision, float* packed, void* stream);
+
+/* All packed operands of a training step in ONE launch.  gfr_conv_tc_pack_job_fill writes one record of the job table (host memory,
+ * gfr_conv_tc_pack_job_size() bytes per record; arguments as gfr_conv_tc_pack_weights_dev_ex; first_block = the sum of the block
+ * counts of the earlier jobs) and returns the job's block count (< 0: error); gfr_conv_tc_pack_weights_batch runs the device copy
+ * of the table.  Replaces ~120 per-layer pack launches of a training iteration (TRAIN:617-656: every conv layer's forward and
+ * data-gradient operand is re-packed after each Adam step, TRAIN:656). */
+int gfr_conv_tc_pack_job_size(void);
+long long gfr_conv_tc_pack_job_fill(void* job_host, const float* w, int is_transposed_conv, int for_dgrad, int Cin, int Cout, int NT,
+                                    int taps, int precision, float* packed, long long first_block);
+int gfr_conv_tc_pack_weights_batch(const void* jobs_dev, int n_jobs, long long n_blocks, void* stream);
 int gfr_conv_tc_fwd_ex(const float* in, const float* w_packed, const float* bias, const float* res, const float* post, float* out,
                        int N, int Cin, int in_groups, int Cout, int Hin, int Win, int H, int W, int NT, int taps, int org,
                        int post_shift, int act, float out_scale, int precision, int weights_static, void* stream);
@@ -212,6 +222,13 @@ int gfr_bn_train_stats(const float* x, const float* gamma, const float* beta, fl
 int gfr_bn_train_stats_ex(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                           long long* num_batches_tracked, double* sums_scratch, float* mean, float* rstd, float* scale,
                           float* shift, int N, int C, int H, int W, float eps, float momentum, void* stream);
+
+/* One more momentum update of running_mean / running_var (+ num_batches_tracked += 1, may be NULL) from the batch sums that a
+ * gfr_bn_train_stats[_ex] call left in `sums_scratch`: exactly what a second train-mode forward over the same input with the same
+ * weights does to the BatchNorm buffers.  The reference runs the discriminator twice on the same composite (TRAIN:619 and 641); on
+ * the iterations without a discriminator update (TRAIN:624) both passes are the same function, so the second is replaced by this. */
+int gfr_bn_running_update(const double* sums_scratch, float* running_mean, float* running_var, long long* num_batches_tracked,
+                          int N, int C, int H, int W, float momentum, void* stream);
 
 /* part 2: y = act(scale*x + shift + res) + up(post)  — BatchNorm + residual add + LeakyReLU(0.2) (act 1) + skip /
  * nearest-x2-upsample add, the epilogue of gfr_conv3x3_tc_fwd as its own pass.  res/post may be NULL. */

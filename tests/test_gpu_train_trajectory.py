@@ -114,3 +114,49 @@ def test_three_iterations_vs_reference_main(epoch):
     dd = np.abs(mine_d - ref_d)[~noise_d]
     assert dd.max() <= 2.0 + 1e-3 and float((dd > 0.3).mean()) < 0.03 and float(np.median(dd)) <= 0.02, \
         (float(dd.max()), float((dd > 0.3).mean()), float(np.median(dd)))
+
+
+def test_single_discriminator_pass_equals_two_passes():
+    """TrainStep.dedup_d: on iterations without a discriminator update (TRAIN:624) D(composite) of TRAIN:619 and of TRAIN:641 are
+    the same pass; the step runs it once and replays the BatchNorm running-statistics update of the pass it skips
+    (gfr_bn_running_update).  Against the literal three-pass step: the discriminator's buffers (running statistics AND
+    num_batches_tracked: 3 forwards per iteration), every loss term and the generator after its Adam step."""
+    from geomconsistentfr_b200 import PatchGAN, RelightNet, intrinsic_matrix
+    from geomconsistentfr_b200.train_loop import LOSS_NAMES, TrainingArrays
+    from geomconsistentfr_b200.trainer import TrainStep
+    from oracle.make_golden_train_iter import inputs, patchgan_init
+    data = TrainingArrays(*inputs())
+    sd0 = torch.load(os.path.join(G, "model_epoch99.pth"), map_location="cpu")
+    runs = []
+    for dedup in (False, True):
+        net = RelightNet(batch_size=3)
+        net.load_state_dict(sd0, strict=True)
+        net = net.float().cuda().train()
+        torch.manual_seed(5)
+        D = patchgan_init(PatchGAN()).cuda().train()
+        step = TrainStep(net, D, intrinsic_matrix().cuda())
+        step.dedup_d = dedup
+        terms_all = []
+        for j in (1, 2, 5, 6):                       # 1, 2, 6: no discriminator update; 5: update (both variants run the same code)
+            b = [t.cuda() for t in data.batch(j % 3, 3)]
+            total, terms = step.step(b[0], 15, *b[1:], j=j)
+            terms_all.append([float(dict(terms, total=total)[k]) for k in LOSS_NAMES])
+        runs.append((terms_all, {k: v.detach().cpu().clone() for k, v in D.state_dict().items()},
+                     {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}))
+    (ta, da, ga), (tb, db, gb) = runs
+    for k in da:
+        if k.endswith("num_batches_tracked"):
+            assert int(da[k]) == int(db[k]) == 12, (k, int(da[k]), int(db[k]))
+        elif "running" in k:
+            # same kernels on (nearly) the same data: the order of the fp64 atomics in the statistics pass, and the generator's
+            # Adam sign noise on zero-gradient biases reaching the composite from the second iteration on
+            assert torch.allclose(da[k], db[k], rtol=1e-3, atol=1e-5), (k, float((da[k] - db[k]).abs().max()))
+        else:
+            # one discriminator Adam step (j = 5, the first: lr * sign(g)): a gradient that is rounding noise flips its sign from
+            # run to run, 2 lr apart; everything else agrees
+            d = (da[k] - db[k]).abs()
+            assert float(d.max()) <= 2.05e-4 and float((d > 2e-5).float().mean()) <= 0.02, (k, float(d.max()), float((d > 2e-5).float().mean()))
+    assert np.allclose(np.array(ta), np.array(tb), rtol=2e-4, atol=1e-6), np.abs(np.array(ta) - np.array(tb)).max()
+    for k in ga:
+        if ga[k].dtype.is_floating_point:
+            assert float((ga[k] - gb[k]).abs().max()) <= 4.5e-4, k        # <= 4 Adam steps x lr of sign noise on zero-gradient biases
