@@ -242,13 +242,20 @@ struct BnApplyArgs {
   const float* scale; const float* shift;      // [C4*4]
   int C4, H, W, post_shift, act;
   long long total;                              // N*C4*H*W
+  int bpp;                                      // 256-element blocks per (n, group) plane when H*W % 256 == 0, else 0
 };
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.total) return;
   const int HW = a.H * a.W;
-  const int g = (int)((i / HW) % a.C4);
+  // plane = (n, group) index, p = pixel inside it.  H*W % 256 == 0 (every layer of the two networks): a CTA sits in ONE plane and
+  // the split is a 32-bit division per CTA; the generic form costs two 64-bit divisions per thread (~150 instructions against
+  // the ~40 of the rest of the kernel — measured issue-bound next to its HBM time)
+  unsigned plane; int p;
+  if (a.bpp > 0) { plane = blockIdx.x / (unsigned)a.bpp; p = (int)(blockIdx.x - plane * (unsigned)a.bpp) * 256 + (int)threadIdx.x; }
+  else { plane = (unsigned)(i / HW); p = (int)(i - (long long)plane * HW); }
+  const int g = (int)(plane % (unsigned)a.C4);
   const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale) + g), sh = __ldg(reinterpret_cast<const float4*>(a.shift) + g);
   const float4 v = __ldg(a.x + i);
   float r[4] = {fmaf(sc.x, v.x, sh.x), fmaf(sc.y, v.y, sh.y), fmaf(sc.z, v.z, sh.z), fmaf(sc.w, v.w, sh.w)};
@@ -258,8 +265,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyArgs a) {
     for (int e = 0; e < 4; ++e) r[e] = r[e] > 0.f ? r[e] : 0.2f * r[e];
   }
   if (a.post) {
-    const int p = (int)(i % HW), y = p / a.W, x = p % a.W;
-    const long long nc = i / HW;
+    const int y = p / a.W, x = p - y * a.W;
+    const long long nc = plane;
     const int pW = a.W >> a.post_shift, pH = a.H >> a.post_shift;
     const float4 t = __ldg(a.post + (nc * pH + (y >> a.post_shift)) * pW + (x >> a.post_shift));
     r[0] += t.x; r[1] += t.y; r[2] += t.z; r[3] += t.w;
@@ -341,9 +348,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   // fp64 sums per channel in EVERY thread: 8 fp64 divisions per element, 75 us for a 16-channel 256^2 layer at B = 16)
   __shared__ float s_c[3][4];
   const bool uniform = (a.HW & 255) == 0;
+  const unsigned plane_u = uniform ? blockIdx.x / ((unsigned)a.HW >> 8) : 0u;          // the CTA's (n, group) plane: one 32-bit division
   if (uniform) {
     if (threadIdx.x < 4) {
-      const int c = (int)(((long long)blockIdx.x * 256 / a.HW) % a.C4) * 4 + threadIdx.x;
+      const int c = (int)(plane_u % (unsigned)a.C4) * 4 + threadIdx.x;
       s_c[0][threadIdx.x] = (float)(a.sums[c] / a.count);
       s_c[1][threadIdx.x] = (float)(a.sums[a.C4 * 4 + c] / a.count);
       s_c[2][threadIdx.x] = ((a.C > 0 && c >= a.C) ? 0.f : __ldg(a.gamma_pad + c)) * __ldg(a.rstd + c);
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
     __syncthreads();
   }
   if (i >= total) return;
-  const int g = (int)((i / a.HW) % a.C4);
+  const int g = uniform ? (int)(plane_u % (unsigned)a.C4) : (int)((i / a.HW) % a.C4);
   float gp[4], xh[4];
   bn_gpre(a, (size_t)i, g, gp, xh);
   if (a.gres) a.gres[i] = make_float4(gp[0], gp[1], gp[2], gp[3]);
@@ -994,7 +1002,8 @@ extern "C" int gfr_bn_apply_fwd(const float* x, const float* scale, const float*
   if (post_shift < 0 || post_shift > 1 || act < 0 || act > 1) return GFR_E_ARG;
   const int C4 = (C + 3) / 4;
   BnApplyArgs a{reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(res), reinterpret_cast<const float4*>(post),
-                reinterpret_cast<float4*>(y), scale, shift, C4, H, W, post_shift, act, (long long)N * C4 * H * W};
+                reinterpret_cast<float4*>(y), scale, shift, C4, H, W, post_shift, act, (long long)N * C4 * H * W,
+                ((H * W) % 256) == 0 ? (H * W) / 256 : 0};
   bn_apply_kernel<<<(unsigned)((a.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
   return gfr_launch_status();
 }

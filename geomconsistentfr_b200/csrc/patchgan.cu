@@ -99,6 +99,57 @@ __global__ void d2s_pad_kernel(const float4* __restrict__ g, float* __restrict__
   else out[(((n * ((C + 3) >> 2) + (c >> 2)) * H + r) * (long long)W + q) * 4 + (c & 3)] = x;
 }
 
+// C4 input with C % 4 == 0: one thread = one 4-channel group x one 2x2 pixel block — four 16-byte loads (the block's pixels, 4 channels
+// each), a 4x4 transpose in registers, four 16-byte stores (output group 4*cg + e holds the four phases of channel 4*cg + e).  The
+// scalar kernels above move 4 bytes per access at a 16-byte stride (1/4 of every sector used).
+__global__ void __launch_bounds__(256) s2d_pad_c4_kernel(const float4* __restrict__ in, float4* __restrict__ out, int C4, int H, int W, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [N][C4][H/2+1][W/2+1]
+  if (i >= total) return;
+  const int Wo = (W >> 1) + 1, Ho = (H >> 1) + 1;
+  const int xo = (int)(i % Wo);
+  long long t = i / Wo;
+  const int yo = (int)(t % Ho); t /= Ho;
+  const int cg = (int)(t % C4);
+  const long long n = t / C4;
+  float v[4][4];                                                              // [phase k][channel e]
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = 2 * yo + (k >> 1) - 1, q = 2 * xo + (k & 1) - 1;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= 0 && r < H && q >= 0 && q < W) x = __ldg(in + ((n * C4 + cg) * H + r) * (long long)W + q);
+    v[k][0] = x.x; v[k][1] = x.y; v[k][2] = x.z; v[k][3] = x.w;
+  }
+  const long long plane = (long long)Ho * Wo;
+  float4* o = out + ((n * (4LL * C4) + 4 * cg) * Ho + yo) * (long long)Wo + xo;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) o[e * plane] = make_float4(v[0][e], v[1][e], v[2][e], v[3][e]);
+}
+
+__global__ void __launch_bounds__(256) d2s_pad_c4_kernel(const float4* __restrict__ g, float4* __restrict__ out, int C4, int H, int W, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over [N][C4][H/2+1][W/2+1]
+  if (i >= total) return;
+  const int Wo = (W >> 1) + 1, Ho = (H >> 1) + 1;
+  const int xo = (int)(i % Wo);
+  long long t = i / Wo;
+  const int yo = (int)(t % Ho); t /= Ho;
+  const int cg = (int)(t % C4);
+  const long long n = t / C4;
+  const long long plane = (long long)Ho * Wo;
+  const float4* gp = g + ((n * (4LL * C4) + 4 * cg) * Ho + yo) * (long long)Wo + xo;
+  float v[4][4];                                                              // [channel e][phase k]
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float4 x = __ldg(gp + e * plane);
+    v[e][0] = x.x; v[e][1] = x.y; v[e][2] = x.z; v[e][3] = x.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = 2 * yo + (k >> 1) - 1, q = 2 * xo + (k & 1) - 1;
+    if (r >= 0 && r < H && q >= 0 && q < W)
+      out[((n * C4 + cg) * H + r) * (long long)W + q] = make_float4(v[0][k], v[1][k], v[2][k], v[3][k]);
+  }
+}
+
 // g_pre = g_y * (y > 0 ? 1 : 0.2)   (y = LeakyReLU(pre): sign(y) = sign(pre))
 __global__ void lrelu_bwd_kernel(const float4* __restrict__ y, const float4* __restrict__ gy, float4* __restrict__ out, long long n4) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,6 +289,12 @@ extern "C" int gfr_conv4x4s1_to1_bwd(const float* in, const float* w, const floa
 extern "C" int gfr_space_to_depth_pad(const float* in, float* out, int N, int C, int H, int W, int in_is_nchw, void* stream) {
   GFR_RETURN_IF_NULL(in); GFR_RETURN_IF_NULL(out);
   if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || ((H | W) & 1)) return GFR_E_SHAPE;
+  if (!in_is_nchw && (C & 3) == 0) {
+    const long long total4 = (long long)N * (C / 4) * ((H >> 1) + 1) * ((W >> 1) + 1);
+    s2d_pad_c4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
+                                                                                         C / 4, H, W, total4);
+    return gfr_launch_status();
+  }
   const long long total = (long long)N * C * ((H >> 1) + 1) * ((W >> 1) + 1);
   s2d_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<float4*>(out), C, H, W, in_is_nchw, total);
   return gfr_launch_status();
@@ -246,6 +303,12 @@ extern "C" int gfr_space_to_depth_pad(const float* in, float* out, int N, int C,
 extern "C" int gfr_depth_to_space_pad(const float* g, float* out, int N, int C, int H, int W, int out_is_nchw, void* stream) {
   GFR_RETURN_IF_NULL(g); GFR_RETURN_IF_NULL(out);
   if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || ((H | W) & 1)) return GFR_E_SHAPE;
+  if (!out_is_nchw && (C & 3) == 0) {
+    const long long total4 = (long long)N * (C / 4) * ((H >> 1) + 1) * ((W >> 1) + 1);
+    d2s_pad_c4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(out),
+                                                                                         C / 4, H, W, total4);
+    return gfr_launch_status();
+  }
   const long long total = (long long)N * C * H * W;
   d2s_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(g), out, C, H, W, out_is_nchw, total);
   return gfr_launch_status();

@@ -358,3 +358,25 @@ def test_wgrad_tc_bf16_both_mma_arrangements_vs_torch(cin, cout, deconv, S):
             assert err <= 2e-5, (form, err)
     finally:
         _lib.load().gfr_wgrad_tc_config(-1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,S,nchw", [(3, 32, True), (8, 16, False), (64, 32, False), (6, 16, False)])
+def test_space_to_depth_pad_and_its_backward_vs_pixel_unshuffle(C, S, nchw):
+    """PatchGAN's input re-blocking (csrc/patchgan.cu): out[n, 4c + 2dy + dx, yo, xo] = pad1(x)[n, c, 2yo + dy, 2xo + dx] and its
+    adjoint — the vectorised C4 kernels (C % 4 == 0), the scalar C4 kernels (C = 6) and the planar-input form, bit-exact
+    against F.pixel_unshuffle of the padded tensor (a pure re-indexing)."""
+    from geomconsistentfr_b200 import ops
+    from geomconsistentfr_b200.patchgan import _SpaceToDepthPad
+    torch.manual_seed(C)
+    x = torch.randn(2, C, S, S, device="cuda")
+    xr = x.clone().requires_grad_()
+    ref = F.pixel_unshuffle(F.pad(xr, (1, 1, 1, 1)), 2)
+    Gy = torch.randn_like(ref)
+    ref.backward(Gy)
+    xin = x.clone().requires_grad_() if nchw else ops.nchw_to_c4(x).data.requires_grad_()
+    out = _SpaceToDepthPad.apply(xin, C, nchw)
+    assert torch.equal(ops.c4_to_nchw(ops.C4(out.detach(), 4 * C)), ref.detach())
+    (out * ops.nchw_to_c4(Gy).data).sum().backward()
+    got = xin.grad if nchw else ops.c4_to_nchw(ops.C4(xin.grad, C))
+    assert torch.equal(got, xr.grad)
