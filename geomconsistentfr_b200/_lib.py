@@ -43,6 +43,7 @@ _PROTOS = {
     "gfr_conv_tc_fwd_ex": [_c_void_p] * 6 + [_c_int] * 13 + [_c_float, _c_int, _c_int, _c_void_p],
     "gfr_bn_train_stats": [_c_void_p] * 10 + [_c_int] * 4 + [_c_float, _c_float, _c_void_p],
     "gfr_bn_train_stats_ex": [_c_void_p] * 11 + [_c_int] * 4 + [_c_float, _c_float, _c_void_p],
+    "gfr_bn_config": [_c_int],
     "gfr_bn_running_update": [_c_void_p] * 4 + [_c_int] * 4 + [_c_float, _c_void_p],
     "gfr_bn_apply_fwd": [_c_void_p] * 6 + [_c_int] * 6 + [_c_void_p],
     "gfr_bn_apply_bwd": [_c_void_p] * 11 + [_c_int] * 5 + [_c_void_p],

@@ -177,6 +177,56 @@ def _wgrad(x, g_raw, w, b, deconv, cin, Cout, taps=9, precision=3):
     return (None if dw else g_w), (None if db else g_b)
 
 
+class ZeroArena:
+    """The fp64 scratch of every BatchNorm pass of a training step (batch sums, ticket counters) as slices of ONE buffer that
+    `begin()` clears with a single memset at the start of the step; while the arena is active the library skips the memset node
+    it otherwise puts in front of each of the ~150 BatchNorm passes of an iteration (gfr_bn_config)."""
+
+    active = None
+
+    def __init__(self, n_doubles=1 << 17):
+        self.n, self.buf, self.off, self.high = n_doubles, None, 0, 0
+
+    def begin(self, device):
+        if self.buf is None:
+            self.buf = torch.zeros(self.n, dtype=torch.float64, device=device)
+        elif self.high:
+            self.buf[:self.high].zero_()
+        self.off = 0
+
+    def take(self, n):
+        if self.buf is None:
+            return None
+        end = self.off + ((n + 1) & ~1)                   # 16-byte aligned slices
+        if end > self.n:
+            return torch.zeros(n, dtype=torch.float64, device=self.buf.device)      # arena exhausted: a zeroed temporary
+        v = self.buf[self.off:self.off + n]
+        self.off = end
+        self.high = max(self.high, end)
+        return v
+
+    def __enter__(self):
+        self._outer = ZeroArena.active
+        ZeroArena.active = self
+        self._old = _lib.load().gfr_bn_config(1)
+        return self
+
+    def __exit__(self, *exc):
+        ZeroArena.active = self._outer
+        _lib.load().gfr_bn_config(self._old)
+        return False
+
+
+def _bn_scratch(n, device):
+    a = ZeroArena.active
+    if a is not None:
+        v = a.take(n)
+        if v is not None:
+            return v
+        return torch.zeros(n, dtype=torch.float64, device=device)
+    return torch.empty(n, dtype=torch.float64, device=device)
+
+
 class _BN:
     """Batch statistics + apply + backward of one BatchNorm2d over a C4 tensor (shared by the unit Functions)."""
 
@@ -184,7 +234,7 @@ class _BN:
     def stats(raw, C, bn):
         N, G, H, W, _ = raw.shape
         dev = raw.device
-        sums = torch.empty(2 * G * 4 + 1, dtype=torch.float64, device=dev)          # + the ticket counter of the fused finalise
+        sums = _bn_scratch(2 * G * 4 + 1, dev)          # + the ticket counter of the fused finalise
         mean, rstd, scale, shift = (torch.empty(G * 4, dtype=torch.float32, device=dev) for _ in range(4))
         track = bn.training and bn.track_running_stats
         nbt = bn.num_batches_tracked if (track and bn.num_batches_tracked is not None and bn.num_batches_tracked.is_cuda
@@ -231,7 +281,7 @@ class _BN:
         .grad; g_conv_bias = sum of g_raw per channel, from the same pass, when `conv_bias` is given)"""
         N, G, H, W, _ = raw.shape
         dev = raw.device
-        sums = torch.empty(2 * G * 4, dtype=torch.float64, device=dev)
+        sums = _bn_scratch(2 * G * 4, dev)
         g_raw = torch.empty_like(raw)
         g_res = torch.empty_like(raw) if want_res else None
         g_gamma, dg = _grad_target(gamma)

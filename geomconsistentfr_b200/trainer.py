@@ -7,6 +7,7 @@
 (TRAIN:617-656): discriminator loss on (composite, real) with an Adam step every GD_ratio-th iteration, then the
 generator loss with the 0.01*BCE(D(composite), 1) term (TRAIN:641-642) and its Adam step.
 TRAIN = train_raytracing_relighting_CelebAHQ_DSSIM_8x.py."""
+import contextlib
 import os
 
 import torch
@@ -26,6 +27,8 @@ class GeneratorStep:
         self.group = group
         self._active_sig = None
         self.batch_packs = os.environ.get("GFR_TRAIN_PACK_PLAN", "1") != "0"      # A/B switch: 0 = every layer packs its own operand
+        self.bn_arena = train_ops.ZeroArena()
+        self.use_bn_arena = os.environ.get("GFR_TRAIN_BN_ARENA", "1") != "0"      # A/B switch: 0 = a memset node per BatchNorm pass
         self.pack_plan = train_ops.PackPlan(list(net.parameters()))      # the generator's packed conv operands: one launch per step
 
     def _declare_active(self, epoch):
@@ -85,7 +88,9 @@ class GeneratorStep:
 
     def step(self, img, epoch, masks_fill, masks, depth_gt, albedo_gt, lighting_gt, **kw):
         """One optimiser step.  Returns (total, terms) as device tensors (no host sync)."""
-        with self.pack_plan:
+        with self.pack_plan, (self.bn_arena if self.use_bn_arena else contextlib.nullcontext()):
+            if self.use_bn_arena:
+                self.bn_arena.begin(img.device)        # every BatchNorm pass's fp64 scratch: one memset
             if self.batch_packs:
                 self.pack_plan.run()                       # every conv operand of the generator from the current parameters, one launch
             try:

@@ -223,6 +223,11 @@ int gfr_bn_train_stats_ex(const float* x, const float* gamma, const float* beta,
                           long long* num_batches_tracked, double* sums_scratch, float* mean, float* rstd, float* scale,
                           float* shift, int N, int C, int H, int W, float eps, float momentum, void* stream);
 
+/* gfr_bn_config(1): the caller guarantees that every `sums_scratch` it hands to gfr_bn_train_stats[_ex] / gfr_bn_apply_bwd[_ex] is
+ * all zero (e.g. slices of one arena cleared once per training step), so the entry points skip their own memset; 0 (default) restores
+ * it.  Other values only query.  Returns the previous setting.  Process-wide. */
+int gfr_bn_config(int scratch_prezeroed);
+
 /* One more momentum update of running_mean / running_var (+ num_batches_tracked += 1, may be NULL) from the batch sums that a
  * gfr_bn_train_stats[_ex] call left in `sums_scratch`: exactly what a second train-mode forward over the same input with the same
  * weights does to the BatchNorm buffers.  The reference runs the discriminator twice on the same composite (TRAIN:619 and 641); on

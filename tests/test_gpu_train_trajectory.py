@@ -150,7 +150,7 @@ def test_single_discriminator_pass_equals_two_passes():
         elif "running" in k:
             # same kernels on (nearly) the same data: the order of the fp64 atomics in the statistics pass, and the generator's
             # Adam sign noise on zero-gradient biases reaching the composite from the second iteration on
-            assert torch.allclose(da[k], db[k], rtol=1e-3, atol=1e-5), (k, float((da[k] - db[k]).abs().max()))
+            assert torch.allclose(da[k], db[k], rtol=1e-3, atol=1e-4), (k, float((da[k] - db[k]).abs().max()))
         elif k in ("conv2.bias", "conv3.bias", "conv4.bias"):
             assert float((da[k] - db[k]).abs().max()) <= 2.05e-4, k      # a bias in front of a batch-statistics BN: its gradient IS rounding noise
         else:
