@@ -252,26 +252,50 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
       }
     }
   } else
-  // =============================== epilogue: warps 0-3, lane = co ===============================
+  // =============================== epilogue: warps 0-3, TMEM lane = co ===============================
+  // The accumulators leave TMEM with one output channel per LANE, but in the parameter layout consecutive addresses run over
+  // (ci, tap) [Conv2d] or (co, tap) [ConvTranspose2d]: a direct atomicAdd per lane scatters every warp instruction over 32 cache
+  // lines (measured: the wide layers spent ~30 us in this epilogue whatever their pixel count).  So a warp stages 16 input
+  // channels x TAPS x its rows through shared memory (the operand ring is free once bar_done has fired) and adds them to global
+  // memory with consecutive lanes on consecutive addresses.
   if (warp < 4 && n_my > 0) {
     mbar_wait(bar_done, 0);
     tc_fence_after_sync();
     // M = 128: D row r is TMEM lane r.  M = 64: rows 16 q .. 16 q + 15 are lanes 32 q .. 32 q + 15 (the other lanes are unused)
-    const int co = a.M == 128 ? cob + warp * 32 + lane : (lane < 16 ? cob + warp * 16 + lane : a.Cout);
-    for (int tap = 0; tap < TAPS; ++tap) {
-      const int t_out = a.flip ? TAPS - 1 - tap : tap;
-      for (int c0 = 0; c0 < NB; c0 += 16) {
+    const int rows = a.M == 128 ? 32 : 16;
+    const int co0 = cob + warp * rows;
+    const int n_co = min(rows, a.Cout - co0);
+    float* st = reinterpret_cast<float*>(smem) + warp * (16 * TAPS * 33);        // [ci_l * TAPS + tap_out][33]: co_l fastest, padded
+    for (int c0 = 0; c0 < NB; c0 += 16) {
+      for (int tap = 0; tap < TAPS; ++tap) {
+        const int t_out = a.flip ? TAPS - 1 - tap : tap;
         uint32_t r[16];
         tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * NB + c0), r);
         tmem_ld_wait();
-        if (co < a.Cout) {
+        if (lane < rows) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int ci = cib + c0 + k;
-            if (ci < a.Cin) atomicAdd(a.dw + co * a.so + ci * a.si + t_out, __uint_as_float(r[k]));
+          for (int k = 0; k < 16; ++k) st[(k * TAPS + t_out) * 33 + lane] = __uint_as_float(r[k]);
+        }
+      }
+      __syncwarp();
+      const int n_ci = min(16, a.Cin - (cib + c0));
+      if (n_ci > 0 && n_co > 0) {
+        if (!a.flip) {            // Conv2d parameter [co][ci][tap]: per output channel a run of n_ci * TAPS consecutive floats
+          for (int co_l = 0; co_l < n_co; ++co_l) {
+            float* dst = a.dw + (long long)(co0 + co_l) * a.so + (long long)(cib + c0) * a.si;
+            for (int L = lane; L < n_ci * TAPS; L += 32) atomicAdd(dst + L, st[L * 33 + co_l]);
+          }
+        } else {                  // ConvTranspose2d parameter [ci][co][tap]: per input channel a run of n_co * TAPS consecutive floats
+          for (int ci_l = 0; ci_l < n_ci; ++ci_l) {
+            float* dst = a.dw + (long long)(cib + c0 + ci_l) * a.si + (long long)co0 * a.so;
+            for (int L = lane; L < n_co * TAPS; L += 32) {
+              const int co_l = L / TAPS, t = L - co_l * TAPS;
+              atomicAdd(dst + L, st[(ci_l * TAPS + t) * 33 + co_l]);
+            }
           }
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before_sync();
@@ -310,6 +334,7 @@ int launch_wgrad_tc(WgradTcArgs a, cudaStream_t s) {
   int gx = 148 / (gy * gz);                // one CTA per SM (all 512 TMEM columns); pixel splits: every split adds one round of atomics on the whole (co, ci, tap) block
   if (gx < 1) gx = 1;
   if (gx > a.n_tiles) gx = a.n_tiles;
+  if (4u * 16u * TAPS * 33u * 4u > (uint32_t)stages * stage) return GFR_E_UNSUPPORTED;      // the epilogue's staging tiles reuse the ring
   wgrad_tc_kernel<TAPS><<<dim3(gx, gy, gz), N_THREADS, (size_t)stages * stage + 256, s>>>(a);
   return gfr_launch_status();
 }

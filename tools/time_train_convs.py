@@ -45,3 +45,18 @@ for Cin, Cout, S, taps, org in shapes:
     flop = 2.0 * B * Ho * Ho * Cin * Cout * taps
     us_p = t(lambda: train_ops._pack_dev(w, False, False, Cin, Cout, NT, taps, 4))
     print("%4d->%4d in %3d^2 taps %d NT %3d: %7.1f us  %6.1f TFLOP/s   (pack %5.1f us)" % (Cin, Cout, S, taps, NT, us, flop / us / 1e6, us_p))
+
+if not NCU:
+    print("weight gradients (gfr_conv_wgrad_tc_bf16), B = 16:")
+    for Cin, Cout, S, taps, deconv in [(16, 16, 256, 9, False), (16, 16, 128, 9, False), (32, 32, 64, 9, False), (64, 64, 32, 9, False), (64, 64, 32, 9, True),
+                                       (155, 155, 16, 9, False), (128, 155, 16, 9, True), (155, 64, 32, 9, True), (256, 128, 64, 4, False), (1024, 512, 16, 4, False)]:
+        G = (Cin + 3) // 4
+        Hin = S + 1 if taps == 4 else S
+        x = torch.randn(B, G, Hin, Hin, 4, device="cuda")
+        g = torch.randn(B, (Cout + 3) // 4, S, S, 4, device="cuda")
+        k = 2 if taps == 4 else 3
+        w = torch.zeros((Cin, Cout, k, k) if deconv else (Cout, Cin, k, k), device="cuda", requires_grad=True)
+        w.grad = torch.zeros_like(w)
+        us = t(lambda: train_ops._wgrad(x, g, w, None, deconv, Cin, Cout, taps, 4))
+        flop = 2.0 * B * S * S * Cin * Cout * taps
+        print("%4d->%4d @%3d^2 taps %d %s: %7.1f us  %6.1f TFLOP/s" % (Cin, Cout, S, taps, "deconv" if deconv else "conv  ", us, flop / us / 1e6))
