@@ -287,6 +287,7 @@ struct BnBwdArgs {
   int C;                       // gamma_pad holds C floats when C > 0 (unpadded parameter), else C4*4
   float* g_gamma; float* g_beta;   // += (either may be null): the BatchNorm parameter gradients, written by CTA 0 of the apply pass
   float* g_bias;                   // += (may be null): sum of g_x per channel = the gradient of the conv bias in front of the BatchNorm
+  int g0;                          // >= 0: this launch covers the planes of channel group g0 only (HW % 256 == 0); -1: every group
 };
 
 __device__ __forceinline__ void bn_gpre(const BnBwdArgs& a, size_t i, int g, float (&gp)[4], float (&xh)[4]) {
@@ -303,7 +304,7 @@ __device__ __forceinline__ void bn_gpre(const BnBwdArgs& a, size_t i, int g, flo
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
   __shared__ double s_red[8][8];
-  const int g = blockIdx.y, n = blockIdx.z;
+  const int g = a.g0 >= 0 ? a.g0 : blockIdx.y, n = blockIdx.z;
   const int per = (a.HW + a.chunks - 1) / a.chunks;
   const int lo = blockIdx.x * per, hi = min(lo + per, a.HW);
   const size_t base = ((size_t)n * a.C4 + g) * a.HW;
@@ -344,13 +345,18 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a) {
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   const long long total = (long long)a.N * a.C4 * a.HW;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   // per-channel constants: mean of g_pre, mean of g_pre * xhat, gamma * rstd.  HW % 256 == 0 (every layer of the network): the
   // 256 elements of a CTA share their channel group, so 4 threads compute them once per CTA (the first version divided two
   // fp64 sums per channel in EVERY thread: 8 fp64 divisions per element, 75 us for a 16-channel 256^2 layer at B = 16)
   __shared__ float s_c[3][4];
   const bool uniform = (a.HW & 255) == 0;
-  const unsigned plane_u = uniform ? blockIdx.x / ((unsigned)a.HW >> 8) : 0u;          // the CTA's (n, group) plane: one 32-bit division
+  unsigned plane_u = uniform ? blockIdx.x / ((unsigned)a.HW >> 8) : 0u;          // the CTA's (n, group) plane: one 32-bit division
+  if (a.g0 >= 0) {                  // one channel group per launch: the grid covers its N planes
+    const unsigned bpp = (unsigned)a.HW >> 8, n = blockIdx.x / bpp;
+    plane_u = n * (unsigned)a.C4 + (unsigned)a.g0;
+    i = (long long)plane_u * a.HW + (long long)(blockIdx.x - n * bpp) * 256 + threadIdx.x;
+  }
   if (uniform) {
     if (threadIdx.x < 4) {
       const int c = (int)(plane_u % (unsigned)a.C4) * 4 + threadIdx.x;
@@ -398,7 +404,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
     }
   }
   if (blockIdx.x == 0 && (a.g_gamma != nullptr || a.g_beta != nullptr)) {
-    for (int c = threadIdx.x; c < a.C; c += 256) {
+    const int c_lo = a.g0 >= 0 ? 4 * a.g0 : 0, c_hi = a.g0 >= 0 ? min(a.C, 4 * a.g0 + 4) : a.C;
+    for (int c = c_lo + threadIdx.x; c < c_hi; c += 256) {
       if (a.g_beta) a.g_beta[c] += (float)a.sums[c];
       if (a.g_gamma) a.g_gamma[c] += (float)a.sums[a.C4 * 4 + c];
     }
@@ -1036,7 +1043,7 @@ extern "C" int gfr_bn_apply_bwd(const float* x, const float* res, const float* g
   }
   BnBwdArgs a{reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(res), reinterpret_cast<const float4*>(g_y), scale,
               shift, mean, rstd, gamma_pad, sums_scratch, reinterpret_cast<float4*>(g_x), reinterpret_cast<float4*>(g_res), N, C4, HW, act,
-              chunks_for(N, C4, HW), (double)N * HW, 0, nullptr, nullptr, nullptr};
+              chunks_for(N, C4, HW), (double)N * HW, 0, nullptr, nullptr, nullptr, -1};
   bn_bwd_reduce_kernel<<<dim3(a.chunks, C4, N), 256, 0, s>>>(a);
   const long long total = (long long)N * C4 * HW;
   bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
@@ -1058,9 +1065,22 @@ extern "C" int gfr_bn_apply_bwd_ex(const float* x, const float* res, const float
   }
   BnBwdArgs a{reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(res), reinterpret_cast<const float4*>(g_y), scale,
               shift, mean, rstd, gamma, sums_scratch, reinterpret_cast<float4*>(g_x), reinterpret_cast<float4*>(g_res), N, C4, HW, act,
-              chunks_for(N, C4, HW), (double)N * HW, C, g_gamma, g_beta, (HW % 256) == 0 ? g_bias : nullptr};
-  bn_bwd_reduce_kernel<<<dim3(a.chunks, C4, N), 256, 0, s>>>(a);
+              chunks_for(N, C4, HW), (double)N * HW, C, g_gamma, g_beta, (HW % 256) == 0 ? g_bias : nullptr, -1};
   const long long total = (long long)N * C4 * HW;
+  // A/B (GFR_BN_BWD_SPLIT=1, off): one channel group at a time, so that a group's x / g_y planes (a quarter of a 16-channel tensor)
+  // could still be in L2 when the apply pass reads them again.  Measured SLOWER on the 67 MB tensors of the 256^2 layers at B = 16:
+  // 101 vs 78 us per layer, 9.52 vs 9.08 ms per iteration — eight short launches over strided planes lose more than the re-read costs.
+  static const bool no_split = [] { const char* e = getenv("GFR_BN_BWD_SPLIT"); return !(e != nullptr && e[0] == '1'); }();
+  if (!no_split && (HW % 256) == 0 && C4 > 1 && total * 16 > (24ll << 20) && N * (HW / 256) >= 148) {
+    a.chunks = chunks_for(N, 1, HW);
+    for (int g = 0; g < C4; ++g) {
+      a.g0 = g;
+      bn_bwd_reduce_kernel<<<dim3(a.chunks, 1, N), 256, 0, s>>>(a);
+      bn_bwd_apply_kernel<<<(unsigned)(N * (HW / 256)), 256, 0, s>>>(a);
+    }
+    return gfr_launch_status();
+  }
+  bn_bwd_reduce_kernel<<<dim3(a.chunks, C4, N), 256, 0, s>>>(a);
   bn_bwd_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
   if (g_bias != nullptr && (HW % 256) != 0) {         // ragged planes: the separate per-channel sum
     const int chunks = chunks_for(N, C4, HW);
