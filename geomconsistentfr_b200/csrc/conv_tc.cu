@@ -348,6 +348,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
     const int C4out = (a.Cout + 3) >> 2;
     const int pH = a.H >> a.post_shift, pW = a.W >> a.post_shift;
     griddep_wait();                                       // residual / skip operands and the output buffer belong to earlier kernels
+    // BF16 kind (the training convolutions): this N tile's bias once per CTA in shared memory, zero beyond Cout
+    __shared__ __align__(16) float s_bias[CUT ? 4 : NT];
+    if constexpr (!CUT) {
+      for (int i = tid - 192; i < NT; i += 128) s_bias[i] = (n0 + i < a.Cout) ? __ldg(a.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     int g = 0, ti = 0;
     for (int mt = blockIdx.x; mt < a.m_tiles; mt += gridDim.x, ++ti) {
       const int tx = mt % a.tiles_x, t2 = mt / a.tiles_x;
@@ -407,6 +413,45 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvTcArgs a)
       } else {
         mbar_wait(bar_accfull + 8 * (ti & 1), (ti >> 1) & 1);
         tc_fence_after_sync();
+      }
+      if constexpr (!CUT && !HEAD) {
+        if (a.res == nullptr && a.post == nullptr) {
+          // The training convolutions (raw = acc + bias, PatchGAN's conv1 + LeakyReLU): nothing but the bias, the activation and the
+          // store per 4-channel group.  The generic code below spends ~77 instructions per group (operand pointers re-read from the
+          // constant bank, per-element bounds) on ONE warp per scheduler — 2.5 us per 128 x 64 tile, more than the tile's MMAs.
+          float* outp = a.out + o_base + (size_t)(n0 >> 2) * o_plane;
+          const int c4_lim = C4out - (n0 >> 2);
+          const int act = a.act;
+          const float scale = a.out_scale;
+          const uint32_t t_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((ti & 1) * S::ACC);
+          constexpr int GW = NT >= 32 ? 32 : 16;            // columns per TMEM round trip
+#pragma unroll
+          for (int cg = 0; cg < NT; cg += GW) {
+            uint32_t rm[GW];
+            tmem_ld16(t_base + cg, *reinterpret_cast<uint32_t(*)[16]>(rm));
+            if constexpr (GW == 32) tmem_ld16(t_base + cg + 16, *reinterpret_cast<uint32_t(*)[16]>(rm + 16));
+            tmem_ld_wait();
+            if (ok) {
+#pragma unroll
+              for (int c0 = 0; c0 < GW; c0 += 4) {
+                const int gi = (cg + c0) >> 2;
+                if (gi < c4_lim) {
+                  const float4 b = *reinterpret_cast<const float4*>(s_bias + cg + c0);
+                  float v[4] = {__uint_as_float(rm[c0]) + b.x, __uint_as_float(rm[c0 + 1]) + b.y, __uint_as_float(rm[c0 + 2]) + b.z,
+                                __uint_as_float(rm[c0 + 3]) + b.w};
+                  if (act == 1) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : 0.2f * v[e];
+                  }
+                  *reinterpret_cast<float4*>(outp + (size_t)gi * o_plane) = make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
+                }
+              }
+            }
+          }
+          tc_fence_before_sync();
+          mbar_arrive(bar_accempty + 8 * (ti & 1));
+          continue;
+        }
       }
       [[maybe_unused]] float yv[HEAD ? NT : 1];
 #pragma unroll
