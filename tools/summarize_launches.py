@@ -6,7 +6,7 @@ last = int(sys.argv[sys.argv.index("--last") + 1]) if "--last" in sys.argv else 
 skip_last = int(sys.argv[sys.argv.index("--skip-last") + 1]) if "--skip-last" in sys.argv else 0
 rows = []
 with open(path, newline="") as f:
-    lines = [l for l in f if not l.startswith("==")]
+    lines = [l for l in f if not l.startswith("==") and not l.startswith("#")]
 rd = csv.reader(lines)
 hdr = next(rd)
 ix = {h: i for i, h in enumerate(hdr)}
