@@ -70,7 +70,8 @@ struct ConvP16Args {
   __half* pool;          // P16 [N][out_groups][2][H/2][W/2][8] or null: the 2x2 / stride 2 max pool of `out`, from the same epilogue
 };
 
-template <int NT, int MH, int KS, int GEO = 0>
+// ES = epilogue column split: every (M-half, TMEM lane quarter) is served by ES warps that take NT / ES output channels each
+template <int NT, int MH, int KS, int GEO = 0, int ES = 1>
 struct Cfg {
   static constexpr int TAPS = GEO == 0 ? 9 : 5;
   static constexpr int PAD_X = GEO == 0 ? 1 : 0, PAD_Y = GEO == 0 ? 1 : 2;
@@ -84,7 +85,8 @@ struct Cfg {
   static constexpr uint32_t W_STEP = TAPS * B_TAP;
   // halo-tile offset (in pixels) of filter tap t
   __host__ __device__ static constexpr uint32_t tap_px(int t) { return GEO == 0 ? (uint32_t)((t / 3) * HALO_W + (t % 3)) : (uint32_t)(t * HALO_W); }
-  static constexpr int EPI_WARPS = 4 * MH, THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int EPI_WARPS = 4 * MH * ES, THREADS = 64 + 32 * EPI_WARPS;
+  static_assert(ES == 1 || (ES == 2 && NT == 16), "the column split hands each warp one 8-channel chunk of a 16-channel tile");
   static constexpr uint32_t ACC_COLS = MH * 2 * NT;             // one accumulator buffer: per M-half [main NT | correction NT]
   static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
   static constexpr uint32_t BAR_BYTES = 512;                    // barriers + TMEM slot (176 B), then bias*16 (NT floats) at +256
@@ -102,12 +104,13 @@ struct HeadParams {
 };
 struct NoHead { int unused; };
 
-template <int NT, int MH, int KS, int GEO = 0, bool HEAD = false>
-__global__ void __launch_bounds__(Cfg<NT, MH, KS, GEO>::THREADS, (NT * MH <= 32) ? GFR_P16_MINBLOCKS : 1)
+template <int NT, int MH, int KS, int GEO = 0, bool HEAD = false, int ES = 1>
+__global__ void __launch_bounds__(Cfg<NT, MH, KS, GEO, ES>::THREADS, (NT * MH <= 32 && ES == 1) ? GFR_P16_MINBLOCKS : 1)
 conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args a,
                    const __grid_constant__ typename std::conditional<HEAD, HeadParams, NoHead>::type hp) {
-  using C = Cfg<NT, MH, KS, GEO>;
+  using C = Cfg<NT, MH, KS, GEO, ES>;
   static_assert(!HEAD || NT == 16, "the fused 1x1 tail works on 16 channels");
+  static_assert(!HEAD || ES == 1, "the fused 1x1 tail needs the pixel's 16 channels in one thread");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool resident = a.nsteps == 1;
@@ -218,7 +221,13 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
     // Everything is computed in the x16 domain of the stored pair (16 v = hi + lo): bias and 1/(x_scale*w_scale) are
     // pre-multiplied, LeakyReLU is homogeneous, residual / post operands are added as hi + lo without rescaling.  The
     // instruction count per tile matters: the epilogue warps share their schedulers with the MMA-issuing warp.
-    const int e = warp - 2, h = e >> 2, q = warp & 3;      // q: the TMEM lane quarter this warp may access
+    // q: the TMEM lane quarter this warp may access (warp % 4, a hardware rule); h: its M-half; cs: its share of the output channels.
+    // ES = 2 (A/B, see launch_p16): 16 epilogue warps, four per scheduler, 8 channels each.  The epilogue warps execute 95 % of the
+    // kernel's instructions (~570 per tile and warp, ncu source page) and wait for accumulators only 7 % of their time, yet doubling
+    // them buys 7 % on the layer alone and costs more than that in the overlapped forward.
+    const int e = warp - 2, h = (e >> 2) % MH, cs = e / (4 * MH), q = warp & 3;
+    constexpr int NC = NT / ES;                             // output channels (TMEM columns of main / correction) of this warp
+    const int col0 = cs * NC, ch0 = col0 >> 3;
     const int m = q * 32 + lane;
     const int n0 = blockIdx.y * NT;
     const int pH = a.H >> a.post_shift, pW = a.W >> a.post_shift;
@@ -245,23 +254,24 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
       // NOW, before the wait for the accumulators, so their L2 / DRAM latency overlaps the MMAs of this tile; wider layers
       // (32 accumulator registers more per thread) keep the L2 prefetch and load after the MMAs.
       constexpr bool EARLY = (NT == 16) && !HEAD && GFR_P16_EARLY_LOADS;
-      uint4 e_res[EARLY ? 4 : 1], e_post[EARLY ? 4 : 1];
+      uint4 e_res[EARLY ? NC / 4 : 1], e_post[EARLY ? NC / 4 : 1];
       if (EARLY) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int l = 0; l < NC / 8; ++l) {
+          const int c = ch0 + l;
           const bool lc = ok && c < n_chunks;
-          e_res[2 * c] = e_res[2 * c + 1] = e_post[2 * c] = e_post[2 * c + 1] = make_uint4(0u, 0u, 0u, 0u);
+          e_res[2 * l] = e_res[2 * l + 1] = e_post[2 * l] = e_post[2 * l + 1] = make_uint4(0u, 0u, 0u, 0u);
           if (res_p && lc) {
-            e_res[2 * c] = __ldg(reinterpret_cast<const uint4*>(res_p + 2 * c * plane));
-            e_res[2 * c + 1] = __ldg(reinterpret_cast<const uint4*>(res_p + (2 * c + 1) * plane));
+            e_res[2 * l] = __ldg(reinterpret_cast<const uint4*>(res_p + 2 * c * plane));
+            e_res[2 * l + 1] = __ldg(reinterpret_cast<const uint4*>(res_p + (2 * c + 1) * plane));
           }
           if (post_p && lc) {
-            e_post[2 * c] = __ldg(reinterpret_cast<const uint4*>(post_p + 2 * c * pplane));
-            e_post[2 * c + 1] = __ldg(reinterpret_cast<const uint4*>(post_p + (2 * c + 1) * pplane));
+            e_post[2 * l] = __ldg(reinterpret_cast<const uint4*>(post_p + 2 * c * pplane));
+            e_post[2 * l + 1] = __ldg(reinterpret_cast<const uint4*>(post_p + (2 * c + 1) * pplane));
           }
         }
       } else if (ok && (res_p || post_p)) {
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = ch0; c < min(n_chunks, ch0 + NC / 8); ++c) {
           if (res_p) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(res_p + 2 * c * plane));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(res_p + (2 * c + 1) * plane));
@@ -272,24 +282,38 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
           }
         }
       }
-      float sum[NT];
+      float sum[NC];
       for (int st = 0; st < a.nsteps; ++st, ++g) {
         const int p = g & 1;
         mbar_wait(bar_accfull + 8 * p, (g >> 1) & 1);
         tc_fence_after_sync();
-        const uint32_t t_main = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * C::ACC_COLS + h * 2 * NT);
-#pragma unroll
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          uint32_t rm[16], rc[16];
-          tmem_ld16(t_main + c0, rm);
-          tmem_ld16(t_main + NT + c0, rc);
+        const uint32_t t_main = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * C::ACC_COLS + h * 2 * NT + col0);
+        if constexpr (NC == 8) {
+          uint32_t rm[8], rc[8];
+          tmem_ld8(t_main, rm);
+          tmem_ld8(t_main + NT, rc);
           tmem_ld_wait();
           if (st == 0) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) sum[c0 + k] = __uint_as_float(rm[k]) + __uint_as_float(rc[k]);
+            for (int k = 0; k < 8; ++k) sum[k] = __uint_as_float(rm[k]) + __uint_as_float(rc[k]);
           } else {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) sum[c0 + k] += __uint_as_float(rm[k]) + __uint_as_float(rc[k]);
+            for (int k = 0; k < 8; ++k) sum[k] += __uint_as_float(rm[k]) + __uint_as_float(rc[k]);
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < NC; c0 += 16) {
+            uint32_t rm[16], rc[16];
+            tmem_ld16(t_main + c0, rm);
+            tmem_ld16(t_main + NT + c0, rc);
+            tmem_ld_wait();
+            if (st == 0) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) sum[c0 + k] = __uint_as_float(rm[k]) + __uint_as_float(rc[k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) sum[c0 + k] += __uint_as_float(rm[k]) + __uint_as_float(rc[k]);
+            }
           }
         }
         tc_fence_before_sync();
@@ -318,16 +342,17 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
       __half* pool_p = a.pool ? a.pool + gfr_p16::unit_offset(n, a.out_groups, n0 >> 3, a.H >> 1, a.W >> 1, y >> 1, x >> 1) : nullptr;
       const bool pool_writer = ok && !(lane & 1) && !(lane & 8);
 #pragma unroll
-      for (int c = 0; c < NT / 8; ++c) {
+      for (int l = 0; l < NC / 8; ++l) {
+        const int c = ch0 + l;                                   // chunk of the N tile; l: this warp's
         if (c >= n_chunks) break;
         float v[8];
         const float4 b0 = *reinterpret_cast<const float4*>(s_bias16 + 8 * c), b1 = *reinterpret_cast<const float4*>(s_bias16 + 8 * c + 4);
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaf(sum[8 * c + k], inv16, bb[k]);
+        for (int k = 0; k < 8; ++k) v[k] = fmaf(sum[8 * l + k], inv16, bb[k]);
         if (res_p && ok) {
           float rv[8];
-          if (EARLY) gfr_p16::join8_x16(e_res[(2 * c) & 3], e_res[(2 * c + 1) & 3], rv);
+          if (EARLY) gfr_p16::join8_x16(e_res[(2 * l) & 3], e_res[(2 * l + 1) & 3], rv);
           else gfr_p16::join8_x16(__ldg(reinterpret_cast<const uint4*>(res_p + 2 * c * plane)),
                                   __ldg(reinterpret_cast<const uint4*>(res_p + (2 * c + 1) * plane)), rv);
 #pragma unroll
@@ -344,7 +369,7 @@ conv3x3_p16_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvP16Args 
         }
         if (post_p && ok) {
           float pv[8];
-          if (EARLY) gfr_p16::join8_x16(e_post[(2 * c) & 3], e_post[(2 * c + 1) & 3], pv);
+          if (EARLY) gfr_p16::join8_x16(e_post[(2 * l) & 3], e_post[(2 * l + 1) & 3], pv);
           else gfr_p16::join8_x16(__ldg(reinterpret_cast<const uint4*>(post_p + 2 * c * pplane)),
                                   __ldg(reinterpret_cast<const uint4*>(post_p + (2 * c + 1) * pplane)), pv);
 #pragma unroll
@@ -433,13 +458,20 @@ int make_p16_map(CUtensorMap* tm, const void* base, int N, int C8, int groups, i
 
 int g_p16_grid_occ = 0;      // 0 = default (environment, else 1), 1 | 2 = persistent CTAs per SM (gfr_conv_p16_config)
 
-template <int NT, int MH, int KS, int GEO = 0, bool HEAD = false>
+template <int NT, int MH, int KS, int GEO = 0, bool HEAD = false, int ES = 1>
 int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s, const HeadParams* head = nullptr) {
-  using C = Cfg<NT, MH, KS, GEO>;
+  if constexpr (ES == 1 && NT == 16 && !HEAD) {
+    // A/B (GFR_P16_EPI_SPLIT=1, off): the 16-channel layers with 16 epilogue warps of 8 channels instead of 8 of 16.  Measured: the
+    // 256^2 layer alone 28.7 -> 26.7 us, but the forward 17.0k vs 19.1k faces/s and 0.535 vs 0.501 ms latency — the 576-thread CTAs
+    // leave less room beside them and start slower on the latency-bound small layers.
+    static const bool split = [] { const char* e = getenv("GFR_P16_EPI_SPLIT"); return e != nullptr && e[0] == '1'; }();
+    if (split) return launch_p16<NT, MH, KS, GEO, HEAD, 2>(tm, a, s, head);
+  }
+  using C = Cfg<NT, MH, KS, GEO, ES>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv3x3_p16_kernel<NT, MH, KS, GEO, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_err = cudaFuncSetAttribute(conv3x3_p16_kernel<NT, MH, KS, GEO, HEAD, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return (int)attr_err;
   const bool resident = a.nsteps == 1;
@@ -487,8 +519,8 @@ int launch_p16(const CUtensorMap& tm, ConvP16Args a, cudaStream_t s, const HeadP
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
   cudaError_t e;
-  if constexpr (HEAD) e = cudaLaunchKernelEx(&cfg, conv3x3_p16_kernel<NT, MH, KS, GEO, true>, tm, a, *head);
-  else e = cudaLaunchKernelEx(&cfg, conv3x3_p16_kernel<NT, MH, KS, GEO, false>, tm, a, NoHead{0});
+  if constexpr (HEAD) e = cudaLaunchKernelEx(&cfg, conv3x3_p16_kernel<NT, MH, KS, GEO, true, ES>, tm, a, *head);
+  else e = cudaLaunchKernelEx(&cfg, conv3x3_p16_kernel<NT, MH, KS, GEO, false, ES>, tm, a, NoHead{0});
   return e == cudaSuccess ? gfr_launch_status() : (int)e;
 }
 
