@@ -604,33 +604,43 @@ struct PwArgs {
 };
 
 __global__ void __launch_bounds__(256) pw_conv16_fwd_kernel(const PwArgs a) {
-  __shared__ float s_w[16][16];
+  __shared__ __align__(16) float s_w[16][16];
   __shared__ float s_b[16];
   for (int i = threadIdx.x; i < 16 * 16; i += 256) s_w[i >> 4][i & 15] = (i >> 4) < a.Cout ? __ldg(a.w + i) : 0.f;
   if (threadIdx.x < 16) s_b[threadIdx.x] = threadIdx.x < a.Cout ? __ldg(a.bias + threadIdx.x) : 0.f;
   __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.total) return;
-  const long long n = i / a.hw, p = i % a.hw;
-  const float4* src = reinterpret_cast<const float4*>(a.in) + n * 4 * a.hw + p;
-  float x[16];
+  // persistent over 256-pixel chunks; hw % 256 == 0 (every layer here): the image index is one 32-bit division per chunk
+  const long long n_chunks = (a.total + 255) >> 8;
+  const unsigned cpi = (a.hw & 255) == 0 ? (unsigned)(a.hw >> 8) : 0u;       // chunks per image
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const long long i = chunk * 256 + threadIdx.x;
+    if (i >= a.total) continue;
+    long long n, p;
+    if (cpi) { const unsigned nn = (unsigned)chunk / cpi; n = nn; p = (long long)((unsigned)chunk - nn * cpi) * 256 + threadIdx.x; }
+    else { n = i / a.hw; p = i - n * a.hw; }
+    const float4* src = reinterpret_cast<const float4*>(a.in) + n * 4 * a.hw + p;
+    float x[16];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) { const float4 v = __ldg(src + q * a.hw); x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w; }
-  float y[16];
+    for (int q = 0; q < 4; ++q) { const float4 v = __ldg(src + q * a.hw); x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w; }
+    float y[16];
 #pragma unroll
-  for (int o = 0; o < 16; ++o) {
-    float s = s_b[o];
+    for (int o = 0; o < 16; ++o) {
+      float s = s_b[o];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) s = fmaf(s_w[o][c], x[c], s);
-    if (a.act == 2) s = 1.0f / (1.0f + expf(-s));
-    y[o] = s * a.scale;
-  }
-  if (a.planar) {
-    for (int o = 0; o < a.Cout; ++o) a.out[(n * a.Cout + o) * a.hw + p] = y[o];
-  } else {
-    float4* dst = reinterpret_cast<float4*>(a.out) + n * 4 * a.hw + p;
+      for (int q = 0; q < 4; ++q) {          // same order as before (c ascending): bit-identical, 64 LDS.128 instead of 256 LDS
+        const float4 w4 = *reinterpret_cast<const float4*>(&s_w[o][4 * q]);
+        s = fmaf(w4.x, x[4 * q], s); s = fmaf(w4.y, x[4 * q + 1], s); s = fmaf(w4.z, x[4 * q + 2], s); s = fmaf(w4.w, x[4 * q + 3], s);
+      }
+      if (a.act == 2) s = 1.0f / (1.0f + expf(-s));
+      y[o] = s * a.scale;
+    }
+    if (a.planar) {
+      for (int o = 0; o < a.Cout; ++o) a.out[(n * a.Cout + o) * a.hw + p] = y[o];
+    } else {
+      float4* dst = reinterpret_cast<float4*>(a.out) + n * 4 * a.hw + p;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) dst[q * a.hw] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+      for (int q = 0; q < 4; ++q) dst[q * a.hw] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+    }
   }
 }
 
@@ -657,12 +667,27 @@ __global__ void __launch_bounds__(256) pw_conv16_bwd_kernel(const PwBwdArgs a) {
   __shared__ __align__(16) float s_x[256 * PW_PITCH], s_g[256 * PW_PITCH];     // this CTA's 256 pixels: forward input and output gradient
   for (int i = threadIdx.x; i < 16 * 16; i += 256) s_w[i >> 4][i & 15] = (i >> 4) < a.Cout ? __ldg(a.w + i) : 0.f;
   __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // Persistent over 256-pixel chunks: the weight / bias gradient partials stay in registers across a CTA's chunks and leave with ONE
+  // round of shared-memory sums + atomics per CTA (one CTA per chunk meant 4 096 CTAs x 272 atomics on the same 272 addresses for a
+  // 256^2 layer at B = 16, and two 64-bit divisions per thread).
+  const long long n_chunks = (a.total + 255) >> 8;
+  const unsigned cpi = (a.hw & 255) == 0 ? (unsigned)(a.hw >> 8) : 0u;       // chunks per image
+  const int blk = threadIdx.x & 15, o4 = blk >> 2, c4 = blk & 3, pg = threadIdx.x >> 4;
+  float acc[4][4];
+  float4 accb = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  for (long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+  const long long i = chunk * 256 + threadIdx.x;
   float x[16], g[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) { x[c] = 0.f; g[c] = 0.f; }
   if (i < a.total) {
-    const long long n = i / a.hw, p = i % a.hw;
+    long long n, p;
+    if (cpi) { const unsigned nn = (unsigned)chunk / cpi; n = nn; p = (long long)((unsigned)chunk - nn * cpi) * 256 + threadIdx.x; }
+    else { n = i / a.hw; p = i - n * a.hw; }
     const float4* src = reinterpret_cast<const float4*>(a.in) + n * 4 * a.hw + p;
 #pragma unroll
     for (int q = 0; q < 4; ++q) { const float4 v = __ldg(src + q * a.hw); x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w; }
@@ -694,20 +719,14 @@ __global__ void __launch_bounds__(256) pw_conv16_bwd_kernel(const PwBwdArgs a) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) dst[q * a.hw] = make_float4(gi[4 * q], gi[4 * q + 1], gi[4 * q + 2], gi[4 * q + 3]);
   }
-  // weight / bias gradients
+  // weight / bias gradient partials of this chunk
+  __syncthreads();                                   // (the previous chunk's readers are done with s_x / s_g)
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     *reinterpret_cast<float4*>(&s_x[threadIdx.x * PW_PITCH + 4 * q]) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
     *reinterpret_cast<float4*>(&s_g[threadIdx.x * PW_PITCH + 4 * q]) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
   }
   __syncthreads();
-  const int blk = threadIdx.x & 15, o4 = blk >> 2, c4 = blk & 3, pg = threadIdx.x >> 4;
-  float acc[4][4];
-  float4 accb = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
 #pragma unroll 4
   for (int j = 0; j < 16; ++j) {
     const int px = 16 * j + pg;
@@ -719,6 +738,7 @@ __global__ void __launch_bounds__(256) pw_conv16_bwd_kernel(const PwBwdArgs a) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(gg[r], xx[c], acc[r][c]);
     accb.x += gv.x; accb.y += gv.y; accb.z += gv.z; accb.w += gv.w;
+  }
   }
   __syncthreads();                                 // s_x / s_g are free: reuse them for the cross-group sums
   float* s_part = s_x;                             // [16 groups][16 blocks][16] = 4096 floats (s_x holds 5120)
@@ -1172,7 +1192,8 @@ extern "C" int gfr_pw_conv16_fwd(const float* in, const float* w, const float* b
   if (N <= 0 || H <= 0 || W <= 0 || Cout < 1 || Cout > 16) return GFR_E_SHAPE;
   if ((act != 0 && act != 2) || (!planar_out && Cout != 16)) return GFR_E_ARG;
   PwArgs a{in, w, bias, out, (long long)H * W, (long long)N * H * W, Cout, planar_out, act, out_scale};
-  pw_conv16_fwd_kernel<<<(unsigned)((a.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  const long long chunks = (a.total + 255) / 256;
+  pw_conv16_fwd_kernel<<<(unsigned)(chunks < 148 * 8 ? chunks : 148 * 8), 256, 0, (cudaStream_t)stream>>>(a);
   return gfr_launch_status();
 }
 
@@ -1183,7 +1204,8 @@ extern "C" int gfr_pw_conv16_bwd(const float* in, const float* w, const float* g
   if (N <= 0 || H <= 0 || W <= 0 || Cout < 1 || Cout > 16) return GFR_E_SHAPE;
   if ((act != 0 && act != 2) || (!planar_out && Cout != 16) || (act == 2 && (out == nullptr || !planar_out))) return GFR_E_ARG;
   PwBwdArgs a{in, w, g_out, out, g_in, g_w, g_bias, (long long)H * W, (long long)N * H * W, Cout, planar_out, act, out_scale};
-  pw_conv16_bwd_kernel<<<(unsigned)((a.total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  const long long chunks = (a.total + 255) / 256;
+  pw_conv16_bwd_kernel<<<(unsigned)(chunks < 148 * 5 ? chunks : 148 * 5), 256, 0, (cudaStream_t)stream>>>(a);      // 5 CTAs of 41 KB per SM
   return gfr_launch_status();
 }
 

@@ -35,3 +35,14 @@ for C, S, res in [(16, 256, False), (16, 256, True), (16, 128, True), (32, 64, T
     n_a, n_b = (3 if res else 2), (2 * (3 if res else 2) + (2 if res else 1))
     print("C %3d @%3d^2 res %d (%5.1f MB/tensor): stats %6.1f us %5.2f TB/s | apply %6.1f us %5.2f TB/s | bwd %6.1f us %5.2f TB/s" %
           (C, S, res, mb, us_s, mb / us_s, us_a, n_a * mb / us_a, us_b, n_b * mb / us_b))
+
+# the decoders' 1x1 tails (16 -> 16 at 256^2): forward and backward (data + weight gradient)
+from geomconsistentfr_b200 import _lib
+from geomconsistentfr_b200.ops import _ptr, _stream
+x = torch.randn(B, 4, 256, 256, 4, device="cuda"); gy = torch.randn_like(x); y = torch.empty_like(x); gx = torch.empty_like(x)
+w = torch.randn(16, 16, device="cuda") * 0.1; b = torch.zeros(16, device="cuda"); gw = torch.zeros_like(w); gb = torch.zeros_like(b)
+L = _lib.load()
+us_f = t(lambda: L.gfr_pw_conv16_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), B, 16, 256, 256, 0, 0, 1.0, _stream()))
+us_b = t(lambda: L.gfr_pw_conv16_bwd(_ptr(x), _ptr(w), _ptr(gy), None, _ptr(gx), _ptr(gw), _ptr(gb), B, 16, 256, 256, 0, 0, 1.0, _stream()))
+mb = x.numel() * 4 / 1e6
+print("1x1 16->16 @256^2: fwd %6.1f us %5.2f TB/s | bwd %6.1f us %5.2f TB/s" % (us_f, 2 * mb / us_f, us_b, 3 * mb / us_b))
