@@ -33,10 +33,14 @@ namespace {
 
 constexpr int TW = 8, TH = 16;                     // pixel tile (128 pixels = 8 K-steps of 16)
 constexpr int HW_ = TW + 2, HH = TH + 2;           // halo tile of the layer input
-constexpr int N_PROD = 256, N_THREADS = N_PROD + 32;
+#ifndef GFR_WGRAD_GROUPS
+#define GFR_WGRAD_GROUPS 2
+#endif
+constexpr int N_PROD = 128 * GFR_WGRAD_GROUPS, N_THREADS = N_PROD + 32, PROD_WARPS = N_PROD / 32;
 constexpr uint32_t G_CHUNK = TH * TW * 16;         // 2048: one 8-channel chunk of the g tile
 constexpr uint32_t G_BYTES = 16 * G_CHUNK;         // M = 128 rows = 16 chunks (M = 64: the first 8), always addressed by the MMA
-constexpr int N_GROUPS = 2, GROUP_THREADS = N_PROD / N_GROUPS;   // producer groups take alternate tiles (two tiles' loads in flight)
+constexpr int N_GROUPS = GFR_WGRAD_GROUPS, GROUP_THREADS = N_PROD / N_GROUPS;   // producer groups of 128 threads take alternate tiles (one tile's loads in flight per group; -DGFR_WGRAD_GROUPS=n, n <= the ring depth)
+static_assert(GROUP_THREADS == 128 && N_GROUPS >= 1 && N_GROUPS <= 4, "groups of four warps, at most one per ring slot");
 constexpr uint32_t X_CHUNK = HH * HW_ * 16;        // 2880
 constexpr int MAX_STAGES = 4;
 #ifndef GFR_WGRAD_XSHIFT_DEFAULT
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
     mbar_init(bar_done, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(bars + TMEM_SLOT, 512);
+  if (warp == PROD_WARPS) tmem_alloc(bars + TMEM_SLOT, 512);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
@@ -112,14 +116,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
   const size_t gplane = (size_t)a.H * a.W, iplane = (size_t)a.Hin * a.Win;
   const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp < 8) {
+  if (warp < PROD_WARPS) {
     // =============================== producers ===============================
     const float4* gsrc = reinterpret_cast<const float4*>(a.g);
     const float4* isrc = reinterpret_cast<const float4*>(a.in);
     const int grp_id = tid / GROUP_THREADS, gtid = tid % GROUP_THREADS;
+    const int n_groups = N_GROUPS < STAGES ? N_GROUPS : STAGES;        // groups beyond that stay idle
     int s = 0, ph = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-      const bool mine = (it % N_GROUPS) == grp_id;
+      // never more groups than ring slots: a group that ran two phases ahead of its slot's `empty` barrier would pass the parity wait
+      const bool mine = (it % n_groups) == grp_id;
       if (!mine) { if (++s == STAGES) { s = 0; ph ^= 1; } continue; }
       const int tx = tile % a.tiles_x, t2 = tile / a.tiles_x;
       const int ty = t2 % a.tiles_y, n = t2 / a.tiles_y;
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) wgrad_tc_kernel(const WgradTcArg
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == PROD_WARPS) tmem_dealloc(tmem, 512);
 }
 
 int g_wgrad_xshift = -1;      // -1 default (environment GFR_WGRAD_XSHIFT, else the built-in choice), 0 / 1 (gfr_wgrad_tc_config)
